@@ -1,0 +1,220 @@
+/*
+ * offk.h -- C ABI of liboffk.so, the sm_100a kernels behind the OFF
+ * (Optical Flow guided Feature) unit and OFF sub-network.
+ *
+ * The reference (JoeHEZHAO/Optical-Flow-Guided-Feature-Pytorch) has no FFI
+ * layer of its own: its boundary is the nn.Module surface and every op on the
+ * path is a stock ATen call.  Each entry point below
+ * therefore names the reference call sites it replaces (file:line into the
+ * reference repository).  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, ints, an opaque stream (cudaStream_t cast
+ *     to void*).  No torch types.  All tensors fp32, NCHW, caller-owned.
+ *   - the library never allocates or frees device memory and never keeps a
+ *     pointer past the call; every call is asynchronous on `stream` and safe
+ *     under CUDA-graph capture.
+ *   - return 0 on success; a positive cudaError_t or a negative OFFK_E_* code
+ *     otherwise.  offk_last_error_string() describes the last failure of the
+ *     calling thread.  No exceptions, no exit().
+ */
+#ifndef OFFK_H_
+#define OFFK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFFK_VERSION 100 /* 0.1.0 */
+
+#define OFFK_E_BADARG   (-1)  /* shape / alignment / null-pointer violation */
+#define OFFK_E_NOTSM100 (-2)  /* device is not compute capability 10.x       */
+#define OFFK_E_LIMIT    (-3)  /* size beyond what the kernel supports        */
+
+/* arithmetic of the dense contractions */
+#define OFFK_PREC_FP32 0  /* CUDA-core FFMA, fp32 accumulate (exact mode)              */
+#define OFFK_PREC_TF32 1  /* tcgen05.mma kind::tf32, operands in smem, fp32 accum TMEM */
+
+/* which frame feeds the spatial branch of pair p=(b,t) */
+#define OFFK_INDEX_REFERENCE_FLAT 0 /* flat frame p, as RGB_OFF.py:609 literally does */
+#define OFFK_INDEX_ALIGNED        1 /* frame (b,t)                                    */
+
+/* dropout on the spatial-gradient channels / pooled head features */
+#define OFFK_DROP_NONE 0
+#define OFFK_DROP_MASK 1 /* caller-supplied uint8 keep-mask (1 = keep)             */
+#define OFFK_DROP_SEED 2 /* counter-hash keep decision from (seed, element index)   */
+
+int offk_version(void);
+const char* offk_last_error_string(void);
+/* fills sm_count, cc_major, cc_minor, l2_bytes of the current device */
+int offk_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_bytes);
+
+/* ------------------------------------------------------------------------
+ * Gather-GEMM:  D[m,n] = sum_k A(m,k) * B(n,k),  then a fused epilogue.
+ *
+ * Every dense contraction on the path is this one kernel: the 1x1
+ * channel-reduction convs of the nine OFF units (RGB_OFF.py:597,610 ...),
+ * the stage-entry 7x7/5x5/3x3 convs (:657,:762,:833), the residual-block
+ * convs (:659-685,:764-780,:835-841), the three FC heads (:787,:793,:847) and
+ * the data-/weight-gradient of all of them (autograd, train_off.py:136-146).
+ * What differs per layer is only WHERE element (m,k) / (n,k) / (m,n) lives;
+ * that is described by separable index tables built once per layer geometry
+ * (offk_conv_tables_*() below, or the Python host mirror):
+ *
+ *   A(m,k) = a_src[a_row[m].off + a_col[k].off]   if 0 <= a_row[m].y + a_col[k].y < a_h
+ *                                                 and 0 <= a_row[m].x + a_col[k].x < a_w, else 0
+ *            (a_h == 0 disables the box test; a_ones_row == m gives A(m,.) = 1 -> bias gradient)
+ *   B(n,k) = b_src[b_row[n] + b_col[k]]
+ *   out[out_row[m] + out_col[n]]  receives the epilogue of D[m,n].
+ *
+ * Epilogue, in this order, each step optional:
+ *   v = D[m,n] + bias[n]
+ *   v = max(v,0)                         if n <  relu_pre_cols
+ *   v = gate[g] > 0 ? v : 0              if gate && gate_first  && n >= gate_col0   (ReLU')
+ *   v = v + addend[a_row + a_col]        if addend
+ *   v = gate[g] > 0 ? v : 0              if gate && !gate_first && n >= gate_col0
+ *   v = max(v,0)                         if relu_post
+ *   out = v   (atomic add when split_k > 1 or atomic_out; then bias / activations are NOT applied)
+ * gate / addend use (gate_row,gate_col) / (add_row,add_col) or, when NULL, the out tables.
+ * ---------------------------------------------------------------------- */
+typedef struct offk_idx {
+  int32_t off; /* element offset contribution                        */
+  int16_t y;   /* row coordinate contribution for the validity box   */
+  int16_t x;   /* column coordinate contribution                     */
+} offk_idx_t;
+
+typedef struct offk_gemm {
+  int32_t M, N, K;
+  /* A operand */
+  const float* a_src;
+  const offk_idx_t* a_row; /* [M] */
+  const offk_idx_t* a_col; /* [K] */
+  int32_t a_h, a_w;        /* validity box; a_h == 0: always valid */
+  int32_t a_relu;          /* max(.,0) on load (consumer of a pre-activation tensor, RGB_OFF.py:658) */
+  int32_t a_ones_row;      /* -1, or the row whose A values are all 1 */
+  int32_t a_klane;         /* 1: source is contiguous along k -> lanes walk k (weight-gradient GEMMs) */
+  /* B operand */
+  const float* b_src;
+  const int32_t* b_row; /* [N] */
+  const int32_t* b_col; /* [K] */
+  int32_t b_klane;      /* 1: contiguous along k */
+  /* epilogue */
+  float* out;
+  const int32_t* out_row; /* [M] */
+  const int32_t* out_col; /* [N] */
+  const float* bias;      /* [N] or NULL */
+  int32_t relu_pre_cols;
+  const float* gate;
+  const int32_t* gate_row;
+  const int32_t* gate_col;
+  int32_t gate_col0;
+  int32_t gate_first;
+  const float* addend;
+  const int32_t* add_row;
+  const int32_t* add_col;
+  int32_t relu_post;
+  int32_t atomic_out;
+  float* ones_row_out; /* wgrad: D[a_ones_row, n] accumulates into ones_row_out[n] (bias gradient) */
+  int32_t split_k;     /* >= 1; > 1 forces atomic accumulation into a zero-initialised `out` */
+  int32_t tile_n;      /* 0 = auto; else the N tile of the tensor-core kernel (multiple of 16, <= 256) */
+  int32_t b_dense;     /* 1: b_col[k] == k, K % 4 == 0 and every b_src + b_row[n] is 16-byte aligned -> float4 loads */
+  int32_t reserved;
+} offk_gemm_t;
+
+int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
+
+/* Table builders for a conv layer  y = conv2d(x, w, stride, pad)  on NCHW
+ * tensors that may be channel slices of wider buffers (ctot = channels of the
+ * buffer, coff = first channel of the slice).  Each fills caller-owned device
+ * arrays; sizes are given by offk_conv_table_sizes().  `which`: 0 forward,
+ * 1 weight gradient, 2 data gradient (stride-s layers are split into s*s
+ * parity classes; `cls` selects one).  */
+typedef struct offk_conv_geom {
+  int32_t n_img, cin, hin, win, cout, hout, wout, kh, kw, stride, pad;
+  int32_t x_ctot, x_coff; /* input buffer  */
+  int32_t y_ctot, y_coff; /* output buffer */
+} offk_conv_geom_t;
+
+/* ------------------------------------------------------------------------
+ * Fused OFF stencil: spatial gradient + temporal difference + dropout +
+ * both torch.cat()s in one pass.  Replaces RGB_OFF.py:599-604 (view / slice /
+ * sub), :611 (depth-wise 3x3, learned weight + bias) or Flow_OFF.py:622
+ * (fixed diagonal kernel) or util.py:46-50 (Sobel x and y, K = 2), :612
+ * (dropout), :616 (cat) and the stage cats :656,:760,:832.
+ *
+ *   g : reduced+ReLU'd features  G[f, c, y, x]  f in [0,B*L), c in [0,Cg); frame stride g_fs floats
+ *   d : spatial-branch features  D[f, c, y, x]  c in [0,Cs);              frame stride d_fs floats
+ *   w : [Cs, K, 3, 3] cross-correlation taps, bias [Cs*K] or NULL
+ *   out[p, out_coff + kk*Cs + c, y, x] = drop( sum_ij w[c,kk,i,j] * D[fs(p), c, y+i-1, x+j-1] + bias )   (zero pad)
+ *   out[p, out_coff + K*Cs + c,  y, x] = G[b*L+t+1, c, y, x] - G[b*L+t, c, y, x]        p = b*(L-1)+t
+ *   fs(p) = p (OFFK_INDEX_REFERENCE_FLAT) or b*L+t (OFFK_INDEX_ALIGNED)
+ * Each G frame is read once.  Cg == 0 or Cs == 0 disables a half (the
+ * stand-alone util.SobelFilter modules use Cg == 0, L == 2 so that p == f).
+ * ---------------------------------------------------------------------- */
+typedef struct offk_stencil {
+  int32_t B, L, Cg, Cs, K, H, W;
+  int64_t g_fs, d_fs;      /* frame strides (floats) of g and d */
+  int32_t out_ctot, out_coff;
+  int32_t index_mode;
+  int32_t drop_mode;       /* OFFK_DROP_* */
+  float keep_scale;        /* 1/(1-p) */
+  float drop_p;            /* p, used by OFFK_DROP_SEED */
+  uint64_t seed;
+  const uint8_t* keep_mask; /* [P, K*Cs, H, W] for OFFK_DROP_MASK */
+} offk_stencil_t;
+
+int offk_stencil_diff_fwd(const offk_stencil_t* s, const float* g, const float* d, const float* w,
+                          const float* bias, float* out, void* stream);
+
+/* Backward of the above.  dout is the gradient of the stage buffer (same
+ * ctot/coff addressing as `out`).  Writes
+ *   dg[f,c,:,:] = (dT[b,t-1] - dT[b,t]) * (G[f,c,:,:] > 0)      (ReLU' of RGB_OFF.py:598 folded in)
+ *   dd[f,c,:,:] = transpose-stencil of the dropped spatial gradient (0 for frames that feed no pair)
+ * and accumulates (atomicAdd into zero-initialised buffers) dw [Cs,K,3,3], dbias [Cs*K] when non-NULL.
+ * g is read for the ReLU mask, d for the weight gradient.  dg/dd frame strides: dg_fs, dd_fs. */
+int offk_stencil_diff_bwd(const offk_stencil_t* s, const float* dout, const float* g, const float* d,
+                          const float* w, float* dg, int64_t dg_fs, float* dd, int64_t dd_fs,
+                          float* dw, float* dbias, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Heads.  RGB_OFF.py:783-793,:844-847; Flow_OFF.py:867-876; basic_ops.py:12-46
+ * ---------------------------------------------------------------------- */
+/* out[p,c] = drop( mean_{hw} x[p, x_coff+c, :] )   x: [P, x_ctot, HW]   (global_pool RGB_OFF.py:262 + dropout :356) */
+int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode,
+                          const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
+                          float* out, void* stream);
+/* dx[p, coff+c, :] = gate( dx_in + drop'(dpooled[p,c]) / HW ) ; dx_in = dx itself when accumulate != 0,
+ * gate = (act[p, coff+c, :] > 0) when act != NULL (ReLU' of the producer). dpooled may be NULL (gate only). */
+int offk_avgpool_drop_bwd(const float* dpooled, int P, int C, int HW, int ctot, int coff, int drop_mode,
+                          const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
+                          const float* act, int accumulate, float* dx, void* stream);
+/* 3x3 stride-2 ceil-mode max pool (motion_pool_trans_28, RGB_OFF.py:353,:783) */
+int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, int x_ctot, int x_coff, float* out,
+                        void* stream);
+/* ConsensusModule('avg', dim=1): out[b,:] = mean_t x[b,t,:]  (basic_ops.py:21-22) and its backward (:30-31) */
+int offk_segment_mean_fwd(const float* x, int B, int T, int C, float* out, void* stream);
+int offk_segment_mean_bwd(const float* dout, int B, int T, int C, float* dx, void* stream);
+/* out = act > 0 ? grad : 0  (ReLU' as a stand-alone pass; n elements) */
+int offk_relu_gate(const float* grad, const float* act, long long n, float* out, void* stream);
+/* dst[p, dst_coff+c, :] = act[p, act_coff+c, :] > 0 ? src[p, src_coff+c, :] : 0  between channel slices of
+ * [P, ctot, HW] buffers (ReLU' of motion_conv3_trans_14b, RGB_OFF.py:777-778, whose gradient arrives as a slice) */
+int offk_gate_copy(const float* src, int src_ctot, int src_coff, const float* act, int act_ctot, int act_coff,
+                   float* dst, int dst_ctot, int dst_coff, int P, int C, int HW, void* stream);
+/* y[p, coff+c, :] += bias[c], then max(.,0) for c < relu_cols: finishes a split-K GEMM output slice */
+int offk_bias_act(float* y, const float* bias, int P, int C, int HW, int ctot, int coff, int relu_cols,
+                  void* stream);
+/* dst[p, dst_coff+c, :] = act(a[p,c,:] + b[p,c,:])  -- sum_14b = relu(sum_14a + conv3_14b), RGB_OFF.py:779-780,
+ * written straight into the 7-stage fusion buffer (cat, :832) */
+int offk_add_relu_slice(const float* a, const float* b, float* dst, int dst_ctot, int dst_coff, int P, int C, int HW,
+                        int relu, void* stream);
+
+/* keep decision of OFFK_DROP_SEED for element `idx` (host mirror for tests): 1 = keep */
+int offk_drop_keep_host(uint64_t seed, uint64_t idx, float drop_p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFFK_H_ */

@@ -1,0 +1,108 @@
+"""ctypes binding of liboffk.so (the C ABI declared in include/offk.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised.  PyTorch is used by the callers only for
+device memory, streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboffk.so")
+
+PREC_FP32, PREC_TF32 = 0, 1
+INDEX_REFERENCE_FLAT, INDEX_ALIGNED = 0, 1
+DROP_NONE, DROP_MASK, DROP_SEED = 0, 1, 2
+
+
+class OffkIdx(C.Structure):
+    _fields_ = [("off", C.c_int32), ("y", C.c_int16), ("x", C.c_int16)]
+
+
+class OffkGemm(C.Structure):
+    """Mirror of offk_gemm_t."""
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a_src", C.c_void_p), ("a_row", C.c_void_p), ("a_col", C.c_void_p),
+        ("a_h", C.c_int32), ("a_w", C.c_int32), ("a_relu", C.c_int32), ("a_ones_row", C.c_int32),
+        ("a_klane", C.c_int32),
+        ("b_src", C.c_void_p), ("b_row", C.c_void_p), ("b_col", C.c_void_p), ("b_klane", C.c_int32),
+        ("out", C.c_void_p), ("out_row", C.c_void_p), ("out_col", C.c_void_p),
+        ("bias", C.c_void_p), ("relu_pre_cols", C.c_int32),
+        ("gate", C.c_void_p), ("gate_row", C.c_void_p), ("gate_col", C.c_void_p),
+        ("gate_col0", C.c_int32), ("gate_first", C.c_int32),
+        ("addend", C.c_void_p), ("add_row", C.c_void_p), ("add_col", C.c_void_p),
+        ("relu_post", C.c_int32), ("atomic_out", C.c_int32),
+        ("ones_row_out", C.c_void_p),
+        ("split_k", C.c_int32), ("tile_n", C.c_int32), ("b_dense", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class OffkStencil(C.Structure):
+    """Mirror of offk_stencil_t."""
+    _fields_ = [
+        ("B", C.c_int32), ("L", C.c_int32), ("Cg", C.c_int32), ("Cs", C.c_int32), ("K", C.c_int32),
+        ("H", C.c_int32), ("W", C.c_int32),
+        ("g_fs", C.c_int64), ("d_fs", C.c_int64),
+        ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
+        ("index_mode", C.c_int32), ("drop_mode", C.c_int32),
+        ("keep_scale", C.c_float), ("drop_p", C.c_float),
+        ("seed", C.c_uint64), ("keep_mask", C.c_void_p),
+    ]
+
+
+_P = C.c_void_p
+_PROTOS = {
+    "offk_version": (C.c_int, []),
+    "offk_last_error_string": (C.c_char_p, []),
+    "offk_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_longlong)]),
+    "offk_gather_gemm": (C.c_int, [C.POINTER(OffkGemm), C.c_int, _P]),
+    "offk_stencil_diff_fwd": (C.c_int, [C.POINTER(OffkStencil), _P, _P, _P, _P, _P, _P]),
+    "offk_stencil_diff_bwd": (C.c_int, [C.POINTER(OffkStencil), _P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64,
+                                        _P, _P, _P]),
+    "offk_avgpool_drop_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64,
+                                        C.c_float, C.c_float, _P, _P]),
+    "offk_avgpool_drop_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64,
+                                        C.c_float, C.c_float, _P, C.c_int, _P, _P]),
+    "offk_maxpool3s2_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "offk_segment_mean_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "offk_segment_mean_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "offk_relu_gate": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
+    "offk_gate_copy": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, _P]),
+    "offk_bias_act": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "offk_add_relu_slice": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "offk_drop_keep_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_float]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names include/offk.h declares (used by the CPU test that checks the .so exports them all)."""
+    return list(_PROTOS)
+
+
+def lib():
+    """Load liboffk.so once.  Raises RuntimeError when it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"liboffk.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (nvcc, sm_100a). The OFF path has no CPU / PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = "offk"):
+    if code != 0:
+        msg = lib().offk_last_error_string()
+        raise RuntimeError(f"{what} failed with code {code}: {msg.decode() if msg else ''}")

@@ -1,0 +1,74 @@
+// Shared helpers for liboffk (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "offk.h"
+
+namespace offk {
+
+// ---- per-thread last-error string (offk_last_error_string) -----------------
+extern thread_local char g_err[512];
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline int cuda_check(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+#define OFFK_LAUNCH_CHECK(what) ::offk::cuda_check(cudaGetLastError(), what)
+#define OFFK_REQUIRE(cond, ...) \
+  do {                          \
+    if (!(cond)) return ::offk::fail(OFFK_E_BADARG, __VA_ARGS__); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- counter-hash dropout (OFFK_DROP_SEED) ----------------------------------
+// keep(idx) = top-24-bits(splitmix64(seed ^ golden*idx)) >= p * 2^24.  Same on host and device so
+// tests can regenerate the mask and the backward kernel never needs it in memory.
+__host__ __device__ __forceinline__ uint32_t drop_hash24(uint64_t seed, uint64_t idx) {
+  uint64_t x = seed + idx * 0x9E3779B97F4A7C15ull;
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (uint32_t)(x >> 40);
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold24(float p) {
+  float t = p * 16777216.0f;
+  return t <= 0.f ? 0u : (t >= 16777216.0f ? 16777216u : (uint32_t)t);
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thr24) {
+  return drop_hash24(seed, idx) >= thr24;
+}
+
+// ---- vector / cache-hinted global access ------------------------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {  // read-once data: keep it out of L1
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+int sm_count();  // cached multiprocessor count of the current device
+
+}  // namespace offk

@@ -1,0 +1,214 @@
+// Head-side kernels of the OFF sub-network: global average pool (+dropout) forward/backward,
+// 3x3/s2 ceil-mode max pool, segment consensus (mean over segments) and small element-wise passes.
+// All are bandwidth-trivial ([P,C,7,7] tensors); they exist so that no ATen op is left on the path.
+#include "offk_common.cuh"
+
+namespace offk {
+
+__device__ __forceinline__ float keep_factor(int mode, const uint8_t* mask, uint64_t seed, uint32_t thr, size_t idx,
+                                             float scale) {
+  if (mode == OFFK_DROP_NONE) return 1.f;
+  const bool keep = mode == OFFK_DROP_MASK ? (mask[idx] != 0) : drop_keep(seed, idx, thr);
+  return keep ? scale : 0.f;
+}
+
+// one warp per (p, c) plane
+__global__ void avgpool_drop_fwd_kernel(const float* __restrict__ x, int P, int C, int HW, int ctot, int coff, int mode,
+                                        const uint8_t* __restrict__ mask, uint64_t seed, float drop_p, float scale,
+                                        float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P * C) return;
+  const int p = warp / C, c = warp - p * C;
+  const float* xp = x + ((size_t)p * ctot + coff + c) * HW;
+  float s = 0.f;
+  for (int i = lane; i < HW; i += 32) s += __ldg(xp + i);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float k = keep_factor(mode, mask, seed, drop_threshold24(drop_p), (size_t)warp, scale);
+    out[warp] = (s / (float)HW) * k;
+  }
+}
+
+__global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P, int C, int HW, int ctot, int coff,
+                                        int mode, const uint8_t* __restrict__ mask, uint64_t seed, float drop_p,
+                                        float scale, const float* __restrict__ act, int accumulate,
+                                        float* __restrict__ dx) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * C * HW;
+  if (i >= total) return;
+  const size_t pc = i / HW;
+  const int hw = (int)(i - pc * HW);
+  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
+  const size_t o = ((size_t)p * ctot + coff + c) * HW + hw;
+  float v = 0.f;
+  if (dpooled) v = __ldg(dpooled + pc) * keep_factor(mode, mask, seed, drop_threshold24(drop_p), pc, scale) / (float)HW;
+  if (accumulate) v += dx[o];
+  if (act) v = __ldg(act + o) > 0.f ? v : 0.f;
+  dx[o] = v;
+}
+
+__global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C, int H, int W, int ctot, int coff,
+                                      int Ho, int Wo, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * C * Ho * Wo;
+  if (i >= total) return;
+  const int ow = (int)(i % Wo);
+  const int oh = (int)((i / Wo) % Ho);
+  const size_t pc = i / ((size_t)Wo * Ho);
+  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
+  const float* xp = x + ((size_t)p * ctot + coff + c) * H * W;
+  float m = -INFINITY;
+  for (int a = 0; a < 3; ++a) {
+    const int y = oh * 2 + a;
+    if (y >= H) break;
+    for (int b = 0; b < 3; ++b) {
+      const int xx = ow * 2 + b;
+      if (xx >= W) break;
+      m = fmaxf(m, __ldg(xp + y * W + xx));
+    }
+  }
+  out[i] = m;
+}
+
+__global__ void segment_mean_fwd_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += __ldg(x + ((size_t)b * T + t) * C + c);
+  out[i] = s / (float)T;
+}
+__global__ void segment_mean_bwd_kernel(const float* __restrict__ dout, int B, int T, int C, float* __restrict__ dx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T * C) return;
+  const int c = i % C, b = i / (T * C);
+  dx[i] = __ldg(dout + (size_t)b * C + c) / (float)T;
+}
+__global__ void relu_gate_kernel(const float* __restrict__ grad, const float* __restrict__ act, long long n,
+                                 float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ldg(act + i) > 0.f ? __ldg(grad + i) : 0.f;
+}
+// dst[p, dcoff+c, :] = act[p, acoff+c, :] > 0 ? src[p, scoff+c, :] : 0   (ReLU' between channel slices)
+__global__ void gate_copy_kernel(const float* __restrict__ src, int sctot, int scoff, const float* __restrict__ act,
+                                 int actot, int acoff, float* __restrict__ dst, int dctot, int dcoff, int P, int C,
+                                 int HW) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * C * HW;
+  if (i >= total) return;
+  const size_t pc = i / HW;
+  const int hw = (int)(i - pc * HW);
+  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
+  const float a = __ldg(act + ((size_t)p * actot + acoff + c) * HW + hw);
+  const float v = __ldg(src + ((size_t)p * sctot + scoff + c) * HW + hw);
+  dst[((size_t)p * dctot + dcoff + c) * HW + hw] = a > 0.f ? v : 0.f;
+}
+// dst[p, coff+c, :] = (relu ? max(.,0) : .)(a[p,c,:] + b[p,c,:])
+__global__ void add_relu_slice_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst,
+                                      int ctot, int coff, int P, int C, int HW, int relu) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * C * HW;
+  if (i >= total) return;
+  const size_t pc = i / HW;
+  const int hw = (int)(i - pc * HW);
+  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
+  float v = __ldg(a + i) + __ldg(b + i);
+  if (relu) v = fmaxf(v, 0.f);
+  dst[((size_t)p * ctot + coff + c) * HW + hw] = v;
+}
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int P, int C, int HW, int ctot,
+                                int coff, int relu_cols) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)P * C * HW;
+  if (i >= total) return;
+  const size_t pc = i / HW;
+  const int hw = (int)(i - pc * HW);
+  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
+  const size_t o = ((size_t)p * ctot + coff + c) * HW + hw;
+  float v = y[o] + (bias ? __ldg(bias + c) : 0.f);
+  if (c < relu_cols) v = fmaxf(v, 0.f);
+  y[o] = v;
+}
+
+static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace offk
+
+using namespace offk;
+
+extern "C" int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode,
+                                     const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
+                                     float* out, void* stream) {
+  OFFK_REQUIRE(x && out && P > 0 && C > 0 && HW > 0 && x_coff >= 0 && x_coff + C <= x_ctot, "avgpool_fwd: bad args");
+  OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_fwd: mask missing");
+  const size_t threads = (size_t)P * C * 32;
+  avgpool_drop_fwd_kernel<<<blocks_for(threads, 256), 256, 0, as_stream(stream)>>>(
+      x, P, C, HW, x_ctot, x_coff, drop_mode, keep_mask, seed, drop_p, keep_scale, out);
+  return OFFK_LAUNCH_CHECK("avgpool_drop_fwd");
+}
+
+extern "C" int offk_avgpool_drop_bwd(const float* dpooled, int P, int C, int HW, int ctot, int coff, int drop_mode,
+                                     const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
+                                     const float* act, int accumulate, float* dx, void* stream) {
+  OFFK_REQUIRE(dx && P > 0 && C > 0 && HW > 0 && coff >= 0 && coff + C <= ctot, "avgpool_bwd: bad args");
+  OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_bwd: mask missing");
+  const size_t total = (size_t)P * C * HW;
+  avgpool_drop_bwd_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+      dpooled, P, C, HW, ctot, coff, drop_mode, keep_mask, seed, drop_p, keep_scale, act, accumulate, dx);
+  return OFFK_LAUNCH_CHECK("avgpool_drop_bwd");
+}
+
+extern "C" int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, int x_ctot, int x_coff, float* out,
+                                   void* stream) {
+  OFFK_REQUIRE(x && out && P > 0 && C > 0 && H >= 3 && W >= 3 && x_coff >= 0 && x_coff + C <= x_ctot,
+               "maxpool: bad args");
+  int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;  // ceil((H-3)/2)+1 ...
+  if ((Ho - 1) * 2 >= H) --Ho;                             // ... and the last window must start inside the input
+  if ((Wo - 1) * 2 >= W) --Wo;
+  const size_t total = (size_t)P * C * Ho * Wo;
+  maxpool3s2_fwd_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(x, P, C, H, W, x_ctot, x_coff, Ho, Wo,
+                                                                               out);
+  return OFFK_LAUNCH_CHECK("maxpool3s2_fwd");
+}
+
+extern "C" int offk_segment_mean_fwd(const float* x, int B, int T, int C, float* out, void* stream) {
+  OFFK_REQUIRE(x && out && B > 0 && T > 0 && C > 0, "segment_mean_fwd: bad args");
+  segment_mean_fwd_kernel<<<blocks_for((size_t)B * C, 256), 256, 0, as_stream(stream)>>>(x, B, T, C, out);
+  return OFFK_LAUNCH_CHECK("segment_mean_fwd");
+}
+extern "C" int offk_segment_mean_bwd(const float* dout, int B, int T, int C, float* dx, void* stream) {
+  OFFK_REQUIRE(dout && dx && B > 0 && T > 0 && C > 0, "segment_mean_bwd: bad args");
+  segment_mean_bwd_kernel<<<blocks_for((size_t)B * T * C, 256), 256, 0, as_stream(stream)>>>(dout, B, T, C, dx);
+  return OFFK_LAUNCH_CHECK("segment_mean_bwd");
+}
+extern "C" int offk_relu_gate(const float* grad, const float* act, long long n, float* out, void* stream) {
+  OFFK_REQUIRE(grad && act && out && n > 0, "relu_gate: bad args");
+  relu_gate_kernel<<<blocks_for((size_t)n, 256), 256, 0, as_stream(stream)>>>(grad, act, n, out);
+  return OFFK_LAUNCH_CHECK("relu_gate");
+}
+extern "C" int offk_bias_act(float* y, const float* bias, int P, int C, int HW, int ctot, int coff, int relu_cols,
+                             void* stream) {
+  OFFK_REQUIRE(y && P > 0 && C > 0 && HW > 0 && coff >= 0 && coff + C <= ctot, "bias_act: bad args");
+  bias_act_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(y, bias, P, C, HW, ctot, coff,
+                                                                                     relu_cols);
+  return OFFK_LAUNCH_CHECK("bias_act");
+}
+
+extern "C" int offk_gate_copy(const float* src, int src_ctot, int src_coff, const float* act, int act_ctot,
+                              int act_coff, float* dst, int dst_ctot, int dst_coff, int P, int C, int HW,
+                              void* stream) {
+  OFFK_REQUIRE(src && act && dst && P > 0 && C > 0 && HW > 0, "gate_copy: bad args");
+  OFFK_REQUIRE(src_coff + C <= src_ctot && act_coff + C <= act_ctot && dst_coff + C <= dst_ctot, "gate_copy: slices");
+  gate_copy_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(
+      src, src_ctot, src_coff, act, act_ctot, act_coff, dst, dst_ctot, dst_coff, P, C, HW);
+  return OFFK_LAUNCH_CHECK("gate_copy");
+}
+
+extern "C" int offk_add_relu_slice(const float* a, const float* b, float* dst, int dst_ctot, int dst_coff, int P,
+                                   int C, int HW, int relu, void* stream) {
+  OFFK_REQUIRE(a && b && dst && P > 0 && C > 0 && HW > 0 && dst_coff >= 0 && dst_coff + C <= dst_ctot,
+               "add_relu_slice: bad args");
+  add_relu_slice_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(a, b, dst, dst_ctot,
+                                                                                           dst_coff, P, C, HW, relu);
+  return OFFK_LAUNCH_CHECK("add_relu_slice");
+}

@@ -1,0 +1,530 @@
+"""OFFEngine: the OFF sub-network (RGB_OFF.py:596-860 / Flow_OFF.py:606-884) as a static plan of
+liboffk kernel launches over preallocated NCHW fp32 buffers.
+
+Every step is one C-ABI call with a descriptor bound at plan-build time, so a forward or backward
+pass is a flat list of launches on one stream: cheap to issue and capturable in a CUDA graph.
+PyTorch supplies device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import spec as S
+from . import tables as T
+
+_SM_TARGET = 148
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Gemm:
+    """One bound gather-GEMM launch (descriptor + device tables kept alive)."""
+
+    def __init__(self, eng: "OFFEngine", spc: T.GemmSpec, key, *, a_src, b_src, out, bias=None, relu_pre_cols=0,
+                 a_relu=False, gate=None, gate_tabs=None, gate_col0=0, gate_first=False, addend=None,
+                 add_tabs=None, relu_post=False, atomic=False, ones_out=None, split_k=1, tile_n=0, name=""):
+        self.eng, self.name, self.spec = eng, name, spc
+        tabs = eng._tables(key, spc)
+        d = L.OffkGemm()
+        d.M, d.N, d.K = spc.M, spc.N, spc.K
+        d.a_src, d.a_row, d.a_col = a_src.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
+        d.a_h, d.a_w, d.a_relu, d.a_ones_row, d.a_klane = spc.a_h, spc.a_w, int(a_relu), spc.a_ones_row, spc.a_klane
+        d.b_src, d.b_row, d.b_col, d.b_klane = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_klane
+        d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.relu_pre_cols = relu_pre_cols
+        d.gate = gate.data_ptr() if gate is not None else None
+        d.gate_row = gate_tabs[0].data_ptr() if gate_tabs else None
+        d.gate_col = gate_tabs[1].data_ptr() if gate_tabs else None
+        d.gate_col0, d.gate_first = gate_col0, int(gate_first)
+        d.addend = addend.data_ptr() if addend is not None else None
+        d.add_row = add_tabs[0].data_ptr() if add_tabs else None
+        d.add_col = add_tabs[1].data_ptr() if add_tabs else None
+        d.relu_post, d.atomic_out = int(relu_post), int(atomic)
+        d.ones_row_out = ones_out.data_ptr() if ones_out is not None else None
+        d.split_k, d.tile_n = split_k, tile_n
+        d.b_dense = spc.b_dense if (b_src.data_ptr() % 16 == 0) else 0
+        self.desc = d
+        self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out)
+        self.flops = 2.0 * spc.M * spc.N * spc.K
+
+    def __call__(self, stream):
+        L.check(self.eng.lib.offk_gather_gemm(C.byref(self.desc), self.eng.prec, stream), self.name)
+
+
+class OFFEngine:
+    """Plan + buffers for one (batch, length) shape on one GPU.
+
+    variant: 'rgb'  learned depth-wise 3x3 spatial gradient + bias, per-pair logits (RGB_OFF.py)
+             'flow' fixed diagonal Sobel, segment consensus over the L-1 pairs (Flow_OFF.py / RGB_OFF_v2.py)
+    precision: 'tf32' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (CUDA-core FFMA, exact mode)
+    """
+
+    def __init__(self, batch: int, length: int, variant: str = "rgb", device="cuda", precision: str = "tf32",
+                 index_mode: str = "reference_flat", consensus=None, tap_grads: bool = False):
+        assert variant in ("rgb", "flow") and length >= 2 and batch >= 1
+        self.lib = L.lib()
+        self.B, self.Lseg, self.variant = batch, length, variant
+        self.N, self.P = batch * length, batch * (length - 1)
+        self.device = torch.device(device)
+        self.prec = {"fp32": L.PREC_FP32, "tf32": L.PREC_TF32}[precision]
+        self.precision = precision
+        self.index_mode = {"reference_flat": L.INDEX_REFERENCE_FLAT, "aligned": L.INDEX_ALIGNED}[index_mode]
+        self.consensus = (variant != "rgb") if consensus is None else bool(consensus)
+        self.tap_grads = tap_grads
+        self._tab_cache = {}
+        self._keep = []
+
+        # ---- parameters: one flat buffer, reference-named views
+        self.layout, self.n_flat = S.flat_layout(variant)
+        self.params_flat = torch.zeros(self.n_flat, device=self.device)
+        self.grads_flat = torch.zeros(self.n_flat, device=self.device)
+        self.params = OrderedDict((n, self._view(self.params_flat, n)) for n in S.param_shapes(variant))
+        self.grads = OrderedDict((n, self._view(self.grads_flat, n)) for n in S.param_shapes(variant))
+        if variant == "flow":
+            # frozen util.SobelFilter_Diagonal taps (util.py:61), [32,1,3,3]
+            k = torch.tensor([[0., 1., 0.], [-1., 0., 1.], [0., -1., 0.]], device=self.device)
+            self.sobel_w = k.expand(S.DOWN_C, 1, 3, 3).contiguous()
+
+        self._alloc()
+        self._build()
+
+    # ------------------------------------------------------------------ helpers
+    def _view(self, flat, name):
+        off, shape = self.layout[name]
+        return flat[off:off + int(np.prod(shape))].view(shape)
+
+    def _unit_w(self, flat, tag):
+        off, _ = self.layout[f"motion_conv_gen_{tag}.weight"]
+        cin = S.LEVELS[tag][0]
+        return flat[off:off + S.UNIT_C * cin].view(S.UNIT_C, cin)
+
+    def _unit_b(self, flat, tag):
+        off, _ = self.layout[f"motion_conv_gen_{tag}.bias"]
+        return flat[off:off + S.UNIT_C]
+
+    def _tables(self, key, spc: T.GemmSpec):
+        if key not in self._tab_cache:
+            dev = self.device
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32).reshape(-1)).to(dev)
+            self._tab_cache[key] = {k: up(getattr(spc, k)) for k in ("a_row", "a_col", "b_row", "b_col", "out_row", "out_col")}
+        return self._tab_cache[key]
+
+    def _buf(self, name, *shape):
+        t = torch.zeros(*shape, device=self.device)
+        self.buf[name] = t
+        return t
+
+    def load_params(self, prm: dict):
+        """Copy reference-named tensors (a state_dict subset) into the flat buffer."""
+        with torch.no_grad():
+            for n, v in self.params.items():
+                v.copy_(prm[n].to(self.device, torch.float32))
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        P, N = self.P, self.N
+        self.buf = {}
+        for tag, (cin, s) in S.LEVELS.items():
+            self._buf("gd_" + tag, N, S.UNIT_C, s, s)
+            self._buf("dgd_" + tag, N, S.UNIT_C, s, s)
+        for st, (ctot, s, _) in S.STAGES.items():
+            self._buf("F" + st, P, ctot, s, s)
+            self._buf("dF" + st, P, ctot, s, s)
+        a = lambda n, c, s: (self._buf(n, P, c, s, s), self._buf("d_" + n, P, c, s, s))
+        a("t28", 64, 14)
+        a("tmp28", 64, 14)
+        for blk in "abc":
+            a("h1_28" + blk, 64, 14)
+            a("h2_28" + blk, 64, 14)
+        a("br28", 256, 14)
+        a("s28a", 256, 14)
+        a("s28b", 256, 14)
+        a("t14", 128, 7)
+        a("tmp14", 128, 7)
+        for blk in "ab":
+            a("h1_14" + blk, 128, 7)
+            a("h2_14" + blk, 128, 7)
+        a("ex14", 512, 7)
+        a("s14a", 512, 7)
+        a("h3_14b", 512, 7)
+        a("t7", 256, 7)
+        a("tmp7", 256, 7)
+        a("h1_7", 256, 7)
+        a("h2_7", 256, 7)
+        a("br7", 1024, 7)
+        a("s7", 1024, 7)
+        self._buf("p28", P, 256, 7, 7)
+        for k, c in (("7", 1024), ("14", 512), ("28", 256)):
+            self._buf("pool" + k, P, c)
+            self._buf("d_pool" + k, P, c)
+            self._buf("fc" + k, P, S.NUM_CLASSES)
+            self._buf("d_fc" + k, P, S.NUM_CLASSES)
+            if self.consensus:
+                self._buf("cfc" + k, self.B, S.NUM_CLASSES)
+        self.taps = OrderedDict((tag, torch.zeros(N, cin, s, s, device=self.device)) for tag, (cin, s) in S.LEVELS.items())
+        if self.tap_grads:
+            self.tap_grad = OrderedDict((tag, torch.zeros_like(t)) for tag, t in self.taps.items())
+        # dropout state (filled per forward call)
+        self.drop_mode = L.DROP_NONE
+        self.drop_seed = 0
+        self.masks = None
+
+    # ------------------------------------------------------------------ plan
+    def _conv_fwd(self, name, x, y, geom, w, b, *, relu=False, relu_cols=None, a_relu=False, addend=None,
+                  add_tabs=None, relu_post=False):
+        spc = T.conv_fwd_spec(geom)
+        m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
+        n_tiles = max(1, math.ceil(spc.N / 256))
+        split = 1
+        if self.prec == L.PREC_TF32 and addend is None and m_tiles * n_tiles < 100 and kb >= 32:
+            split = max(1, min(_SM_TARGET // (m_tiles * n_tiles), kb // 8))
+        cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
+        if split > 1:
+            g = Gemm(self, spc, ("fwd", _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
+            hw = geom.hout * geom.wout
+
+            def run(stream, g=g, y=y, b=b, geom=geom, hw=hw, cols=cols):
+                y.zero_()
+                g(stream)
+                L.check(self.lib.offk_bias_act(_ptr(y), _ptr(b), geom.n_img, geom.cout, hw, geom.y_ctot, geom.y_coff,
+                                               cols, stream), name + ".bias_act")
+            assert geom.y_coff == 0 and geom.y_ctot == geom.cout
+            self.flops_fwd += g.flops
+            return run
+        g = Gemm(self, spc, ("fwd", _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
+                 addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
+        self.flops_fwd += g.flops
+        return g
+
+    def _conv_wgrad(self, name, x, dy, geom, dw, db, *, a_relu=False):
+        spc = T.conv_wgrad_spec(geom)
+        m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
+        n_tiles = max(1, math.ceil(spc.N / 256))
+        split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
+        g = Gemm(self, spc, ("wgrad", _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
+                 atomic=True, split_k=split, name=name + ".wgrad")
+        self.flops_bwd += g.flops
+        return g
+
+    def _conv_dgrad(self, name, dy, w, dx, geom, *, gate=None, gate_col0=0, gate_first=False, addend=None,
+                    add_geom=None):
+        out = []
+        for i, spc in enumerate(T.conv_dgrad_specs(geom)):
+            add_tabs = None
+            if addend is not None and add_geom is not None:
+                # addend lives in a differently-shaped buffer: tables of the same logical (img, c, y, x) element
+                aspec = T.conv_dgrad_specs(add_geom)[i]
+                t = self._tables(("dgrad", _gkey(add_geom), i), aspec)
+                add_tabs = (t["out_row"], t["out_col"])
+            g = Gemm(self, spc, ("dgrad", _gkey(geom), i), a_src=dy, b_src=w, out=dx, gate=gate, gate_col0=gate_col0,
+                     gate_first=gate_first, addend=addend, add_tabs=add_tabs, name=f"{name}.dgrad{i}")
+            self.flops_bwd += g.flops
+            out.append(g)
+        return out
+
+    def _build(self):
+        P, N, B, Lg = self.P, self.N, self.B, self.Lseg
+        bf, pr, gr = self.buf, self.params, self.grads
+        self.flops_fwd = self.flops_bwd = 0.0
+        fwd, bwd_units, bwd_stage = [], [], []
+        lib = self.lib
+
+        # ============ OFF units (RGB_OFF.py:596-616 and the eight copies)
+        self._stencils = {}
+        for li, (tag, (cin, s)) in enumerate(S.LEVELS.items()):
+            st = S.LEVEL_STAGE[tag]
+            ctot, _, members = S.STAGES[st]
+            coff = dict(members)[tag]
+            geom = T.ConvGeom(N, cin, s, s, S.UNIT_C)
+            gd, dgd = bf["gd_" + tag], bf["dgd_" + tag]
+            # K1: gen (ReLU) and down (linear) 1x1 convs as ONE GEMM with 160 output channels
+            fwd.append(self._conv_fwd("unit_" + tag, self.taps[tag], gd, geom, self._unit_w(self.params_flat, tag),
+                                      self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C))
+            # K2: fused spatial stencil + temporal difference + dropout + cat, into the stage buffer
+            sd = L.OffkStencil()
+            sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, S.GEN_C, S.DOWN_C, 1, s, s
+            sd.g_fs = sd.d_fs = S.UNIT_C * s * s
+            sd.out_ctot, sd.out_coff, sd.index_mode = ctot, coff, self.index_mode
+            sd.drop_mode, sd.keep_scale, sd.drop_p = L.DROP_NONE, 1.0 / (1.0 - S.DROP_P), S.DROP_P
+            self._stencils[tag] = sd
+            if self.variant == "rgb":
+                w3, b3 = pr[f"motion_spatial_grad_{tag}.weight"], pr[f"motion_spatial_grad_{tag}.bias"]
+                dw3, db3 = gr[f"motion_spatial_grad_{tag}.weight"], gr[f"motion_spatial_grad_{tag}.bias"]
+            else:
+                w3, b3, dw3, db3 = self.sobel_w, None, None, None
+            Fst, dFst = bf["F" + st], bf["dF" + st]
+            g_ptr, d_ptr = gd.data_ptr(), gd.data_ptr() + 4 * S.GEN_C * s * s
+            dg_ptr, dd_ptr = dgd.data_ptr(), dgd.data_ptr() + 4 * S.GEN_C * s * s
+            fs = S.UNIT_C * s * s
+
+            def k2(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, b3=b3, Fst=Fst, tag=tag):
+                L.check(lib.offk_stencil_diff_fwd(C.byref(sd), g_ptr, d_ptr, _ptr(w3), _ptr(b3), _ptr(Fst), stream),
+                        "stencil_fwd_" + tag)
+            fwd.append(k2)
+
+            def k3(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, dFst=dFst, dg_ptr=dg_ptr, dd_ptr=dd_ptr, fs=fs,
+                   dw3=dw3, db3=db3, tag=tag):
+                L.check(lib.offk_stencil_diff_bwd(C.byref(sd), _ptr(dFst), g_ptr, d_ptr, _ptr(w3), dg_ptr, fs, dd_ptr,
+                                                  fs, _ptr(dw3), _ptr(db3), stream), "stencil_bwd_" + tag)
+            bwd_units.append(k3)
+            # K4: weight / bias gradient of the fused 1x1 (no dX for the frozen taps unless asked, train_off.py:39-46)
+            bwd_units.append(self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
+                                              self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag)))
+            if self.tap_grads:
+                bwd_units += self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
+                                              self.tap_grad[tag], geom)
+
+        # ============ stage convs
+        def geom_of(name, n_img, s_in, x_ctot=0, x_coff=0, y_ctot=0, y_coff=0):
+            _, cout, cin, k, stride, pad = S.CONV_BY_NAME[name]
+            return T.ConvGeom(n_img, cin, s_in, s_in, cout, k, k, stride, pad, x_ctot, x_coff, y_ctot, y_coff)
+
+        def W(n): return pr[n + ".weight"]
+        def Bv(n): return pr[n + ".bias"]
+        def dW(n): return gr[n + ".weight"]
+        def dB(n): return gr[n + ".bias"]
+
+        def layer(name, x, y, s_in, *, relu=False, a_relu=False, addend=None, relu_post=False,
+                  x_ctot=0, x_coff=0, y_ctot=0, y_coff=0, dy=None, dy_geom=None):
+            """forward conv + its weight gradient; returns geom for the data-gradient wiring."""
+            geom = geom_of(name, P, s_in, x_ctot, x_coff, y_ctot, y_coff)
+            fwd.append(self._conv_fwd(name, x, y, geom, W(name), Bv(name), relu=relu, a_relu=a_relu, addend=addend,
+                                      relu_post=relu_post))
+            return geom
+
+        # ---- resolution 28 (RGB_OFF.py:655-685)
+        g_t28 = layer("motion_conv_trans_28", bf["F28"], bf["t28"], 28)                       # pre-ReLU kept (:665)
+        g_c1a = layer("motion_conv1_trans_28a", bf["t28"], bf["h1_28a"], 14, relu=True, a_relu=True)
+        g_c2a = layer("motion_conv2_trans_28a", bf["h1_28a"], bf["h2_28a"], 14, relu=True)
+        g_bra = layer("motion_conv_branch_28a", bf["t28"], bf["br28"], 14)
+        g_c3a = layer("motion_conv3_trans_28a", bf["h2_28a"], bf["s28a"], 14, addend=bf["br28"], relu_post=True)
+        g_c1b = layer("motion_conv1_trans_28b", bf["s28a"], bf["h1_28b"], 14, relu=True)
+        g_c2b = layer("motion_conv2_trans_28b", bf["h1_28b"], bf["h2_28b"], 14, relu=True)
+        g_c3b = layer("motion_conv3_trans_28b", bf["h2_28b"], bf["s28b"], 14, addend=bf["s28a"], relu_post=True)
+        g_c1c = layer("motion_conv1_trans_28c", bf["s28b"], bf["h1_28c"], 14, relu=True)
+        g_c2c = layer("motion_conv2_trans_28c", bf["h1_28c"], bf["h2_28c"], 14, relu=True)
+        # sum_28c goes straight into the 14-stage fusion buffer at channel 800 (cat, :760)
+        g_c3c = geom_of("motion_conv3_trans_28c", P, 14, y_ctot=1056, y_coff=800)
+        g_s28b_as_f14 = T.ConvGeom(P, 256, 14, 14, 256, y_ctot=256)  # tables for the s28b addend (plain [P,256,14,14])
+        spc_add = T.conv_fwd_spec(g_s28b_as_f14)
+        tabs_add = self._tables(("fwd", _gkey(g_s28b_as_f14)), spc_add)
+        fwd.append(self._conv_fwd("motion_conv3_trans_28c", bf["h2_28c"], bf["F14"], g_c3c,
+                                  W("motion_conv3_trans_28c"), Bv("motion_conv3_trans_28c"), addend=bf["s28b"],
+                                  add_tabs=(tabs_add["out_row"], tabs_add["out_col"]), relu_post=True))
+
+        # ---- resolution 14 (RGB_OFF.py:759-780)
+        g_t14 = layer("motion_conv_trans_14", bf["F14"], bf["t14"], 14, relu=True)
+        g_14a1 = layer("motion_conv1_trans_14a", bf["t14"], bf["h1_14a"], 7, relu=True)
+        g_14a2 = layer("motion_conv2_trans_14a", bf["h1_14a"], bf["h2_14a"], 7, relu=True)
+        g_14ex = layer("motion_conv_expand_trans_14a", bf["t14"], bf["ex14"], 7)
+        g_14a3 = layer("motion_conv3_trans_14a", bf["h2_14a"], bf["s14a"], 7, addend=bf["ex14"], relu_post=True)
+        g_14b1 = layer("motion_conv1_trans_14b", bf["s14a"], bf["h1_14b"], 7, relu=True)
+        g_14b2 = layer("motion_conv2_trans_14b", bf["h1_14b"], bf["h2_14b"], 7, relu=True)
+        g_14b3 = layer("motion_conv3_trans_14b", bf["h2_14b"], bf["h3_14b"], 7, relu=True)   # 3x3 + ReLU (:316,:778)
+
+        # sum_14b = relu(s14a + h3_14b) -> 7-stage fusion buffer channels [320,832)  (:779-780, cat :832)
+        fwd.append(self._add_into_slice(bf["s14a"], bf["h3_14b"], bf["F7"], 832, 320, 512, 49))
+
+        # ---- heads 28 / 14 (RGB_OFF.py:783-793)
+        fwd.append(lambda stream: L.check(lib.offk_maxpool3s2_fwd(_ptr(bf["F14"]), P, 256, 14, 14, 1056, 800,
+                                                                   _ptr(bf["p28"]), stream), "maxpool28"))
+        fwd.append(self._pool_fwd("28", bf["p28"], 256, 256, 0))
+        fwd.append(self._fc_fwd("fc_action_motion_28", "28", 256))
+        fwd.append(self._pool_fwd("14", bf["F7"], 512, 832, 320))
+        fwd.append(self._fc_fwd("fc_action_motion_14", "14", 512))
+
+        # ---- resolution 7 (RGB_OFF.py:831-847)
+        g_t7 = layer("motion_conv_trans", bf["F7"], bf["t7"], 7, relu=True)
+        g_71 = layer("motion_conv1_trans", bf["t7"], bf["h1_7"], 7, relu=True)
+        g_72 = layer("motion_conv2_trans", bf["h1_7"], bf["h2_7"], 7, relu=True)
+        g_7br = layer("motion_conv_branch_trans", bf["t7"], bf["br7"], 7)
+        g_73 = layer("motion_conv3_trans", bf["h2_7"], bf["s7"], 7, addend=bf["br7"])        # no final ReLU (:841)
+        fwd.append(self._pool_fwd("7", bf["s7"], 1024, 1024, 0))
+        fwd.append(self._fc_fwd("fc_action_motion", "7", 1024))
+        if self.consensus:
+            for k in ("7", "28", "14"):
+                fwd.append(lambda stream, k=k: L.check(lib.offk_segment_mean_fwd(
+                    _ptr(bf["fc" + k]), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["cfc" + k]), stream), "consensus" + k))
+
+        # ============ backward of the stages (reverse order); every d_* buffer holds dL/d(pre-activation)
+        bs = bwd_stage
+        d = lambda n: bf["d_" + n]
+        if self.consensus:
+            self.d_out7 = torch.zeros(B, S.NUM_CLASSES, device=self.device)
+            self.d_out14 = torch.zeros(B, S.NUM_CLASSES, device=self.device)
+            for k, src in (("7", self.d_out7), ("14", self.d_out14)):
+                bs.append(lambda stream, k=k, src=src: L.check(lib.offk_segment_mean_bwd(
+                    _ptr(src), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["d_fc" + k]), stream), "consensus_bwd" + k))
+        else:
+            self.d_out7, self.d_out14 = bf["d_fc7"], bf["d_fc14"]
+        # FC heads (fc28 receives no gradient: never returned, RGB_OFF.py:860)
+        for fcname, k, c in (("fc_action_motion", "7", 1024), ("fc_action_motion_14", "14", 512)):
+            gfc = T.ConvGeom(P, c, 1, 1, S.NUM_CLASSES)
+            bs.append(self._conv_wgrad(fcname, bf["pool" + k], bf["d_fc" + k], gfc, dW(fcname), dB(fcname)))
+            bs += self._conv_dgrad(fcname, bf["d_fc" + k], W(fcname), bf["d_pool" + k], gfc)
+        # ds7 = avgpool'(dropout'(d_pool7))
+        bs.append(self._pool_bwd("7", d("s7"), 1024, 1024, 0, act=None, accumulate=False))
+
+        def back(name, x, dy, geom, *, a_relu=False):
+            bs.append(self._conv_wgrad(name, x, dy, geom, dW(name), dB(name), a_relu=a_relu))
+
+        def dgrad(name, dy, dx, geom, **kw):
+            bs.extend(self._conv_dgrad(name, dy, W(name), dx, geom, **kw))
+
+        # ---- 7
+        back("motion_conv3_trans", bf["h2_7"], d("s7"), g_73)
+        dgrad("motion_conv3_trans", d("s7"), d("h2_7"), g_73, gate=bf["h2_7"])
+        back("motion_conv_branch_trans", bf["t7"], d("s7"), g_7br)
+        dgrad("motion_conv_branch_trans", d("s7"), d("tmp7"), g_7br)
+        back("motion_conv2_trans", bf["h1_7"], d("h2_7"), g_72)
+        dgrad("motion_conv2_trans", d("h2_7"), d("h1_7"), g_72, gate=bf["h1_7"])
+        back("motion_conv1_trans", bf["t7"], d("h1_7"), g_71)
+        dgrad("motion_conv1_trans", d("h1_7"), d("t7"), g_71, gate=bf["t7"], addend=d("tmp7"))
+        back("motion_conv_trans", bf["F7"], d("t7"), g_t7)
+        dgrad("motion_conv_trans", d("t7"), bf["dF7"], g_t7)
+        # d sum_14b = (dF7[:,320:] + head-14 pool gradient) * [sum_14b > 0]   (in place in the dF7 slice)
+        bs.append(self._pool_bwd("14", bf["dF7"], 512, 832, 320, act=bf["F7"], accumulate=True))
+        # ---- 14b:  sum_14b = relu(s14a + relu(conv3_14b(h2b)))
+        bs.append(lambda stream: L.check(lib.offk_gate_copy(_ptr(bf["dF7"]), 832, 320, _ptr(bf["h3_14b"]), 512, 0,
+                                                            _ptr(d("h3_14b")), 512, 0, P, 512, 49, stream), "gate_h3b"))
+        back("motion_conv3_trans_14b", bf["h2_14b"], d("h3_14b"), g_14b3)
+        dgrad("motion_conv3_trans_14b", d("h3_14b"), d("h2_14b"), g_14b3, gate=bf["h2_14b"])
+        back("motion_conv2_trans_14b", bf["h1_14b"], d("h2_14b"), g_14b2)
+        dgrad("motion_conv2_trans_14b", d("h2_14b"), d("h1_14b"), g_14b2, gate=bf["h1_14b"])
+        back("motion_conv1_trans_14b", bf["s14a"], d("h1_14b"), g_14b1)
+        g_slice7 = T.ConvGeom(P, 512, 7, 7, 128, x_ctot=832, x_coff=320)   # addresses dF7[:,320:832] like a conv input
+        dgrad("motion_conv1_trans_14b", d("h1_14b"), d("s14a"), g_14b1, gate=bf["s14a"], addend=bf["dF7"],
+              add_geom=g_slice7)
+        # ---- 14a
+        back("motion_conv3_trans_14a", bf["h2_14a"], d("s14a"), g_14a3)
+        dgrad("motion_conv3_trans_14a", d("s14a"), d("h2_14a"), g_14a3, gate=bf["h2_14a"])
+        back("motion_conv_expand_trans_14a", bf["t14"], d("s14a"), g_14ex)
+        dgrad("motion_conv_expand_trans_14a", d("s14a"), d("tmp14"), g_14ex)
+        back("motion_conv2_trans_14a", bf["h1_14a"], d("h2_14a"), g_14a2)
+        dgrad("motion_conv2_trans_14a", d("h2_14a"), d("h1_14a"), g_14a2, gate=bf["h1_14a"])
+        back("motion_conv1_trans_14a", bf["t14"], d("h1_14a"), g_14a1)
+        dgrad("motion_conv1_trans_14a", d("h1_14a"), d("t14"), g_14a1, gate=bf["t14"], addend=d("tmp14"))
+        back("motion_conv_trans_14", bf["F14"], d("t14"), g_t14)
+        # dF14; channels >= 800 are sum_28c = relu(.) -> gate them here (fc28 contributes nothing)
+        dgrad("motion_conv_trans_14", d("t14"), bf["dF14"], g_t14, gate=bf["F14"], gate_col0=800)
+        # ---- 28c / 28b (identity residuals): the incoming gradient of 28c is the dF14 slice [800,1056)
+        g_dy_c3c = g_c3c
+        back("motion_conv3_trans_28c", bf["h2_28c"], bf["dF14"], g_dy_c3c)
+        dgrad("motion_conv3_trans_28c", bf["dF14"], d("h2_28c"), g_dy_c3c, gate=bf["h2_28c"])
+        back("motion_conv2_trans_28c", bf["h1_28c"], d("h2_28c"), g_c2c)
+        dgrad("motion_conv2_trans_28c", d("h2_28c"), d("h1_28c"), g_c2c, gate=bf["h1_28c"])
+        back("motion_conv1_trans_28c", bf["s28b"], d("h1_28c"), g_c1c)
+        g_slice14 = T.ConvGeom(P, 256, 14, 14, 64, x_ctot=1056, x_coff=800)
+        dgrad("motion_conv1_trans_28c", d("h1_28c"), d("s28b"), g_c1c, gate=bf["s28b"], addend=bf["dF14"],
+              add_geom=g_slice14)
+        back("motion_conv3_trans_28b", bf["h2_28b"], d("s28b"), g_c3b)
+        dgrad("motion_conv3_trans_28b", d("s28b"), d("h2_28b"), g_c3b, gate=bf["h2_28b"])
+        back("motion_conv2_trans_28b", bf["h1_28b"], d("h2_28b"), g_c2b)
+        dgrad("motion_conv2_trans_28b", d("h2_28b"), d("h1_28b"), g_c2b, gate=bf["h1_28b"])
+        back("motion_conv1_trans_28b", bf["s28a"], d("h1_28b"), g_c1b)
+        dgrad("motion_conv1_trans_28b", d("h1_28b"), d("s28a"), g_c1b, gate=bf["s28a"], addend=d("s28b"))
+        # ---- 28a: the branch consumes the PRE-ReLU conv_trans_28 output (:665), conv1 the ReLU'd one (:659)
+        back("motion_conv3_trans_28a", bf["h2_28a"], d("s28a"), g_c3a)
+        dgrad("motion_conv3_trans_28a", d("s28a"), d("h2_28a"), g_c3a, gate=bf["h2_28a"])
+        back("motion_conv_branch_28a", bf["t28"], d("s28a"), g_bra)
+        dgrad("motion_conv_branch_28a", d("s28a"), d("tmp28"), g_bra)
+        back("motion_conv2_trans_28a", bf["h1_28a"], d("h2_28a"), g_c2a)
+        dgrad("motion_conv2_trans_28a", d("h2_28a"), d("h1_28a"), g_c2a, gate=bf["h1_28a"])
+        back("motion_conv1_trans_28a", bf["t28"], d("h1_28a"), g_c1a, a_relu=True)
+        dgrad("motion_conv1_trans_28a", d("h1_28a"), d("t28"), g_c1a, gate=bf["t28"], gate_first=True,
+              addend=d("tmp28"))
+        back("motion_conv_trans_28", bf["F28"], d("t28"), g_t28)
+        dgrad("motion_conv_trans_28", d("t28"), bf["dF28"], g_t28)
+
+        self.fwd_steps = fwd
+        self.bwd_steps = bwd_stage + bwd_units
+
+    # ------------------------------------------------------------------ small step factories
+    def _add_into_slice(self, a, b, dst, ctot, coff, c, hw):
+        P, lib = self.P, self.lib
+        return lambda stream: L.check(lib.offk_add_relu_slice(_ptr(a), _ptr(b), _ptr(dst), ctot, coff, P, c, hw, 1,
+                                                               stream), "sum_14b")
+
+    def _site_seed(self, site):
+        return (self.drop_seed * 64 + site) & 0xFFFFFFFFFFFFFFFF
+
+    def _pool_fwd(self, k, x, c, ctot, coff):
+        lib, P = self.lib, self.P
+        site = {"28": 9, "14": 10, "7": 11}[k]
+
+        def run(stream):
+            m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
+            L.check(lib.offk_avgpool_drop_fwd(_ptr(x), P, c, 49, ctot, coff, self.drop_mode, _ptr(m),
+                                              self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
+                                              _ptr(self.buf["pool" + k]), stream), "pool" + k)
+        return run
+
+    def _pool_bwd(self, k, dx, c, ctot, coff, act, accumulate):
+        lib, P = self.lib, self.P
+        site = {"28": 9, "14": 10, "7": 11}[k]
+
+        def run(stream):
+            m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
+            L.check(lib.offk_avgpool_drop_bwd(_ptr(self.buf["d_pool" + k]), P, c, 49, ctot, coff, self.drop_mode,
+                                              _ptr(m), self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
+                                              _ptr(act), int(accumulate), _ptr(dx), stream), "pool_bwd" + k)
+        return run
+
+    def _fc_fwd(self, name, k, c):
+        g = T.ConvGeom(self.P, c, 1, 1, S.NUM_CLASSES)
+        return self._conv_fwd(name, self.buf["pool" + k], self.buf["fc" + k], g, self.params[name + ".weight"],
+                              self.params[name + ".bias"])
+
+    # ------------------------------------------------------------------ run
+    def _set_dropout(self, train, masks, seed):
+        if not train:
+            self.drop_mode, self.masks = L.DROP_NONE, None
+        elif masks is not None:
+            self.drop_mode = L.DROP_MASK
+            self.masks = {k: v.to(self.device, torch.uint8).contiguous() for k, v in masks.items()}
+        else:
+            self.drop_mode, self.masks = L.DROP_SEED, None
+            self.drop_seed = int(seed)
+        for i, (tag, sd) in enumerate(self._stencils.items()):
+            sd.drop_mode = self.drop_mode
+            sd.seed = self._site_seed(i)
+            sd.keep_mask = self.masks[tag].data_ptr() if self.drop_mode == L.DROP_MASK else None
+
+    def set_taps(self, taps: dict):
+        for tag, t in self.taps.items():
+            t.copy_(taps[tag], non_blocking=True)
+
+    def forward(self, taps: dict = None, train: bool = False, masks: dict = None, seed: int = 0):
+        """Run the forward plan.  Returns (fc7, fc28, fc14): [P,101] each, or [B,101] with consensus."""
+        if taps is not None:
+            self.set_taps(taps)
+        self._set_dropout(train, masks, seed)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for step in self.fwd_steps:
+            step(stream)
+        pre = "cfc" if self.consensus else "fc"
+        return self.buf[pre + "7"], self.buf[pre + "28"], self.buf[pre + "14"]
+
+    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True):
+        """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads)."""
+        self.d_out7.copy_(g7.reshape(self.d_out7.shape))
+        self.d_out14.copy_(g14.reshape(self.d_out14.shape))
+        if zero_grads:
+            self.grads_flat.zero_()
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for step in self.bwd_steps:
+            step(stream)
+        return self.grads
+
+
+def _gkey(g: T.ConvGeom):
+    return (g.n_img, g.cin, g.hin, g.win, g.cout, g.kh, g.kw, g.stride, g.pad, g.x_ctot, g.x_coff, g.y_ctot, g.y_coff)
