@@ -80,6 +80,14 @@ int offk_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_
  *   out = v   (atomic add when split_k > 1 or atomic_out; then bias / activations are NOT applied)
  * gate / addend use (gate_row,gate_col) / (add_row,add_col) or, when NULL, the out tables.
  * ---------------------------------------------------------------------- */
+/* Operand fetch modes.  The tables are always element-granular; a vector mode is a promise by the caller
+ * that groups of 4 consecutive indices are contiguous in memory, 16-byte aligned and share validity. */
+#define OFFK_LOAD_SCALAR_ROW 0 /* 4-byte loads, lanes walk rows (source contiguous along m / n)                 */
+#define OFFK_LOAD_SCALAR_K   1 /* 4-byte loads, lanes walk k    (source contiguous along k)                     */
+#define OFFK_LOAD_VEC_K      2 /* 16-byte loads of 4 consecutive k (K % 4 == 0): NHWC activations, dense weights */
+#define OFFK_LOAD_VEC_ROW    3 /* 16-byte loads of 4 consecutive rows, 4x4 register transpose into the K-major
+                                  tile: NCHW taps as A(m = pixel), NHWC tensors in weight-gradient GEMMs       */
+
 typedef struct offk_idx {
   int32_t off; /* element offset contribution                        */
   int16_t y;   /* row coordinate contribution for the validity box   */
@@ -95,12 +103,12 @@ typedef struct offk_gemm {
   int32_t a_h, a_w;        /* validity box; a_h == 0: always valid */
   int32_t a_relu;          /* max(.,0) on load (consumer of a pre-activation tensor, RGB_OFF.py:658) */
   int32_t a_ones_row;      /* -1, or the row whose A values are all 1 */
-  int32_t a_klane;         /* 1: source is contiguous along k -> lanes walk k (weight-gradient GEMMs) */
+  int32_t a_mode;          /* OFFK_LOAD_*: how the producer warps may fetch this operand */
   /* B operand */
   const float* b_src;
   const int32_t* b_row; /* [N] */
   const int32_t* b_col; /* [K] */
-  int32_t b_klane;      /* 1: contiguous along k */
+  int32_t b_mode;       /* OFFK_LOAD_* */
   /* epilogue */
   float* out;
   const int32_t* out_row; /* [M] */
@@ -120,7 +128,8 @@ typedef struct offk_gemm {
   float* ones_row_out; /* wgrad: D[a_ones_row, n] accumulates into ones_row_out[n] (bias gradient) */
   int32_t split_k;     /* >= 1; > 1 forces atomic accumulation into a zero-initialised `out` */
   int32_t tile_n;      /* 0 = auto; else the N tile of the tensor-core kernel (multiple of 16, <= 256) */
-  int32_t b_dense;     /* 1: b_col[k] == k, K % 4 == 0 and every b_src + b_row[n] is 16-byte aligned -> float4 loads */
+  int32_t out_vec;     /* 1: out/gate/addend are contiguous along n (out_col[n] = out_col[0] + n, N % 4 == 0, all
+                          offsets and bias 16-byte aligned): float4 epilogue (NHWC outputs) */
   int32_t reserved;
 } offk_gemm_t;
 
@@ -145,11 +154,15 @@ typedef struct offk_conv_geom {
  * (fixed diagonal kernel) or util.py:46-50 (Sobel x and y, K = 2), :612
  * (dropout), :616 (cat) and the stage cats :656,:760,:832.
  *
- *   g : reduced+ReLU'd features  G[f, c, y, x]  f in [0,B*L), c in [0,Cg); frame stride g_fs floats
- *   d : spatial-branch features  D[f, c, y, x]  c in [0,Cs);              frame stride d_fs floats
+ * Tensors are channels-last (the library's internal layout; the reference's NCHW taps are converted by the
+ * unit's 1x1 GEMM epilogue):
+ *   g : reduced+ReLU'd features  G[f, y, x, c]  f in [0,B*L), c in [0,Cg); frame stride g_fs, pixel stride g_ps floats
+ *   d : spatial-branch features  D[f, y, x, c]  c in [0,Cs);              frame stride d_fs, pixel stride d_ps
  *   w : [Cs, K, 3, 3] cross-correlation taps, bias [Cs*K] or NULL
- *   out[p, out_coff + kk*Cs + c, y, x] = drop( sum_ij w[c,kk,i,j] * D[fs(p), c, y+i-1, x+j-1] + bias )   (zero pad)
- *   out[p, out_coff + K*Cs + c,  y, x] = G[b*L+t+1, c, y, x] - G[b*L+t, c, y, x]        p = b*(L-1)+t
+ *   out: [P, H, W, out_ctot]
+ *   out[p, y, x, out_coff + kk*Cs + c] = drop( sum_ij w[c,kk,i,j] * D[fs(p), y+i-1, x+j-1, c] + bias )   (zero pad)
+ *   out[p, y, x, out_coff + K*Cs + c]  = G[b*L+t+1, y, x, c] - G[b*L+t, y, x, c]        p = b*(L-1)+t
+ *   keep_mask / seeded dropout are indexed like the reference's dropout input [P, K*Cs, H, W] (RGB_OFF.py:612)
  *   fs(p) = p (OFFK_INDEX_REFERENCE_FLAT) or b*L+t (OFFK_INDEX_ALIGNED)
  * Each G frame is read once.  Cg == 0 or Cs == 0 disables a half (the
  * stand-alone util.SobelFilter modules use Cg == 0, L == 2 so that p == f).
@@ -157,13 +170,14 @@ typedef struct offk_conv_geom {
 typedef struct offk_stencil {
   int32_t B, L, Cg, Cs, K, H, W;
   int64_t g_fs, d_fs;      /* frame strides (floats) of g and d */
+  int32_t g_ps, d_ps;      /* pixel strides (floats) of g and d: channels-last [f, y, x, c] */
   int32_t out_ctot, out_coff;
   int32_t index_mode;
   int32_t drop_mode;       /* OFFK_DROP_* */
   float keep_scale;        /* 1/(1-p) */
   float drop_p;            /* p, used by OFFK_DROP_SEED */
   uint64_t seed;
-  const uint8_t* keep_mask; /* [P, K*Cs, H, W] for OFFK_DROP_MASK */
+  const uint8_t* keep_mask; /* [P, K*Cs, H, W] (NCHW order) for OFFK_DROP_MASK */
 } offk_stencil_t;
 
 int offk_stencil_diff_fwd(const offk_stencil_t* s, const float* g, const float* d, const float* w,
@@ -182,7 +196,8 @@ int offk_stencil_diff_bwd(const offk_stencil_t* s, const float* dout, const floa
 /* ------------------------------------------------------------------------
  * Heads.  RGB_OFF.py:783-793,:844-847; Flow_OFF.py:867-876; basic_ops.py:12-46
  * ---------------------------------------------------------------------- */
-/* out[p,c] = drop( mean_{hw} x[p, x_coff+c, :] )   x: [P, x_ctot, HW]   (global_pool RGB_OFF.py:262 + dropout :356) */
+/* All head tensors are channels-last: x[P, HW, ctot], slices are channel ranges [coff, coff+C).
+ * out[p,c] = drop( mean_{hw} x[p, hw, x_coff+c] )   (global_pool RGB_OFF.py:262 + dropout :356) */
 int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode,
                           const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
                           float* out, void* stream);
@@ -210,6 +225,11 @@ int offk_bias_act(float* y, const float* bias, int P, int C, int HW, int ctot, i
  * written straight into the 7-stage fusion buffer (cat, :832) */
 int offk_add_relu_slice(const float* a, const float* b, float* dst, int dst_ctot, int dst_coff, int P, int C, int HW,
                         int relu, void* stream);
+
+/* Conv weights: the reference's OIHW [cout,cin,kh,kw] <-> OHWI [cout,kh,kw,cin], the K order of the channels-last
+ * implicit GEMM.  to_ohwi = 1: dst(OHWI) = src(OIHW) (before forward); 0: dst(OIHW) = src(OHWI);
+ * 2: dst(OIHW) += src(OHWI) (weight gradients) */
+int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi, void* stream);
 
 /* keep decision of OFFK_DROP_SEED for element `idx` (host mirror for tests): 1 = keep */
 int offk_drop_keep_host(uint64_t seed, uint64_t idx, float drop_p);

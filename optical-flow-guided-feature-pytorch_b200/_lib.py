@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "liboffk.so")
 PREC_FP32, PREC_TF32 = 0, 1
 INDEX_REFERENCE_FLAT, INDEX_ALIGNED = 0, 1
 DROP_NONE, DROP_MASK, DROP_SEED = 0, 1, 2
+LOAD_SCALAR_ROW, LOAD_SCALAR_K, LOAD_VEC_K, LOAD_VEC_ROW = 0, 1, 2, 3
 
 
 class OffkIdx(C.Structure):
@@ -27,8 +28,8 @@ class OffkGemm(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("a_src", C.c_void_p), ("a_row", C.c_void_p), ("a_col", C.c_void_p),
         ("a_h", C.c_int32), ("a_w", C.c_int32), ("a_relu", C.c_int32), ("a_ones_row", C.c_int32),
-        ("a_klane", C.c_int32),
-        ("b_src", C.c_void_p), ("b_row", C.c_void_p), ("b_col", C.c_void_p), ("b_klane", C.c_int32),
+        ("a_mode", C.c_int32),
+        ("b_src", C.c_void_p), ("b_row", C.c_void_p), ("b_col", C.c_void_p), ("b_mode", C.c_int32),
         ("out", C.c_void_p), ("out_row", C.c_void_p), ("out_col", C.c_void_p),
         ("bias", C.c_void_p), ("relu_pre_cols", C.c_int32),
         ("gate", C.c_void_p), ("gate_row", C.c_void_p), ("gate_col", C.c_void_p),
@@ -36,7 +37,7 @@ class OffkGemm(C.Structure):
         ("addend", C.c_void_p), ("add_row", C.c_void_p), ("add_col", C.c_void_p),
         ("relu_post", C.c_int32), ("atomic_out", C.c_int32),
         ("ones_row_out", C.c_void_p),
-        ("split_k", C.c_int32), ("tile_n", C.c_int32), ("b_dense", C.c_int32), ("reserved", C.c_int32),
+        ("split_k", C.c_int32), ("tile_n", C.c_int32), ("out_vec", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -45,7 +46,7 @@ class OffkStencil(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("L", C.c_int32), ("Cg", C.c_int32), ("Cs", C.c_int32), ("K", C.c_int32),
         ("H", C.c_int32), ("W", C.c_int32),
-        ("g_fs", C.c_int64), ("d_fs", C.c_int64),
+        ("g_fs", C.c_int64), ("d_fs", C.c_int64), ("g_ps", C.c_int32), ("d_ps", C.c_int32),
         ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
         ("index_mode", C.c_int32), ("drop_mode", C.c_int32),
         ("keep_scale", C.c_float), ("drop_p", C.c_float),
@@ -75,6 +76,7 @@ _PROTOS = {
                                  C.c_int, _P]),
     "offk_bias_act": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_add_relu_slice": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "offk_permute_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_drop_keep_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_float]),
 }
 

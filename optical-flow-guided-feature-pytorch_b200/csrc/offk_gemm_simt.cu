@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(SM_THREADS) gather_gemm_simt_kernel(const offk
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int row, kk;
-      if (g.a_klane) { kk = tid & 15; row = (tid >> 4) + 16 * i; }
+      if (g.a_mode == OFFK_LOAD_SCALAR_K || g.a_mode == OFFK_LOAD_VEC_K) { kk = tid & 15; row = (tid >> 4) + 16 * i; }
       else           { row = tid & 63; kk = (tid >> 6) + 4 * i; }
       const int m = m0 + row, k = k0 + kk;
       float v = 0.f;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(SM_THREADS) gather_gemm_simt_kernel(const offk
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int row, kk;
-      if (g.b_klane) { kk = tid & 15; row = (tid >> 4) + 16 * i; }
+      if (g.b_mode == OFFK_LOAD_SCALAR_K || g.b_mode == OFFK_LOAD_VEC_K) { kk = tid & 15; row = (tid >> 4) + 16 * i; }
       else           { row = tid & 63; kk = (tid >> 6) + 4 * i; }
       const int n = n0 + row, k = k0 + kk;
       float v = 0.f;

@@ -1,4 +1,4 @@
-// Head-side kernels of the OFF sub-network: global average pool (+dropout) forward/backward,
+// Head-side kernels of the OFF sub-network (channels-last tensors [P, HW, C]): global average pool (+dropout) forward/backward,
 // 3x3/s2 ceil-mode max pool, segment consensus (mean over segments) and small element-wise passes.
 // All are bandwidth-trivial ([P,C,7,7] tensors); they exist so that no ATen op is left on the path.
 #include "offk_common.cuh"
@@ -12,21 +12,18 @@ __device__ __forceinline__ float keep_factor(int mode, const uint8_t* mask, uint
   return keep ? scale : 0.f;
 }
 
-// one warp per (p, c) plane
+// thread per (p, c); x is channels-last [P, HW, ctot]: consecutive threads read consecutive channels
 __global__ void avgpool_drop_fwd_kernel(const float* __restrict__ x, int P, int C, int HW, int ctot, int coff, int mode,
                                         const uint8_t* __restrict__ mask, uint64_t seed, float drop_p, float scale,
                                         float* __restrict__ out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= P * C) return;
-  const int p = warp / C, c = warp - p * C;
-  const float* xp = x + ((size_t)p * ctot + coff + c) * HW;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * C) return;
+  const int p = i / C, c = i - p * C;
+  const float* xp = x + (size_t)p * HW * ctot + coff + c;
   float s = 0.f;
-  for (int i = lane; i < HW; i += 32) s += __ldg(xp + i);
-  s = warp_sum(s);
-  if (lane == 0) {
-    const float k = keep_factor(mode, mask, seed, drop_threshold24(drop_p), (size_t)warp, scale);
-    out[warp] = (s / (float)HW) * k;
-  }
+  for (int h = 0; h < HW; ++h) s += __ldg(xp + (size_t)h * ctot);
+  const float k = keep_factor(mode, mask, seed, drop_threshold24(drop_p), (size_t)i, scale);
+  out[i] = (s / (float)HW) * k;
 }
 
 __global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P, int C, int HW, int ctot, int coff,
@@ -36,10 +33,10 @@ __global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
-  const size_t pc = i / HW;
-  const int hw = (int)(i - pc * HW);
-  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
-  const size_t o = ((size_t)p * ctot + coff + c) * HW + hw;
+  const int c = (int)(i % C);
+  const size_t ph = i / C;            // p*HW + hw
+  const size_t pc = (ph / HW) * C + c;
+  const size_t o = ph * ctot + coff + c;
   float v = 0.f;
   if (dpooled) v = __ldg(dpooled + pc) * keep_factor(mode, mask, seed, drop_threshold24(drop_p), pc, scale) / (float)HW;
   if (accumulate) v += dx[o];
@@ -52,11 +49,11 @@ __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C,
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * Ho * Wo;
   if (i >= total) return;
-  const int ow = (int)(i % Wo);
-  const int oh = (int)((i / Wo) % Ho);
-  const size_t pc = i / ((size_t)Wo * Ho);
-  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
-  const float* xp = x + ((size_t)p * ctot + coff + c) * H * W;
+  const int c = (int)(i % C);
+  const int ow = (int)((i / C) % Wo);
+  const int oh = (int)((i / ((size_t)C * Wo)) % Ho);
+  const int p = (int)(i / ((size_t)C * Wo * Ho));
+  const float* xp = x + (size_t)p * H * W * ctot + coff + c;
   float m = -INFINITY;
   for (int a = 0; a < 3; ++a) {
     const int y = oh * 2 + a;
@@ -64,10 +61,10 @@ __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C,
     for (int b = 0; b < 3; ++b) {
       const int xx = ow * 2 + b;
       if (xx >= W) break;
-      m = fmaxf(m, __ldg(xp + y * W + xx));
+      m = fmaxf(m, __ldg(xp + (size_t)(y * W + xx) * ctot));
     }
   }
-  out[i] = m;
+  out[i] = m;   // [P, Ho, Wo, C]
 }
 
 __global__ void segment_mean_fwd_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
@@ -96,12 +93,11 @@ __global__ void gate_copy_kernel(const float* __restrict__ src, int sctot, int s
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
-  const size_t pc = i / HW;
-  const int hw = (int)(i - pc * HW);
-  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
-  const float a = __ldg(act + ((size_t)p * actot + acoff + c) * HW + hw);
-  const float v = __ldg(src + ((size_t)p * sctot + scoff + c) * HW + hw);
-  dst[((size_t)p * dctot + dcoff + c) * HW + hw] = a > 0.f ? v : 0.f;
+  const int c = (int)(i % C);
+  const size_t ph = i / C;
+  const float a = __ldg(act + ph * actot + acoff + c);
+  const float v = __ldg(src + ph * sctot + scoff + c);
+  dst[ph * dctot + dcoff + c] = a > 0.f ? v : 0.f;
 }
 // dst[p, coff+c, :] = (relu ? max(.,0) : .)(a[p,c,:] + b[p,c,:])
 __global__ void add_relu_slice_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst,
@@ -109,25 +105,38 @@ __global__ void add_relu_slice_kernel(const float* __restrict__ a, const float* 
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
-  const size_t pc = i / HW;
-  const int hw = (int)(i - pc * HW);
-  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
+  const int c = (int)(i % C);
+  const size_t ph = i / C;
   float v = __ldg(a + i) + __ldg(b + i);
   if (relu) v = fmaxf(v, 0.f);
-  dst[((size_t)p * ctot + coff + c) * HW + hw] = v;
+  dst[ph * ctot + coff + c] = v;
 }
 __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int P, int C, int HW, int ctot,
                                 int coff, int relu_cols) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
-  const size_t pc = i / HW;
-  const int hw = (int)(i - pc * HW);
-  const int p = (int)(pc / C), c = (int)(pc - (size_t)p * C);
-  const size_t o = ((size_t)p * ctot + coff + c) * HW + hw;
+  const int c = (int)(i % C);
+  const size_t o = (i / C) * ctot + coff + c;
   float v = y[o] + (bias ? __ldg(bias + c) : 0.f);
   if (c < relu_cols) v = fmaxf(v, 0.f);
   y[o] = v;
+}
+
+// weight layouts: canonical OIHW [cout, cin, R, Q] (the reference's state_dict) <-> OHWI [cout, R, Q, cin] (k order of
+// the channels-last implicit GEMM).  to_ohwi != 0: dst(OHWI) = src(OIHW); else dst(OIHW) = src(OHWI).
+__global__ void permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int rq,
+                                      int to_ohwi) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into the OHWI tensor
+  const size_t total = (size_t)cout * cin * rq;
+  if (i >= total) return;
+  const int ci = (int)(i % cin);
+  const int t = (int)((i / cin) % rq);
+  const size_t o = i / ((size_t)cin * rq);
+  const size_t j = (o * cin + ci) * rq + t;                         // index into the OIHW tensor
+  if (to_ohwi == 1) dst[i] = __ldg(src + j);
+  else if (to_ohwi == 0) dst[j] = __ldg(src + i);
+  else dst[j] += __ldg(src + i);   // 2: accumulate into the OIHW gradient
 }
 
 static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -141,8 +150,7 @@ extern "C" int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x
                                      float* out, void* stream) {
   OFFK_REQUIRE(x && out && P > 0 && C > 0 && HW > 0 && x_coff >= 0 && x_coff + C <= x_ctot, "avgpool_fwd: bad args");
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_fwd: mask missing");
-  const size_t threads = (size_t)P * C * 32;
-  avgpool_drop_fwd_kernel<<<blocks_for(threads, 256), 256, 0, as_stream(stream)>>>(
+  avgpool_drop_fwd_kernel<<<blocks_for((size_t)P * C, 128), 128, 0, as_stream(stream)>>>(
       x, P, C, HW, x_ctot, x_coff, drop_mode, keep_mask, seed, drop_p, keep_scale, out);
   return OFFK_LAUNCH_CHECK("avgpool_drop_fwd");
 }
@@ -211,4 +219,12 @@ extern "C" int offk_add_relu_slice(const float* a, const float* b, float* dst, i
   add_relu_slice_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(a, b, dst, dst_ctot,
                                                                                            dst_coff, P, C, HW, relu);
   return OFFK_LAUNCH_CHECK("add_relu_slice");
+}
+
+extern "C" int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi,
+                                   void* stream) {
+  OFFK_REQUIRE(src && dst && cout > 0 && cin > 0 && kh > 0 && kw > 0, "permute_weight: bad args");
+  permute_weight_kernel<<<blocks_for((size_t)cout * cin * kh * kw, 256), 256, 0, as_stream(stream)>>>(
+      src, dst, cout, cin, kh * kw, to_ohwi);
+  return OFFK_LAUNCH_CHECK("permute_weight");
 }

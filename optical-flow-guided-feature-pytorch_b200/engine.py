@@ -1,5 +1,9 @@
 """OFFEngine: the OFF sub-network (RGB_OFF.py:596-860 / Flow_OFF.py:606-884) as a static plan of
-liboffk kernel launches over preallocated NCHW fp32 buffers.
+liboffk kernel launches over preallocated fp32 buffers.
+
+Layout: the taps arrive NCHW (the reference's layout); the unit's fused 1x1 GEMM converts to channels-last in
+its epilogue and everything downstream (reduced features, stage-fusion buffers, residual blocks, gradients) is
+NHWC, so that every implicit-GEMM operand is fetched with 16-byte loads.
 
 Every step is one C-ABI call with a descriptor bound at plan-build time, so a forward or backward
 pass is a flat list of launches on one stream: cheap to issue and capturable in a CUDA graph.
@@ -36,8 +40,8 @@ class Gemm:
         d = L.OffkGemm()
         d.M, d.N, d.K = spc.M, spc.N, spc.K
         d.a_src, d.a_row, d.a_col = a_src.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
-        d.a_h, d.a_w, d.a_relu, d.a_ones_row, d.a_klane = spc.a_h, spc.a_w, int(a_relu), spc.a_ones_row, spc.a_klane
-        d.b_src, d.b_row, d.b_col, d.b_klane = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_klane
+        d.a_h, d.a_w, d.a_relu, d.a_ones_row, d.a_mode = spc.a_h, spc.a_w, int(a_relu), spc.a_ones_row, spc.a_mode
+        d.b_src, d.b_row, d.b_col, d.b_mode = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
         d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
         d.bias = bias.data_ptr() if bias is not None else None
         d.relu_pre_cols = relu_pre_cols
@@ -51,7 +55,8 @@ class Gemm:
         d.relu_post, d.atomic_out = int(relu_post), int(atomic)
         d.ones_row_out = ones_out.data_ptr() if ones_out is not None else None
         d.split_k, d.tile_n = split_k, tile_n
-        d.b_dense = spc.b_dense if (b_src.data_ptr() % 16 == 0) else 0
+        d.out_vec = spc.out_vec if (gate_tabs is None or True) else 0
+        T.check_modes(spc)
         self.desc = d
         self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out)
         self.flops = 2.0 * spc.M * spc.N * spc.K
@@ -134,12 +139,12 @@ class OFFEngine:
         P, N = self.P, self.N
         self.buf = {}
         for tag, (cin, s) in S.LEVELS.items():
-            self._buf("gd_" + tag, N, S.UNIT_C, s, s)
-            self._buf("dgd_" + tag, N, S.UNIT_C, s, s)
+            self._buf("gd_" + tag, N, s, s, S.UNIT_C)
+            self._buf("dgd_" + tag, N, s, s, S.UNIT_C)
         for st, (ctot, s, _) in S.STAGES.items():
-            self._buf("F" + st, P, ctot, s, s)
-            self._buf("dF" + st, P, ctot, s, s)
-        a = lambda n, c, s: (self._buf(n, P, c, s, s), self._buf("d_" + n, P, c, s, s))
+            self._buf("F" + st, P, s, s, ctot)
+            self._buf("dF" + st, P, s, s, ctot)
+        a = lambda n, c, s: (self._buf(n, P, s, s, c), self._buf("d_" + n, P, s, s, c))
         a("t28", 64, 14)
         a("tmp28", 64, 14)
         for blk in "abc":
@@ -162,7 +167,7 @@ class OFFEngine:
         a("h2_7", 256, 7)
         a("br7", 1024, 7)
         a("s7", 1024, 7)
-        self._buf("p28", P, 256, 7, 7)
+        self._buf("p28", P, 7, 7, 256)
         for k, c in (("7", 1024), ("14", 512), ("28", 256)):
             self._buf("pool" + k, P, c)
             self._buf("d_pool" + k, P, c)
@@ -173,6 +178,18 @@ class OFFEngine:
         self.taps = OrderedDict((tag, torch.zeros(N, cin, s, s, device=self.device)) for tag, (cin, s) in S.LEVELS.items())
         if self.tap_grads:
             self.tap_grad = OrderedDict((tag, torch.zeros_like(t)) for tag, t in self.taps.items())
+        # OHWI copies of the KxK conv weights (k order of the channels-last implicit GEMM) and of their gradients
+        self.wp, self.dwp = {}, {}
+        kxk = [(name, cout, cin, k) for name, cout, cin, k, _, _ in S.STAGE_CONVS if k > 1]
+        total = sum(cout * cin * k * k for _, cout, cin, k in kxk)
+        self.wp_flat = torch.zeros(total, device=self.device)
+        self.dwp_flat = torch.zeros(total, device=self.device)
+        off = 0
+        for name, cout, cin, k in kxk:
+            n = cout * cin * k * k
+            self.wp[name] = self.wp_flat[off:off + n].view(cout, k, k, cin)
+            self.dwp[name] = self.dwp_flat[off:off + n].view(cout, k, k, cin)
+            off += n
         # dropout state (filled per forward call)
         self.drop_mode = L.DROP_NONE
         self.drop_seed = 0
@@ -180,16 +197,16 @@ class OFFEngine:
 
     # ------------------------------------------------------------------ plan
     def _conv_fwd(self, name, x, y, geom, w, b, *, relu=False, relu_cols=None, a_relu=False, addend=None,
-                  add_tabs=None, relu_post=False):
-        spc = T.conv_fwd_spec(geom)
+                  add_tabs=None, relu_post=False, x_layout="nhwc"):
+        spc = T.conv_fwd_spec(geom, x_layout, "nhwc")
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = 1
-        if self.prec == L.PREC_TF32 and addend is None and m_tiles * n_tiles < 100 and kb >= 32:
-            split = max(1, min(_SM_TARGET // (m_tiles * n_tiles), kb // 8))
+        if self.prec == L.PREC_TF32 and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
+            split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), kb // 8))
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
         if split > 1:
-            g = Gemm(self, spc, ("fwd", _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
+            g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
             hw = geom.hout * geom.wout
 
             def run(stream, g=g, y=y, b=b, geom=geom, hw=hw, cols=cols):
@@ -200,32 +217,32 @@ class OFFEngine:
             assert geom.y_coff == 0 and geom.y_ctot == geom.cout
             self.flops_fwd += g.flops
             return run
-        g = Gemm(self, spc, ("fwd", _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
+        g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
                  addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
         self.flops_fwd += g.flops
         return g
 
-    def _conv_wgrad(self, name, x, dy, geom, dw, db, *, a_relu=False):
-        spc = T.conv_wgrad_spec(geom)
+    def _conv_wgrad(self, name, x, dy, geom, dw, db, *, a_relu=False, x_layout="nhwc"):
+        spc = T.conv_wgrad_spec(geom, x_layout, "nhwc")
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
-        g = Gemm(self, spc, ("wgrad", _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
+        g = Gemm(self, spc, ("wgrad", x_layout, _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
                  atomic=True, split_k=split, name=name + ".wgrad")
         self.flops_bwd += g.flops
         return g
 
     def _conv_dgrad(self, name, dy, w, dx, geom, *, gate=None, gate_col0=0, gate_first=False, addend=None,
-                    add_geom=None):
+                    add_geom=None, x_layout="nhwc"):
         out = []
-        for i, spc in enumerate(T.conv_dgrad_specs(geom)):
+        for i, spc in enumerate(T.conv_dgrad_specs(geom, x_layout, "nhwc", "nhwc")):
             add_tabs = None
             if addend is not None and add_geom is not None:
                 # addend lives in a differently-shaped buffer: tables of the same logical (img, c, y, x) element
-                aspec = T.conv_dgrad_specs(add_geom)[i]
-                t = self._tables(("dgrad", _gkey(add_geom), i), aspec)
+                aspec = T.conv_dgrad_specs(add_geom, "nhwc", "nhwc", "nhwc")[i]
+                t = self._tables(("dgrad", "nhwc", _gkey(add_geom), i), aspec)
                 add_tabs = (t["out_row"], t["out_col"])
-            g = Gemm(self, spc, ("dgrad", _gkey(geom), i), a_src=dy, b_src=w, out=dx, gate=gate, gate_col0=gate_col0,
+            g = Gemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), a_src=dy, b_src=w, out=dx, gate=gate, gate_col0=gate_col0,
                      gate_first=gate_first, addend=addend, add_tabs=add_tabs, name=f"{name}.dgrad{i}")
             self.flops_bwd += g.flops
             out.append(g)
@@ -248,11 +265,12 @@ class OFFEngine:
             gd, dgd = bf["gd_" + tag], bf["dgd_" + tag]
             # K1: gen (ReLU) and down (linear) 1x1 convs as ONE GEMM with 160 output channels
             fwd.append(self._conv_fwd("unit_" + tag, self.taps[tag], gd, geom, self._unit_w(self.params_flat, tag),
-                                      self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C))
+                                      self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nchw"))
             # K2: fused spatial stencil + temporal difference + dropout + cat, into the stage buffer
             sd = L.OffkStencil()
             sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, S.GEN_C, S.DOWN_C, 1, s, s
             sd.g_fs = sd.d_fs = S.UNIT_C * s * s
+            sd.g_ps = sd.d_ps = S.UNIT_C
             sd.out_ctot, sd.out_coff, sd.index_mode = ctot, coff, self.index_mode
             sd.drop_mode, sd.keep_scale, sd.drop_p = L.DROP_NONE, 1.0 / (1.0 - S.DROP_P), S.DROP_P
             self._stencils[tag] = sd
@@ -262,8 +280,8 @@ class OFFEngine:
             else:
                 w3, b3, dw3, db3 = self.sobel_w, None, None, None
             Fst, dFst = bf["F" + st], bf["dF" + st]
-            g_ptr, d_ptr = gd.data_ptr(), gd.data_ptr() + 4 * S.GEN_C * s * s
-            dg_ptr, dd_ptr = dgd.data_ptr(), dgd.data_ptr() + 4 * S.GEN_C * s * s
+            g_ptr, d_ptr = gd.data_ptr(), gd.data_ptr() + 4 * S.GEN_C     # D = channels [128,160) of every pixel
+            dg_ptr, dd_ptr = dgd.data_ptr(), dgd.data_ptr() + 4 * S.GEN_C
             fs = S.UNIT_C * s * s
 
             def k2(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, b3=b3, Fst=Fst, tag=tag):
@@ -278,19 +296,20 @@ class OFFEngine:
             bwd_units.append(k3)
             # K4: weight / bias gradient of the fused 1x1 (no dX for the frozen taps unless asked, train_off.py:39-46)
             bwd_units.append(self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
-                                              self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag)))
+                                              self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag),
+                                              x_layout="nchw"))
             if self.tap_grads:
                 bwd_units += self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
-                                              self.tap_grad[tag], geom)
+                                              self.tap_grad[tag], geom, x_layout="nchw")
 
         # ============ stage convs
         def geom_of(name, n_img, s_in, x_ctot=0, x_coff=0, y_ctot=0, y_coff=0):
             _, cout, cin, k, stride, pad = S.CONV_BY_NAME[name]
             return T.ConvGeom(n_img, cin, s_in, s_in, cout, k, k, stride, pad, x_ctot, x_coff, y_ctot, y_coff)
 
-        def W(n): return pr[n + ".weight"]
+        def W(n): return self.wp[n] if n in self.wp else pr[n + ".weight"]     # OHWI copy for KxK convs
         def Bv(n): return pr[n + ".bias"]
-        def dW(n): return gr[n + ".weight"]
+        def dW(n): return self.dwp[n] if n in self.dwp else gr[n + ".weight"]
         def dB(n): return gr[n + ".bias"]
 
         def layer(name, x, y, s_in, *, relu=False, a_relu=False, addend=None, relu_post=False,
@@ -314,9 +333,9 @@ class OFFEngine:
         g_c2c = layer("motion_conv2_trans_28c", bf["h1_28c"], bf["h2_28c"], 14, relu=True)
         # sum_28c goes straight into the 14-stage fusion buffer at channel 800 (cat, :760)
         g_c3c = geom_of("motion_conv3_trans_28c", P, 14, y_ctot=1056, y_coff=800)
-        g_s28b_as_f14 = T.ConvGeom(P, 256, 14, 14, 256, y_ctot=256)  # tables for the s28b addend (plain [P,256,14,14])
-        spc_add = T.conv_fwd_spec(g_s28b_as_f14)
-        tabs_add = self._tables(("fwd", _gkey(g_s28b_as_f14)), spc_add)
+        g_s28b_as_f14 = T.ConvGeom(P, 256, 14, 14, 256, y_ctot=256)  # tables for the s28b addend (plain [P,14,14,256])
+        spc_add = T.conv_fwd_spec(g_s28b_as_f14, "nhwc", "nhwc")
+        tabs_add = self._tables(("fwd", "nhwc", _gkey(g_s28b_as_f14)), spc_add)
         fwd.append(self._conv_fwd("motion_conv3_trans_28c", bf["h2_28c"], bf["F14"], g_c3c,
                                   W("motion_conv3_trans_28c"), Bv("motion_conv3_trans_28c"), addend=bf["s28b"],
                                   add_tabs=(tabs_add["out_row"], tabs_add["out_col"]), relu_post=True))
@@ -445,8 +464,16 @@ class OFFEngine:
         back("motion_conv_trans_28", bf["F28"], d("t28"), g_t28)
         dgrad("motion_conv_trans_28", d("t28"), bf["dF28"], g_t28)
 
-        self.fwd_steps = fwd
-        self.bwd_steps = bwd_stage + bwd_units
+        # OHWI weight copies before the forward, OHWI -> OIHW weight gradients after the backward
+        pre, post = [], []
+        for name, cout, cin, k, _, _ in S.STAGE_CONVS:
+            if k > 1:
+                pre.append(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
+                    _ptr(pr[n + ".weight"]), _ptr(self.wp[n]), co, ci, k, k, 1, stream), "permute " + n))
+                post.append(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
+                    _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n))
+        self.fwd_steps = pre + fwd
+        self.bwd_steps = bwd_stage + bwd_units + post
 
     # ------------------------------------------------------------------ small step factories
     def _add_into_slice(self, a, b, dst, ctot, coff, c, hw):
@@ -520,6 +547,7 @@ class OFFEngine:
         self.d_out14.copy_(g14.reshape(self.d_out14.shape))
         if zero_grads:
             self.grads_flat.zero_()
+        self.dwp_flat.zero_()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         for step in self.bwd_steps:
             step(stream)

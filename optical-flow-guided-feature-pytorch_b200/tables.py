@@ -72,14 +72,18 @@ class GemmSpec:
     a_h: int = 0
     a_w: int = 0
     a_ones_row: int = -1
-    a_klane: int = 0
-    b_klane: int = 0
-    b_dense: int = 0
+    a_mode: int = 0
+    b_mode: int = 0
+    out_vec: int = 0
     kind: str = ""
     extra: dict = field(default_factory=dict)
 
 
+LOAD_SCALAR_ROW, LOAD_SCALAR_K, LOAD_VEC_K, LOAD_VEC_ROW = 0, 1, 2, 3
+
+
 def _idx(off, y, x):
+    off, y, x = np.broadcast_arrays(off, y, x)
     t = np.empty(off.shape, IDX_DTYPE)
     t["off"] = off
     t["y"] = y
@@ -87,61 +91,100 @@ def _idx(off, y, x):
     return np.ascontiguousarray(t.reshape(-1))
 
 
-def _pixel_tables(g: ConvGeom):
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a).reshape(-1).astype(np.int32))
+
+
+def _pixel_tables(g: ConvGeom, x_layout: str, y_layout: str):
     """Per output pixel m=(img,oh,ow): where its receptive field starts in x, and where it lives in y."""
     img, oh, ow = np.meshgrid(np.arange(g.n_img), np.arange(g.hout), np.arange(g.wout), indexing="ij")
     y0 = oh * g.stride - g.pad
     x0 = ow * g.stride - g.pad
-    off = (img * g.x_ctot + g.x_coff) * (g.hin * g.win) + y0 * g.win + x0
-    y_off = (img * g.y_ctot + g.y_coff) * (g.hout * g.wout) + oh * g.wout + ow
-    return _idx(off, y0, x0), y_off.reshape(-1).astype(np.int32)
+    if x_layout == "nchw":
+        off = (img * g.x_ctot + g.x_coff) * (g.hin * g.win) + y0 * g.win + x0
+    else:
+        off = ((img * g.hin + y0) * g.win + x0) * g.x_ctot + g.x_coff
+    pix = oh * g.wout + ow
+    if y_layout == "nchw":
+        y_off = (img * g.y_ctot + g.y_coff) * (g.hout * g.wout) + pix
+    else:
+        y_off = (img * (g.hout * g.wout) + pix) * g.y_ctot + g.y_coff
+    return _idx(off, y0, x0), _i32(y_off)
 
 
-def _filter_tables(g: ConvGeom):
-    """Per filter tap k=(c,r,q): offset inside the receptive field."""
-    c, r, q = np.meshgrid(np.arange(g.cin), np.arange(g.kh), np.arange(g.kw), indexing="ij")
-    return _idx(c * (g.hin * g.win) + r * g.win + q, r, q)
+def _filter_tables(g: ConvGeom, x_layout: str):
+    """Per filter tap: offset inside the receptive field.  k order is (c,r,q) for NCHW inputs (the canonical
+    weight layout [cout,cin,kh,kw]) and (r,q,c) for NHWC inputs (weights permuted to [cout,kh,kw,cin])."""
+    if x_layout == "nchw":
+        c, r, q = np.meshgrid(np.arange(g.cin), np.arange(g.kh), np.arange(g.kw), indexing="ij")
+        return _idx(c * (g.hin * g.win) + r * g.win + q, r, q)
+    r, q, c = np.meshgrid(np.arange(g.kh), np.arange(g.kw), np.arange(g.cin), indexing="ij")
+    return _idx((r * g.win + q) * g.x_ctot + c, r, q)
 
 
-def conv_fwd_spec(g: ConvGeom) -> GemmSpec:
-    """y = conv2d(x, w) + epilogue.  A = im2col(x) gathered on the fly, B = w viewed as [cout, cin*kh*kw]."""
-    a_row, y_off = _pixel_tables(g)
+def _is1x1(g):
+    return g.kh == 1 and g.kw == 1 and g.pad == 0 and g.stride == 1
+
+
+def conv_fwd_spec(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw") -> GemmSpec:
+    """y = conv2d(x, w) + epilogue.  A = im2col(x) gathered on the fly, B = w viewed as [cout, K]
+    (K ordered like the x layout, see _filter_tables)."""
+    a_row, y_off = _pixel_tables(g, x_layout, y_layout)
     K = g.kdim
+    hw, hwo = g.hin * g.win, g.hout * g.wout
     box = not (g.kh == 1 and g.kw == 1 and g.pad == 0)
+    if x_layout == "nhwc":
+        a_mode = LOAD_VEC_K if (g.cin % 4 == 0 and g.x_ctot % 4 == 0 and g.x_coff % 4 == 0) else LOAD_SCALAR_ROW
+    else:
+        a_mode = LOAD_VEC_ROW if (_is1x1(g) and hw % 4 == 0) else LOAD_SCALAR_ROW
+    if y_layout == "nhwc":
+        out_col = np.arange(g.cout)
+        out_vec = int(g.cout % 4 == 0 and g.y_ctot % 4 == 0 and g.y_coff % 4 == 0)
+    else:
+        out_col, out_vec = np.arange(g.cout) * hwo, 0
     return GemmSpec(
-        M=g.n_img * g.hout * g.wout, N=g.cout, K=K,
-        a_row=a_row, a_col=_filter_tables(g),
-        b_row=(np.arange(g.cout) * K).astype(np.int32), b_col=np.arange(K, dtype=np.int32),
-        out_row=y_off, out_col=(np.arange(g.cout) * (g.hout * g.wout)).astype(np.int32),
-        a_h=g.hin if box else 0, a_w=g.win if box else 0,
-        b_klane=1, b_dense=1 if K % 4 == 0 else 0, kind="fwd")
+        M=g.n_img * hwo, N=g.cout, K=K, a_row=a_row, a_col=_filter_tables(g, x_layout),
+        b_row=_i32(np.arange(g.cout) * K), b_col=_i32(np.arange(K)), out_row=y_off, out_col=_i32(out_col),
+        a_h=g.hin if box else 0, a_w=g.win if box else 0, a_mode=a_mode,
+        b_mode=LOAD_VEC_K if K % 4 == 0 else LOAD_SCALAR_K, out_vec=out_vec, kind="fwd")
 
 
-def conv_wgrad_spec(g: ConvGeom) -> GemmSpec:
-    """dW[cout, (c,r,q)] += sum_pixels dY * im2col(x);  the extra all-ones A row yields db[cout].
-    Rows are the filter taps (so the store into dW is contiguous along rows), k walks output pixels."""
-    pix, y_off = _pixel_tables(g)
+def conv_wgrad_spec(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw") -> GemmSpec:
+    """dW[cout, K_w] += sum_pixels dY * im2col(x);  the extra all-ones A row yields db[cout].
+    Rows are the filter taps in the x-layout k order (stores into dW are contiguous along rows),
+    k walks output pixels."""
+    pix, _ = _pixel_tables(g, x_layout, y_layout)
     K_w = g.kdim
-    hw = g.hout * g.wout
+    hw, hwo = g.hin * g.win, g.hout * g.wout
     box = not (g.kh == 1 and g.kw == 1 and g.pad == 0)
-    a_row = np.concatenate([_filter_tables(g), np.zeros(1, IDX_DTYPE)])
-    img = np.repeat(np.arange(g.n_img), hw)
-    b_col = (img * g.y_ctot * hw + np.tile(np.arange(hw), g.n_img)).astype(np.int32)
+    a_row = np.concatenate([_filter_tables(g, x_layout), np.zeros(1, IDX_DTYPE)])
+    img = np.repeat(np.arange(g.n_img), hwo)
+    p = np.tile(np.arange(hwo), g.n_img)
+    if x_layout == "nhwc":
+        a_mode = LOAD_VEC_ROW if (g.cin % 4 == 0 and g.x_ctot % 4 == 0 and g.x_coff % 4 == 0) else LOAD_SCALAR_ROW
+    else:
+        a_mode = LOAD_VEC_K if (_is1x1(g) and hw % 4 == 0) else LOAD_SCALAR_K
+    if y_layout == "nhwc":
+        b_row, b_col = np.arange(g.cout) + g.y_coff, (img * hwo + p) * g.y_ctot
+        b_mode = LOAD_VEC_ROW if (g.cout % 4 == 0 and g.y_ctot % 4 == 0 and g.y_coff % 4 == 0) else LOAD_SCALAR_ROW
+    else:
+        b_row, b_col = (np.arange(g.cout) + g.y_coff) * hwo, img * g.y_ctot * hwo + p
+        b_mode = LOAD_VEC_K if hwo % 4 == 0 else LOAD_SCALAR_K
     return GemmSpec(
-        M=K_w + 1, N=g.cout, K=g.n_img * hw,
-        a_row=a_row, a_col=pix,
-        b_row=((np.arange(g.cout) + g.y_coff) * hw).astype(np.int32), b_col=b_col,
-        out_row=np.arange(K_w + 1, dtype=np.int32), out_col=(np.arange(g.cout) * K_w).astype(np.int32),
-        a_h=g.hin if box else 0, a_w=g.win if box else 0,
-        a_ones_row=K_w, a_klane=1, b_klane=1, kind="wgrad")
+        M=K_w + 1, N=g.cout, K=g.n_img * hwo, a_row=a_row, a_col=pix, b_row=_i32(b_row), b_col=_i32(b_col),
+        out_row=_i32(np.arange(K_w + 1)), out_col=_i32(np.arange(g.cout) * K_w),
+        a_h=g.hin if box else 0, a_w=g.win if box else 0, a_ones_row=K_w, a_mode=a_mode, b_mode=b_mode, kind="wgrad")
 
 
-def conv_dgrad_specs(g: ConvGeom):
+def conv_dgrad_specs(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw", w_layout: str = None):
     """dX = conv_transpose(dY, w), one GEMM per stride-parity class (a,b) of the input pixel
     (ih = s*ih' + a):  only filter rows r = r0 + s*r' with r0 = (a+pad) % s reach that class, so the
-    zero-stuffed taps of a strided transposed conv are never multiplied."""
+    zero-stuffed taps of a strided transposed conv are never multiplied.
+    w_layout: 'nchw' = canonical [cout,cin,kh,kw], 'nhwc' = permuted [cout,kh,kw,cin] (default: x_layout)."""
+    w_layout = w_layout or x_layout
     s, p = g.stride, g.pad
-    hwo = g.hout * g.wout
+    hwo, hwi = g.hout * g.wout, g.hin * g.win
+    kw_tot = g.cin * g.kh * g.kw
     specs = []
     for a in range(s):
         for b in range(s):
@@ -153,19 +196,72 @@ def conv_dgrad_specs(g: ConvGeom):
             assert len(rs) > 0 and len(qs) > 0, "stride larger than kernel is not on the OFF path"
             dh, dw = (a + p - r0) // s, (b + p - q0) // s
             img, ih, iw = np.meshgrid(np.arange(g.n_img), np.arange(hc), np.arange(wc), indexing="ij")
-            a_row = _idx((img * g.y_ctot + g.y_coff) * hwo + (ih + dh) * g.wout + (iw + dw), ih + dh, iw + dw)
-            co, rr, qq = np.meshgrid(np.arange(g.cout), np.arange(len(rs)), np.arange(len(qs)), indexing="ij")
-            a_col = _idx(co * hwo - rr * g.wout - qq, -rr, -qq)
-            b_col = (co * (g.cin * g.kh * g.kw) + (r0 + s * rr) * g.kw + (q0 + s * qq)).reshape(-1).astype(np.int32)
-            out_row = ((img * g.x_ctot + g.x_coff) * (g.hin * g.win) + (s * ih + a) * g.win + (s * iw + b))
+            oy, ox = ih + dh, iw + dw
+            if y_layout == "nchw":
+                a_row = _idx((img * g.y_ctot + g.y_coff) * hwo + oy * g.wout + ox, oy, ox)
+                co, rr, qq = np.meshgrid(np.arange(g.cout), np.arange(len(rs)), np.arange(len(qs)), indexing="ij")
+                a_col = _idx(co * hwo - rr * g.wout - qq, -rr, -qq)
+                a_mode = LOAD_SCALAR_ROW
+            else:
+                a_row = _idx(((img * g.hout + oy) * g.wout + ox) * g.y_ctot + g.y_coff, oy, ox)
+                rr, qq, co = np.meshgrid(np.arange(len(rs)), np.arange(len(qs)), np.arange(g.cout), indexing="ij")
+                a_col = _idx((-rr * g.wout - qq) * g.y_ctot + co, -rr, -qq)
+                a_mode = LOAD_VEC_K if (g.cout % 4 == 0 and g.y_ctot % 4 == 0 and g.y_coff % 4 == 0) else LOAD_SCALAR_ROW
+            r_full, q_full = r0 + s * rr, q0 + s * qq
+            if w_layout == "nchw":
+                b_row = np.arange(g.cin) * (g.kh * g.kw)
+                b_col = co * kw_tot + r_full * g.kw + q_full
+                b_mode = LOAD_SCALAR_ROW
+            else:
+                b_row = np.arange(g.cin)
+                b_col = co * kw_tot + (r_full * g.kw + q_full) * g.cin
+                b_mode = LOAD_VEC_ROW if g.cin % 4 == 0 else LOAD_SCALAR_ROW
+            iy, ix = s * ih + a, s * iw + b
+            if x_layout == "nchw":
+                out_row = (img * g.x_ctot + g.x_coff) * hwi + iy * g.win + ix
+                out_col, out_vec = np.arange(g.cin) * hwi, 0
+            else:
+                out_row = ((img * g.hin + iy) * g.win + ix) * g.x_ctot + g.x_coff
+                out_col = np.arange(g.cin)
+                out_vec = int(g.cin % 4 == 0 and g.x_ctot % 4 == 0 and g.x_coff % 4 == 0)
             specs.append(GemmSpec(
-                M=g.n_img * hc * wc, N=g.cin, K=g.cout * len(rs) * len(qs),
-                a_row=a_row, a_col=a_col,
-                b_row=(np.arange(g.cin) * (g.kh * g.kw)).astype(np.int32), b_col=b_col,
-                out_row=out_row.reshape(-1).astype(np.int32),
-                out_col=(np.arange(g.cin) * (g.hin * g.win)).astype(np.int32),
-                a_h=g.hout, a_w=g.wout, kind=f"dgrad[{a},{b}]"))
+                M=g.n_img * hc * wc, N=g.cin, K=g.cout * len(rs) * len(qs), a_row=a_row, a_col=a_col,
+                b_row=_i32(b_row), b_col=_i32(b_col), out_row=_i32(out_row), out_col=_i32(out_col),
+                a_h=g.hout, a_w=g.wout, a_mode=a_mode, b_mode=b_mode, out_vec=out_vec, kind=f"dgrad[{a},{b}]"))
     return specs
+
+
+def check_modes(spec: GemmSpec):
+    """Assert the promises behind the vector load / store modes (contiguity, alignment, shared validity)."""
+    def quads(tab, n):
+        t = tab[: n - n % 4].reshape(-1, 4)
+        return t
+
+    if spec.a_mode == LOAD_VEC_K:
+        assert spec.K % 4 == 0
+        q = quads(spec.a_col, spec.K)
+        assert (q["off"] == q["off"][:, :1] + np.arange(4)).all() and (q["off"][:, 0] % 4 == 0).all()
+        assert spec.a_h == 0 or ((q["y"] == q["y"][:, :1]).all() and (q["x"] == q["x"][:, :1]).all())
+        rows = spec.a_row if spec.a_ones_row < 0 else np.delete(spec.a_row, spec.a_ones_row)
+        assert (rows["off"] % 4 == 0).all()
+    if spec.a_mode == LOAD_VEC_ROW:
+        m_real = spec.M - (1 if spec.a_ones_row >= 0 else 0)
+        assert m_real % 4 == 0 and spec.a_ones_row in (-1, m_real)
+        q = quads(spec.a_row[:m_real], m_real)
+        assert (q["off"] == q["off"][:, :1] + np.arange(4)).all() and (q["off"][:, 0] % 4 == 0).all()
+        assert spec.a_h == 0 or ((q["y"] == q["y"][:, :1]).all() and (q["x"] == q["x"][:, :1]).all())
+        assert (spec.a_col["off"] % 4 == 0).all()
+    if spec.b_mode == LOAD_VEC_K:
+        assert spec.K % 4 == 0
+        q = quads(spec.b_col, spec.K)
+        assert (q == q[:, :1] + np.arange(4)).all() and (q[:, 0] % 4 == 0).all() and (spec.b_row % 4 == 0).all()
+    if spec.b_mode == LOAD_VEC_ROW:
+        assert spec.N % 4 == 0
+        q = quads(spec.b_row, spec.N)
+        assert (q == q[:, :1] + np.arange(4)).all() and (q[:, 0] % 4 == 0).all() and (spec.b_col % 4 == 0).all()
+    if spec.out_vec:
+        assert spec.N % 4 == 0 and (spec.out_col == spec.out_col[0] + np.arange(spec.N)).all()
+        assert spec.out_col[0] % 4 == 0 and (spec.out_row % 4 == 0).all()
 
 
 def emulate(spec: GemmSpec, a_src: np.ndarray, b_src: np.ndarray, a_relu: bool = False) -> np.ndarray:

@@ -17,6 +17,60 @@ CASES = [
 ]
 
 
+CASES_NHWC = [
+    (3, 8, 7, 7, 8, 1, 1, 0, 8, 0, 8, 0),
+    (2, 8, 9, 8, 4, 3, 1, 1, 12, 4, 8, 4),
+    (2, 4, 14, 14, 8, 7, 2, 3, 4, 0, 8, 0),
+    (2, 4, 14, 14, 12, 5, 2, 2, 12, 8, 12, 0),
+    (4, 16, 1, 1, 7, 1, 1, 0, 16, 0, 7, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES_NHWC)
+@pytest.mark.parametrize("xl,yl", [("nhwc", "nhwc"), ("nchw", "nhwc")])
+def test_tables_match_conv_nhwc(case, xl, yl):
+    """Same, for the internal channels-last layout (and the NCHW-tap -> NHWC boundary of the unit conv);
+    also checks the promises behind the vector load modes."""
+    n, cin, h, w, cout, k, s, p, xct, xco, yct, yco = case
+    g = T.ConvGeom(n, cin, h, w, cout, k, k, s, p, xct, xco, yct, yco)
+    rng = np.random.default_rng(1)
+    x_nchw = rng.standard_normal((n, xct, h, w))
+    wt = rng.standard_normal((cout, cin, k, k))
+    x = torch.tensor(x_nchw[:, xco:xco + cin], requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    y = F.conv2d(x, wtt, None, s, p)
+    dy_nchw = rng.standard_normal((n, yct, g.hout, g.wout))
+    dy = torch.tensor(dy_nchw[:, yco:yco + cout])
+    y.backward(dy)
+    to = lambda a, lay: np.ascontiguousarray(a.transpose(0, 2, 3, 1)) if lay == "nhwc" else a
+    back = lambda a, lay: a.transpose(0, 3, 1, 2) if lay == "nhwc" else a
+    xbuf, dybuf = to(x_nchw, xl), to(dy_nchw, yl)
+    w_l = np.ascontiguousarray(wt.transpose(0, 2, 3, 1)) if xl == "nhwc" else wt   # [cout,kh,kw,cin] for NHWC inputs
+
+    spec = T.conv_fwd_spec(g, xl, yl)
+    T.check_modes(spec)
+    ybuf = np.zeros(to(np.zeros((n, yct, g.hout, g.wout)), yl).shape)
+    T.scatter(spec, T.emulate(spec, xbuf, w_l), ybuf)
+    np.testing.assert_allclose(back(ybuf, yl)[:, yco:yco + cout], y.detach().numpy(), atol=1e-10)
+
+    spec = T.conv_wgrad_spec(g, xl, yl)
+    T.check_modes(spec)
+    dw = np.zeros_like(w_l)
+    db = np.zeros(cout)
+    T.scatter(spec, T.emulate(spec, xbuf, dybuf), dw, db, accumulate=True)
+    dw_c = dw.transpose(0, 3, 1, 2) if xl == "nhwc" else dw
+    np.testing.assert_allclose(dw_c, wtt.grad.numpy(), atol=1e-9)
+    np.testing.assert_allclose(db, dy.sum((0, 2, 3)).numpy(), atol=1e-9)
+
+    dxbuf = np.full(xbuf.shape, np.nan)
+    for spec in T.conv_dgrad_specs(g, xl, yl):
+        T.check_modes(spec)
+        T.scatter(spec, T.emulate(spec, dybuf, w_l), dxbuf)
+    got = back(dxbuf, xl)[:, xco:xco + cin]
+    assert not np.isnan(got).any()
+    np.testing.assert_allclose(got, x.grad.numpy(), atol=1e-9)
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_tables_match_conv(case):
     n, cin, h, w, cout, k, s, p, xct, xco, yct, yco = case

@@ -27,12 +27,13 @@ def run_spec(spc, a_src, b_src, out_shape, prec, bias=None, ones=None, split_k=1
     d = L.OffkGemm()
     d.M, d.N, d.K = spc.M, spc.N, spc.K
     d.a_src, d.a_row, d.a_col = a_src.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
-    d.a_h, d.a_w, d.a_relu, d.a_ones_row, d.a_klane = spc.a_h, spc.a_w, int(a_relu), spc.a_ones_row, spc.a_klane
-    d.b_src, d.b_row, d.b_col, d.b_klane = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_klane
+    d.a_h, d.a_w, d.a_relu, d.a_ones_row, d.a_mode = spc.a_h, spc.a_w, int(a_relu), spc.a_ones_row, spc.a_mode
+    d.b_src, d.b_row, d.b_col, d.b_mode = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
     d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     d.ones_row_out = ones.data_ptr() if ones is not None else None
-    d.split_k, d.atomic_out, d.tile_n, d.b_dense = split_k, int(atomic), tile_n, spc.b_dense
+    d.split_k, d.atomic_out, d.tile_n, d.out_vec = split_k, int(atomic), tile_n, spc.out_vec
+    T.check_modes(spc)
     L.check(lib.offk_gather_gemm(C.byref(d), prec, None), "gemm")
     torch.cuda.synchronize()
     return out
@@ -54,7 +55,21 @@ def gemm_cases():
 def check_gemm(prec, label):
     torch.manual_seed(0)
     worst = 0.0
-    for name, g in gemm_cases():
+    nhwc_cases = [
+        ("1x1 unit-like", T.ConvGeom(6, 256, 28, 28, 160)),
+        ("1x1 7x7 C1024", T.ConvGeom(6, 1024, 7, 7, 160)),
+        ("3x3 p1", T.ConvGeom(4, 64, 14, 14, 64, 3, 3, 1, 1)),
+        ("7x7 s2", T.ConvGeom(2, 32, 28, 28, 64, 7, 7, 2, 3)),
+        ("5x5 s2 slice", T.ConvGeom(2, 24, 14, 14, 128, 5, 5, 2, 2, 40, 8, 160, 32)),
+        ("fc", T.ConvGeom(8, 1024, 1, 1, 101)),
+        ("1x1 N=1024", T.ConvGeom(4, 256, 7, 7, 1024)),
+        ("3x3 N=512", T.ConvGeom(3, 128, 7, 7, 512, 3, 3, 1, 1)),
+    ]
+    runs = [(n, g, "nchw", "nchw") for n, g in gemm_cases()] + [(n, g, "nhwc", "nhwc") for n, g in nhwc_cases] + \
+           [(n, g, "nchw", "nhwc") for n, g in nhwc_cases[:2]]
+    to = lambda a, lay: a.permute(0, 2, 3, 1).contiguous() if lay == "nhwc" else a
+    back = lambda a, lay: a.permute(0, 3, 1, 2) if lay == "nhwc" else a
+    for name, g, xl, yl in runs:
         x = torch.randn(g.n_img, g.x_ctot, g.hin, g.win, device=dev)
         w = torch.randn(g.cout, g.cin, g.kh, g.kw, device=dev) / (g.kdim ** 0.5)
         b = torch.randn(g.cout, device=dev)
@@ -63,27 +78,27 @@ def check_gemm(prec, label):
         wd = w.double().requires_grad_(True)
         y = torch.nn.functional.conv2d(xs, wd, b.double(), g.stride, g.pad)
         y.backward(dy[:, g.y_coff:g.y_coff + g.cout].double())
-        # fwd
+        xb, dyb = to(x, xl), to(dy, yl)
+        wl = w.permute(0, 2, 3, 1).contiguous() if xl == "nhwc" else w
+        oshape = tuple(dyb.shape)
         t0 = time.time()
-        out = run_spec(T.conv_fwd_spec(g), x, w, (g.n_img, g.y_ctot, g.hout, g.wout), prec, bias=b)
+        out = back(run_spec(T.conv_fwd_spec(g, xl, yl), xb, wl, oshape, prec, bias=b), yl)
         e_f = (out[:, g.y_coff:g.y_coff + g.cout].double() - y).abs().max().item() / y.abs().max().item()
-        # fwd split-K (atomic, no bias)
-        out2 = run_spec(T.conv_fwd_spec(g), x, w, (g.n_img, g.y_ctot, g.hout, g.wout), prec, split_k=3)
+        out2 = back(run_spec(T.conv_fwd_spec(g, xl, yl), xb, wl, oshape, prec, split_k=3), yl)
         y_nb = y - b.double().view(1, -1, 1, 1)
         e_s = (out2[:, g.y_coff:g.y_coff + g.cout].double() - y_nb).abs().max().item() / y.abs().max().item()
-        # wgrad
         db = torch.zeros(g.cout, device=dev)
-        dw = run_spec(T.conv_wgrad_spec(g), x, dy, tuple(w.shape), prec, ones=db, split_k=4, atomic=True)
-        e_w = (dw.double() - wd.grad).abs().max().item() / wd.grad.abs().max().item()
+        dw = run_spec(T.conv_wgrad_spec(g, xl, yl), xb, dyb, tuple(wl.shape), prec, ones=db, split_k=4, atomic=True)
+        dwc = dw.permute(0, 3, 1, 2) if xl == "nhwc" else dw
+        e_w = (dwc.double() - wd.grad).abs().max().item() / wd.grad.abs().max().item()
         e_b = (db.double() - dy[:, g.y_coff:g.y_coff + g.cout].double().sum((0, 2, 3))).abs().max().item() / db.abs().max().item()
-        # dgrad
-        dx = torch.zeros_like(x)
-        for spc in T.conv_dgrad_specs(g):
-            part = run_spec(spc, dy, w, tuple(x.shape), prec)
-            dx += part
-        e_d = (dx[:, g.x_coff:g.x_coff + g.cin].double() - xs.grad).abs().max().item() / xs.grad.abs().max().item()
+        dx = torch.zeros_like(xb)
+        for spc in T.conv_dgrad_specs(g, xl, yl, xl):
+            dx += run_spec(spc, dyb, wl, tuple(xb.shape), prec)
+        dxc = back(dx, xl)
+        e_d = (dxc[:, g.x_coff:g.x_coff + g.cin].double() - xs.grad).abs().max().item() / xs.grad.abs().max().item()
         worst = max(worst, e_f, e_s, e_w, e_b, e_d)
-        print(f"[{label}] {name:16s} rel-err fwd {e_f:.2e} splitK {e_s:.2e} wgrad {e_w:.2e} bgrad {e_b:.2e} dgrad {e_d:.2e}  ({time.time()-t0:.2f}s)", flush=True)
+        print(f"[{label}] {xl}->{yl} {name:16s} rel-err fwd {e_f:.2e} splitK {e_s:.2e} wgrad {e_w:.2e} bgrad {e_b:.2e} dgrad {e_d:.2e}  ({time.time()-t0:.2f}s)", flush=True)
     print(f"[{label}] worst {worst:.3e}", flush=True)
 
 
@@ -92,25 +107,28 @@ def check_stencil():
     torch.manual_seed(1)
     for (B, Lg, S, K, mode, drop) in [(2, 3, 28, 1, 0, 0), (3, 4, 14, 1, 1, 1), (2, 2, 7, 1, 0, 2), (2, 3, 7, 2, 0, 0), (1, 3, 28, 1, 0, 1)]:
         N, P, Cg, Cs = B * Lg, B * (Lg - 1), 128, 32
-        gd = torch.randn(N, Cg + Cs, S, S, device=dev)
-        gd[:, :Cg].relu_()
+        gd_c = torch.randn(N, Cg + Cs, S, S, device=dev)
+        gd_c[:, :Cg].relu_()
+        gd = gd_c.permute(0, 2, 3, 1).contiguous()            # channels-last [N,S,S,160]
         w = torch.randn(Cs, K, 3, 3, device=dev)
         bias = torch.randn(Cs * K, device=dev)
         ctot, coff = 400, 64
-        out = torch.zeros(P, ctot, S, S, device=dev)
+        out = torch.zeros(P, S, S, ctot, device=dev)
         sd = L.OffkStencil()
         sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, Cg, Cs, K, S, S
         sd.g_fs = sd.d_fs = (Cg + Cs) * S * S
+        sd.g_ps = sd.d_ps = Cg + Cs
         sd.out_ctot, sd.out_coff, sd.index_mode = ctot, coff, mode
         sd.drop_mode, sd.keep_scale, sd.drop_p, sd.seed = drop, 5.0, 0.8, 1234
         mask = (torch.rand(P, K * Cs, S, S, device=dev) > 0.8).to(torch.uint8)
         sd.keep_mask = mask.data_ptr()
-        L.check(lib.offk_stencil_diff_fwd(C.byref(sd), gd.data_ptr(), gd.data_ptr() + 4 * Cg * S * S, w.data_ptr(),
+        L.check(lib.offk_stencil_diff_fwd(C.byref(sd), gd.data_ptr(), gd.data_ptr() + 4 * Cg, w.data_ptr(),
                                           bias.data_ptr(), out.data_ptr(), None), "stencil_fwd")
         torch.cuda.synchronize()
         # reference
-        G = gd[:, :Cg].double()
-        D = gd[:, Cg:].double()
+        G = gd_c[:, :Cg].double()
+        D = gd_c[:, Cg:].double()
+        out = out.permute(0, 3, 1, 2)
         Gv = G.view(B, Lg, Cg, S, S)
         Tref = (Gv[:, 1:] - Gv[:, :-1]).reshape(P, Cg, S, S)
         if mode == 0:
@@ -144,13 +162,15 @@ def check_stencil():
         e = (got - ref.detach()).abs().max().item()
         untouched = out[:, :coff].abs().max().item() + out[:, coff + K * Cs + Cg:].abs().max().item()
         # backward
-        dout = torch.randn(P, ctot, S, S, device=dev)
-        dgd = torch.full((N, Cg + Cs, S, S), float("nan"), device=dev)
+        dout_l = torch.randn(P, S, S, ctot, device=dev)
+        dout = dout_l.permute(0, 3, 1, 2)
+        dgd_l = torch.full((N, S, S, Cg + Cs), float("nan"), device=dev)
+        dgd = dgd_l.permute(0, 3, 1, 2)
         dw = torch.zeros_like(w)
         dbias = torch.zeros_like(bias)
         fs = (Cg + Cs) * S * S
-        L.check(lib.offk_stencil_diff_bwd(C.byref(sd), dout.data_ptr(), gd.data_ptr(), gd.data_ptr() + 4 * Cg * S * S,
-                                          w.data_ptr(), dgd.data_ptr(), fs, dgd.data_ptr() + 4 * Cg * S * S, fs,
+        L.check(lib.offk_stencil_diff_bwd(C.byref(sd), dout_l.data_ptr(), gd.data_ptr(), gd.data_ptr() + 4 * Cg,
+                                          w.data_ptr(), dgd_l.data_ptr(), fs, dgd_l.data_ptr() + 4 * Cg, fs,
                                           dw.data_ptr(), dbias.data_ptr(), None), "stencil_bwd")
         torch.cuda.synchronize()
         dS = dout[:, coff:coff + K * Cs].double()
@@ -177,7 +197,11 @@ def check_engine(precision, variant="rgb", B=2, Lg=3, train=False):
     taps = O.make_taps(seed, B, Lg)
     prm = O.make_params(seed, variant)
     masks = O.make_dropout_masks(seed, B, Lg) if train else None
-    ref, gref = O.off_forward_backward(taps, prm, B, Lg, variant, masks, torch.float64)
+    r7 = O.hash_normal(77, (B * (Lg - 1) if variant == "rgb" else B, 101)).double()
+    r14 = O.hash_normal(78, (B * (Lg - 1) if variant == "rgb" else B, 101)).double()
+    lossf = lambda o: (o["fc7"].reshape(r7.shape) * r7).sum() + (o["fc14"].reshape(r14.shape) * r14).sum()
+    ref, gref = O.off_forward_backward(taps, prm, B, Lg, variant, masks, torch.float64, loss=lossf)
+    _, g32 = O.off_forward_backward(taps, prm, B, Lg, variant, masks, torch.float32, loss=lambda o: (o["fc7"].reshape(r7.shape) * r7.float()).sum() + (o["fc14"].reshape(r14.shape) * r14.float()).sum())
     eng = E.OFFEngine(B, Lg, variant, dev, precision)
     eng.load_params(prm)
     fc7, fc28, fc14 = eng.forward({k: v.to(dev) for k, v in taps.items()}, train=train, masks=masks)
@@ -185,14 +209,14 @@ def check_engine(precision, variant="rgb", B=2, Lg=3, train=False):
     rel = lambda a, b: (a.double().cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
     print(f"[engine {precision} {variant} B{B} L{Lg} train={train}]")
     for k, st in (("fusion28", "F28"), ("fusion14", "F14"), ("fusion7", "F7")):
-        a, b = eng.buf[st].double().cpu(), ref[k]
-        print(f"   {k}: max-abs {(a-b).abs().max().item():.3e} rel {rel(eng.buf[st], b):.3e} (|ref|max {b.abs().max().item():.3f})")
-    print(f"   sum7: rel {rel(eng.buf['s7'], ref['sum7']):.3e}")
+        a, b = eng.buf[st].permute(0, 3, 1, 2).double().cpu(), ref[k]
+        print(f"   {k}: max-abs {(a-b).abs().max().item():.3e} rel {rel(eng.buf[st].permute(0, 3, 1, 2), b):.3e} (|ref|max {b.abs().max().item():.3f})")
+    print(f"   sum7: rel {rel(eng.buf['s7'].permute(0, 3, 1, 2), ref['sum7']):.3e}")
     for nme, got, key in (("fc7", fc7, "fc7"), ("fc28", fc28, "fc28"), ("fc14", fc14, "fc14")):
         b = ref[key].reshape(got.shape)
         print(f"   {nme}: max-abs {(got.double().cpu()-b).abs().max().item():.3e} rel {rel(got, b):.3e}")
-    g7 = torch.ones_like(fc7)
-    g14 = torch.ones_like(fc14)
+    g7 = r7.float().to(dev).reshape(fc7.shape)
+    g14 = r14.float().to(dev).reshape(fc14.shape)
     grads = eng.backward(g7, g14)
     torch.cuda.synchronize()
     worst = ("", 0.0)
@@ -206,7 +230,8 @@ def check_engine(precision, variant="rgb", B=2, Lg=3, train=False):
             worst = (n, r)
         if r > (1e-4 if precision == "fp32" else 3e-2):
             print(f"   grad {n}: rel {r:.3e}  <-- large")
-    print(f"   worst grad rel err: {worst[0]} {worst[1]:.3e}", flush=True)
+    floor = max((g32[n].double() - gref[n]).abs().max().item() / max(gref[n].abs().max().item(), 1e-30) for n in gref if gref[n].abs().max().item() > 0)
+    print(f"   worst grad rel err: {worst[0]} {worst[1]:.3e}   (fp32 CPU oracle vs fp64: {floor:.3e})", flush=True)
 
 
 if __name__ == "__main__":
