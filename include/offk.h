@@ -79,6 +79,11 @@ int offk_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_
  *   v = max(v,0)                         if relu_post
  *   out = v   (atomic add when split_k > 1 or atomic_out; then bias / activations are NOT applied)
  * gate / addend use (gate_row,gate_col) / (add_row,add_col) or, when NULL, the out tables.
+ *
+ * Table padding contract (so the kernels never bounds-check an index): a_row has ceil(M/128)*128 entries, a_col
+ * and b_col have ceil(K/32)*32 + 64 entries, b_row has ceil(N/256)*256 entries.  Padding entries of a_row /
+ * a_col carry y = -16384 (the box test is always on; pass a_h = a_w = 32767 for "no box"), padding entries of
+ * b_row / b_col are 0.  The entry of a_ones_row is never gathered.
  * ---------------------------------------------------------------------- */
 /* Operand fetch modes.  The tables are always element-granular; a vector mode is a promise by the caller
  * that groups of 4 consecutive indices are contiguous in memory, 16-byte aligned and share validity. */
@@ -100,7 +105,7 @@ typedef struct offk_gemm {
   const float* a_src;
   const offk_idx_t* a_row; /* [M] */
   const offk_idx_t* a_col; /* [K] */
-  int32_t a_h, a_w;        /* validity box; a_h == 0: always valid */
+  int32_t a_h, a_w;        /* validity box (>= 1); 32767 = every real element is valid */
   int32_t a_relu;          /* max(.,0) on load (consumer of a pre-activation tensor, RGB_OFF.py:658) */
   int32_t a_ones_row;      /* -1, or the row whose A values are all 1 */
   int32_t a_mode;          /* OFFK_LOAD_*: how the producer warps may fetch this operand */

@@ -148,286 +148,321 @@ __device__ __forceinline__ float4 f4relu(float4 v) {
   return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
 }
 
-// Operand views: A has the validity box / ReLU-on-load / ones row, B is a plain gather.
-struct OpA {
-  const offk_gemm_t& g;
-  __device__ __forceinline__ OpA(const offk_gemm_t& g_) : g(g_) {}
-  __device__ __forceinline__ int rows() const { return g.M; }
-  __device__ __forceinline__ const float* src() const { return g.a_src; }
-  __device__ __forceinline__ offk_idx_t row(int m) const { return g.a_row[m]; }
-  __device__ __forceinline__ offk_idx_t col(int k) const { return g.a_col[k]; }
-  __device__ __forceinline__ bool ok(offk_idx_t r, offk_idx_t c) const {
-    return (g.a_h == 0) || ((unsigned)((int)r.y + (int)c.y) < (unsigned)g.a_h &&
-                            (unsigned)((int)r.x + (int)c.x) < (unsigned)g.a_w);
-  }
-  __device__ __forceinline__ bool relu() const { return g.a_relu != 0; }
-  __device__ __forceinline__ int ones_row() const { return g.a_ones_row; }
+// ---- table contract of the tensor-core path (the host pads, the kernel never bounds-checks an index):
+//   a_row : ceil(M/128)*128 entries, a_col : ceil(K/32)*32 + 64 entries; padding entries have y = -16384, so the
+//           box test (always on: a_h >= 1, 32767 = "no box") rejects them and the element is 0;
+//   b_row : ceil(N/256)*256 entries, b_col : ceil(K/32)*32 + 64 entries; padding entries are 0 (they read real,
+//           finite data that only ever meets a zero of A or lands in an accumulator column that is never stored).
+__device__ __forceinline__ bool box_ok(const offk_gemm_t& g, uint32_t ryx, uint32_t cyx) {
+  // packed (x << 16 | y) int16 pairs; per-half add without carry between halves
+  const int y = (int)(short)(ryx & 0xFFFFu) + (int)(short)(cyx & 0xFFFFu);
+  const int x = ((int)ryx >> 16) + ((int)cyx >> 16);
+  return (unsigned)y < (unsigned)g.a_h && (unsigned)x < (unsigned)g.a_w;
+}
+struct Idx2 {           // offk_idx_t viewed as two 32-bit words
+  int off;
+  uint32_t yx;
 };
-struct OpB {
-  const offk_gemm_t& g;
-  __device__ __forceinline__ OpB(const offk_gemm_t& g_) : g(g_) {}
-  __device__ __forceinline__ int rows() const { return g.N; }
-  __device__ __forceinline__ const float* src() const { return g.b_src; }
-  __device__ __forceinline__ offk_idx_t row(int n) const { return offk_idx_t{g.b_row[n], 0, 0}; }
-  __device__ __forceinline__ offk_idx_t col(int k) const { return offk_idx_t{g.b_col[k], 0, 0}; }
-  __device__ __forceinline__ bool ok(offk_idx_t, offk_idx_t) const { return true; }
-  __device__ __forceinline__ bool relu() const { return false; }
-  __device__ __forceinline__ int ones_row() const { return -1; }
-};
+__device__ __forceinline__ Idx2 ld_idx(const offk_idx_t* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return Idx2{(int)v.x, v.y};
+}
 
-// One pass = a [128 rows x 32 k] sub-tile (rows row0..row0+127 of the operand tile, limited to `nrows`).
-// Each of the 256 producer threads moves 16 floats of it per K-block.  The column-table entries a thread needs
-// for a K-block ("Cols") are fetched one or two K-blocks ahead so that no table load sits on the critical path.
-struct Cols {
-  offk_idx_t c[4];
-  uint32_t valid;   // bit e: entry e is a real column (k < K)
-};
-
-template <int MODE, class OP>
-struct TileLoader {
-  // ---- per-pass row state (constant over the K loop)
-  offk_idx_t r[4];
-  uint32_t dst[4];   // swizzled byte offset of this thread's first chunk of row (group) i inside the tile
-  uint32_t flags;    // bit i: row (group) i valid, bit 8+i: it is the ones row
-  __device__ __forceinline__ void init(const OP& op, int row_base /*global row of tile row 0*/, int row0, int nrows,
-                                       int tid) {
-    flags = 0;
+// ============================ A operand (validity box, ReLU-on-load, ones row)
+// VEC_K  : thread = (row (tid>>3)+32i, chunk tid&7), i < 4.   cp.async, zero-fill for invalid.
+// VEC_ROW: thread = 4x4 block (row-quad rq, k-quad kq); LDG.128 along rows, transpose on store.
+template <int MODE>
+struct LoaderA {
+  Idx2 r[4];
+  uint32_t dst[4];
+  uint32_t ones;       // VEC_K: bit i; VEC_ROW: bit 0
+  Idx2 c_cur[4], c_nxt[4];
+  float4 d_cur[4], d_nxt[4];
+  __device__ __forceinline__ void init(const offk_gemm_t& g, int m0, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
+    ones = 0;
     if (MODE == OFFK_LOAD_VEC_K) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int tr = row0 + (tid >> 3) + 32 * i;
-        const int m = row_base + tr;
-        const bool intile = tr < nrows;
-        const bool v = intile && m < op.rows();
-        const bool one = v && m == op.ones_row();
-        r[i] = (v && !one) ? op.row(m) : offk_idx_t{0, 0, 0};
+        const int tr = (tid >> 3) + 32 * i;
+        r[i] = ld_idx(g.a_row + m0 + tr);
         dst[i] = swz(tr, tid & 7);
-        flags |= (v ? 1u : 0u) << i;
-        flags |= (one ? 1u : 0u) << (8 + i);
-        flags |= (intile ? 1u : 0u) << (16 + i);
+        ones |= (m0 + tr == g.a_ones_row ? 1u : 0u) << i;
       }
     } else if (MODE == OFFK_LOAD_VEC_ROW) {
       const int rq = (warp & 3) * 8 + (lane >> 2), kq = (warp >> 2) * 4 + (lane & 3);
-      const int tr = row0 + 4 * rq;
-      const int m = row_base + tr;
-      const bool intile = tr < nrows;
-      const bool v = intile && m < op.rows();
-      const bool one = v && m == op.ones_row();
-      r[0] = (v && !one) ? op.row(m) : offk_idx_t{0, 0, 0};
+      r[0] = ld_idx(g.a_row + m0 + 4 * rq);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = swz(tr + j, kq);
-      flags = (v ? 1u : 0u) | ((one ? 1u : 0u) << 8) | ((intile ? 1u : 0u) << 16);
+      for (int j = 0; j < 4; ++j) dst[j] = swz(4 * rq + j, kq);
+      ones = (m0 + 4 * rq == g.a_ones_row) ? 1u : 0u;
     } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
-      const int tr = row0 + (tid & 127);
-      const int m = row_base + tr;
-      const bool intile = tr < nrows;
-      const bool v = intile && m < op.rows();
-      const bool one = v && m == op.ones_row();
-      r[0] = (v && !one) ? op.row(m) : offk_idx_t{0, 0, 0};
-      flags = (v ? 1u : 0u) | ((one ? 1u : 0u) << 8) | ((intile ? 1u : 0u) << 16);
+      r[0] = ld_idx(g.a_row + m0 + (tid & 127));
+      ones = (m0 + (tid & 127) == g.a_ones_row) ? 1u : 0u;
     }
   }
-  // column entries this thread needs for the K-block starting at k0 (vector modes only; scalar modes look them
-  // up inside load())
-  __device__ __forceinline__ void fetch_cols(const OP& op, int k0, int K, int tid, Cols& cc) const {
+  __device__ __forceinline__ void fetch_cols(const offk_gemm_t& g, int k0, int tid, Idx2 (&c)[4]) const {
     if (MODE == OFFK_LOAD_VEC_K) {
-      const int k = k0 + 4 * (tid & 7);
-      cc.c[0] = k < K ? op.col(k) : offk_idx_t{0, 0, 0};
-      cc.valid = k < K ? 1u : 0u;
+      c[0] = ld_idx(g.a_col + k0 + 4 * (tid & 7));
     } else if (MODE == OFFK_LOAD_VEC_ROW) {
       const int kq = ((tid >> 5) >> 2) * 4 + (tid & 3);
-      cc.valid = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = k0 + 4 * kq + e;
-        cc.c[e] = k < K ? op.col(k) : offk_idx_t{0, 0, 0};
-        cc.valid |= (k < K ? 1u : 0u) << e;
-      }
+      const uint4* p = reinterpret_cast<const uint4*>(g.a_col + k0 + 4 * kq);   // 4 entries = 32 bytes, aligned
+      const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+      c[0] = Idx2{(int)lo.x, lo.y};
+      c[1] = Idx2{(int)lo.z, lo.w};
+      c[2] = Idx2{(int)hi.x, hi.y};
+      c[3] = Idx2{(int)hi.z, hi.w};
     }
   }
-  __device__ __forceinline__ float scalar(const OP& op, offk_idx_t rr, offk_idx_t cc, bool one) const {
-    if (one) return 1.f;
-    float x = 0.f;
-    if (op.ok(rr, cc)) {
-      x = __ldg(op.src() + (rr.off + cc.off));
-      if (op.relu()) x = fmaxf(x, 0.f);
-    }
-    return x;
-  }
-  __device__ __forceinline__ void load(const OP& op, const Cols& cc, int row_base, int row0, int nrows, int k0, int K,
-                                       int tid, float4 (&v)[4]) const {
-    const int warp = tid >> 5, lane = tid & 31;
-    if (MODE == OFFK_LOAD_VEC_K) {
-      const bool kv = cc.valid != 0;
-      const offk_idx_t c = cc.c[0];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 x = f4zero();
-        if (kv && ((flags >> i) & 1u)) {
-          if ((flags >> (8 + i)) & 1u) x = make_float4(1.f, 1.f, 1.f, 1.f);
-          else if (op.ok(r[i], c)) {
-            x = ldg128(op.src() + (r[i].off + c.off));
-            if (op.relu()) x = f4relu(x);
-          }
-        }
-        v[i] = x;
-      }
-    } else if (MODE == OFFK_LOAD_VEC_ROW) {
+  // register-staged load of the K-block whose column entries are `c` (VEC_ROW / scalar modes)
+  __device__ __forceinline__ void load(const offk_gemm_t& g, const Idx2 (&c)[4], int m0, int k0, int tid,
+                                       float4 (&v)[4]) const {
+    if (MODE == OFFK_LOAD_VEC_ROW) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float4 x = f4zero();
-        const offk_idx_t c = cc.c[e];
-        if (((cc.valid >> e) & 1u) && (flags & 1u)) {
-          if ((flags >> 8) & 1u) x = make_float4(1.f, 0.f, 0.f, 0.f);  // ones row heads its own row-quad
-          else if (op.ok(r[0], c)) {
-            x = ldg128(op.src() + (r[0].off + c.off));
-            if (op.relu()) x = f4relu(x);
-          }
-        }
+        if (box_ok(g, r[0].yx, c[e].yx)) x = ldg128(g.a_src + (r[0].off + c[e].off));
         v[e] = x;
+      }
+      if (ones) {   // all-ones row heads its own row-quad: (1,0,0,0) for real columns
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = make_float4((short)(c[e].yx & 0xFFFFu) > -8192 ? 1.f : 0.f, 0.f, 0.f, 0.f);
       }
     } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
       const int half = tid >> 7;
       float t[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int k = k0 + half * 16 + i;
-        t[i] = ((flags & 1u) && k < K) ? scalar(op, r[0], op.col(k), (flags >> 8) & 1u) : 0.f;
+        const Idx2 cc = ld_idx(g.a_col + k0 + half * 16 + i);
+        float x = 0.f;
+        if (ones) x = (short)(cc.yx & 0xFFFFu) > -8192 ? 1.f : 0.f;
+        else if (box_ok(g, r[0].yx, cc.yx)) x = __ldg(g.a_src + (r[0].off + cc.off));
+        t[i] = x;
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
-    } else {  // OFFK_LOAD_SCALAR_K: lane owns column k0+lane, warp w owns tile rows row0 + w + 8*i
-      const int k = k0 + lane;
-      const bool kv = k < K;
-      const offk_idx_t c = kv ? op.col(k) : offk_idx_t{0, 0, 0};
+    } else if (MODE == OFFK_LOAD_SCALAR_K) {   // lane owns column k0+lane, warp w owns tile rows w + 8*i
+      const int warp = tid >> 5, lane = tid & 31;
+      const Idx2 cc = ld_idx(g.a_col + k0 + lane);
       float t[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int tr = row0 + warp + 8 * i;
-        const int m = row_base + tr;
+        const int m = m0 + warp + 8 * i;
+        const Idx2 rr = ld_idx(g.a_row + m);
         float x = 0.f;
-        if (kv && tr < nrows && m < op.rows()) {
-          const bool one = (m == op.ones_row());
-          x = scalar(op, one ? offk_idx_t{0, 0, 0} : op.row(m), c, one);
-        }
+        if (m == g.a_ones_row) x = (short)(cc.yx & 0xFFFFu) > -8192 ? 1.f : 0.f;
+        else if (box_ok(g, rr.yx, cc.yx)) x = __ldg(g.a_src + (rr.off + cc.off));
         t[i] = x;
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
     }
   }
-  // OFFK_LOAD_VEC_K without ReLU-on-load: no register staging at all.  One cp.async per (row, 16-byte chunk);
-  // invalid rows / out-of-box taps / k >= K are zero-filled by the copy engine.  Returns true when a plain
-  // st.shared was used (the all-ones row), which then needs the generic->async proxy fence.
-  template <bool L1_ALLOCATE>
-  __device__ __forceinline__ bool issue_async(const OP& op, const Cols& cc, uint32_t tile_base) const {
-    const bool kv = cc.valid != 0;
-    const offk_idx_t c = cc.c[0];
-    bool stored = false;
+  __device__ __forceinline__ void store(const offk_gemm_t& g, uint32_t tile, int tid, float4 (&v)[4]) const {
+    if (g.a_relu) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (!((flags >> (16 + i)) & 1u)) continue;
-      const uint32_t d = tile_base + dst[i];
-      if ((flags >> (8 + i)) & 1u) {
-        const float one = kv ? 1.f : 0.f;
-        sts128(d, one, one, one, one);
-        stored = true;
-        continue;
-      }
-      const bool ok = kv && ((flags >> i) & 1u) && op.ok(r[i], c);
-      const float* src = ok ? op.src() + (r[i].off + c.off) : op.src();
-      if (L1_ALLOCATE) cp_async16_ca(d, src, ok ? 16u : 0u);
-      else             cp_async16_cg(d, src, ok ? 16u : 0u);
+      for (int i = 0; i < 4; ++i) v[i] = f4relu(v[i]);
     }
-    return stored;
-  }
-  // tile_base: smem address of tile row 0
-  __device__ __forceinline__ void store(uint32_t tile_base, int row0, int nrows, int tid, const float4 (&v)[4]) const {
-    const int warp = tid >> 5, lane = tid & 31;
-    if (MODE == OFFK_LOAD_VEC_K) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if ((flags >> (16 + i)) & 1u) sts128(tile_base + dst[i], v[i].x, v[i].y, v[i].z, v[i].w);
-    } else if (MODE == OFFK_LOAD_VEC_ROW) {
-      if ((flags >> 16) & 1u) {
-        sts128(tile_base + dst[0], v[0].x, v[1].x, v[2].x, v[3].x);
-        sts128(tile_base + dst[1], v[0].y, v[1].y, v[2].y, v[3].y);
-        sts128(tile_base + dst[2], v[0].z, v[1].z, v[2].z, v[3].z);
-        sts128(tile_base + dst[3], v[0].w, v[1].w, v[2].w, v[3].w);
-      }
+    if (MODE == OFFK_LOAD_VEC_ROW) {
+      sts128(tile + dst[0], v[0].x, v[1].x, v[2].x, v[3].x);
+      sts128(tile + dst[1], v[0].y, v[1].y, v[2].y, v[3].y);
+      sts128(tile + dst[2], v[0].z, v[1].z, v[2].z, v[3].z);
+      sts128(tile + dst[3], v[0].w, v[1].w, v[2].w, v[3].w);
     } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
-      const int tr = row0 + (tid & 127), half = tid >> 7;
-      if (tr < nrows) {
+      const int tr = tid & 127, half = tid >> 7;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sts128(tile_base + swz(tr, half * 4 + c), v[c].x, v[c].y, v[c].z, v[c].w);
-      }
-    } else {
+      for (int c = 0; c < 4; ++c) sts128(tile + swz(tr, half * 4 + c), v[c].x, v[c].y, v[c].z, v[c].w);
+    } else if (MODE == OFFK_LOAD_SCALAR_K) {
+      const int warp = tid >> 5, lane = tid & 31;
       const float t[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
                            v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int tr = row0 + warp + 8 * i;
-        if (tr < nrows) sts32(tile_base + swz(tr, lane >> 2) + (lane & 3) * 4, t[i]);
-      }
+      for (int i = 0; i < 16; ++i) sts32(tile + swz(warp + 8 * i, lane >> 2) + (lane & 3) * 4, t[i]);
     }
   }
-};
-
-// An operand's whole producer pipeline (one or two 128-row passes).  Async (cp.async) operands prefetch their
-// column entries one K-block ahead; register-staged operands prefetch column entries two and data one ahead.
-template <int MODE, class OP, bool L1_ALLOCATE>
-struct OperandPipe {
-  TileLoader<MODE, OP> p0, p1;
-  Cols c_cur, c_nxt;        // async: cols of block i / i+1;  register: cols of block i+1 / i+2
-  float4 d_cur[4], d_nxt[4];
-  int row_base, nrows;
-  bool two;
-  static constexpr bool async = (MODE == OFFK_LOAD_VEC_K);   // ReLU-on-load operands are never launched as VEC_K
-  __device__ __forceinline__ void init(const OP& op, int row_base_, int nrows_, int tid) {
-    row_base = row_base_;
-    nrows = nrows_;
-    two = nrows_ > 128;
-    p0.init(op, row_base, 0, nrows, tid);
-    if (two) p1.init(op, row_base, 128, nrows, tid);
-  }
-  __device__ __forceinline__ void prologue(const OP& op, int k_first, int K, int tid) {
-    p0.fetch_cols(op, k_first, K, tid, c_cur);
-    if (!async) {
-      p0.load(op, c_cur, row_base, 0, nrows, k_first, K, tid, d_cur);
-      p0.fetch_cols(op, k_first + TC_BK, K, tid, c_cur);
-    }
-  }
-  // before blocking on the smem slot of K-block k0: issue the long-latency prefetches
-  __device__ __forceinline__ void pre_wait(const OP& op, int k0, int K, int tid, bool has_next) {
-    if (async) {
-      p0.fetch_cols(op, k0 + TC_BK, K, tid, c_nxt);
-    } else {
-      if (has_next) p0.load(op, c_cur, row_base, 0, nrows, k0 + TC_BK, K, tid, d_nxt);
-      p0.fetch_cols(op, k0 + 2 * TC_BK, K, tid, c_nxt);
-    }
-  }
-  // after the slot is free: move K-block k0 into shared memory.  Returns true if st.shared was used.
-  __device__ __forceinline__ bool post_wait(const OP& op, uint32_t tile_base, int k0, int K, int tid) {
+  // VEC_K: straight to shared memory.  Returns true when st.shared was used (ones row).
+  __device__ __forceinline__ bool issue_async(const offk_gemm_t& g, const Idx2& c, uint32_t tile) const {
     bool stored = false;
-    if (async) {
-      stored |= p0.template issue_async<L1_ALLOCATE>(op, c_cur, tile_base);
-      if (two) stored |= p1.template issue_async<L1_ALLOCATE>(op, c_cur, tile_base);
-    } else {
-      p0.store(tile_base, 0, nrows, tid, d_cur);
-      if (two) {   // second pass of a wide B tile: not prefetched (only dgrad / wgrad tiles wider than 128)
-        Cols ct;
-        float4 vt[4];
-        p1.fetch_cols(op, k0, K, tid, ct);
-        p1.load(op, ct, row_base, 128, nrows, k0, K, tid, vt);
-        p1.store(tile_base, 128, nrows, tid, vt);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t d = tile + dst[i];
+      if ((ones >> i) & 1u) {
+        const float one = (short)(c.yx & 0xFFFFu) > -8192 ? 1.f : 0.f;
+        sts128(d, one, one, one, one);
+        stored = true;
+      } else {
+        const bool ok = box_ok(g, r[i].yx, c.yx);
+        cp_async16_ca(d, ok ? g.a_src + (r[i].off + c.off) : g.a_src, ok ? 16u : 0u);
       }
+    }
+    return stored;
+  }
+  static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K);
+  static constexpr bool kVec = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
+  __device__ __forceinline__ void prologue(const offk_gemm_t& g, int m0, int k_first, int tid) {
+    if (kVec) fetch_cols(g, k_first, tid, c_cur);
+    if (!kAsync) {
+      load(g, c_cur, m0, k_first, tid, d_cur);
+      if (kVec) fetch_cols(g, k_first + TC_BK, tid, c_cur);
+    }
+  }
+  __device__ __forceinline__ void pre_wait(const offk_gemm_t& g, int m0, int k0, int tid, bool has_next) {
+    if (kAsync) {
+      fetch_cols(g, k0 + TC_BK, tid, c_nxt);
+    } else {
+      if (has_next) load(g, c_cur, m0, k0 + TC_BK, tid, d_nxt);
+      if (kVec) fetch_cols(g, k0 + 2 * TC_BK, tid, c_nxt);
+    }
+  }
+  __device__ __forceinline__ bool post_wait(const offk_gemm_t& g, uint32_t tile, int tid) {
+    bool stored;
+    if (kAsync) {
+      stored = issue_async(g, c_cur[0], tile);
+    } else {
+      store(g, tile, tid, d_cur);
       stored = true;
 #pragma unroll
       for (int q = 0; q < 4; ++q) d_cur[q] = d_nxt[q];
     }
-    c_cur = c_nxt;
+    if (kVec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c_cur[q] = c_nxt[q];
+    }
     return stored;
+  }
+};
+
+// ============================ B operand (plain gather, up to 256 rows = two 128-row passes)
+template <int MODE>
+struct LoaderB {
+  int r[8];            // VEC_K: rows (tid>>3)+32i, i<8;  VEC_ROW: row-quads of pass 0 / pass 1 in r[0], r[1]
+  uint32_t dst[8];
+  int c_cur[4], c_nxt[4];
+  float4 d_cur[4], d_nxt[4];
+  int bn;
+  __device__ __forceinline__ void init(const offk_gemm_t& g, int n0, int bn_, int tid) {
+    bn = bn_;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (MODE == OFFK_LOAD_VEC_K) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int tr = (tid >> 3) + 32 * i;
+        r[i] = __ldg(g.b_row + n0 + (tr < bn ? tr : 0));
+        dst[i] = swz(tr, tid & 7);
+      }
+    } else if (MODE == OFFK_LOAD_VEC_ROW) {
+      const int rq = (warp & 3) * 8 + (lane >> 2), kq = (warp >> 2) * 4 + (lane & 3);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int tr = 128 * p + 4 * rq;
+        r[p] = __ldg(g.b_row + n0 + (tr < bn ? tr : 0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[4 * p + j] = swz(tr + j, kq);
+      }
+    }
+  }
+  __device__ __forceinline__ void fetch_cols(const offk_gemm_t& g, int k0, int tid, int (&c)[4]) const {
+    if (MODE == OFFK_LOAD_VEC_K) {
+      c[0] = __ldg(g.b_col + k0 + 4 * (tid & 7));
+    } else if (MODE == OFFK_LOAD_VEC_ROW) {
+      const int kq = ((tid >> 5) >> 2) * 4 + (tid & 3);
+      const int4 v = __ldg(reinterpret_cast<const int4*>(g.b_col + k0 + 4 * kq));
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    }
+  }
+  __device__ __forceinline__ void load(const offk_gemm_t& g, const int (&c)[4], int n0, int k0, int tid, int pass,
+                                       float4 (&v)[4]) const {
+    if (MODE == OFFK_LOAD_VEC_ROW) {
+      const int rq = ((tid >> 5) & 3) * 8 + ((tid & 31) >> 2);
+      const bool in = 128 * pass + 4 * rq < bn;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = in ? ldg128(g.b_src + (r[pass] + c[e])) : f4zero();
+    } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
+      // thread = row (tid & 127) of this pass, k-half (tid >> 7): 16 scalar gathers
+      const int tr = 128 * pass + (tid & 127), half = tid >> 7;
+      const int rb = __ldg(g.b_row + n0 + (tr < bn ? tr : 0));
+      float t[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t[i] = tr < bn ? __ldg(g.b_src + (rb + __ldg(g.b_col + k0 + half * 16 + i))) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+    } else if (MODE == OFFK_LOAD_SCALAR_K) {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int cc = __ldg(g.b_col + k0 + lane);
+      float t[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int tr = 128 * pass + warp + 8 * i;
+        t[i] = tr < bn ? __ldg(g.b_src + (__ldg(g.b_row + n0 + tr) + cc)) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+    }
+  }
+  __device__ __forceinline__ void store(uint32_t tile, int tid, int pass, const float4 (&v)[4]) const {
+    if (MODE == OFFK_LOAD_VEC_ROW) {
+      const int rq = ((tid >> 5) & 3) * 8 + ((tid & 31) >> 2);
+      if (128 * pass + 4 * rq < bn) {
+        sts128(tile + dst[4 * pass + 0], v[0].x, v[1].x, v[2].x, v[3].x);
+        sts128(tile + dst[4 * pass + 1], v[0].y, v[1].y, v[2].y, v[3].y);
+        sts128(tile + dst[4 * pass + 2], v[0].z, v[1].z, v[2].z, v[3].z);
+        sts128(tile + dst[4 * pass + 3], v[0].w, v[1].w, v[2].w, v[3].w);
+      }
+    } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
+      const int tr = 128 * pass + (tid & 127), half = tid >> 7;
+      if (tr < bn) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128(tile + swz(tr, half * 4 + c), v[c].x, v[c].y, v[c].z, v[c].w);
+      }
+    } else if (MODE == OFFK_LOAD_SCALAR_K) {
+      const int warp = tid >> 5, lane = tid & 31;
+      const float t[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
+                           v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int tr = 128 * pass + warp + 8 * i;
+        if (tr < bn) sts32(tile + swz(tr, lane >> 2) + (lane & 3) * 4, t[i]);
+      }
+    }
+  }
+  static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K);
+  static constexpr bool kVec = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
+  __device__ __forceinline__ void prologue(const offk_gemm_t& g, int n0, int k_first, int tid) {
+    if (kVec) fetch_cols(g, k_first, tid, c_cur);
+    if (!kAsync) {
+      load(g, c_cur, n0, k_first, tid, 0, d_cur);
+      if (kVec) fetch_cols(g, k_first + TC_BK, tid, c_cur);
+    }
+  }
+  __device__ __forceinline__ void pre_wait(const offk_gemm_t& g, int n0, int k0, int tid, bool has_next) {
+    if (kAsync) {
+      fetch_cols(g, k0 + TC_BK, tid, c_nxt);
+    } else {
+      if (has_next) load(g, c_cur, n0, k0 + TC_BK, tid, 0, d_nxt);
+      if (kVec) fetch_cols(g, k0 + 2 * TC_BK, tid, c_nxt);
+    }
+  }
+  __device__ __forceinline__ void post_wait(const offk_gemm_t& g, uint32_t tile, int n0, int k0, int tid) {
+    if (kAsync) {
+      const int nrow = (bn + 31) >> 5;          // 32 rows per i
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nrow && (tid >> 3) + 32 * i < bn) cp_async16_cg(tile + dst[i], g.b_src + (r[i] + c_cur[0]), 16u);
+    } else {
+      store(tile, tid, 0, d_cur);
+      if (bn > 128) {   // second pass of a wide tile: not prefetched (only gradient GEMMs wider than 128)
+        int ct[4];
+        float4 vt[4];
+        if (kVec) fetch_cols(g, k0, tid, ct);
+        load(g, ct, n0, k0, tid, 1, vt);
+        store(tile, tid, 1, vt);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d_cur[q] = d_nxt[q];
+    }
+    if (kVec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c_cur[q] = c_nxt[q];
+    }
   }
 };
 
@@ -499,15 +534,13 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
     // ================= producers =================
     // VEC_K operands go global->smem with cp.async (up to `stages` K-blocks in flight, no registers); the other
     // modes are staged through registers with the NEXT K-block's loads issued before this K-block is stored.
-    const OpA opa(g);
-    const OpB opb(g);
-    OperandPipe<A_MODE, OpA, true> pa;
-    OperandPipe<B_MODE, OpB, false> pb;
-    pa.init(opa, m0, TC_BM, tid);
-    pb.init(opb, n0, bn, tid);
+    LoaderA<A_MODE> pa;
+    LoaderB<B_MODE> pb;
+    pa.init(g, m0, tid);
+    pb.init(g, n0, bn, tid);
     if (nkb > 0) {
-      pa.prologue(opa, kb_begin * TC_BK, g.K, tid);
-      pb.prologue(opb, kb_begin * TC_BK, g.K, tid);
+      pa.prologue(g, m0, kb_begin * TC_BK, tid);
+      pb.prologue(g, n0, kb_begin * TC_BK, tid);
     }
     int s = 0;
     uint32_t parity = 1;                                       // empty-barrier parity of the current round
@@ -515,11 +548,11 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
       const int k0 = (kb_begin + i) * TC_BK;
       const uint32_t a_base = smem_base + s * stage_bytes;
       const uint32_t b_base = a_base + TC_A_BYTES;
-      pa.pre_wait(opa, k0, g.K, tid, i + 1 < nkb);
-      pb.pre_wait(opb, k0, g.K, tid, i + 1 < nkb);
+      pa.pre_wait(g, m0, k0, tid, i + 1 < nkb);
+      pb.pre_wait(g, n0, k0, tid, i + 1 < nkb);
       mbar_wait(smem_u32(&sh->empty[s]), parity);              // slot free (first round passes at once)
-      bool stored = pa.post_wait(opa, a_base, k0, g.K, tid);
-      stored |= pb.post_wait(opb, b_base, k0, g.K, tid);
+      const bool stored = pa.post_wait(g, a_base, tid) | !LoaderB<B_MODE>::kAsync;
+      pb.post_wait(g, b_base, n0, k0, tid);
       if (stored) fence_proxy_async_smem();   // generic-proxy st.shared -> visible to the tensor core (async proxy)
       cp_async_mbar_arrive_noinc(smem_u32(&sh->full[s]));
       if (++s == stages) { s = 0; parity ^= 1u; }

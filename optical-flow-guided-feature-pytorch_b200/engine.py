@@ -40,7 +40,8 @@ class Gemm:
         d = L.OffkGemm()
         d.M, d.N, d.K = spc.M, spc.N, spc.K
         d.a_src, d.a_row, d.a_col = a_src.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
-        d.a_h, d.a_w, d.a_relu, d.a_ones_row, d.a_mode = spc.a_h, spc.a_w, int(a_relu), spc.a_ones_row, spc.a_mode
+        d.a_h, d.a_w = (spc.a_h, spc.a_w) if spc.a_h else (T.NO_BOX, T.NO_BOX)
+        d.a_relu, d.a_ones_row, d.a_mode = int(a_relu), spc.a_ones_row, spc.a_mode
         d.b_src, d.b_row, d.b_col, d.b_mode = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
         d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
         d.bias = bias.data_ptr() if bias is not None else None
@@ -119,8 +120,7 @@ class OFFEngine:
     def _tables(self, key, spc: T.GemmSpec):
         if key not in self._tab_cache:
             dev = self.device
-            up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32).reshape(-1)).to(dev)
-            self._tab_cache[key] = {k: up(getattr(spc, k)) for k in ("a_row", "a_col", "b_row", "b_col", "out_row", "out_col")}
+            self._tab_cache[key] = {k: torch.from_numpy(v).to(dev) for k, v in T.padded_tables(spc).items()}
         return self._tab_cache[key]
 
     def _buf(self, name, *shape):

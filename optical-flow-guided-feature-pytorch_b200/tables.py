@@ -264,6 +264,37 @@ def check_modes(spec: GemmSpec):
         assert spec.out_col[0] % 4 == 0 and (spec.out_row % 4 == 0).all()
 
 
+NO_BOX = 32767          # a_h / a_w value meaning "every real element is valid"
+PAD_Y = -16384          # y of padding entries: never inside any box
+
+
+def padded_tables(spec: GemmSpec):
+    """Device-ready int32 arrays obeying the padding contract of the tensor-core kernel (include/offk.h):
+    a_row -> ceil(M/128)*128 entries, a_col / b_col -> ceil(K/32)*32 + 64, b_row -> ceil(N/256)*256;
+    A padding entries have y = PAD_Y (rejected by the always-on box test), B padding entries are 0."""
+    def pad_idx(t, n):
+        out = np.zeros(n, IDX_DTYPE)
+        out["y"] = PAD_Y
+        out[: len(t)] = t
+        return out
+
+    def pad_i32(t, n):
+        out = np.zeros(n, np.int32)
+        out[: len(t)] = t
+        return out
+
+    kp = (spec.K + 31) // 32 * 32 + 64
+    a_row = pad_idx(spec.a_row, (spec.M + 127) // 128 * 128)
+    if spec.a_ones_row >= 0:
+        a_row[spec.a_ones_row]["y"] = PAD_Y          # never gathered; the kernel synthesises the ones
+    tabs = {
+        "a_row": a_row, "a_col": pad_idx(spec.a_col, kp),
+        "b_row": pad_i32(spec.b_row, (spec.N + 255) // 256 * 256), "b_col": pad_i32(spec.b_col, kp),
+        "out_row": spec.out_row, "out_col": spec.out_col,
+    }
+    return {k: np.ascontiguousarray(v).view(np.int32).reshape(-1) for k, v in tabs.items()}
+
+
 def emulate(spec: GemmSpec, a_src: np.ndarray, b_src: np.ndarray, a_relu: bool = False) -> np.ndarray:
     """Dense D[M,N] of a spec, evaluated with numpy (float64).  CPU-side check of the tables only."""
     a_src = a_src.reshape(-1).astype(np.float64)
