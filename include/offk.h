@@ -62,7 +62,8 @@ int offk_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_
  * the data-/weight-gradient of all of them (autograd, train_off.py:136-146).
  * What differs per layer is only WHERE element (m,k) / (n,k) / (m,n) lives;
  * that is described by separable index tables built once per layer geometry
- * (offk_conv_tables_*() below, or the Python host mirror):
+ * (by the host: optical-flow-guided-feature-pytorch_b200/tables.py builds them with numpy for forward,
+ * weight-gradient and data-gradient of a conv in NCHW or channels-last layout):
  *
  *   A(m,k) = a_src[a_row[m].off + a_col[k].off]   if 0 <= a_row[m].y + a_col[k].y < a_h
  *                                                 and 0 <= a_row[m].x + a_col[k].x < a_w, else 0
@@ -139,18 +140,6 @@ typedef struct offk_gemm {
 } offk_gemm_t;
 
 int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
-
-/* Table builders for a conv layer  y = conv2d(x, w, stride, pad)  on NCHW
- * tensors that may be channel slices of wider buffers (ctot = channels of the
- * buffer, coff = first channel of the slice).  Each fills caller-owned device
- * arrays; sizes are given by offk_conv_table_sizes().  `which`: 0 forward,
- * 1 weight gradient, 2 data gradient (stride-s layers are split into s*s
- * parity classes; `cls` selects one).  */
-typedef struct offk_conv_geom {
-  int32_t n_img, cin, hin, win, cout, hout, wout, kh, kw, stride, pad;
-  int32_t x_ctot, x_coff; /* input buffer  */
-  int32_t y_ctot, y_coff; /* output buffer */
-} offk_conv_geom_t;
 
 /* ------------------------------------------------------------------------
  * Fused OFF stencil: spatial gradient + temporal difference + dropout +

@@ -216,6 +216,9 @@ class OFFEngine:
                                                cols, stream), name + ".bias_act")
             assert geom.y_coff == 0 and geom.y_ctot == geom.cout
             self.flops_fwd += g.flops
+            run._split = True
+            run.name = name
+            run.flops = g.flops
             return run
         g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
                  addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
@@ -473,7 +476,19 @@ class OFFEngine:
                 post.append(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
                     _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n))
         self.fwd_steps = pre + fwd
-        self.bwd_steps = bwd_stage + bwd_units + post
+        # kernels of liboffk launched per pass (split-K forward convs = GEMM + bias/activation pass; the learned
+        # stencil's backward = data-gradient kernel + tap-gradient kernel)
+        count = lambda steps: sum(2 if getattr(st, "_split", False) else 1 for st in steps)
+        self.launches_fwd = count(self.fwd_steps)
+        self.launches_bwd = count(bwd_stage + post + bwd_units) + (len(S.LEVELS) if self.variant == "rgb" else 0)
+        # the stage / head gradients are complete before the units run: their bucket can be all-reduced meanwhile
+        self.bwd_stage_steps = bwd_stage + post
+        self.bwd_unit_steps = bwd_units
+        self.bwd_steps = self.bwd_stage_steps + self.bwd_unit_steps
+        unit_end = max(self.layout[f"motion_{k}_{t}.bias"][0] + (S.GEN_C if k == "conv_gen" else S.DOWN_C)
+                       for t in S.LEVELS for k in (("conv_gen", "spatial_down") + (("spatial_grad",) if self.variant == "rgb" else ())))
+        self.unit_range = (0, (unit_end + 3) // 4 * 4)          # flat offsets of the nine units' parameters
+        self.stage_range = (self.unit_range[1], self.n_flat)    # stage convs + FC heads
 
     # ------------------------------------------------------------------ small step factories
     def _add_into_slice(self, a, b, dst, ctot, coff, c, hw):
@@ -541,15 +556,21 @@ class OFFEngine:
         pre = "cfc" if self.consensus else "fc"
         return self.buf[pre + "7"], self.buf[pre + "28"], self.buf[pre + "14"]
 
-    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True):
-        """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads)."""
+    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None):
+        """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads).
+        ``after_stage()`` is called once the stage/head gradients (flat range ``stage_range``) are final and
+        before the unit gradients are computed (used to overlap their all-reduce)."""
         self.d_out7.copy_(g7.reshape(self.d_out7.shape))
         self.d_out14.copy_(g14.reshape(self.d_out14.shape))
         if zero_grads:
             self.grads_flat.zero_()
         self.dwp_flat.zero_()
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for step in self.bwd_steps:
+        for step in self.bwd_stage_steps:
+            step(stream)
+        if after_stage is not None:
+            after_stage()
+        for step in self.bwd_unit_steps:
             step(stream)
         return self.grads
 

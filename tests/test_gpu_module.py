@@ -1,0 +1,167 @@
+"""GPU: nn.Module surface, state_dict contract, autograd semantics, mirrors of basic_ops / util, full-size properties."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import off_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import off_b200  # noqa: F401
+    return torch.device("cuda")
+
+
+@pytest.mark.parametrize("variant", ["rgb", "flow"])
+def test_state_dict_round_trip(dev, variant):
+    from off_b200.modules import OFFSubNetwork
+    net = OFFSubNetwork(1, 3, variant, device=dev)
+    want = {}
+    for line in open(os.path.join(GOLD, f"state_dict_keys_{variant}.txt")):
+        f = line.split()
+        want[f[0]] = tuple(int(x) for x in f[1:])
+    sd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want          # keys AND shapes of the reference
+    assert all("motion" in n for n, p in net.named_parameters() if p.requires_grad)   # train_off.py:40 filter works
+    other = OFFSubNetwork(1, 3, variant, device=dev)
+    other.load_state_dict(sd)
+    assert torch.equal(other.engine.params_flat, net.engine.params_flat)
+    # DataParallel-style checkpoints carry a "module." prefix (test_flow_off.py:52-58)
+    other.load_state_dict({k[len("module."):]: v for k, v in {"module." + k: v for k, v in sd.items()}.items()})
+
+
+def test_autograd_accumulates_like_torch(dev):
+    from off_b200.modules import OFFSubNetwork
+    B, Lg = 1, 3
+    net = OFFSubNetwork(B, Lg, "rgb", precision="fp32", device=dev).eval()
+    taps = {k: v.to(dev) for k, v in O.make_taps(3, B, Lg).items()}
+    fc7, _, fc14 = net(taps)
+    (fc7.sum() + fc14.sum()).backward()
+    g1 = net.motion_conv_trans.weight.grad.clone()
+    fc7, _, fc14 = net(taps)
+    (fc7.sum() + fc14.sum()).backward()                     # second backward without zero_grad: gradients add up
+    assert torch.allclose(net.motion_conv_trans.weight.grad, 2 * g1, rtol=1e-4, atol=1e-6)
+    net.zero_grad(set_to_none=True)
+    fc7, _, fc14 = net(taps)
+    (fc7.sum() + fc14.sum()).backward()
+    assert torch.allclose(net.motion_conv_trans.weight.grad, g1, rtol=1e-4, atol=1e-6)
+    assert net.fc_action_motion_28.weight.grad is None or net.fc_action_motion_28.weight.grad.abs().max() == 0
+
+
+def test_tap_gradients_when_requested(dev):
+    from off_b200.modules import OFFSubNetwork
+    B, Lg = 1, 3
+    taps = O.make_taps(9, B, Lg)
+    prm = O.make_params(9, "rgb")
+    net = OFFSubNetwork(B, Lg, "rgb", precision="fp32", tap_grads=True, device=dev).eval()
+    net.load_state_dict(prm)
+    tg = {k: v.to(dev).requires_grad_(True) for k, v in taps.items()}
+    fc7, _, fc14 = net(tg)
+    (fc7.sum() + fc14.sum()).backward()
+    _, _, tref = O.off_forward_backward(taps, prm, B, Lg, "rgb", None, torch.float64, tap_grads=True)
+    for k in taps:
+        err = (tg[k].grad.double().cpu() - tref[k]).norm() / tref[k].norm()
+        assert err < 2e-3, (k, float(err))
+
+
+def test_consensus_module(dev):
+    """basic_ops.ConsensusModule: mean over segments and its expand/T backward."""
+    from off_b200.basic_ops import ConsensusModule, Identity
+    x = torch.randn(5, 6, 101, device=dev, requires_grad=True)
+    y = ConsensusModule("avg", dim=1)(x)
+    assert y.shape == (5, 1, 101) and torch.allclose(y, x.mean(1, keepdim=True), atol=1e-6)
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert torch.allclose(x.grad, g.expand(5, 6, 101) / 6.0, atol=1e-7)
+    assert ConsensusModule("rnn")(x) is x and ConsensusModule("identity").consensus_type == "identity"
+    assert Identity()(x) is x
+    with pytest.raises(RuntimeError):
+        ConsensusModule("avg")(x.cpu())                     # no CPU fallback
+
+
+def test_sobel_modules_known_answers(dev):
+    """util.SobelFilter / SobelFilter_Diagonal against the reference's own outputs (tests/golden/sobel_kat.npz)."""
+    from off_b200.util import SobelFilter, SobelFilter_Diagonal
+    fix = np.load(os.path.join(GOLD, "sobel_kat.npz"))
+    xr = O.hash_normal(int(fix["rand_seed"]), (2, 4, 9, 7)).to(dev)
+    gx, gy = SobelFilter(4, 4)(xr)
+    assert torch.allclose(gx.cpu(), torch.from_numpy(fix["rand_gx"]), atol=2e-6)
+    assert torch.allclose(gy.cpu(), torch.from_numpy(fix["rand_gy"]), atol=2e-6)
+    assert torch.allclose(SobelFilter_Diagonal(4, 4)(xr).cpu(), torch.from_numpy(fix["rand_diag"]), atol=2e-6)
+    # the reference's own smoke shape (util.py:101-108): SobelFilter(192,192) on [64,192,56,56] -> reduced batch here
+    x = torch.rand(2, 192, 56, 56, device=dev, requires_grad=True)
+    m = SobelFilter(192, 192).to(dev)
+    ox, oy = m(x)
+    rx, ry = O.sobel_xy(x.detach().cpu())
+    assert torch.allclose(ox.cpu(), rx, atol=1e-5) and torch.allclose(oy.cpu(), ry, atol=1e-5)
+    (ox.sum() + 2 * oy.sum()).backward()
+    xc = x.detach().cpu().requires_grad_(True)
+    a, b = O.sobel_xy(xc)
+    (a.sum() + 2 * b.sum()).backward()
+    assert torch.allclose(x.grad.cpu(), xc.grad, atol=1e-4)
+    assert set(m.state_dict()) == {"conv1.weight", "conv2.weight"}
+
+
+def test_full_size_properties(dev):
+    """BASELINE config 2 size (48 clips x 3 segments): size-independent properties instead of an oracle run."""
+    from off_b200.engine import OFFEngine
+    B, Lg = 48, 3
+    eng = OFFEngine(B, Lg, "rgb", dev, "tf32", index_mode="aligned")
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for n, v in eng.params.items():
+            v.uniform_(-0.05, 0.05)
+    for t in eng.taps.values():
+        t.copy_(torch.relu(torch.randn_like(t)))
+    a = [x.clone() for x in eng.forward(train=False)]
+    b = [x.clone() for x in eng.forward(train=False)]
+    # split-K layers accumulate with fp32 atomics: two runs agree to round-off of the tf32 operands downstream of
+    # them (an fp32 ulp can move a tf32 rounding boundary), not bit-for-bit
+    rep = [(x - y).abs().max().item() / x.abs().max().item() for x, y in zip(a, b)]
+    assert max(rep) <= 2e-3, rep
+    # clips are independent (aligned mode): reversing the clip order reverses the per-pair logits
+    for t in eng.taps.values():
+        t.copy_(t.view(B, Lg, *t.shape[1:]).flip(0).reshape(t.shape))
+    c = [x.clone() for x in eng.forward(train=False)]
+    for x, y in zip(a, c):
+        xf = x.view(B, Lg - 1, -1).flip(0).reshape(x.shape)
+        assert (xf - y).abs().max().item() <= 2e-3 * x.abs().max().item()
+    # telescoping of the temporal channels in the 28x28 fusion buffer: sum_t T[b,t] = G[b,L-1] - G[b,0]
+    F28 = eng.buf["F28"].view(B, Lg - 1, 28, 28, 320)
+    G = eng.buf["gd_3a"].view(B, Lg, 28, 28, 160)[..., :128]
+    assert (F28[..., 32:160].sum(1) - (G[:, -1] - G[:, 0])).abs().max().item() < 1e-4
+    # seeded dropout: ~20 % kept, scaled by 5, identical mask regenerated for the same seed
+    eng.forward(train=True, seed=7)
+    s1 = eng.buf["F7"][..., :32].clone()
+    eng.forward(train=True, seed=7)
+    assert torch.equal(s1 != 0, eng.buf["F7"][..., :32] != 0)
+    eng.forward(train=False)
+    s0 = eng.buf["F7"][..., :32]
+    kept = (s1 != 0).float().mean().item() / max((s0 != 0).float().mean().item(), 1e-9)
+    assert 0.17 < kept < 0.23
+    nz = s1 != 0
+    assert torch.allclose(s1[nz], 5.0 * s0[nz], rtol=1e-5, atol=1e-6)
+    # backward linearity in the upstream gradient
+    g7, g14 = torch.randn(eng.P, 101, device=dev), torch.randn(eng.P, 101, device=dev)
+    g1 = eng.backward(g7, g14)["motion_conv_trans.weight"].clone()
+    g2 = eng.backward(2 * g7, 2 * g14)["motion_conv_trans.weight"].clone()
+    assert (g2 - 2 * g1).norm().item() <= 1e-3 * g2.norm().item()
+    assert eng.grads["fc_action_motion_28.weight"].abs().max().item() == 0
+
+
+def test_bad_arguments_raise(dev):
+    from off_b200 import _lib as L
+    import ctypes as C
+    lib = L.lib()
+    s = L.OffkStencil()
+    s.B, s.L, s.Cg, s.Cs, s.K, s.H, s.W = 1, 1, 128, 32, 1, 7, 7          # L = 1: no pairs
+    with pytest.raises(RuntimeError, match="L >= 2"):
+        L.check(lib.offk_stencil_diff_fwd(C.byref(s), None, None, None, None, None, None), "stencil")
+    x = torch.zeros(4, device=dev)
+    with pytest.raises(RuntimeError):
+        L.check(lib.offk_avgpool_drop_fwd(x.data_ptr(), 1, 8, 49, 4, 0, 0, None, 0, 0.0, 1.0, x.data_ptr(), None), "pool")

@@ -1,0 +1,265 @@
+"""GPU: parity of the sm_100a path with the CPU oracle, through the C ABI (liboffk.so).
+
+Tolerances (stated per mode, as BASELINE.json's north_star asks):
+  fp32 mode (CUDA-core FFMA, fp32 accumulate): <= 2e-5 max-abs relative to the tensor's max, per level / head;
+  tf32 mode (tcgen05 kind::tf32, fp32 accumulate): <= 5e-3 on the stage-fusion tensors, <= 1e-2 on the logits;
+  gradients are compared in relative L2 norm (a single ReLU whose pre-activation sits within round-off of 0 may flip
+  between fp32 and the fp64 oracle, which moves individual entries but not the norm): fp32 <= 2e-3, tf32 <= 0.2.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import off_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import off_b200  # noqa: F401
+    from off_b200 import _lib
+    _lib.lib()            # raises if the extension is missing: no fallback
+    return torch.device("cuda")
+
+
+def _rel(a, b):
+    b = b.double()
+    return (a.detach().double().cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _rel_l2(a, b):
+    b = b.double()
+    return (a.detach().double().cpu() - b).norm().item() / max(b.norm().item(), 1e-30)
+
+
+def _run_spec(spc, a_src, b_src, out_shape, prec, dev, bias=None, ones=None, split_k=1, atomic=False):
+    from off_b200 import _lib as L, tables as T
+    tabs = {k: torch.from_numpy(v).to(dev) for k, v in T.padded_tables(spc).items()}
+    out = torch.zeros(out_shape, device=dev)
+    d = L.OffkGemm()
+    d.M, d.N, d.K = spc.M, spc.N, spc.K
+    d.a_src, d.a_row, d.a_col = a_src.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
+    d.a_h, d.a_w = (spc.a_h, spc.a_w) if spc.a_h else (T.NO_BOX, T.NO_BOX)
+    d.a_ones_row, d.a_mode = spc.a_ones_row, spc.a_mode
+    d.b_src, d.b_row, d.b_col, d.b_mode = b_src.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
+    d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.ones_row_out = ones.data_ptr() if ones is not None else None
+    d.split_k, d.atomic_out, d.out_vec = split_k, int(atomic), spc.out_vec
+    L.check(L.lib().offk_gather_gemm(C.byref(d), prec, None), "gemm")
+    torch.cuda.synchronize()
+    return out
+
+
+GEMM_CASES = [
+    # n, cin, h, w, cout, k, s, p, x_ctot, x_coff, y_ctot, y_coff, x_layout, y_layout
+    (3, 8, 7, 7, 8, 1, 1, 0, 8, 0, 8, 0, "nchw", "nhwc"),          # unit conv, 7x7 taps (scalar NCHW loader)
+    (5, 64, 14, 14, 160, 1, 1, 0, 64, 0, 160, 0, "nchw", "nhwc"),  # unit conv, vectorised transposing loader
+    (4, 64, 14, 14, 64, 3, 1, 1, 64, 0, 64, 0, "nhwc", "nhwc"),
+    (2, 32, 28, 28, 64, 7, 2, 3, 32, 0, 64, 0, "nhwc", "nhwc"),  # motion_conv_trans_28 geometry
+    (2, 24, 14, 14, 128, 5, 2, 2, 40, 8, 160, 32, "nhwc", "nhwc"),  # 5x5 s2 on channel slices
+    (3, 128, 7, 7, 512, 3, 1, 1, 128, 0, 512, 0, "nhwc", "nhwc"),  # N > 256: two N tiles
+    (8, 1024, 1, 1, 101, 1, 1, 0, 1024, 0, 101, 0, "nhwc", "nhwc"),  # FC head, N not a multiple of 4
+    (2, 6, 9, 8, 4, 3, 1, 1, 10, 3, 7, 2, "nchw", "nchw"),       # ragged everything (scalar paths)
+]
+
+
+@pytest.mark.parametrize("prec,tol", [(0, 5e-6), (1, 3e-3)], ids=["fp32", "tf32"])
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[f"{c[1]}x{c[2]}k{c[5]}s{c[6]}{c[12]}" for c in GEMM_CASES])
+def test_gather_gemm_conv_parity(dev, case, prec, tol):
+    from off_b200 import tables as T
+    n, cin, h, w, cout, k, s, p, xct, xco, yct, yco, xl, yl = case
+    g = T.ConvGeom(n, cin, h, w, cout, k, k, s, p, xct, xco, yct, yco)
+    torch.manual_seed(0)
+    x = torch.randn(n, xct, h, w, device=dev)
+    wt = torch.randn(cout, cin, k, k, device=dev) / (g.kdim ** 0.5)
+    b = torch.randn(cout, device=dev)
+    dy = torch.randn(n, yct, g.hout, g.wout, device=dev)
+    xs = x[:, xco:xco + cin].double().requires_grad_(True)
+    wd = wt.double().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xs, wd, b.double(), s, p)
+    y.backward(dy[:, yco:yco + cout].double())
+    to = lambda a, lay: a.permute(0, 2, 3, 1).contiguous() if lay == "nhwc" else a
+    back = lambda a, lay: a.permute(0, 3, 1, 2) if lay == "nhwc" else a
+    xb, dyb = to(x, xl), to(dy, yl)
+    wl = wt.permute(0, 2, 3, 1).contiguous() if xl == "nhwc" else wt
+    out = back(_run_spec(T.conv_fwd_spec(g, xl, yl), xb, wl, tuple(dyb.shape), prec, dev, bias=b), yl)
+    assert _rel(out[:, yco:yco + cout], y.detach().cpu()) < tol
+    other = torch.cat([out[:, :yco], out[:, yco + cout:]], 1)
+    assert other.abs().max().item() == 0 if other.numel() else True           # channel slice only
+    out2 = back(_run_spec(T.conv_fwd_spec(g, xl, yl), xb, wl, tuple(dyb.shape), prec, dev, split_k=3), yl)
+    assert _rel(out2[:, yco:yco + cout], (y - b.double().view(1, -1, 1, 1)).detach().cpu()) < tol
+    db = torch.zeros(cout, device=dev)
+    dw = _run_spec(T.conv_wgrad_spec(g, xl, yl), xb, dyb, tuple(wl.shape), prec, dev, ones=db, split_k=4, atomic=True)
+    dwc = dw.permute(0, 3, 1, 2) if xl == "nhwc" else dw
+    assert _rel(dwc, wd.grad.cpu()) < tol
+    assert _rel(db, dy[:, yco:yco + cout].double().sum((0, 2, 3)).cpu()) < tol
+    dx = torch.zeros_like(xb)
+    for spc in T.conv_dgrad_specs(g, xl, yl, xl):
+        dx += _run_spec(spc, dyb, wl, tuple(xb.shape), prec, dev)
+    assert _rel(back(dx, xl)[:, xco:xco + cin], xs.grad.cpu()) < tol
+
+
+STENCIL_CASES = [
+    # B, L, S, K, index_mode, drop_mode
+    (2, 3, 28, 1, 0, 0), (3, 4, 14, 1, 1, 1), (2, 2, 7, 1, 0, 2), (2, 3, 7, 2, 0, 0), (1, 7, 14, 1, 0, 1), (1, 2, 5, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", STENCIL_CASES, ids=[f"B{c[0]}L{c[1]}S{c[2]}K{c[3]}m{c[4]}d{c[5]}" for c in STENCIL_CASES])
+def test_stencil_diff_fwd_bwd(dev, case):
+    """Fused stencil (RGB_OFF.py:599-616): spatial gradient + temporal difference + dropout + cat, and its backward."""
+    from off_b200 import _lib as L
+    lib = L.lib()
+    B, Lg, S, K, mode, drop = case
+    N, P, Cg, Cs = B * Lg, B * (Lg - 1), 128, 32
+    torch.manual_seed(1)
+    gd_c = torch.randn(N, Cg + Cs, S, S, device=dev)
+    gd_c[:, :Cg].relu_()
+    gd = gd_c.permute(0, 2, 3, 1).contiguous()
+    w = torch.randn(Cs, K, 3, 3, device=dev)
+    bias = torch.randn(Cs * K, device=dev)
+    ctot, coff = 400, 64
+    out_l = torch.zeros(P, S, S, ctot, device=dev)
+    sd = L.OffkStencil()
+    sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, Cg, Cs, K, S, S
+    sd.g_fs = sd.d_fs = (Cg + Cs) * S * S
+    sd.g_ps = sd.d_ps = Cg + Cs
+    sd.out_ctot, sd.out_coff, sd.index_mode = ctot, coff, mode
+    sd.drop_mode, sd.keep_scale, sd.drop_p, sd.seed = drop, 5.0, 0.8, 1234
+    mask = (torch.rand(P, K * Cs, S, S, device=dev) > 0.8).to(torch.uint8)
+    sd.keep_mask = mask.data_ptr()
+    L.check(lib.offk_stencil_diff_fwd(C.byref(sd), gd.data_ptr(), gd.data_ptr() + 4 * Cg, w.data_ptr(), bias.data_ptr(),
+                                      out_l.data_ptr(), None), "fwd")
+    torch.cuda.synchronize()
+    out = out_l.permute(0, 3, 1, 2)
+    G, D = gd_c[:, :Cg].double(), gd_c[:, Cg:].double()
+    Gv = G.view(B, Lg, Cg, S, S)
+    Tref = (Gv[:, 1:] - Gv[:, :-1]).reshape(P, Cg, S, S)
+    Ds = (D[:P] if mode == 0 else D.view(B, Lg, Cs, S, S)[:, :-1].reshape(P, Cs, S, S)).clone().requires_grad_(True)
+    wd, bd = w.double().clone().requires_grad_(True), bias.double().clone().requires_grad_(True)
+    Sg = torch.nn.functional.conv2d(Ds.repeat(1, K, 1, 1), wd.permute(1, 0, 2, 3).reshape(K * Cs, 1, 3, 3), bd, 1, 1, 1, K * Cs)
+    if drop == 1:
+        keep = mask.double() * 5.0
+    elif drop == 2:      # counter-hash dropout: regenerate on the host with the library's own hash
+        idx = np.arange(P * K * Cs * S * S, dtype=np.uint64)
+        x = np.uint64(1234) + idx * np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9); x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB); x ^= x >> np.uint64(31)
+        k24 = (x >> np.uint64(40)).astype(np.int64) >= int(0.8 * 16777216.0)
+        assert all(bool(k24[i]) == bool(lib.offk_drop_keep_host(1234, int(i), 0.8)) for i in range(0, min(4096, len(k24)), 7))
+        assert 0.15 < k24.mean() < 0.25
+        keep = torch.from_numpy(k24.astype(np.float64)).to(dev).view(P, K * Cs, S, S) * 5.0
+    else:
+        keep = torch.ones(P, K * Cs, S, S, device=dev, dtype=torch.float64)
+    Sg = Sg * keep
+    ref = torch.cat([Sg, Tref], 1)
+    assert (out[:, coff:coff + K * Cs + Cg].double() - ref.detach()).abs().max().item() < 2e-5
+    assert out[:, :coff].abs().max().item() == 0 and out[:, coff + K * Cs + Cg:].abs().max().item() == 0
+    # temporal rows are exact fp32 differences: bit-exact against torch on the GPU
+    Gf = gd_c[:, :Cg].view(B, Lg, Cg, S, S)
+    assert torch.equal(out[:, coff + K * Cs:coff + K * Cs + Cg], (Gf[:, 1:] - Gf[:, :-1]).reshape(P, Cg, S, S))
+    # telescoping: sum_t T[b,t] == G[b,L-1] - G[b,0]
+    tel = out[:, coff + K * Cs:coff + K * Cs + Cg].reshape(B, Lg - 1, Cg, S, S).double().sum(1)
+    assert (tel - (Gv[:, -1] - Gv[:, 0])).abs().max().item() < 1e-5
+
+    dout_l = torch.randn(P, S, S, ctot, device=dev)
+    dout = dout_l.permute(0, 3, 1, 2)
+    dgd_l = torch.full((N, S, S, Cg + Cs), float("nan"), device=dev)
+    dw, dbias = torch.zeros_like(w), torch.zeros_like(bias)
+    fs = (Cg + Cs) * S * S
+    L.check(lib.offk_stencil_diff_bwd(C.byref(sd), dout_l.data_ptr(), gd.data_ptr(), gd.data_ptr() + 4 * Cg, w.data_ptr(),
+                                      dgd_l.data_ptr(), fs, dgd_l.data_ptr() + 4 * Cg, fs, dw.data_ptr(), dbias.data_ptr(),
+                                      None), "bwd")
+    torch.cuda.synchronize()
+    dgd = dgd_l.permute(0, 3, 1, 2)
+    assert not torch.isnan(dgd).any()
+    dT = dout[:, coff + K * Cs:coff + K * Cs + Cg].double().reshape(B, Lg - 1, Cg, S, S)
+    dG = torch.zeros(B, Lg, Cg, S, S, device=dev, dtype=torch.float64)
+    dG[:, 1:] += dT
+    dG[:, :-1] -= dT
+    dG = dG.view(N, Cg, S, S) * (G > 0)
+    Sg.backward(dout[:, coff:coff + K * Cs].double())
+    dD = torch.zeros(N, Cs, S, S, device=dev, dtype=torch.float64)
+    if mode == 0:
+        dD[:P] = Ds.grad
+    else:
+        dD.view(B, Lg, Cs, S, S)[:, :-1] = Ds.grad.view(B, Lg - 1, Cs, S, S)
+    assert (dgd[:, :Cg].double() - dG).abs().max().item() < 1e-5
+    assert (dgd[:, Cg:].double() - dD).abs().max().item() < 5e-5
+    assert _rel(dw, wd.grad.cpu()) < 1e-5 and _rel(dbias, bd.grad.cpu()) < 1e-5
+
+
+def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit, tol_grad):
+    from off_b200 import engine as E
+    seed = 5
+    taps, prm = O.make_taps(seed, B, Lg), O.make_params(seed, variant)
+    masks = O.make_dropout_masks(seed, B, Lg) if train else None
+    n_out = B * (Lg - 1) if variant == "rgb" else B
+    r7, r14 = O.hash_normal(77, (n_out, 101)).double(), O.hash_normal(78, (n_out, 101)).double()
+    lossf = lambda o: (o["fc7"].reshape(r7.shape) * r7).sum() + (o["fc14"].reshape(r14.shape) * r14).sum()
+    ref, gref = O.off_forward_backward(taps, prm, B, Lg, variant, masks, torch.float64, loss=lossf)
+    eng = E.OFFEngine(B, Lg, variant, dev, precision)
+    eng.load_params(prm)
+    fc7, fc28, fc14 = eng.forward({k: v.to(dev) for k, v in taps.items()}, train=train, masks=masks)
+    report = {}
+    for k, st in (("fusion28", "F28"), ("fusion14", "F14"), ("fusion7", "F7")):      # per-level error (channels-last -> NCHW)
+        report[k] = _rel(eng.buf[st].permute(0, 3, 1, 2), ref[k])
+        assert report[k] < tol_fuse, (k, report[k])
+    for name, got in (("fc7", fc7), ("fc28", fc28), ("fc14", fc14)):
+        report[name] = _rel(got, ref[name].reshape(got.shape))
+        assert report[name] < tol_logit, (name, report[name])
+    grads = eng.backward(r7.float().to(dev), r14.float().to(dev))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for n, g in grads.items():
+        if gref[n].abs().max().item() == 0:
+            assert g.abs().max().item() == 0, n            # fc_action_motion_28.* never gets a gradient
+            continue
+        worst = max(worst, _rel_l2(g, gref[n]))
+    assert worst < tol_grad, worst
+    return report, worst
+
+
+@pytest.mark.parametrize("variant,B,Lg,train", [("rgb", 2, 3, False), ("flow", 2, 3, False), ("rgb", 2, 2, True),
+                                                ("flow", 1, 4, False), ("rgb", 1, 3, False)])
+def test_engine_fp32_mode_matches_oracle(dev, variant, B, Lg, train):
+    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, 2e-5, 2e-5, 2e-3)
+
+
+@pytest.mark.parametrize("variant,B,Lg,train", [("rgb", 2, 3, False), ("flow", 2, 3, False), ("rgb", 2, 2, True)])
+def test_engine_tf32_mode_matches_oracle(dev, variant, B, Lg, train):
+    _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, 5e-3, 1e-2, 0.2)
+
+
+@pytest.mark.parametrize("name", ["rgb_b1_l3", "rgb_b2_l3", "flow_b2_l3", "rgb_b2_l2_train", "flow_b1_l4"])
+def test_module_matches_reference_golden(dev, name):
+    """The nn.Module surface against vectors produced by the reference itself (tests/golden, make_golden.py)."""
+    from off_b200.modules import OFFSubNetwork
+    fix = np.load(os.path.join(GOLD, f"off_{name}.npz"))
+    variant, B, Lg, seed, train = str(fix["variant"]), int(fix["batch"]), int(fix["length"]), int(fix["seed"]), int(fix["train"])
+    net = OFFSubNetwork(B, Lg, variant, precision="fp32", device=dev)
+    net.train(bool(train))
+    net.load_state_dict(O.make_params(seed, variant), strict=(variant == "rgb"))
+    masks = O.make_dropout_masks(seed, B, Lg) if train else None
+    fc7, fc28, fc14 = net({k: v.to(dev) for k, v in O.make_taps(seed, B, Lg).items()}, masks=masks)
+    for k, got in (("fc7", fc7), ("fc28", fc28), ("fc14", fc14)):
+        want = torch.from_numpy(fix[k]).reshape(got.shape)
+        assert _rel(got, want) < 2e-5, k
+    (fc7.sum() + fc14.sum()).backward()
+    for n, p in net.named_parameters():
+        if not p.requires_grad:
+            continue
+        l2 = float(fix[f"grad.{n}.l2"])
+        if l2 == 0:
+            assert p.grad is None or p.grad.abs().max().item() == 0
+            continue
+        idx, val = torch.from_numpy(fix[f"grad.{n}.idx"]), torch.from_numpy(fix[f"grad.{n}.val"])
+        got = p.grad.reshape(-1)[idx.to(dev)].double().cpu()
+        assert abs(p.grad.double().norm().item() - l2) / l2 < 2e-3, n
+        assert (got - val).norm().item() <= 5e-3 * max(val.norm().item(), 1e-3 * l2), n

@@ -1,0 +1,101 @@
+"""CPU: host-side logic of the product package (no kernel launches)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import off_b200  # noqa: F401
+from off_b200 import _lib as L, spec as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("variant", ["rgb", "flow"])
+def test_state_dict_contract(variant):
+    """Parameter names / shapes equal the reference's state_dict (captured from the reference classes)."""
+    want = {}
+    for line in open(os.path.join(GOLD, f"state_dict_keys_{variant}.txt")):
+        f = line.split()
+        want[f[0]] = tuple(int(x) for x in f[1:])
+    mine = S.param_shapes(variant)
+    frozen = {"sobel_edge_diagonal.conv.weight"}
+    assert set(mine) == set(want) - frozen
+    for k, shp in mine.items():
+        assert tuple(shp) == want[k], k
+    assert sum(int(np.prod(s)) for s in mine.values()) == (9872975 if variant == "rgb" else 9870095)
+
+
+@pytest.mark.parametrize("variant", ["rgb", "flow"])
+def test_flat_layout(variant):
+    layout, total = S.flat_layout(variant)
+    spans = sorted((off, off + int(np.prod(shp))) for off, shp in layout.values())
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0                                        # no overlap
+    assert spans[-1][1] <= total
+    for tag, (cin, _) in S.LEVELS.items():                     # gen|down adjacent -> one [160, cin] GEMM operand
+        g, d = layout[f"motion_conv_gen_{tag}.weight"][0], layout[f"motion_spatial_down_{tag}.weight"][0]
+        assert d == g + S.GEN_C * cin and g % 4 == 0
+        gb, db = layout[f"motion_conv_gen_{tag}.bias"][0], layout[f"motion_spatial_down_{tag}.bias"][0]
+        assert db == gb + S.GEN_C and gb % 4 == 0
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "offk.h")).read()
+    declared = set(re.findall(r"\b(offk_[a-z0-9_]+)\s*\(", hdr))
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/offk.h but not exported by liboffk.so"
+    assert declared == set(L.exported_symbols()), declared ^ set(L.exported_symbols())
+    assert lib.offk_version() == 100
+    assert lib.offk_drop_keep_host(1, 2, 0.0) == 1 and lib.offk_drop_keep_host(1, 2, 1.0) == 0
+
+
+def test_ctypes_structs_match_the_c_header():
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "offk.h"
+    int main(void) {
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(offk_idx_t), sizeof(offk_gemm_t), offsetof(offk_gemm_t, out),
+             offsetof(offk_gemm_t, split_k), sizeof(offk_stencil_t), offsetof(offk_stencil_t, seed),
+             offsetof(offk_stencil_t, keep_mask));
+      return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    got = [int(x) for x in out]
+    assert got == [C.sizeof(L.OffkIdx), C.sizeof(L.OffkGemm), L.OffkGemm.out.offset, L.OffkGemm.split_k.offset,
+                   C.sizeof(L.OffkStencil), L.OffkStencil.seed.offset, L.OffkStencil.keep_mask.offset]
+
+
+def test_cpu_calls_fail_loudly():
+    """No CPU fallback: bad arguments give error codes + messages, not silent success."""
+    lib = L.lib()
+    g = L.OffkGemm()
+    assert lib.offk_gather_gemm(C.byref(g), L.PREC_TF32, None) == -1
+    assert b"empty problem" in lib.offk_last_error_string()
+    s = L.OffkStencil()
+    assert lib.offk_stencil_diff_fwd(C.byref(s), None, None, None, None, None, None) == -1
+    with pytest.raises(RuntimeError):
+        L.check(-1, "probe")
+
+
+def test_engine_plan_builds_without_a_gpu():
+    """The plan (tables, descriptors, launch list) is pure host logic."""
+    from off_b200 import engine as E, tables as T
+    eng = E.OFFEngine(2, 3, "rgb", "cpu", "tf32")
+    assert eng.launches_fwd > 40 and eng.launches_bwd > 60
+    assert eng.unit_range[1] == eng.stage_range[0] and eng.stage_range[1] == eng.n_flat
+    # forward FLOPs follow the survey's scaling law 0.28897*N + 1.29305*P GFLOP (+ the down rows of the N-P extra frames)
+    gf = 0.28897 * eng.N + 1.29305 * eng.P + 0.07235 * (eng.N - eng.P)
+    assert abs(eng.flops_fwd / 1e9 - gf) / gf < 0.01
+    flow = E.OFFEngine(1, 4, "flow", "cpu", "fp32", tap_grads=True)
+    assert flow.consensus and "motion_spatial_grad_3a.weight" not in flow.params
