@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboffk.so")
+LIB_PATH = os.environ.get("OFFK_LIB") or os.path.join(_HERE, "liboffk.so")   # OFFK_LIB: bring-up builds only
 
 PREC_FP32, PREC_TF32 = 0, 1
 INDEX_REFERENCE_FLAT, INDEX_ALIGNED = 0, 1

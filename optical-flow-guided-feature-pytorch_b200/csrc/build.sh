@@ -3,14 +3,16 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
-OUT="$HERE/../liboffk.so"
+OUT="${OFFK_OUT:-$HERE/../liboffk.so}"
+ODIR="${OFFK_OBJDIR:-$HERE}"
+mkdir -p "$ODIR"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v
-       -I"$ROOT/include" -I"$HERE")
+       -I"$ROOT/include" -I"$HERE" ${OFFK_EXTRA_FLAGS:-})
 OBJS=()
 for f in offk_api offk_gemm_simt offk_gemm_tc offk_stencil offk_head; do
-  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/$f.o" 2> "$HERE/$f.ptxas.log" || { cat "$HERE/$f.ptxas.log" >&2; exit 1; }
-  OBJS+=("$HERE/$f.o")
+  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$ODIR/$f.o" 2> "$ODIR/$f.ptxas.log" || { cat "$ODIR/$f.ptxas.log" >&2; exit 1; }
+  OBJS+=("$ODIR/$f.o")
 done
 "$NVCC" -shared -o "$OUT" "${OBJS[@]}" -gencode arch=compute_100a,code=sm_100a -lcudart
 echo "built $OUT"

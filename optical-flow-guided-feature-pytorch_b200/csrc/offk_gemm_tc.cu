@@ -5,10 +5,13 @@
 // Warp roles (288 threads):
 //   warps 0-7  producers: gather A and B through the index tables (NHWC implicit-GEMM im2col / col2im,
 //              NCHW taps, pixel-major weight-gradient operands), with 16-byte loads wherever the
-//              caller promises contiguity (OFFK_LOAD_VEC_K: straight LDG.128 -> STS.128;
-//              OFFK_LOAD_VEC_ROW: LDG.128 along rows + 4x4 register transpose), write them into the
-//              canonical K-major SWIZZLE_128B shared-memory layout, fence to the async proxy and
-//              arrive on the stage's "full" mbarrier.  After the main loop the same
+//              caller promises contiguity: 16-byte cp.async straight into shared memory, never through
+//              registers.  OFFK_LOAD_VEC_K (source contiguous along k) fills the canonical K-major
+//              SWIZZLE_128B tile; OFFK_LOAD_VEC_ROW (source contiguous along m / n: NCHW taps as A(m = pixel),
+//              channels-last tensors in weight- and data-gradient GEMMs) fills the canonical MN-major
+//              SWIZZLE_128B tile and the instruction descriptor marks that operand MN-major, so no transpose
+//              is ever executed.  The scalar modes go through registers.  Producers then fence to the async
+//              proxy and arrive on the stage's "full" mbarrier.  After the main loop the same
 //              warps run the epilogue: tcgen05.ld the accumulator rows out of TMEM, apply
 //              bias / ReLU / gate / residual, store coalesced along pixels (or atomically for
 //              split-K and weight gradients).
@@ -106,10 +109,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operands of kind::tf32 have exactly one legal swizzled layout: SWIZZLE_128B_BASE32B (layout type 1;
+// cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only available smem layout").
+// The tile is a grid of 512-byte atoms: 32 consecutive m|n (one 128-byte row) times 4 consecutive k, with the
+// 32-byte units of a row XOR-ed by the row index (byte-address bits [5,7) ^= bits [7,9), cute Swizzle<2,5,2>).
+// LBO = byte stride between atoms along m|n, SBO = byte stride between 4-k groups
+// (cute::UMMA::make_umma_desc<Major::MN>: leading_byte_offset = MN-atom stride, stride_byte_offset = k-group stride).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
-// A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// A / B major at bits 15 / 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+// byte offset of (16-byte chunk `c` of 4 consecutive m|n, column k) inside an MN-major SWIZZLE_128B_BASE32B tile whose
+// 512-byte atoms are ordered [4-k group][atom along m|n]; atoms_mn = number of 32-wide atoms along m|n.
+__device__ __forceinline__ uint32_t swz_mn(int c, int k, int atoms_mn) {
+  const int kl = k & 3, cc = c & 7;
+  return (uint32_t)((((k >> 2) * atoms_mn + (c >> 3)) << 9) + (kl << 7) + (((((cc >> 1) ^ kl) << 1) | (cc & 1)) << 4));
 }
 // byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B tile (8-row atoms of 1024 B)
 __device__ __forceinline__ uint32_t swz(int r, int c) {
@@ -169,8 +194,8 @@ __device__ __forceinline__ Idx2 ld_idx(const offk_idx_t* p) {
 }
 
 // ============================ A operand (validity box, ReLU-on-load, ones row)
-// VEC_K  : thread = (row (tid>>3)+32i, chunk tid&7), i < 4.   cp.async, zero-fill for invalid.
-// VEC_ROW: thread = 4x4 block (row-quad rq, k-quad kq); LDG.128 along rows, transpose on store.
+// VEC_K  : thread = (row (tid>>3)+32i, chunk tid&7), i < 4.   cp.async, zero-fill for invalid.   K-major tile.
+// VEC_ROW: thread = (row-quad tid&31, column (tid>>5)+8i), i < 4.   cp.async, zero-fill.          MN-major tile.
 template <int MODE>
 struct LoaderA {
   Idx2 r[4];
@@ -190,11 +215,10 @@ struct LoaderA {
         ones |= (m0 + tr == g.a_ones_row ? 1u : 0u) << i;
       }
     } else if (MODE == OFFK_LOAD_VEC_ROW) {
-      const int rq = (warp & 3) * 8 + (lane >> 2), kq = (warp >> 2) * 4 + (lane & 3);
-      r[0] = ld_idx(g.a_row + m0 + 4 * rq);
+      r[0] = ld_idx(g.a_row + m0 + 4 * lane);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[j] = swz(4 * rq + j, kq);
-      ones = (m0 + 4 * rq == g.a_ones_row) ? 1u : 0u;
+      for (int i = 0; i < 4; ++i) dst[i] = swz_mn(lane, warp + 8 * i, TC_BM / 32);
+      ones = (m0 + 4 * lane == g.a_ones_row) ? 1u : 0u;
     } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
       r[0] = ld_idx(g.a_row + m0 + (tid & 127));
       ones = (m0 + (tid & 127) == g.a_ones_row) ? 1u : 0u;
@@ -204,30 +228,14 @@ struct LoaderA {
     if (MODE == OFFK_LOAD_VEC_K) {
       c[0] = ld_idx(g.a_col + k0 + 4 * (tid & 7));
     } else if (MODE == OFFK_LOAD_VEC_ROW) {
-      const int kq = ((tid >> 5) >> 2) * 4 + (tid & 3);
-      const uint4* p = reinterpret_cast<const uint4*>(g.a_col + k0 + 4 * kq);   // 4 entries = 32 bytes, aligned
-      const uint4 lo = __ldg(p), hi = __ldg(p + 1);
-      c[0] = Idx2{(int)lo.x, lo.y};
-      c[1] = Idx2{(int)lo.z, lo.w};
-      c[2] = Idx2{(int)hi.x, hi.y};
-      c[3] = Idx2{(int)hi.z, hi.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[i] = ld_idx(g.a_col + k0 + (tid >> 5) + 8 * i);
     }
   }
-  // register-staged load of the K-block whose column entries are `c` (VEC_ROW / scalar modes)
+  // register-staged load of the K-block whose column entries are `c` (scalar modes)
   __device__ __forceinline__ void load(const offk_gemm_t& g, const Idx2 (&c)[4], int m0, int k0, int tid,
                                        float4 (&v)[4]) const {
-    if (MODE == OFFK_LOAD_VEC_ROW) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float4 x = f4zero();
-        if (box_ok(g, r[0].yx, c[e].yx)) x = ldg128(g.a_src + (r[0].off + c[e].off));
-        v[e] = x;
-      }
-      if (ones) {   // all-ones row heads its own row-quad: (1,0,0,0) for real columns
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = make_float4((short)(c[e].yx & 0xFFFFu) > -8192 ? 1.f : 0.f, 0.f, 0.f, 0.f);
-      }
-    } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
+    if (MODE == OFFK_LOAD_SCALAR_ROW) {
       const int half = tid >> 7;
       float t[16];
 #pragma unroll
@@ -262,12 +270,7 @@ struct LoaderA {
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = f4relu(v[i]);
     }
-    if (MODE == OFFK_LOAD_VEC_ROW) {
-      sts128(tile + dst[0], v[0].x, v[1].x, v[2].x, v[3].x);
-      sts128(tile + dst[1], v[0].y, v[1].y, v[2].y, v[3].y);
-      sts128(tile + dst[2], v[0].z, v[1].z, v[2].z, v[3].z);
-      sts128(tile + dst[3], v[0].w, v[1].w, v[2].w, v[3].w);
-    } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
+    if (MODE == OFFK_LOAD_SCALAR_ROW) {
       const int tr = tid & 127, half = tid >> 7;
 #pragma unroll
       for (int c = 0; c < 4; ++c) sts128(tile + swz(tr, half * 4 + c), v[c].x, v[c].y, v[c].z, v[c].w);
@@ -279,24 +282,39 @@ struct LoaderA {
       for (int i = 0; i < 16; ++i) sts32(tile + swz(warp + 8 * i, lane >> 2) + (lane & 3) * 4, t[i]);
     }
   }
-  // VEC_K: straight to shared memory.  Returns true when st.shared was used (ones row).
-  __device__ __forceinline__ bool issue_async(const offk_gemm_t& g, const Idx2& c, uint32_t tile) const {
+  // VEC_K / VEC_ROW: straight to shared memory.  Returns true when st.shared was used (ones row).
+  __device__ __forceinline__ bool issue_async(const offk_gemm_t& g, const Idx2 (&c)[4], uint32_t tile) const {
     bool stored = false;
+    if (MODE == OFFK_LOAD_VEC_K) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t d = tile + dst[i];
-      if ((ones >> i) & 1u) {
-        const float one = (short)(c.yx & 0xFFFFu) > -8192 ? 1.f : 0.f;
-        sts128(d, one, one, one, one);
-        stored = true;
-      } else {
-        const bool ok = box_ok(g, r[i].yx, c.yx);
-        cp_async16_ca(d, ok ? g.a_src + (r[i].off + c.off) : g.a_src, ok ? 16u : 0u);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t d = tile + dst[i];
+        if ((ones >> i) & 1u) {
+          const float one = (short)(c[0].yx & 0xFFFFu) > -8192 ? 1.f : 0.f;
+          sts128(d, one, one, one, one);
+          stored = true;
+        } else {
+          const bool ok = box_ok(g, r[i].yx, c[0].yx);
+          cp_async16_ca(d, ok ? g.a_src + (r[i].off + c[0].off) : g.a_src, ok ? 16u : 0u);
+        }
+      }
+    } else {   // VEC_ROW: 4 consecutive rows of column k = (tid>>5)+8i
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t d = tile + dst[i];
+        if (ones) {   // the all-ones row heads its own row-quad: (1,0,0,0) for real columns
+          sts128(d, (short)(c[i].yx & 0xFFFFu) > -8192 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+          stored = true;
+        } else {
+          const bool ok = box_ok(g, r[0].yx, c[i].yx);
+          cp_async16_cg(d, ok ? g.a_src + (r[0].off + c[i].off) : g.a_src, ok ? 16u : 0u);
+        }
       }
     }
     return stored;
   }
-  static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K);
+  static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
+  static constexpr bool kMN = (MODE == OFFK_LOAD_VEC_ROW);
   static constexpr bool kVec = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
   __device__ __forceinline__ void prologue(const offk_gemm_t& g, int m0, int k_first, int tid) {
     if (kVec) fetch_cols(g, k_first, tid, c_cur);
@@ -316,7 +334,7 @@ struct LoaderA {
   __device__ __forceinline__ bool post_wait(const offk_gemm_t& g, uint32_t tile, int tid) {
     bool stored;
     if (kAsync) {
-      stored = issue_async(g, c_cur[0], tile);
+      stored = issue_async(g, c_cur, tile);
     } else {
       store(g, tile, tid, d_cur);
       stored = true;
@@ -350,33 +368,28 @@ struct LoaderB {
         dst[i] = swz(tr, tid & 7);
       }
     } else if (MODE == OFFK_LOAD_VEC_ROW) {
-      const int rq = (warp & 3) * 8 + (lane >> 2), kq = (warp >> 2) * 4 + (lane & 3);
+      // MN-major tile: thread = (row-quad lane of pass p, column warp+8i); atoms ordered [k-group][n-atom]
+      const int atoms = (bn + 31) >> 5;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        const int tr = 128 * p + 4 * rq;
+        const int tr = 128 * p + 4 * lane;
         r[p] = __ldg(g.b_row + n0 + (tr < bn ? tr : 0));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[4 * p + j] = swz(tr + j, kq);
+        dst[p] = swz_mn(32 * p + lane, warp, atoms);     // + i * atoms * 1024 for column warp + 8i
       }
+      dst[2] = (uint32_t)atoms << 10;
     }
   }
   __device__ __forceinline__ void fetch_cols(const offk_gemm_t& g, int k0, int tid, int (&c)[4]) const {
     if (MODE == OFFK_LOAD_VEC_K) {
       c[0] = __ldg(g.b_col + k0 + 4 * (tid & 7));
     } else if (MODE == OFFK_LOAD_VEC_ROW) {
-      const int kq = ((tid >> 5) >> 2) * 4 + (tid & 3);
-      const int4 v = __ldg(reinterpret_cast<const int4*>(g.b_col + k0 + 4 * kq));
-      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[i] = __ldg(g.b_col + k0 + (tid >> 5) + 8 * i);
     }
   }
   __device__ __forceinline__ void load(const offk_gemm_t& g, const int (&c)[4], int n0, int k0, int tid, int pass,
                                        float4 (&v)[4]) const {
-    if (MODE == OFFK_LOAD_VEC_ROW) {
-      const int rq = ((tid >> 5) & 3) * 8 + ((tid & 31) >> 2);
-      const bool in = 128 * pass + 4 * rq < bn;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = in ? ldg128(g.b_src + (r[pass] + c[e])) : f4zero();
-    } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
+    if (MODE == OFFK_LOAD_SCALAR_ROW) {
       // thread = row (tid & 127) of this pass, k-half (tid >> 7): 16 scalar gathers
       const int tr = 128 * pass + (tid & 127), half = tid >> 7;
       const int rb = __ldg(g.b_row + n0 + (tr < bn ? tr : 0));
@@ -399,15 +412,7 @@ struct LoaderB {
     }
   }
   __device__ __forceinline__ void store(uint32_t tile, int tid, int pass, const float4 (&v)[4]) const {
-    if (MODE == OFFK_LOAD_VEC_ROW) {
-      const int rq = ((tid >> 5) & 3) * 8 + ((tid & 31) >> 2);
-      if (128 * pass + 4 * rq < bn) {
-        sts128(tile + dst[4 * pass + 0], v[0].x, v[1].x, v[2].x, v[3].x);
-        sts128(tile + dst[4 * pass + 1], v[0].y, v[1].y, v[2].y, v[3].y);
-        sts128(tile + dst[4 * pass + 2], v[0].z, v[1].z, v[2].z, v[3].z);
-        sts128(tile + dst[4 * pass + 3], v[0].w, v[1].w, v[2].w, v[3].w);
-      }
-    } else if (MODE == OFFK_LOAD_SCALAR_ROW) {
+    if (MODE == OFFK_LOAD_SCALAR_ROW) {
       const int tr = 128 * pass + (tid & 127), half = tid >> 7;
       if (tr < bn) {
 #pragma unroll
@@ -424,7 +429,8 @@ struct LoaderB {
       }
     }
   }
-  static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K);
+  static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
+  static constexpr bool kMN = (MODE == OFFK_LOAD_VEC_ROW);
   static constexpr bool kVec = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
   __device__ __forceinline__ void prologue(const offk_gemm_t& g, int n0, int k_first, int tid) {
     if (kVec) fetch_cols(g, k_first, tid, c_cur);
@@ -442,11 +448,18 @@ struct LoaderB {
     }
   }
   __device__ __forceinline__ void post_wait(const offk_gemm_t& g, uint32_t tile, int n0, int k0, int tid) {
-    if (kAsync) {
+    if (MODE == OFFK_LOAD_VEC_K) {
       const int nrow = (bn + 31) >> 5;          // 32 rows per i
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (i < nrow && (tid >> 3) + 32 * i < bn) cp_async16_cg(tile + dst[i], g.b_src + (r[i] + c_cur[0]), 16u);
+    } else if (MODE == OFFK_LOAD_VEC_ROW) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+        if (128 * p + 4 * (tid & 31) < bn) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) cp_async16_cg(tile + dst[p] + i * dst[2], g.b_src + (r[p] + c_cur[i]), 16u);
+        }
     } else {
       store(tile, tid, 0, d_cur);
       if (bn > 128) {   // second pass of a wide tile: not prefetched (only gradient GEMMs wider than 128)
@@ -498,6 +511,10 @@ __device__ __forceinline__ void epi_store4(const offk_gemm_t& g, const EpiRow& r
   *reinterpret_cast<float4*>(o) = v;
 }
 
+#ifdef OFFK_DEBUG_DUMP
+__device__ float* g_offk_dump = nullptr;   // bring-up only: CTA (0,0,0) copies its stage-0 shared memory here
+#endif
+
 // ---------------------------------------------------------------------------- kernel
 template <int A_MODE, int B_MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -505,8 +522,8 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16 KB | B bn*128)] then the barrier block
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)bn * 128u;
-  const uint32_t stage_bytes = TC_A_BYTES + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t b_bytes = ((uint32_t)(bn + 31) >> 5) << 12;      // whole 32-row groups (MN-major atoms are 32 wide)
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
   TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -560,7 +577,9 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
   } else {
     if (lane == 0) {
       // ================= MMA issuer (one thread) =================
-      const uint32_t idesc = make_idesc_tf32(bn);
+      constexpr bool A_MN = LoaderA<A_MODE>::kMN, B_MN = LoaderB<B_MODE>::kMN;
+      const uint32_t idesc = make_idesc_tf32(bn, A_MN, B_MN);
+      const uint32_t b_kgroup = (uint32_t)((bn + 31) >> 5) << 10;     // MN-major B: bytes per 8-k group
       int s = 0;
       uint32_t parity = 0;
       for (int i = 0; i < nkb; ++i) {
@@ -569,12 +588,14 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
         tc_fence_after();
         const uint32_t a_base = smem_base + s * stage_bytes;
         const uint32_t b_base = a_base + TC_A_BYTES;
-        const uint64_t adesc = make_smem_desc(a_base), bdesc = make_smem_desc(b_base);
+        // K-major: advance 8 tf32 = 32 bytes inside the 128-byte swizzle row (+2 in the addr>>4 field);
+        // MN-major: advance two 4-k groups of 512-byte atoms (A: 2 x 4 atoms = 4 KB; B: 2 x ceil(bn/32) atoms)
+        const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, 512u, 2048u) : make_smem_desc(a_base);
+        const uint64_t bdesc = B_MN ? make_smem_desc_mn(b_base, 512u, b_kgroup >> 1) : make_smem_desc(b_base);
+        const uint64_t a_step = A_MN ? (uint64_t)(4096 >> 4) : 2ull, b_step = B_MN ? (uint64_t)(b_kgroup >> 4) : 2ull;
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j) {
-          // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          umma_tf32(tmem_d, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), idesc, (i > 0 || j > 0) ? 1u : 0u);
-        }
+        for (int j = 0; j < TC_BK / 8; ++j)
+          umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
         umma_commit(smem_u32(&sh->empty[s]));          // frees the smem slot when these MMAs retire
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
@@ -614,6 +635,12 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
       }
     }
   }
+#ifdef OFFK_DEBUG_DUMP
+  if (g_offk_dump && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp < 8) {
+    const float* sp = reinterpret_cast<const float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    for (uint32_t i = tid; i < stage_bytes / 4; i += TC_PRODUCERS) g_offk_dump[i] = sp[i];
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 8) {
@@ -655,7 +682,7 @@ int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st) {
   const int num_kb = (g.K + TC_BK - 1) / TC_BK;
   const int split = g.split_k > 1 ? g.split_k : 1;
   const int kb_per = (num_kb + split - 1) / split;
-  const uint32_t stage_bytes = TC_A_BYTES + ((bn * 128 + 1023) & ~1023);
+  const uint32_t stage_bytes = TC_A_BYTES + (((bn + 31) >> 5) << 12);
   const long long ctas = (long long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + bn - 1) / bn) * ((num_kb + kb_per - 1) / kb_per);
   const int budget = ctas <= sm_count() ? 200 * 1024 : 108 * 1024;   // one resident CTA per SM -> deeper pipeline
   int stages = budget / (int)stage_bytes;
@@ -668,7 +695,7 @@ int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st) {
   dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + bn - 1) / bn, (num_kb + kb_per - 1) / kb_per);
   if (grid.y > 65535 || grid.z > 65535) return fail(OFFK_E_LIMIT, "gather_gemm: grid too large");
   // cp.async cannot apply ReLU-on-load: such operands (one small 1x1 conv) take the scalar register path
-  const int a_mode = (g.a_relu && g.a_mode == OFFK_LOAD_VEC_K) ? OFFK_LOAD_SCALAR_ROW : g.a_mode;
+  const int a_mode = (g.a_relu && g.a_mode >= OFFK_LOAD_VEC_K) ? OFFK_LOAD_SCALAR_ROW : g.a_mode;
 #define OFFK_TC_CASE(AM, BM) \
   if (a_mode == AM && g.b_mode == BM) return launch_tc_t<AM, BM>(g, bn, stages, kb_per, tmem_cols, grid, smem, st);
   OFFK_TC_CASE(0, 0) OFFK_TC_CASE(0, 1) OFFK_TC_CASE(0, 2) OFFK_TC_CASE(0, 3)
@@ -680,3 +707,7 @@ int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st) {
 }
 
 }  // namespace offk
+
+#ifdef OFFK_DEBUG_DUMP
+extern "C" int offk_debug_set_dump(float* p) { return (int)cudaMemcpyToSymbol(offk::g_offk_dump, &p, sizeof(p)); }
+#endif

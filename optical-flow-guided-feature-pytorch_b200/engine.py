@@ -61,6 +61,7 @@ class Gemm:
         self.desc = d
         self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out)
         self.flops = 2.0 * spc.M * spc.N * spc.K
+        self.launches = [name]
 
     def __call__(self, stream):
         L.check(self.eng.lib.offk_gather_gemm(C.byref(self.desc), self.eng.prec, stream), self.name)
@@ -219,6 +220,7 @@ class OFFEngine:
             run._split = True
             run.name = name
             run.flops = g.flops
+            run.launches = [name + ".zero", name + ".splitk", name + ".bias_act"]
             return run
         g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
                  addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
@@ -290,12 +292,14 @@ class OFFEngine:
             def k2(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, b3=b3, Fst=Fst, tag=tag):
                 L.check(lib.offk_stencil_diff_fwd(C.byref(sd), g_ptr, d_ptr, _ptr(w3), _ptr(b3), _ptr(Fst), stream),
                         "stencil_fwd_" + tag)
+            k2.launches = ["stencil_fwd_" + tag]
             fwd.append(k2)
 
             def k3(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, dFst=dFst, dg_ptr=dg_ptr, dd_ptr=dd_ptr, fs=fs,
                    dw3=dw3, db3=db3, tag=tag):
                 L.check(lib.offk_stencil_diff_bwd(C.byref(sd), _ptr(dFst), g_ptr, d_ptr, _ptr(w3), dg_ptr, fs, dd_ptr,
                                                   fs, _ptr(dw3), _ptr(db3), stream), "stencil_bwd_" + tag)
+            k3.launches = ["stencil_bwd_" + tag] + (["stencil_tapgrad_" + tag] if self.variant == "rgb" else [])
             bwd_units.append(k3)
             # K4: weight / bias gradient of the fused 1x1 (no dX for the frozen taps unless asked, train_off.py:39-46)
             bwd_units.append(self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
@@ -357,8 +361,8 @@ class OFFEngine:
         fwd.append(self._add_into_slice(bf["s14a"], bf["h3_14b"], bf["F7"], 832, 320, 512, 49))
 
         # ---- heads 28 / 14 (RGB_OFF.py:783-793)
-        fwd.append(lambda stream: L.check(lib.offk_maxpool3s2_fwd(_ptr(bf["F14"]), P, 256, 14, 14, 1056, 800,
-                                                                   _ptr(bf["p28"]), stream), "maxpool28"))
+        fwd.append(_nm(lambda stream: L.check(lib.offk_maxpool3s2_fwd(_ptr(bf["F14"]), P, 256, 14, 14, 1056, 800,
+                                                                       _ptr(bf["p28"]), stream), "maxpool28"), "maxpool28"))
         fwd.append(self._pool_fwd("28", bf["p28"], 256, 256, 0))
         fwd.append(self._fc_fwd("fc_action_motion_28", "28", 256))
         fwd.append(self._pool_fwd("14", bf["F7"], 512, 832, 320))
@@ -374,8 +378,9 @@ class OFFEngine:
         fwd.append(self._fc_fwd("fc_action_motion", "7", 1024))
         if self.consensus:
             for k in ("7", "28", "14"):
-                fwd.append(lambda stream, k=k: L.check(lib.offk_segment_mean_fwd(
-                    _ptr(bf["fc" + k]), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["cfc" + k]), stream), "consensus" + k))
+                fwd.append(_nm(lambda stream, k=k: L.check(lib.offk_segment_mean_fwd(
+                    _ptr(bf["fc" + k]), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["cfc" + k]), stream), "consensus" + k),
+                    "consensus" + k))
 
         # ============ backward of the stages (reverse order); every d_* buffer holds dL/d(pre-activation)
         bs = bwd_stage
@@ -384,8 +389,9 @@ class OFFEngine:
             self.d_out7 = torch.zeros(B, S.NUM_CLASSES, device=self.device)
             self.d_out14 = torch.zeros(B, S.NUM_CLASSES, device=self.device)
             for k, src in (("7", self.d_out7), ("14", self.d_out14)):
-                bs.append(lambda stream, k=k, src=src: L.check(lib.offk_segment_mean_bwd(
-                    _ptr(src), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["d_fc" + k]), stream), "consensus_bwd" + k))
+                bs.append(_nm(lambda stream, k=k, src=src: L.check(lib.offk_segment_mean_bwd(
+                    _ptr(src), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["d_fc" + k]), stream), "consensus_bwd" + k),
+                    "consensus_bwd" + k))
         else:
             self.d_out7, self.d_out14 = bf["d_fc7"], bf["d_fc14"]
         # FC heads (fc28 receives no gradient: never returned, RGB_OFF.py:860)
@@ -416,8 +422,9 @@ class OFFEngine:
         # d sum_14b = (dF7[:,320:] + head-14 pool gradient) * [sum_14b > 0]   (in place in the dF7 slice)
         bs.append(self._pool_bwd("14", bf["dF7"], 512, 832, 320, act=bf["F7"], accumulate=True))
         # ---- 14b:  sum_14b = relu(s14a + relu(conv3_14b(h2b)))
-        bs.append(lambda stream: L.check(lib.offk_gate_copy(_ptr(bf["dF7"]), 832, 320, _ptr(bf["h3_14b"]), 512, 0,
-                                                            _ptr(d("h3_14b")), 512, 0, P, 512, 49, stream), "gate_h3b"))
+        bs.append(_nm(lambda stream: L.check(lib.offk_gate_copy(_ptr(bf["dF7"]), 832, 320, _ptr(bf["h3_14b"]), 512, 0,
+                                                                _ptr(d("h3_14b")), 512, 0, P, 512, 49, stream), "gate_h3b"),
+                      "gate_h3b"))
         back("motion_conv3_trans_14b", bf["h2_14b"], d("h3_14b"), g_14b3)
         dgrad("motion_conv3_trans_14b", d("h3_14b"), d("h2_14b"), g_14b3, gate=bf["h2_14b"])
         back("motion_conv2_trans_14b", bf["h1_14b"], d("h2_14b"), g_14b2)
@@ -471,10 +478,10 @@ class OFFEngine:
         pre, post = [], []
         for name, cout, cin, k, _, _ in S.STAGE_CONVS:
             if k > 1:
-                pre.append(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
-                    _ptr(pr[n + ".weight"]), _ptr(self.wp[n]), co, ci, k, k, 1, stream), "permute " + n))
-                post.append(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
-                    _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n))
+                pre.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
+                    _ptr(pr[n + ".weight"]), _ptr(self.wp[n]), co, ci, k, k, 1, stream), "permute " + n), "permute " + name))
+                post.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
+                    _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n), "unpermute " + name))
         self.fwd_steps = pre + fwd
         # kernels of liboffk launched per pass (split-K forward convs = GEMM + bias/activation pass; the learned
         # stencil's backward = data-gradient kernel + tap-gradient kernel)
@@ -493,8 +500,8 @@ class OFFEngine:
     # ------------------------------------------------------------------ small step factories
     def _add_into_slice(self, a, b, dst, ctot, coff, c, hw):
         P, lib = self.P, self.lib
-        return lambda stream: L.check(lib.offk_add_relu_slice(_ptr(a), _ptr(b), _ptr(dst), ctot, coff, P, c, hw, 1,
-                                                               stream), "sum_14b")
+        return _nm(lambda stream: L.check(lib.offk_add_relu_slice(_ptr(a), _ptr(b), _ptr(dst), ctot, coff, P, c, hw, 1,
+                                                                   stream), "sum_14b"), "sum_14b")
 
     def _site_seed(self, site):
         return (self.drop_seed * 64 + site) & 0xFFFFFFFFFFFFFFFF
@@ -508,7 +515,7 @@ class OFFEngine:
             L.check(lib.offk_avgpool_drop_fwd(_ptr(x), P, c, 49, ctot, coff, self.drop_mode, _ptr(m),
                                               self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
                                               _ptr(self.buf["pool" + k]), stream), "pool" + k)
-        return run
+        return _nm(run, "pool_fwd" + k)
 
     def _pool_bwd(self, k, dx, c, ctot, coff, act, accumulate):
         lib, P = self.lib, self.P
@@ -519,7 +526,7 @@ class OFFEngine:
             L.check(lib.offk_avgpool_drop_bwd(_ptr(self.buf["d_pool" + k]), P, c, 49, ctot, coff, self.drop_mode,
                                               _ptr(m), self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
                                               _ptr(act), int(accumulate), _ptr(dx), stream), "pool_bwd" + k)
-        return run
+        return _nm(run, "pool_bwd" + k)
 
     def _fc_fwd(self, name, k, c):
         g = T.ConvGeom(self.P, c, 1, 1, S.NUM_CLASSES)
@@ -556,6 +563,13 @@ class OFFEngine:
         pre = "cfc" if self.consensus else "fc"
         return self.buf[pre + "7"], self.buf[pre + "28"], self.buf[pre + "14"]
 
+    def launch_names(self):
+        """One name per device launch of forward() + backward(), in issue order (for annotating ncu launch lists)."""
+        out = [n for st in self.fwd_steps for n in _names(st)]
+        out += ["zero grads_flat", "zero dwp_flat"]          # (the d_out copies are cudaMemcpyAsync, not kernels)
+        out += [n for st in self.bwd_steps for n in _names(st)]
+        return out
+
     def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None):
         """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads).
         ``after_stage()`` is called once the stage/head gradients (flat range ``stage_range``) are final and
@@ -573,6 +587,18 @@ class OFFEngine:
         for step in self.bwd_unit_steps:
             step(stream)
         return self.grads
+
+
+def _nm(fn, name):
+    fn.launches = [name]
+    return fn
+
+
+def _names(step):
+    ls = getattr(step, "launches", None)
+    if ls is not None:
+        return list(ls)
+    return [getattr(step, "name", None) or getattr(step, "__name__", "step")]
 
 
 def _gkey(g: T.ConvGeom):
