@@ -164,18 +164,17 @@ def run_ours(args):
     taps_host = {k: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for k, t in taps_dev.items()}
     loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
 
-    def step(e2e=False):
-        if e2e:
-            for k, t in taps_dev.items():
-                t.copy_(taps_host[k], non_blocking=True)
-        fc7, _, fc14 = net(taps_dev)
+    def step(inputs=None):
+        """One forward+backward.  inputs = None: taps already resident in HBM (device-timed `value`);
+        inputs = a prefetch handle: the end-to-end path (taps staged from pinned host memory, loss read back)."""
+        fc7, _, fc14 = net(taps_dev if inputs is None else inputs)
         loss = F.cross_entropy(fc7, target) + F.cross_entropy(fc14, target)
         # backward through the module's autograd.Function; the OFF-parameter gradients land in the flat buffer
         g7, g14 = torch.autograd.grad(loss, [fc7, fc14])
         dp.backward(g7, g14)
-        if e2e:
+        if inputs is not None:
             loss_host.copy_(loss.detach(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream().synchronize()       # the user reads the loss every step
         return loss
 
     def barrier():
@@ -187,8 +186,17 @@ def run_ours(args):
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        for _ in range(n):
-            step(e2e)
+        if e2e:
+            # public API: net.prefetch(host taps) starts the H2D copy of step i+1 into the idle input set while
+            # step i computes; every step's 650 MB copy and 4-byte loss read-back are inside the timed region
+            h = net.prefetch(taps_host)
+            for i in range(n):
+                h_next = net.prefetch(taps_host) if i + 1 < n else None
+                step(h)
+                h = h_next
+        else:
+            for _ in range(n):
+                step()
         t1.record()
         barrier()
         ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
@@ -197,14 +205,13 @@ def run_ours(args):
         return ms.item()
 
     for _ in range(max(3, args.warmup)):
-        step(False)
+        step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(args.steps, False)
     sampler.stop_flag = True
-    for _ in range(2):
-        step(True)
+    timed(2, True)                                            # warm the staged path
     ms_e2e = timed(max(3, args.steps // 2), True) / max(3, args.steps // 2) * args.steps
 
     clips_total = B * world * args.steps
@@ -218,7 +225,7 @@ def run_ours(args):
         import ctypes as C
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        stencil_steps = [st for st in eng.fwd_steps if getattr(st, "__name__", "") == "k2"]
+        stencil_steps = list(eng.stencil_fwd_steps.values())
         tot_ms, tot_bytes, per_level = 0.0, 0.0, {}
         for (tag, (cin, s)), st in zip(S.LEVELS.items(), stencil_steps):
             nbytes = 4.0 * s * s * (S.GEN_C * eng.N + S.DOWN_C * eng.P + S.UNIT_C * eng.P)   # read G, read D, write M
@@ -258,7 +265,8 @@ def run_ours(args):
                        "l2": f"inputs larger than L2: {tap_bytes / 1e6:.0f} MB of taps per step vs 126 MB L2",
                        "parallelism": f"dp{world} (clip-sharded, NCCL all-reduce of {eng.n_flat} fp32 gradients)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tap_bytes, "d2h_bytes_per_step": 4,
-                    "note": "taps copied from pinned host memory every step, loss read back every step"},
+                    "note": "taps copied from pinned host memory every step (copy of step i+1 overlaps compute of step i: "
+                            "two input sets), loss read back every step"},
             "gpu_launches": (eng.launches_fwd + eng.launches_bwd) * args.steps,
             "clocks": sampler.summary(),
             "roofline": roof,

@@ -206,6 +206,9 @@ int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, int x_ctot, 
 /* ConsensusModule('avg', dim=1): out[b,:] = mean_t x[b,t,:]  (basic_ops.py:21-22) and its backward (:30-31) */
 int offk_segment_mean_fwd(const float* x, int B, int T, int C, float* out, void* stream);
 int offk_segment_mean_bwd(const float* dout, int B, int T, int C, float* dx, void* stream);
+/* p[0..n) = 0 on `stream` (cudaMemsetAsync): zero-initialises split-K / atomic accumulation targets, e.g. the
+ * gradient buffers before autograd of train_off.py:136-146 accumulates into them */
+int offk_fill_zero(float* p, long long n, void* stream);
 /* out = act > 0 ? grad : 0  (ReLU' as a stand-alone pass; n elements) */
 int offk_relu_gate(const float* grad, const float* act, long long n, float* out, void* stream);
 /* dst[p, dst_coff+c, :] = act[p, act_coff+c, :] > 0 ? src[p, src_coff+c, :] : 0  between channel slices of

@@ -71,6 +71,7 @@ _PROTOS = {
     "offk_maxpool3s2_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "offk_segment_mean_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "offk_segment_mean_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "offk_fill_zero": (C.c_int, [_P, C.c_longlong, _P]),
     "offk_relu_gate": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
     "offk_gate_copy": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, _P]),

@@ -684,7 +684,8 @@ int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st) {
   const int kb_per = (num_kb + split - 1) / split;
   const uint32_t stage_bytes = TC_A_BYTES + (((bn + 31) >> 5) << 12);
   const long long ctas = (long long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + bn - 1) / bn) * ((num_kb + kb_per - 1) / kb_per);
-  const int budget = ctas <= sm_count() ? 200 * 1024 : 108 * 1024;   // one resident CTA per SM -> deeper pipeline
+  (void)ctas;
+  const int budget = 108 * 1024;   // two CTAs per SM: tiles of the same or of a concurrent kernel (another lane) co-reside
   int stages = budget / (int)stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

@@ -125,18 +125,33 @@ __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__
 
 // weight layouts: canonical OIHW [cout, cin, R, Q] (the reference's state_dict) <-> OHWI [cout, R, Q, cin] (k order of
 // the channels-last implicit GEMM).  to_ohwi != 0: dst(OHWI) = src(OIHW); else dst(OIHW) = src(OHWI).
-__global__ void permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int rq,
-                                      int to_ohwi) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into the OHWI tensor
-  const size_t total = (size_t)cout * cin * rq;
-  if (i >= total) return;
-  const int ci = (int)(i % cin);
-  const int t = (int)((i / cin) % rq);
-  const size_t o = i / ((size_t)cin * rq);
-  const size_t j = (o * cin + ci) * rq + t;                         // index into the OIHW tensor
-  if (to_ohwi == 1) dst[i] = __ldg(src + j);
-  else if (to_ohwi == 0) dst[j] = __ldg(src + i);
-  else dst[j] += __ldg(src + i);   // 2: accumulate into the OIHW gradient
+// One block = one output channel x 32 input channels x all taps, staged through shared memory so that both the OIHW
+// side (32*rq contiguous floats) and the OHWI side (32 contiguous channels per tap) are accessed coalesced.
+__global__ void __launch_bounds__(256)
+permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int rq, int to_ohwi) {
+  extern __shared__ float tile[];                       // [32][rq] in OIHW order (rq is odd on this path: no conflicts)
+  const int o = blockIdx.y, c0 = blockIdx.x * 32;
+  const int n = min(32, cin - c0), cnt = n * rq;
+  const size_t oihw = ((size_t)o * cin + c0) * rq;      // start of the contiguous OIHW chunk
+  const size_t ohwi = (size_t)o * rq * cin + c0;        // element (tap t, channel ci) at ohwi + t*cin + ci
+  if (to_ohwi == 1) {
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) tile[i] = __ldg(src + oihw + i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int t = i / n, ci = i - t * n;
+      dst[ohwi + (size_t)t * cin + ci] = tile[ci * rq + t];
+    }
+  } else {
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int t = i / n, ci = i - t * n;
+      tile[ci * rq + t] = __ldg(src + ohwi + (size_t)t * cin + ci);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      if (to_ohwi == 0) dst[oihw + i] = tile[i];
+      else dst[oihw + i] += tile[i];                    // 2: accumulate into the OIHW gradient
+    }
+  }
 }
 
 static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -221,10 +236,18 @@ extern "C" int offk_add_relu_slice(const float* a, const float* b, float* dst, i
   return OFFK_LAUNCH_CHECK("add_relu_slice");
 }
 
+extern "C" int offk_fill_zero(float* p, long long n, void* stream) {
+  OFFK_REQUIRE(p != nullptr && n >= 0, "fill_zero: bad args");
+  if (n == 0) return 0;
+  return cuda_check(cudaMemsetAsync(p, 0, (size_t)n * sizeof(float), as_stream(stream)), "fill_zero");
+}
+
 extern "C" int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi,
                                    void* stream) {
   OFFK_REQUIRE(src && dst && cout > 0 && cin > 0 && kh > 0 && kw > 0, "permute_weight: bad args");
-  permute_weight_kernel<<<blocks_for((size_t)cout * cin * kh * kw, 256), 256, 0, as_stream(stream)>>>(
-      src, dst, cout, cin, kh * kw, to_ohwi);
+  OFFK_REQUIRE(kh * kw <= 256 && cout <= 65535, "permute_weight: filter too large");
+  dim3 grid((cin + 31) / 32, cout);
+  permute_weight_kernel<<<grid, 256, (size_t)32 * kh * kw * sizeof(float), as_stream(stream)>>>(src, dst, cout, cin,
+                                                                                                 kh * kw, to_ohwi);
   return OFFK_LAUNCH_CHECK("permute_weight");
 }

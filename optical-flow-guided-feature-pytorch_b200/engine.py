@@ -55,6 +55,8 @@ class Gemm:
         d.add_col = add_tabs[1].data_ptr() if add_tabs else None
         d.relu_post, d.atomic_out = int(relu_post), int(atomic)
         d.ones_row_out = ones_out.data_ptr() if ones_out is not None else None
+        if tile_n == 0 and split_k == 1:
+            tile_n = _auto_tile_n(spc.M, spc.N)
         d.split_k, d.tile_n = split_k, tile_n
         d.out_vec = spc.out_vec if (gate_tabs is None or True) else 0
         T.check_modes(spc)
@@ -62,6 +64,9 @@ class Gemm:
         self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out)
         self.flops = 2.0 * spc.M * spc.N * spc.K
         self.launches = [name]
+        self.reads = [a_src, b_src, addend, gate, bias]
+        self.writes = [out, ones_out]
+        self.lane = 0
 
     def __call__(self, stream):
         L.check(self.eng.lib.offk_gather_gemm(C.byref(self.desc), self.eng.prec, stream), self.name)
@@ -87,6 +92,7 @@ class OFFEngine:
         self.index_mode = {"reference_flat": L.INDEX_REFERENCE_FLAT, "aligned": L.INDEX_ALIGNED}[index_mode]
         self.consensus = (variant != "rgb") if consensus is None else bool(consensus)
         self.tap_grads = tap_grads
+        self.single_stream = False       # True: issue every lane on the caller's stream (profiling / debugging)
         self._tab_cache = {}
         self._keep = []
 
@@ -147,6 +153,7 @@ class OFFEngine:
             self._buf("dF" + st, P, s, s, ctot)
         a = lambda n, c, s: (self._buf(n, P, s, s, c), self._buf("d_" + n, P, s, s, c))
         a("t28", 64, 14)
+        self._buf("t28r", P, 14, 14, 64)          # relu(t28): conv1_trans_28a consumes the activated copy (RGB_OFF.py:658-659)
         a("tmp28", 64, 14)
         for blk in "abc":
             a("h1_28" + blk, 64, 14)
@@ -176,7 +183,14 @@ class OFFEngine:
             self._buf("d_fc" + k, P, S.NUM_CLASSES)
             if self.consensus:
                 self._buf("cfc" + k, self.B, S.NUM_CLASSES)
-        self.taps = OrderedDict((tag, torch.zeros(N, cin, s, s, device=self.device)) for tag, (cin, s) in S.LEVELS.items())
+        # two input sets: while one is being consumed (forward AND backward read the taps) the other can be filled by
+        # an asynchronous host->device copy (stage_taps)
+        self.tap_sets = [OrderedDict((tag, torch.zeros(N, cin, s, s, device=self.device)) for tag, (cin, s) in S.LEVELS.items())
+                         for _ in range(2)]
+        self.taps = self.tap_sets[0]
+        self._tap_set = 0
+        self._tap_users = {tag: [] for tag in S.LEVELS}      # bound GEMMs whose A operand is the tap
+        self._copy_stream = None
         if self.tap_grads:
             self.tap_grad = OrderedDict((tag, torch.zeros_like(t)) for tag, t in self.taps.items())
         # OHWI copies of the KxK conv weights (k order of the channels-last implicit GEMM) and of their gradients
@@ -211,7 +225,7 @@ class OFFEngine:
             hw = geom.hout * geom.wout
 
             def run(stream, g=g, y=y, b=b, geom=geom, hw=hw, cols=cols):
-                y.zero_()
+                L.check(self.lib.offk_fill_zero(_ptr(y), y.numel(), stream), name + ".zero")
                 g(stream)
                 L.check(self.lib.offk_bias_act(_ptr(y), _ptr(b), geom.n_img, geom.cout, hw, geom.y_ctot, geom.y_coff,
                                                cols, stream), name + ".bias_act")
@@ -221,6 +235,8 @@ class OFFEngine:
             run.name = name
             run.flops = g.flops
             run.launches = [name + ".zero", name + ".splitk", name + ".bias_act"]
+            run.gemm = g
+            run.reads, run.writes, run.lane = g.reads, g.writes, 0
             return run
         g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
                  addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
@@ -228,6 +244,9 @@ class OFFEngine:
         return g
 
     def _conv_wgrad(self, name, x, dy, geom, dw, db, *, a_relu=False, x_layout="nhwc"):
+        # dW is accumulated in the k order of the implicit GEMM (OHWI: consecutive accumulator rows = consecutive
+        # addresses, so the split-K reductions coalesce) and un-permuted once at the end; writing OIHW directly
+        # (dw_layout="oihw") was measured slower: the strided atomics cost more than the permute pass
         spc = T.conv_wgrad_spec(geom, x_layout, "nhwc")
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
@@ -262,15 +281,20 @@ class OFFEngine:
 
         # ============ OFF units (RGB_OFF.py:596-616 and the eight copies)
         self._stencils = {}
+        fwd_lane = {"3a": 0, "3b": 0, "3c": 1, "4a": 1, "4b": 1, "4c": 1, "4d": 1, "5a": 2, "5b": 2}
+        self.stencil_fwd_steps = OrderedDict()
         for li, (tag, (cin, s)) in enumerate(S.LEVELS.items()):
             st = S.LEVEL_STAGE[tag]
+            fl, bl = fwd_lane[tag], li % 3
             ctot, _, members = S.STAGES[st]
             coff = dict(members)[tag]
             geom = T.ConvGeom(N, cin, s, s, S.UNIT_C)
             gd, dgd = bf["gd_" + tag], bf["dgd_" + tag]
             # K1: gen (ReLU) and down (linear) 1x1 convs as ONE GEMM with 160 output channels
-            fwd.append(self._conv_fwd("unit_" + tag, self.taps[tag], gd, geom, self._unit_w(self.params_flat, tag),
-                                      self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nchw"))
+            k1 = self._conv_fwd("unit_" + tag, self.taps[tag], gd, geom, self._unit_w(self.params_flat, tag),
+                                self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nchw")
+            fwd.append(_on(k1, fl))
+            self._tap_users[tag].append(getattr(k1, "gemm", k1))
             # K2: fused spatial stencil + temporal difference + dropout + cat, into the stage buffer
             sd = L.OffkStencil()
             sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, S.GEN_C, S.DOWN_C, 1, s, s
@@ -292,22 +316,24 @@ class OFFEngine:
             def k2(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, b3=b3, Fst=Fst, tag=tag):
                 L.check(lib.offk_stencil_diff_fwd(C.byref(sd), g_ptr, d_ptr, _ptr(w3), _ptr(b3), _ptr(Fst), stream),
                         "stencil_fwd_" + tag)
-            k2.launches = ["stencil_fwd_" + tag]
-            fwd.append(k2)
+            fwd.append(_nm(k2, "stencil_fwd_" + tag, reads=[gd], writes=[Fst], lane=fl))
+            self.stencil_fwd_steps[tag] = k2
 
             def k3(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, dFst=dFst, dg_ptr=dg_ptr, dd_ptr=dd_ptr, fs=fs,
                    dw3=dw3, db3=db3, tag=tag):
                 L.check(lib.offk_stencil_diff_bwd(C.byref(sd), _ptr(dFst), g_ptr, d_ptr, _ptr(w3), dg_ptr, fs, dd_ptr,
                                                   fs, _ptr(dw3), _ptr(db3), stream), "stencil_bwd_" + tag)
+            _nm(k3, "stencil_bwd_" + tag, reads=[dFst, gd], writes=[dgd, dw3, db3], lane=bl)
             k3.launches = ["stencil_bwd_" + tag] + (["stencil_tapgrad_" + tag] if self.variant == "rgb" else [])
             bwd_units.append(k3)
             # K4: weight / bias gradient of the fused 1x1 (no dX for the frozen taps unless asked, train_off.py:39-46)
-            bwd_units.append(self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
-                                              self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag),
-                                              x_layout="nchw"))
+            k4 = self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
+                                  self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag), x_layout="nchw")
+            bwd_units.append(_on(k4, bl))
+            self._tap_users[tag].append(k4)
             if self.tap_grads:
-                bwd_units += self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
-                                              self.tap_grad[tag], geom, x_layout="nchw")
+                bwd_units += [_on(g, bl) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
+                                                                   self.tap_grad[tag], geom, x_layout="nchw")]
 
         # ============ stage convs
         def geom_of(name, n_img, s_in, x_ctot=0, x_coff=0, y_ctot=0, y_coff=0):
@@ -320,18 +346,22 @@ class OFFEngine:
         def dB(n): return gr[n + ".bias"]
 
         def layer(name, x, y, s_in, *, relu=False, a_relu=False, addend=None, relu_post=False,
-                  x_ctot=0, x_coff=0, y_ctot=0, y_coff=0, dy=None, dy_geom=None):
-            """forward conv + its weight gradient; returns geom for the data-gradient wiring."""
+                  x_ctot=0, x_coff=0, y_ctot=0, y_coff=0, lane=0):
+            """forward conv; returns geom for the gradient wiring."""
             geom = geom_of(name, P, s_in, x_ctot, x_coff, y_ctot, y_coff)
-            fwd.append(self._conv_fwd(name, x, y, geom, W(name), Bv(name), relu=relu, a_relu=a_relu, addend=addend,
-                                      relu_post=relu_post))
+            fwd.append(_on(self._conv_fwd(name, x, y, geom, W(name), Bv(name), relu=relu, a_relu=a_relu, addend=addend,
+                                          relu_post=relu_post), lane))
             return geom
 
         # ---- resolution 28 (RGB_OFF.py:655-685)
         g_t28 = layer("motion_conv_trans_28", bf["F28"], bf["t28"], 28)                       # pre-ReLU kept (:665)
-        g_c1a = layer("motion_conv1_trans_28a", bf["t28"], bf["h1_28a"], 14, relu=True, a_relu=True)
+        n28 = bf["t28"].numel()
+        fwd.append(_nm(lambda stream: L.check(lib.offk_relu_gate(_ptr(bf["t28"]), _ptr(bf["t28"]), n28, _ptr(bf["t28r"]),
+                                                                  stream), "relu_t28"), "relu_t28",
+                       reads=[bf["t28"]], writes=[bf["t28r"]]))
+        g_c1a = layer("motion_conv1_trans_28a", bf["t28r"], bf["h1_28a"], 14, relu=True)
         g_c2a = layer("motion_conv2_trans_28a", bf["h1_28a"], bf["h2_28a"], 14, relu=True)
-        g_bra = layer("motion_conv_branch_28a", bf["t28"], bf["br28"], 14)
+        g_bra = layer("motion_conv_branch_28a", bf["t28"], bf["br28"], 14, lane=2)
         g_c3a = layer("motion_conv3_trans_28a", bf["h2_28a"], bf["s28a"], 14, addend=bf["br28"], relu_post=True)
         g_c1b = layer("motion_conv1_trans_28b", bf["s28a"], bf["h1_28b"], 14, relu=True)
         g_c2b = layer("motion_conv2_trans_28b", bf["h1_28b"], bf["h2_28b"], 14, relu=True)
@@ -351,7 +381,7 @@ class OFFEngine:
         g_t14 = layer("motion_conv_trans_14", bf["F14"], bf["t14"], 14, relu=True)
         g_14a1 = layer("motion_conv1_trans_14a", bf["t14"], bf["h1_14a"], 7, relu=True)
         g_14a2 = layer("motion_conv2_trans_14a", bf["h1_14a"], bf["h2_14a"], 7, relu=True)
-        g_14ex = layer("motion_conv_expand_trans_14a", bf["t14"], bf["ex14"], 7)
+        g_14ex = layer("motion_conv_expand_trans_14a", bf["t14"], bf["ex14"], 7, lane=2)
         g_14a3 = layer("motion_conv3_trans_14a", bf["h2_14a"], bf["s14a"], 7, addend=bf["ex14"], relu_post=True)
         g_14b1 = layer("motion_conv1_trans_14b", bf["s14a"], bf["h1_14b"], 7, relu=True)
         g_14b2 = layer("motion_conv2_trans_14b", bf["h1_14b"], bf["h2_14b"], 7, relu=True)
@@ -362,17 +392,18 @@ class OFFEngine:
 
         # ---- heads 28 / 14 (RGB_OFF.py:783-793)
         fwd.append(_nm(lambda stream: L.check(lib.offk_maxpool3s2_fwd(_ptr(bf["F14"]), P, 256, 14, 14, 1056, 800,
-                                                                       _ptr(bf["p28"]), stream), "maxpool28"), "maxpool28"))
-        fwd.append(self._pool_fwd("28", bf["p28"], 256, 256, 0))
-        fwd.append(self._fc_fwd("fc_action_motion_28", "28", 256))
-        fwd.append(self._pool_fwd("14", bf["F7"], 512, 832, 320))
-        fwd.append(self._fc_fwd("fc_action_motion_14", "14", 512))
+                                                                       _ptr(bf["p28"]), stream), "maxpool28"), "maxpool28",
+                       reads=[bf["F14"]], writes=[bf["p28"]], lane=1))
+        fwd.append(_on(self._pool_fwd("28", bf["p28"], 256, 256, 0), 1))
+        fwd.append(_on(self._fc_fwd("fc_action_motion_28", "28", 256), 1))
+        fwd.append(_on(self._pool_fwd("14", bf["F7"], 512, 832, 320), 1))
+        fwd.append(_on(self._fc_fwd("fc_action_motion_14", "14", 512), 1))
 
         # ---- resolution 7 (RGB_OFF.py:831-847)
         g_t7 = layer("motion_conv_trans", bf["F7"], bf["t7"], 7, relu=True)
         g_71 = layer("motion_conv1_trans", bf["t7"], bf["h1_7"], 7, relu=True)
         g_72 = layer("motion_conv2_trans", bf["h1_7"], bf["h2_7"], 7, relu=True)
-        g_7br = layer("motion_conv_branch_trans", bf["t7"], bf["br7"], 7)
+        g_7br = layer("motion_conv_branch_trans", bf["t7"], bf["br7"], 7, lane=2)
         g_73 = layer("motion_conv3_trans", bf["h2_7"], bf["s7"], 7, addend=bf["br7"])        # no final ReLU (:841)
         fwd.append(self._pool_fwd("7", bf["s7"], 1024, 1024, 0))
         fwd.append(self._fc_fwd("fc_action_motion", "7", 1024))
@@ -380,7 +411,7 @@ class OFFEngine:
             for k in ("7", "28", "14"):
                 fwd.append(_nm(lambda stream, k=k: L.check(lib.offk_segment_mean_fwd(
                     _ptr(bf["fc" + k]), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["cfc" + k]), stream), "consensus" + k),
-                    "consensus" + k))
+                    "consensus" + k, reads=[bf["fc" + k]], writes=[bf["cfc" + k]]))
 
         # ============ backward of the stages (reverse order); every d_* buffer holds dL/d(pre-activation)
         bs = bwd_stage
@@ -391,28 +422,28 @@ class OFFEngine:
             for k, src in (("7", self.d_out7), ("14", self.d_out14)):
                 bs.append(_nm(lambda stream, k=k, src=src: L.check(lib.offk_segment_mean_bwd(
                     _ptr(src), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["d_fc" + k]), stream), "consensus_bwd" + k),
-                    "consensus_bwd" + k))
+                    "consensus_bwd" + k, reads=[src], writes=[bf["d_fc" + k]]))
         else:
             self.d_out7, self.d_out14 = bf["d_fc7"], bf["d_fc14"]
         # FC heads (fc28 receives no gradient: never returned, RGB_OFF.py:860)
         for fcname, k, c in (("fc_action_motion", "7", 1024), ("fc_action_motion_14", "14", 512)):
             gfc = T.ConvGeom(P, c, 1, 1, S.NUM_CLASSES)
-            bs.append(self._conv_wgrad(fcname, bf["pool" + k], bf["d_fc" + k], gfc, dW(fcname), dB(fcname)))
+            bs.append(_on(self._conv_wgrad(fcname, bf["pool" + k], bf["d_fc" + k], gfc, dW(fcname), dB(fcname)), 1))
             bs += self._conv_dgrad(fcname, bf["d_fc" + k], W(fcname), bf["d_pool" + k], gfc)
         # ds7 = avgpool'(dropout'(d_pool7))
         bs.append(self._pool_bwd("7", d("s7"), 1024, 1024, 0, act=None, accumulate=False))
 
         def back(name, x, dy, geom, *, a_relu=False):
-            bs.append(self._conv_wgrad(name, x, dy, geom, dW(name), dB(name), a_relu=a_relu))
+            bs.append(_on(self._conv_wgrad(name, x, dy, geom, dW(name), dB(name), a_relu=a_relu), 1))   # wgrad lane
 
-        def dgrad(name, dy, dx, geom, **kw):
-            bs.extend(self._conv_dgrad(name, dy, W(name), dx, geom, **kw))
+        def dgrad(name, dy, dx, geom, lane=0, **kw):
+            bs.extend(_on(g, lane) for g in self._conv_dgrad(name, dy, W(name), dx, geom, **kw))
 
         # ---- 7
         back("motion_conv3_trans", bf["h2_7"], d("s7"), g_73)
         dgrad("motion_conv3_trans", d("s7"), d("h2_7"), g_73, gate=bf["h2_7"])
         back("motion_conv_branch_trans", bf["t7"], d("s7"), g_7br)
-        dgrad("motion_conv_branch_trans", d("s7"), d("tmp7"), g_7br)
+        dgrad("motion_conv_branch_trans", d("s7"), d("tmp7"), g_7br, lane=2)
         back("motion_conv2_trans", bf["h1_7"], d("h2_7"), g_72)
         dgrad("motion_conv2_trans", d("h2_7"), d("h1_7"), g_72, gate=bf["h1_7"])
         back("motion_conv1_trans", bf["t7"], d("h1_7"), g_71)
@@ -424,7 +455,7 @@ class OFFEngine:
         # ---- 14b:  sum_14b = relu(s14a + relu(conv3_14b(h2b)))
         bs.append(_nm(lambda stream: L.check(lib.offk_gate_copy(_ptr(bf["dF7"]), 832, 320, _ptr(bf["h3_14b"]), 512, 0,
                                                                 _ptr(d("h3_14b")), 512, 0, P, 512, 49, stream), "gate_h3b"),
-                      "gate_h3b"))
+                      "gate_h3b", reads=[bf["dF7"], bf["h3_14b"]], writes=[d("h3_14b")]))
         back("motion_conv3_trans_14b", bf["h2_14b"], d("h3_14b"), g_14b3)
         dgrad("motion_conv3_trans_14b", d("h3_14b"), d("h2_14b"), g_14b3, gate=bf["h2_14b"])
         back("motion_conv2_trans_14b", bf["h1_14b"], d("h2_14b"), g_14b2)
@@ -437,7 +468,7 @@ class OFFEngine:
         back("motion_conv3_trans_14a", bf["h2_14a"], d("s14a"), g_14a3)
         dgrad("motion_conv3_trans_14a", d("s14a"), d("h2_14a"), g_14a3, gate=bf["h2_14a"])
         back("motion_conv_expand_trans_14a", bf["t14"], d("s14a"), g_14ex)
-        dgrad("motion_conv_expand_trans_14a", d("s14a"), d("tmp14"), g_14ex)
+        dgrad("motion_conv_expand_trans_14a", d("s14a"), d("tmp14"), g_14ex, lane=2)
         back("motion_conv2_trans_14a", bf["h1_14a"], d("h2_14a"), g_14a2)
         dgrad("motion_conv2_trans_14a", d("h2_14a"), d("h1_14a"), g_14a2, gate=bf["h1_14a"])
         back("motion_conv1_trans_14a", bf["t14"], d("h1_14a"), g_14a1)
@@ -465,10 +496,10 @@ class OFFEngine:
         back("motion_conv3_trans_28a", bf["h2_28a"], d("s28a"), g_c3a)
         dgrad("motion_conv3_trans_28a", d("s28a"), d("h2_28a"), g_c3a, gate=bf["h2_28a"])
         back("motion_conv_branch_28a", bf["t28"], d("s28a"), g_bra)
-        dgrad("motion_conv_branch_28a", d("s28a"), d("tmp28"), g_bra)
+        dgrad("motion_conv_branch_28a", d("s28a"), d("tmp28"), g_bra, lane=2)
         back("motion_conv2_trans_28a", bf["h1_28a"], d("h2_28a"), g_c2a)
         dgrad("motion_conv2_trans_28a", d("h2_28a"), d("h1_28a"), g_c2a, gate=bf["h1_28a"])
-        back("motion_conv1_trans_28a", bf["t28"], d("h1_28a"), g_c1a, a_relu=True)
+        back("motion_conv1_trans_28a", bf["t28r"], d("h1_28a"), g_c1a)
         dgrad("motion_conv1_trans_28a", d("h1_28a"), d("t28"), g_c1a, gate=bf["t28"], gate_first=True,
               addend=d("tmp28"))
         back("motion_conv_trans_28", bf["F28"], d("t28"), g_t28)
@@ -479,19 +510,36 @@ class OFFEngine:
         for name, cout, cin, k, _, _ in S.STAGE_CONVS:
             if k > 1:
                 pre.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
-                    _ptr(pr[n + ".weight"]), _ptr(self.wp[n]), co, ci, k, k, 1, stream), "permute " + n), "permute " + name))
+                    _ptr(pr[n + ".weight"]), _ptr(self.wp[n]), co, ci, k, k, 1, stream), "permute " + n), "permute " + name,
+                    writes=[self.wp[name]]))
                 post.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
-                    _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n), "unpermute " + name))
+                    _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n), "unpermute " + name,
+                    reads=[self.dwp[name]], writes=[gr[name + ".weight"]], lane=1))
         self.fwd_steps = pre + fwd
         # kernels of liboffk launched per pass (split-K forward convs = GEMM + bias/activation pass; the learned
         # stencil's backward = data-gradient kernel + tap-gradient kernel)
         count = lambda steps: sum(2 if getattr(st, "_split", False) else 1 for st in steps)
         self.launches_fwd = count(self.fwd_steps)
         self.launches_bwd = count(bwd_stage + post + bwd_units) + (len(S.LEVELS) if self.variant == "rgb" else 0)
+        # gradient accumulators start from zero (split-K / atomic accumulation); grads_flat only when asked
+        self._zero_grads = True
+        gflat, dwflat = self.grads_flat, self.dwp_flat
+        zero = [_nm(lambda stream: self._zero_grads and L.check(lib.offk_fill_zero(_ptr(gflat), gflat.numel(), stream),
+                                                                 "zero grads"), "zero grads_flat", writes=[gflat]),
+                _nm(lambda stream: L.check(lib.offk_fill_zero(_ptr(dwflat), dwflat.numel(), stream), "zero dwp"),
+                    "zero dwp_flat", writes=[dwflat], lane=1)]
         # the stage / head gradients are complete before the units run: their bucket can be all-reduced meanwhile
-        self.bwd_stage_steps = bwd_stage + post
+        self.bwd_stage_steps = zero + bwd_stage + post
         self.bwd_unit_steps = bwd_units
         self.bwd_steps = self.bwd_stage_steps + self.bwd_unit_steps
+        # parameters and taps are read-only inside a pass: never a hazard
+        ro = [self.params_flat] + [t for ts in self.tap_sets for t in ts.values()]
+        if self.variant == "flow":
+            ro.append(self.sobel_w)
+        self.fwd_sched = Schedule(self.fwd_steps, ignore=ro)
+        self.bwd_sched = Schedule(self.bwd_steps, ignore=ro)
+        self._lanes = max(self.fwd_sched.n_lanes, self.bwd_sched.n_lanes)
+        self._side = None
         unit_end = max(self.layout[f"motion_{k}_{t}.bias"][0] + (S.GEN_C if k == "conv_gen" else S.DOWN_C)
                        for t in S.LEVELS for k in (("conv_gen", "spatial_down") + (("spatial_grad",) if self.variant == "rgb" else ())))
         self.unit_range = (0, (unit_end + 3) // 4 * 4)          # flat offsets of the nine units' parameters
@@ -501,7 +549,7 @@ class OFFEngine:
     def _add_into_slice(self, a, b, dst, ctot, coff, c, hw):
         P, lib = self.P, self.lib
         return _nm(lambda stream: L.check(lib.offk_add_relu_slice(_ptr(a), _ptr(b), _ptr(dst), ctot, coff, P, c, hw, 1,
-                                                                   stream), "sum_14b"), "sum_14b")
+                                                                   stream), "sum_14b"), "sum_14b", reads=[a, b], writes=[dst])
 
     def _site_seed(self, site):
         return (self.drop_seed * 64 + site) & 0xFFFFFFFFFFFFFFFF
@@ -515,7 +563,7 @@ class OFFEngine:
             L.check(lib.offk_avgpool_drop_fwd(_ptr(x), P, c, 49, ctot, coff, self.drop_mode, _ptr(m),
                                               self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
                                               _ptr(self.buf["pool" + k]), stream), "pool" + k)
-        return _nm(run, "pool_fwd" + k)
+        return _nm(run, "pool_fwd" + k, reads=[x], writes=[self.buf["pool" + k]])
 
     def _pool_bwd(self, k, dx, c, ctot, coff, act, accumulate):
         lib, P = self.lib, self.P
@@ -526,7 +574,7 @@ class OFFEngine:
             L.check(lib.offk_avgpool_drop_bwd(_ptr(self.buf["d_pool" + k]), P, c, 49, ctot, coff, self.drop_mode,
                                               _ptr(m), self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
                                               _ptr(act), int(accumulate), _ptr(dx), stream), "pool_bwd" + k)
-        return _nm(run, "pool_bwd" + k)
+        return _nm(run, "pool_bwd" + k, reads=[self.buf["d_pool" + k], act, dx if accumulate else None], writes=[dx])
 
     def _fc_fwd(self, name, k, c):
         g = T.ConvGeom(self.P, c, 1, 1, S.NUM_CLASSES)
@@ -552,22 +600,47 @@ class OFFEngine:
         for tag, t in self.taps.items():
             t.copy_(taps[tag], non_blocking=True)
 
+    def select_taps(self, idx: int):
+        """Make input set ``idx`` the one forward() and backward() read (re-binds the A operand of the unit GEMMs)."""
+        self._tap_set = idx
+        self.taps = self.tap_sets[idx]
+        for tag, users in self._tap_users.items():
+            ptr = self.taps[tag].data_ptr()
+            for g in users:
+                g.desc.a_src = ptr
+
+    def stage_taps(self, taps: dict):
+        """Asynchronously copy ``taps`` (host -- ideally pinned -- or device tensors) into the IDLE input set on a
+        side stream, so the transfer overlaps the forward/backward still running on the other set.  Returns
+        (set index, event); pass the index to select_taps() after making the compute stream wait on the event."""
+        idx = 1 - self._tap_set
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        # everything enqueued so far (incl. the last backward that read set idx) must finish before it is overwritten
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            for tag, t in self.tap_sets[idx].items():
+                t.copy_(taps[tag], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return idx, ev
+
     def forward(self, taps: dict = None, train: bool = False, masks: dict = None, seed: int = 0):
         """Run the forward plan.  Returns (fc7, fc28, fc14): [P,101] each, or [B,101] with consensus."""
         if taps is not None:
             self.set_taps(taps)
         self._set_dropout(train, masks, seed)
-        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for step in self.fwd_steps:
-            step(stream)
+        streams = self._fork()
+        self.fwd_sched.run(streams)
+        self._join(streams)
         pre = "cfc" if self.consensus else "fc"
         return self.buf[pre + "7"], self.buf[pre + "28"], self.buf[pre + "14"]
 
     def launch_names(self):
         """One name per device launch of forward() + backward(), in issue order (for annotating ncu launch lists)."""
         out = [n for st in self.fwd_steps for n in _names(st)]
-        out += ["zero grads_flat", "zero dwp_flat"]          # (the d_out copies are cudaMemcpyAsync, not kernels)
-        out += [n for st in self.bwd_steps for n in _names(st)]
+        out += [n for st in self.bwd_steps for n in _names(st)]    # (the d_out copies are cudaMemcpyAsync, not kernels)
         return out
 
     def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None):
@@ -576,22 +649,122 @@ class OFFEngine:
         before the unit gradients are computed (used to overlap their all-reduce)."""
         self.d_out7.copy_(g7.reshape(self.d_out7.shape))
         self.d_out14.copy_(g14.reshape(self.d_out14.shape))
-        if zero_grads:
-            self.grads_flat.zero_()
-        self.dwp_flat.zero_()
-        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for step in self.bwd_stage_steps:
-            step(stream)
+        self._zero_grads = bool(zero_grads)
+        streams = self._fork()
+        n_stage = len(self.bwd_stage_steps)
+        self.bwd_sched.run(streams, 0, n_stage)
         if after_stage is not None:
+            self._join(streams)                      # the caller's stream now trails every stage-gradient kernel
             after_stage()
-        for step in self.bwd_unit_steps:
-            step(stream)
+        self.bwd_sched.run(streams, n_stage)
+        self._join(streams)
         return self.grads
 
+    def _fork(self):
+        """[caller's stream, side streams...]; the side lanes start behind everything already enqueued by the caller."""
+        main = torch.cuda.current_stream(self.device)
+        if self.single_stream or self._lanes == 1:
+            return [main] * self._lanes
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self._lanes - 1)]
+        for s_ in self._side:
+            s_.wait_stream(main)
+        return [main] + self._side
 
-def _nm(fn, name):
+    def _join(self, streams):
+        for s_ in streams[1:]:
+            if s_ is not streams[0]:
+                streams[0].wait_stream(s_)
+
+
+def _auto_tile_n(M: int, N: int) -> int:
+    """N tile of a GEMM that would otherwise launch far fewer CTAs than the GPU has SMs (the 7x7-resolution layers:
+    37 M tiles): a narrower tile multiplies the CTA count; 0 = the kernel's default (widest legal tile)."""
+    mt = math.ceil(M / 128)
+    bn0 = (N + 15) // 16 * 16 if N <= 256 else 256
+    if mt * math.ceil(N / bn0) >= 120:
+        return 0
+    best = 0
+    for bn in (128, 64, 32):
+        if bn < bn0 and N % bn == 0:
+            best = bn
+            if mt * (N // bn) >= 140:
+                break
+    return best
+
+
+def _nm(fn, name, reads=(), writes=(), lane=0):
+    """Annotate a plan step: launch name, the buffers it reads / writes (for cross-stream hazard analysis), its lane."""
     fn.launches = [name]
+    fn.reads, fn.writes, fn.lane = list(reads), list(writes), lane
     return fn
+
+
+def _on(step, lane):
+    step.lane = lane
+    return step
+
+
+def _span(t):
+    return (t.data_ptr(), t.data_ptr() + t.numel() * t.element_size())
+
+
+class Schedule:
+    """A fixed list of steps spread over a few CUDA streams ("lanes").  Steps on one lane run in issue order; a step
+    that touches a buffer last written (or still being read) by a step on another lane waits on an event recorded
+    behind that step.  The hazards (RAW / WAW / WAR on byte ranges) are derived from the steps' declared reads and
+    writes, so lane assignment is purely a performance choice: any assignment is correct."""
+
+    def __init__(self, steps, ignore=()):
+        self.steps = list(steps)
+        n = len(self.steps)
+        self.n_lanes = 1 + max((getattr(st, "lane", 0) for st in self.steps), default=0)
+        ign = [_span(t) for t in ignore]
+
+        def spans(ts):
+            out = []
+            for t in ts:
+                if t is None:
+                    continue
+                sp = _span(t)
+                if any(lo <= sp[0] and sp[1] <= hi for lo, hi in ign):
+                    continue                      # read-only inputs (parameters, taps): never a hazard
+                out.append(sp)
+            return out
+
+        rd = [spans(getattr(st, "reads", ())) for st in self.steps]
+        wr = [spans(getattr(st, "writes", ())) for st in self.steps]
+        hit = lambda A, B: any(a[0] < b[1] and b[0] < a[1] for a in A for b in B)
+        lanes = [getattr(st, "lane", 0) for st in self.steps]
+        self.lanes = lanes
+        covered = [[-1] * self.n_lanes for _ in range(self.n_lanes)]   # covered[a][b]: latest step of lane b that a awaited
+        self.waits = [[] for _ in range(n)]
+        record = set()
+        for i in range(n):
+            need = {}
+            for j in range(i):
+                if lanes[j] == lanes[i] or j <= covered[lanes[i]][lanes[j]]:
+                    continue
+                if hit(wr[j], rd[i]) or hit(wr[j], wr[i]) or hit(rd[j], wr[i]):
+                    need[lanes[j]] = j
+            for lane_j, j in need.items():
+                self.waits[i].append(j)
+                covered[lanes[i]][lane_j] = j
+                record.add(j)
+        self.record = record
+        self.events = {j: torch.cuda.Event() for j in record}
+
+    def run(self, streams, lo=0, hi=None):
+        """Issue steps [lo, hi) on ``streams`` (torch.cuda.Stream per lane; lane 0 = the caller's stream)."""
+        hi = len(self.steps) if hi is None else hi
+        handles = [C.c_void_p(st.cuda_stream) for st in streams]
+        for i in range(lo, hi):
+            lane = self.lanes[i]
+            for j in self.waits[i]:
+                streams[lane].wait_event(self.events[j])
+            self.steps[i](handles[lane])
+            if i in self.record:
+                self.events[i].record(streams[lane])
 
 
 def _names(step):

@@ -27,14 +27,32 @@ class _Holder(nn.Module):
             self.bias = nn.Parameter(bias, requires_grad=trainable)
 
 
+class _Prefetched:
+    """Handle returned by OFFSubNetwork.prefetch(): an input set that is being filled on the copy stream."""
+
+    def __init__(self, index, event):
+        self.index, self.event = index, event
+
+
 class _OFFFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, train, masks, seed, n_taps, *tensors):
         eng = net.engine
         taps = tensors[:n_taps]
-        for (tag, buf), t in zip(eng.taps.items(), taps):
-            if t.data_ptr() != buf.data_ptr():          # the engine's own input buffers need no copy
-                buf.copy_(t, non_blocking=True)
+        if any(t.device.type != "cuda" for t in taps):
+            # host tensors: stage them into the idle input set on the copy stream, then switch to it
+            idx, ev = eng.stage_taps(dict(zip(eng.taps, taps)))
+            torch.cuda.current_stream(eng.device).wait_event(ev)
+            eng.select_taps(idx)
+        else:
+            own = [i for i, ts in enumerate(eng.tap_sets)
+                   if all(t.data_ptr() == b.data_ptr() for t, b in zip(taps, ts.values()))]
+            if own:                                     # the engine's own input buffers need no copy
+                if own[0] != eng._tap_set:
+                    eng.select_taps(own[0])
+            else:
+                for buf, t in zip(eng.taps.values(), taps):
+                    buf.copy_(t, non_blocking=True)
         fc7, fc28, fc14 = eng.forward(train=train, masks=masks, seed=seed)
         ctx.net = net
         ctx.n_taps = n_taps
@@ -107,6 +125,14 @@ class OFFSubNetwork(nn.Module):
         """The engine's static input buffers; filling these (e.g. as the H2D copy target) avoids a device copy."""
         return self.engine.taps
 
+    def prefetch(self, taps):
+        """Start the asynchronous host->device copy of the NEXT step's taps (dict or list of host tensors, pinned
+        for a truly asynchronous copy) into the idle input set while the current step still computes.  Returns a
+        handle to pass to forward() in place of the taps."""
+        if not isinstance(taps, dict):
+            taps = dict(zip(S.LEVELS, taps))
+        return _Prefetched(*self.engine.stage_taps(taps))
+
     def _apply(self, fn, recurse=True):
         probe = fn(self.engine.params_flat[:1])
         if probe.device == self.engine.params_flat.device and probe.dtype == torch.float32:
@@ -115,6 +141,11 @@ class OFFSubNetwork(nn.Module):
                            "device instead of moving / casting it")
 
     def forward(self, taps, masks=None):
+        if isinstance(taps, _Prefetched):
+            eng = self.engine
+            torch.cuda.current_stream(eng.device).wait_event(taps.event)
+            eng.select_taps(taps.index)
+            taps = eng.taps
         if isinstance(taps, dict):
             taps = [taps[t] for t in S.LEVELS]
         train = self.training

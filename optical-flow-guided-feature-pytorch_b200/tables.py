@@ -149,10 +149,11 @@ def conv_fwd_spec(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw") -
         b_mode=LOAD_VEC_K if K % 4 == 0 else LOAD_SCALAR_K, out_vec=out_vec, kind="fwd")
 
 
-def conv_wgrad_spec(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw") -> GemmSpec:
+def conv_wgrad_spec(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw", dw_layout: str = None) -> GemmSpec:
     """dW[cout, K_w] += sum_pixels dY * im2col(x);  the extra all-ones A row yields db[cout].
-    Rows are the filter taps in the x-layout k order (stores into dW are contiguous along rows),
-    k walks output pixels."""
+    Rows are the filter taps in the x-layout k order, k walks output pixels.  dw_layout: where row (c,r,q) lands in
+    dW -- default = the x-layout k order (OHWI for channels-last inputs); 'oihw' = the reference's canonical
+    [cout,cin,kh,kw] whatever the input layout (the gradient then needs no un-permute pass)."""
     pix, _ = _pixel_tables(g, x_layout, y_layout)
     K_w = g.kdim
     hw, hwo = g.hin * g.win, g.hout * g.wout
@@ -170,9 +171,13 @@ def conv_wgrad_spec(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw")
     else:
         b_row, b_col = (np.arange(g.cout) + g.y_coff) * hwo, img * g.y_ctot * hwo + p
         b_mode = LOAD_VEC_K if hwo % 4 == 0 else LOAD_SCALAR_K
+    out_row = np.arange(K_w + 1)
+    if dw_layout == "oihw" and x_layout == "nhwc":
+        r, q, c = np.meshgrid(np.arange(g.kh), np.arange(g.kw), np.arange(g.cin), indexing="ij")
+        out_row = np.concatenate([(c * (g.kh * g.kw) + r * g.kw + q).reshape(-1), [0]])
     return GemmSpec(
         M=K_w + 1, N=g.cout, K=g.n_img * hwo, a_row=a_row, a_col=pix, b_row=_i32(b_row), b_col=_i32(b_col),
-        out_row=_i32(np.arange(K_w + 1)), out_col=_i32(np.arange(g.cout) * K_w),
+        out_row=_i32(out_row), out_col=_i32(np.arange(g.cout) * K_w),
         a_h=g.hin if box else 0, a_w=g.win if box else 0, a_ones_row=K_w, a_mode=a_mode, b_mode=b_mode, kind="wgrad")
 
 

@@ -23,13 +23,19 @@ for t in eng.taps.values():
     t.copy_(torch.relu(torch.randn_like(t)))
 g7 = torch.randn(eng.P, 101, device="cuda") * 0.01
 g14 = torch.randn(eng.P, 101, device="cuda") * 0.01
+import time
+eng.single_stream = os.environ.get("OFFK_SINGLE_STREAM", "0") == "1"
 for i in range(iters):
     if i == iters - 1:                      # ncu --profile-from-start off: only the last iteration is profiled
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
+    t0 = time.perf_counter()
     eng.forward(train=True, seed=1)
     eng.backward(g7, g14)
-torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"iter {i}: CPU issue {1e3*(t1-t0):.2f} ms, until done {1e3*(t2-t0):.2f} ms")
 torch.cuda.cudart().cudaProfilerStop()
 with open(os.path.join(ROOT, "gpurun_out", "step_names.txt"), "w") as f:
     f.write("\n".join(eng.launch_names()))
