@@ -26,6 +26,9 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 METRIC = "off_unit_clips_per_sec_fwd_bwd"
+# dram__bytes_read.sum + dram__bytes_write.sum of the three stencil_diff_fwd launches of one step, from the committed
+# ncu --set full capture (profiles/); None until measured for the current kernel
+NCU_TRAFFIC_BYTES = None
 UNIT = "clips/s"
 
 
@@ -218,34 +221,66 @@ def run_ours(args):
     value = clips_total / (ms * 1e-3)
     e2e_value = clips_total / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant memory-bound kernel: the fused stencil (forward), all nine levels, L2 flushed
+    # ---- roofline of the memory-bound kernel BASELINE.json names: the fused stencil (forward), one launch per
+    # stage-fusion buffer (28: 3a,3b | 14: 3c..4d | 7: 5a,5b).  Timed live with CUDA events on the launching stream:
+    # (1) cold, L2 flushed before every launch (the headline `achieved`), (2) in-step, events recorded around the
+    # launches during extra forward passes (inputs just written by the unit GEMMs, partly L2-resident).
     pk, pk_src = peaks()
     roof = None
     if rank == 0:
         import ctypes as C
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush_r = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+        flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        stencil_steps = list(eng.stencil_fwd_steps.values())
-        tot_ms, tot_bytes, per_level = 0.0, 0.0, {}
-        for (tag, (cin, s)), st in zip(S.LEVELS.items(), stencil_steps):
-            nbytes = 4.0 * s * s * (S.GEN_C * eng.N + S.DOWN_C * eng.P + S.UNIT_C * eng.P)   # read G, read D, write M
+        stage_levels = {st: [t for t in S.LEVELS if S.LEVEL_STAGE[t] == st] for st in S.STAGES}
+        lvl_bytes = {t: 4.0 * s * s * (S.GEN_C * eng.N + S.DOWN_C * eng.P + S.UNIT_C * eng.P)     # read G, read D, write M
+                     for t, (cin, s) in S.LEVELS.items()}
+        tot_ms, tot_bytes, per_stage = 0.0, 0.0, {}
+        for st, step_fn in eng.stencil_fwd_steps.items():
+            nbytes = sum(lvl_bytes[t] for t in stage_levels[st])
             reps, acc = 10, 0.0
             for _ in range(reps):
-                flush.fill_(1)                                                                # evict L2 (126 MB)
+                # evict L2 (126 MB): write a 256 MB buffer, then read a second one so that the evicted lines are
+                # written back BEFORE the timed launch (dirty lines would otherwise drain during it)
+                flush.fill_(1)
+                flush_sink.add_(flush_r.view(torch.int64).sum())
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                st(stream)
+                step_fn(stream)
                 b.record()
                 torch.cuda.synchronize()
                 acc += a.elapsed_time(b)
-            per_level[tag] = round(nbytes / (acc / reps * 1e-3) / 1e9, 1)
+            per_stage[st] = {"MB": round(nbytes / 1e6, 1), "us": round(acc / reps * 1e3, 1),
+                             "GBs": round(nbytes / (acc / reps * 1e-3) / 1e9, 1)}
             tot_ms += acc / reps
             tot_bytes += nbytes
         achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "stencil_diff_fwd_kernel (9 launches, one per OFF unit)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": None, "bytes_per_step": tot_bytes, "per_level_GBs": per_level,
-                "note": "algorithmic bytes 4*S^2*(128*N + 32*P + 160*P) per level, L2 flushed before every launch"}
+        # in-step: same launches timed inside full forward passes (single-stream issue so the events bracket them)
+        eng.single_stream = True
+        evs = []
+        for _ in range(5):
+            eng._set_dropout(True, None, 1)
+            streams = eng._fork()
+            for i, stp in enumerate(eng.fwd_sched.steps):
+                hit = stp in eng.stencil_fwd_steps.values()
+                if hit:
+                    a = torch.cuda.Event(enable_timing=True); a.record()
+                stp(C.c_void_p(streams[0].cuda_stream))
+                if hit:
+                    b = torch.cuda.Event(enable_timing=True); b.record(); evs.append((a, b))
+        torch.cuda.synchronize()
+        eng.single_stream = False
+        in_step_ms = sum(a.elapsed_time(b) for a, b in evs) / 5
+        roof = {"bound": "hbm", "kernel": "stencil_diff_fwd_kernel (3 launches per step: one per stage-fusion buffer, 9 OFF units)",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES, "bytes_per_step": tot_bytes,
+                "per_stage": per_stage,
+                "in_step": {"GBs": round(tot_bytes / (in_step_ms * 1e-3) / 1e9, 1), "us": round(in_step_ms * 1e3, 1),
+                            "note": "same 3 launches timed inside forward passes (inputs fresh from the unit GEMMs, partly L2-resident)"},
+                "note": "algorithmic bytes 4*S^2*(128*N + 32*P + 160*P) per level (read G once, read D once, write the "
+                        "160-channel slice once); `achieved` = cold launches, L2 flushed before each; traffic = ncu "
+                        "dram__bytes_read+write summed over the same 3 launches (profiles/)"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -46,6 +46,9 @@ extern "C" {
 #define OFFK_DROP_NONE 0
 #define OFFK_DROP_MASK 1 /* caller-supplied uint8 keep-mask (1 = keep)             */
 #define OFFK_DROP_SEED 2 /* counter-hash keep decision from (seed, element index)   */
+/* OFFK_DROP_SEED element index: channels-last, ((p*H*W + pix) * K*Cs + channel) for the spatial-gradient channels
+ * of pair p, p*C + c for pooled head features; four consecutive indices share one 64-bit hash
+ * (offk_drop_keep_host mirrors the device decision). */
 
 int offk_version(void);
 const char* offk_last_error_string(void);
@@ -156,7 +159,8 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
  *   out: [P, H, W, out_ctot]
  *   out[p, y, x, out_coff + kk*Cs + c] = drop( sum_ij w[c,kk,i,j] * D[fs(p), y+i-1, x+j-1, c] + bias )   (zero pad)
  *   out[p, y, x, out_coff + K*Cs + c]  = G[b*L+t+1, y, x, c] - G[b*L+t, y, x, c]        p = b*(L-1)+t
- *   keep_mask / seeded dropout are indexed like the reference's dropout input [P, K*Cs, H, W] (RGB_OFF.py:612)
+ *   keep_mask is indexed like the reference's dropout input [P, K*Cs, H, W] (RGB_OFF.py:612); seeded dropout hashes
+ *   the channels-last element index (see OFFK_DROP_SEED)
  *   fs(p) = p (OFFK_INDEX_REFERENCE_FLAT) or b*L+t (OFFK_INDEX_ALIGNED)
  * Each G frame is read once.  Cg == 0 or Cs == 0 disables a half (the
  * stand-alone util.SobelFilter modules use Cg == 0, L == 2 so that p == f).
@@ -176,6 +180,29 @@ typedef struct offk_stencil {
 
 int offk_stencil_diff_fwd(const offk_stencil_t* s, const float* g, const float* d, const float* w,
                           const float* bias, float* out, void* stream);
+
+/* Buffers of one OFF unit for the batched entry points below (forward uses g, d, w, bias, out; backward uses
+ * dout, g, d, w, dg, dg_fs, dd, dd_fs, dw, dbias -- same meaning as the single-unit calls). */
+typedef struct offk_stencil_io {
+  const float* g;
+  const float* d;
+  const float* w;
+  const float* bias;
+  float* out;
+  const float* dout;
+  float* dg;
+  int64_t dg_fs;
+  float* dd;
+  int64_t dd_fs;
+  float* dw;
+  float* dbias;
+} offk_stencil_io_t;
+
+/* n (<= 12) OFF units in ONE launch: the units that feed one stage-fusion buffer (RGB_OFF.py:656: 3a,3b; :760:
+ * 3c,4a,4b,4c,4d; :832: 5a,5b), so the small 14x14 / 7x7 levels do not pay a launch latency each.  s and io are
+ * host arrays of n entries; semantics per entry are those of offk_stencil_diff_fwd / _bwd. */
+int offk_stencil_diff_fwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream);
+int offk_stencil_diff_bwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream);
 
 /* Backward of the above.  dout is the gradient of the stage buffer (same
  * ctot/coff addressing as `out`).  Writes

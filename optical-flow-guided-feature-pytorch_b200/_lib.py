@@ -54,6 +54,15 @@ class OffkStencil(C.Structure):
     ]
 
 
+class OffkStencilIO(C.Structure):
+    """Mirror of offk_stencil_io_t."""
+    _fields_ = [
+        ("g", C.c_void_p), ("d", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("dout", C.c_void_p), ("dg", C.c_void_p), ("dg_fs", C.c_int64), ("dd", C.c_void_p), ("dd_fs", C.c_int64),
+        ("dw", C.c_void_p), ("dbias", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 _PROTOS = {
     "offk_version": (C.c_int, []),
@@ -64,6 +73,8 @@ _PROTOS = {
     "offk_stencil_diff_fwd": (C.c_int, [C.POINTER(OffkStencil), _P, _P, _P, _P, _P, _P]),
     "offk_stencil_diff_bwd": (C.c_int, [C.POINTER(OffkStencil), _P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                         _P, _P, _P]),
+    "offk_stencil_diff_fwd_batch": (C.c_int, [C.c_int, C.POINTER(OffkStencil), C.POINTER(OffkStencilIO), _P]),
+    "offk_stencil_diff_bwd_batch": (C.c_int, [C.c_int, C.POINTER(OffkStencil), C.POINTER(OffkStencilIO), _P]),
     "offk_avgpool_drop_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64,
                                         C.c_float, C.c_float, _P, _P]),
     "offk_avgpool_drop_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64,

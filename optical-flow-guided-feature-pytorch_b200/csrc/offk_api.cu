@@ -33,7 +33,7 @@ extern "C" int offk_device_info(int* sm_count_out, int* cc_major, int* cc_minor,
 }
 
 extern "C" int offk_drop_keep_host(uint64_t seed, uint64_t idx, float drop_p) {
-  return drop_keep(seed, idx, drop_threshold24(drop_p)) ? 1 : 0;
+  return drop_keep(seed, idx, drop_threshold16(drop_p)) ? 1 : 0;
 }
 
 extern "C" int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream) {

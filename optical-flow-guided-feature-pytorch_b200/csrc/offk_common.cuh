@@ -31,23 +31,30 @@ inline int cuda_check(cudaError_t e, const char* what) {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---- counter-hash dropout (OFFK_DROP_SEED) ----------------------------------
-// keep(idx) = top-24-bits(splitmix64(seed ^ golden*idx)) >= p * 2^24.  Same on host and device so
-// tests can regenerate the mask and the backward kernel never needs it in memory.
-__host__ __device__ __forceinline__ uint32_t drop_hash24(uint64_t seed, uint64_t idx) {
-  uint64_t x = seed + idx * 0x9E3779B97F4A7C15ull;
+// One splitmix64 hash serves FOUR consecutive elements (a channel quad of a channels-last tensor):
+//   keep(idx) = 16-bit field (idx & 3) of splitmix64(seed + golden * (idx >> 2)) >= p * 2^16.
+// Same on host and device so tests can regenerate the mask and the backward kernels never need it in memory.
+__host__ __device__ __forceinline__ uint64_t drop_hash64(uint64_t seed, uint64_t quad) {
+  uint64_t x = seed + quad * 0x9E3779B97F4A7C15ull;
   x ^= x >> 30;
   x *= 0xBF58476D1CE4E5B9ull;
   x ^= x >> 27;
   x *= 0x94D049BB133111EBull;
   x ^= x >> 31;
-  return (uint32_t)(x >> 40);
+  return x;
 }
-__host__ __device__ __forceinline__ uint32_t drop_threshold24(float p) {
-  float t = p * 16777216.0f;
-  return t <= 0.f ? 0u : (t >= 16777216.0f ? 16777216u : (uint32_t)t);
+__host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
+  float t = p * 65536.0f;
+  return t <= 0.f ? 0u : (t >= 65536.0f ? 65536u : (uint32_t)t);
 }
-__host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thr24) {
-  return drop_hash24(seed, idx) >= thr24;
+// bit i = keep decision of element 4*quad + i
+__host__ __device__ __forceinline__ uint32_t drop_keep4(uint64_t seed, uint64_t quad, uint32_t thr16) {
+  const uint64_t h = drop_hash64(seed, quad);
+  return ((uint32_t)(h & 0xFFFFu) >= thr16 ? 1u : 0u) | ((uint32_t)((h >> 16) & 0xFFFFu) >= thr16 ? 2u : 0u) |
+         ((uint32_t)((h >> 32) & 0xFFFFu) >= thr16 ? 4u : 0u) | ((uint32_t)(h >> 48) >= thr16 ? 8u : 0u);
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thr16) {
+  return (drop_keep4(seed, idx >> 2, thr16) >> (idx & 3u)) & 1u;
 }
 
 // ---- vector / cache-hinted global access ------------------------------------

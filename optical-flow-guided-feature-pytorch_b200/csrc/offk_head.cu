@@ -22,7 +22,7 @@ __global__ void avgpool_drop_fwd_kernel(const float* __restrict__ x, int P, int 
   const float* xp = x + (size_t)p * HW * ctot + coff + c;
   float s = 0.f;
   for (int h = 0; h < HW; ++h) s += __ldg(xp + (size_t)h * ctot);
-  const float k = keep_factor(mode, mask, seed, drop_threshold24(drop_p), (size_t)i, scale);
+  const float k = keep_factor(mode, mask, seed, drop_threshold16(drop_p), (size_t)i, scale);
   out[i] = (s / (float)HW) * k;
 }
 
@@ -38,7 +38,7 @@ __global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P
   const size_t pc = (ph / HW) * C + c;
   const size_t o = ph * ctot + coff + c;
   float v = 0.f;
-  if (dpooled) v = __ldg(dpooled + pc) * keep_factor(mode, mask, seed, drop_threshold24(drop_p), pc, scale) / (float)HW;
+  if (dpooled) v = __ldg(dpooled + pc) * keep_factor(mode, mask, seed, drop_threshold16(drop_p), pc, scale) / (float)HW;
   if (accumulate) v += dx[o];
   if (act) v = __ldg(act + o) > 0.f ? v : 0.f;
   dx[o] = v;

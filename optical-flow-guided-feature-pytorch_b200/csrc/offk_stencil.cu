@@ -1,28 +1,73 @@
 // Fused OFF stencil kernels (forward and backward) on channels-last tensors; HBM-bound by construction.
 //
-// Forward (one launch per OFF unit) reads the unit's reduced features once and writes the unit's 160 channels
-// straight into the concatenated stage-fusion buffer [P, H, W, Ctot] at its channel offset:
-//   temporal blocks : a thread owns up to 4 (pixel, 4-channel) positions of a clip and walks t = 0..L-1 keeping the
-//                     previous frame in registers, so every G frame is read exactly once (128-bit, coalesced: one
-//                     warp = the 128 channels of one pixel) and every difference G(t+1)-G(t) is written once.
-//   spatial blocks  : a thread owns (pair, pixel, 4 channels): nine predicated 128-bit neighbour loads (zero padding by
-//                     predication, neighbours come from L1/L2), per-channel 3x3 taps cached in shared memory, bias,
-//                     dropout, one 128-bit store.  K = 2 emits two maps per channel (Sobel x and y).
+// One launch serves a BATCH of OFF units (the units feeding one stage-fusion buffer, or all nine in the backward
+// pass), so the 14x14 and 7x7 levels -- a few MB each -- do not pay one launch latency apiece.  A block is either
+//   a temporal block : (clip, 32 pixels).  One warp = the 128 reduced channels of a pixel (lane = channel quad), so
+//                      there is no index arithmetic beyond pointer increments.  The warp walks t = 0..L-1 with the
+//                      loads of frame t+1 issued before the difference of frame t is stored: every G frame is read
+//                      exactly once (128-bit, 512 contiguous bytes per warp), every difference written once, and
+//                      8 independent 16-byte loads per thread are in flight.
+//   a spatial block  : (pair, band of rows).  The D band plus a one-pixel halo is staged in shared memory with
+//                      16-byte cp.async (zero-fill gives the conv's zero padding), then each thread produces
+//                      (pixel, 4 channels) outputs from nine LDS.128 neighbours and per-channel taps kept in
+//                      shared memory; bias, dropout and the store at the unit's channel offset of the stage buffer
+//                      follow.  K = 2 emits two maps per channel (Sobel x and y).
 // No torch.cat, no sub, no conv2d, no separate dropout launch.
 //
-// Backward mirrors it: dG = (dT(t-1) - dT(t)) * [G > 0], dD = transposed stencil of the dropped spatial gradient, and
-// the learned-tap / bias gradients are accumulated in registers by a few persistent blocks, reduced with warp
-// shuffles + shared-memory atomics, then one global atomicAdd per tap and block.
+// Backward mirrors it: dG = (dT(t-1) - dT(t)) * [G > 0]; the spatial blocks stage the DROPPED spatial gradient dS
+// (band + halo) once and use the same nine neighbours twice: dD = transposed stencil of dS, and
+// dw[a,b] += D(y,x) * dS(y-a+1, x-b+1) (the tap gradient re-indexed so that it needs D only at the centre pixel).
+// Tap / bias gradients are accumulated in registers by persistent spatial blocks, reduced with warp shuffles and
+// shared-memory atomics, then one global atomicAdd per tap and block.
 #include "offk_common.cuh"
 
 namespace offk {
 
 constexpr int ST_THREADS = 256;
-constexpr int ST_TPOS = 4;      // positions per thread (temporal half)
-constexpr int ST_MAX_CS = 64;   // spatial channels cached in smem (32 on the path)
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr int ST_MAX_LEVELS = 12;
+constexpr int ST_MAX_CS = 64;                 // spatial channels per level (32 on the path)
+constexpr int ST_TJ = 2;                      // pixels per warp of a temporal block (lane = channel quad)
+constexpr int ST_FC = 3;                      // frames loaded per chunk, forward
+constexpr int ST_BC = 2;                      // frames loaded per chunk, backward (two tensors per frame)
+constexpr int ST_TILE_BUDGET = 24 * 1024;     // target size of a halo tile (bytes)
+constexpr int ST_SMEM_MAX = 64 * 1024;
+
+struct StLevel {
+  offk_stencil_t s;
+  const float* g;
+  const float* d;
+  const float* w;
+  const float* bias;
+  float* out;          // forward: stage buffer
+  const float* dout;   // backward: gradient of the stage buffer
+  float* dg;
+  float* dd;
+  float* dw;
+  float* dbias;
+  long long dg_fs, dd_fs;
+  int blk0;            // first block of this level
+  int n_sblocks;       // spatial blocks (forward: one per item; backward: persistent over items)
+  int n_sitems;        // spatial items = (pair | frame) x band
+  int bands, band_rows;
+  int t_chunks;        // temporal blocks per clip
+  int lq, ltcp, lxw;   // log2: channel quads per pixel, tile column pitch, x positions per pass
+};
+struct StBatch {
+  int n;
+  StLevel lv[ST_MAX_LEVELS];
+};
 
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_cp_async16(uint32_t dst, const float* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void st_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 __device__ __forceinline__ int spatial_frame(const offk_stencil_t& s, int p) {
   if (s.index_mode == OFFK_INDEX_REFERENCE_FLAT) return p;
@@ -36,288 +81,358 @@ __device__ __forceinline__ int spatial_pair_of_frame(const offk_stencil_t& s, in
   const int b = f / s.L, t = f - b * s.L;
   return t < s.L - 1 ? b * (s.L - 1) + t : -1;
 }
-// keep-factor of spatial output element (p, och, y, x); the mask / hash index is the NCHW flat index of the
+// keep-factors of the 4 spatial outputs (p, och..och+3, pix).  OFFK_DROP_MASK: the mask is indexed like the
 // reference's dropout input [P, K*Cs, H, W] (RGB_OFF.py:612), so injected masks keep the reference's layout.
-__device__ __forceinline__ float drop_factor(const offk_stencil_t& s, uint32_t thr, int p, int och, int pix) {
-  if (s.drop_mode == OFFK_DROP_NONE) return 1.f;
-  const size_t idx = ((size_t)p * (s.K * s.Cs) + och) * (size_t)(s.H * s.W) + pix;
-  const bool keep = s.drop_mode == OFFK_DROP_MASK ? (s.keep_mask[idx] != 0) : drop_keep(s.seed, idx, thr);
-  return keep ? s.keep_scale : 0.f;
+// OFFK_DROP_SEED: one 64-bit hash per channel quad of the channels-last element index ((p*HW + pix)*K*Cs + och).
+__device__ __forceinline__ float4 drop_factor4(const offk_stencil_t& s, uint32_t thr, int p, int och, int pix, int HW) {
+  if (s.drop_mode == OFFK_DROP_NONE) return make_float4(1.f, 1.f, 1.f, 1.f);
+  const int KC = s.K * s.Cs;
+  uint32_t keep;
+  if (s.drop_mode == OFFK_DROP_MASK) {
+    const uint8_t* m = s.keep_mask + ((size_t)p * KC + och) * (size_t)HW + pix;
+    keep = (m[0] != 0 ? 1u : 0u) | (m[HW] != 0 ? 2u : 0u) | (m[2 * (size_t)HW] != 0 ? 4u : 0u) | (m[3 * (size_t)HW] != 0 ? 8u : 0u);
+  } else {
+    keep = drop_keep4(s.seed, (((uint64_t)p * HW + pix) * KC + och) >> 2, thr);
+  }
+  const float k = s.keep_scale;
+  return make_float4(keep & 1u ? k : 0.f, keep & 2u ? k : 0.f, keep & 4u ? k : 0.f, keep & 8u ? k : 0.f);
 }
-__device__ __forceinline__ float4 drop_factor4(const offk_stencil_t& s, uint32_t thr, int p, int och, int pix) {
-  return make_float4(drop_factor(s, thr, p, och, pix), drop_factor(s, thr, p, och + 1, pix),
-                     drop_factor(s, thr, p, och + 2, pix), drop_factor(s, thr, p, och + 3, pix));
+
+__device__ __forceinline__ const StLevel& find_level(const StBatch& bt, int blk) {
+  int li = 0;
+#pragma unroll 1
+  while (li + 1 < bt.n && blk >= bt.lv[li + 1].blk0) ++li;
+  return bt.lv[li];
+}
+
+// per-channel taps and bias as float4 over 4 consecutive channels: ws4[(kk*9 + j)*CQ + c4], bs4[kk*CQ + c4]
+__device__ __forceinline__ void load_taps(const StLevel& lv, float4* ws4, float4* bs4, int tid) {
+  const offk_stencil_t& s = lv.s;
+  const int CQ = 1 << lv.lq, K9 = s.K * 9;
+  for (int i = tid; i < K9 * CQ; i += ST_THREADS) {
+    const int c4 = i & (CQ - 1), kj = i >> lv.lq;
+    const float* b = lv.w + (size_t)(c4 * 4) * K9 + kj;          // w[c][kk][3][3]: channel stride K*9
+    ws4[i] = make_float4(__ldg(b), __ldg(b + K9), __ldg(b + 2 * K9), __ldg(b + 3 * K9));
+  }
+  if (bs4) {
+    for (int i = tid; i < s.K * CQ; i += ST_THREADS) {
+      const int c4 = i & (CQ - 1), kk = i >> lv.lq;
+      bs4[i] = lv.bias ? ldg4(lv.bias + kk * s.Cs + c4 * 4) : f4zero();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(ST_THREADS)
-stencil_diff_fwd_kernel(const offk_stencil_t s, const float* __restrict__ g, const float* __restrict__ d,
-                        const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                        int t_blocks_per_clip, int n_tblocks) {
-  const int HW = s.H * s.W;
-  const int tid = threadIdx.x;
-  if ((int)blockIdx.x < n_tblocks) {
-    // ------------------------------ temporal difference (RGB_OFF.py:599-604)
-    const int b = blockIdx.x / t_blocks_per_clip;
-    const int blk = blockIdx.x - b * t_blocks_per_clip;
-    const int cq = s.Cg >> 2;                       // channel quads per pixel
-    const int npos = HW * cq;
-    const int base = blk * (ST_THREADS * ST_TPOS) + tid;
-    const float* gb = g + (size_t)b * s.L * s.g_fs;
-    float* ob = out + (size_t)b * (s.L - 1) * HW * s.out_ctot + s.out_coff + s.K * s.Cs;
-    const size_t o_ps = (size_t)HW * s.out_ctot;
-    size_t goff[ST_TPOS], ooff[ST_TPOS];
-    float4 prev[ST_TPOS];
+// temporal difference (RGB_OFF.py:599-604): thread = (ST_TJ pixels, one channel quad); frames are walked in chunks of
+// ST_FC so that ST_TJ*ST_FC independent 16-byte loads are in flight per thread at ~50 % occupancy.
+__device__ __forceinline__ void temporal_fwd(const StLevel& lv, int r2, int tid) {
+  const int L = lv.s.L, Cg = lv.s.Cg, HW = lv.s.H * lv.s.W;
+  const int g_ps = lv.s.g_ps, ctot = lv.s.out_ctot;
+  const size_t g_fs = (size_t)lv.s.g_fs, o_fs = (size_t)HW * ctot;
+  const int b = r2 / lv.t_chunks, chunk = r2 - b * lv.t_chunks;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pix0 = chunk * (ST_WARPS * ST_TJ) + warp * ST_TJ;
+  bool ok[ST_TJ];
 #pragma unroll
-    for (int u = 0; u < ST_TPOS; ++u) {
-      const int e = base + u * ST_THREADS;
-      const int pix = e / cq, c = (e - pix * cq) << 2;
-      goff[u] = (size_t)pix * s.g_ps + c;
-      ooff[u] = (size_t)pix * s.out_ctot + c;
-      if (e < npos) prev[u] = ldg_stream4(gb + goff[u]);
-    }
-    for (int t = 1; t < s.L; ++t) {
-      float4 cur[ST_TPOS];
+  for (int j = 0; j < ST_TJ; ++j) ok[j] = pix0 + j < HW;
+  for (int c = lane * 4; c < Cg; c += 128) {
+    const float* gp = lv.g + (size_t)b * L * g_fs + (size_t)pix0 * g_ps + c;
+    float* op = lv.out + ((size_t)b * (L - 1) * HW + pix0) * ctot + lv.s.out_coff + lv.s.K * lv.s.Cs + c;
+    float4 prev[ST_TJ];
 #pragma unroll
-      for (int u = 0; u < ST_TPOS; ++u)
-        if (base + u * ST_THREADS < npos) cur[u] = ldg_stream4(gb + (size_t)t * s.g_fs + goff[u]);
+    for (int j = 0; j < ST_TJ; ++j) prev[j] = ok[j] ? ldg_stream4(gp + j * g_ps) : f4zero();
+    for (int t0 = 1; t0 < L; t0 += ST_FC) {
+      float4 cur[ST_FC][ST_TJ];
 #pragma unroll
-      for (int u = 0; u < ST_TPOS; ++u)
-        if (base + u * ST_THREADS < npos) {
-          stg_stream4(ob + (size_t)(t - 1) * o_ps + ooff[u], f4sub(cur[u], prev[u]));
-          prev[u] = cur[u];
+      for (int i = 0; i < ST_FC; ++i) {
+        gp += g_fs;
+#pragma unroll
+        for (int j = 0; j < ST_TJ; ++j) cur[i][j] = (ok[j] && t0 + i < L) ? ldg_stream4(gp + j * g_ps) : f4zero();
+      }
+#pragma unroll
+      for (int i = 0; i < ST_FC; ++i) {
+        if (t0 + i < L) {
+#pragma unroll
+          for (int j = 0; j < ST_TJ; ++j) {
+            if (ok[j]) stg_stream4(op + j * ctot, f4sub(cur[i][j], prev[j]));
+            prev[j] = cur[i][j];
+          }
         }
+        op += o_fs;
+      }
     }
-    return;
-  }
-  // ------------------------------ spatial gradient (RGB_OFF.py:611 / Flow_OFF.py:622 / util.py:46-50) + dropout
-  __shared__ float ws[ST_MAX_CS * 2 * 9];
-  __shared__ float bs[ST_MAX_CS * 2];
-  for (int i = tid; i < s.Cs * s.K * 9; i += ST_THREADS) ws[i] = __ldg(w + i);
-  for (int i = tid; i < s.Cs * s.K; i += ST_THREADS) bs[i] = bias ? __ldg(bias + i) : 0.f;
-  __syncthreads();
-  const int cq = s.Cs >> 2;
-  const int P = s.B * (s.L - 1);
-  const size_t total = (size_t)P * HW * cq;
-  const size_t e = (size_t)(blockIdx.x - n_tblocks) * ST_THREADS + tid;
-  if (e >= total) return;
-  const int c = (int)(e % cq) << 2;
-  const int pix = (int)((e / cq) % HW);
-  const int p = (int)(e / ((size_t)cq * HW));
-  const int y = pix / s.W, x = pix - y * s.W;
-  const float* dp = d + (size_t)spatial_frame(s, p) * s.d_fs + c;
-  float4 nb[9];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int bb = 0; bb < 3; ++bb) {
-      const int yy = y + a - 1, xx = x + bb - 1;
-      nb[a * 3 + bb] = (yy >= 0 && yy < s.H && xx >= 0 && xx < s.W) ? ldg4(dp + (size_t)(yy * s.W + xx) * s.d_ps)
-                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  const uint32_t thr = drop_threshold24(s.drop_p);
-  float* op = out + ((size_t)p * HW + pix) * s.out_ctot + s.out_coff;
-  for (int kk = 0; kk < s.K; ++kk) {
-    const int och = kk * s.Cs + c;
-    float4 acc = make_float4(bs[och], bs[och + 1], bs[och + 2], bs[och + 3]);
-    const float* w0 = ws + ((c + 0) * s.K + kk) * 9;
-    const float* w1 = ws + ((c + 1) * s.K + kk) * 9;
-    const float* w2 = ws + ((c + 2) * s.K + kk) * 9;
-    const float* w3 = ws + ((c + 3) * s.K + kk) * 9;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      acc.x = fmaf(w0[j], nb[j].x, acc.x);
-      acc.y = fmaf(w1[j], nb[j].y, acc.y);
-      acc.z = fmaf(w2[j], nb[j].z, acc.z);
-      acc.w = fmaf(w3[j], nb[j].w, acc.w);
-    }
-    const float4 k4 = drop_factor4(s, thr, p, och, pix);
-    stg_stream4(op + och, make_float4(acc.x * k4.x, acc.y * k4.y, acc.z * k4.z, acc.w * k4.w));
   }
 }
 
-// ---------------------------------------------------------------------------------------------- backward
-__global__ void __launch_bounds__(ST_THREADS)
-stencil_diff_bwd_kernel(const offk_stencil_t s, const float* __restrict__ dout, const float* __restrict__ g,
-                        const float* __restrict__ d, const float* __restrict__ w, float* __restrict__ dg,
-                        long long dg_fs, float* __restrict__ dd, long long dd_fs,
-                        int t_blocks_per_clip, int n_tblocks) {
-  const int HW = s.H * s.W;
+__global__ void __launch_bounds__(ST_THREADS, 4)
+stencil_diff_fwd_kernel(const __grid_constant__ StBatch bt) {
+  extern __shared__ __align__(16) float4 st_smem[];
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  const int rel = (int)blockIdx.x - lv.blk0;
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x < n_tblocks) {
-    // ------------------------------ dG[b,t] = (dT[b,t-1] - dT[b,t]) * (G[b,t] > 0)
-    const int b = blockIdx.x / t_blocks_per_clip;
-    const int blk = blockIdx.x - b * t_blocks_per_clip;
-    const int cq = s.Cg >> 2;
-    const int npos = HW * cq;
-    const int base = blk * (ST_THREADS * ST_TPOS) + tid;
-    const float* gb = g + (size_t)b * s.L * s.g_fs;
-    float* dgb = dg + (size_t)b * s.L * dg_fs;
-    const float* ob = dout + (size_t)b * (s.L - 1) * HW * s.out_ctot + s.out_coff + s.K * s.Cs;
-    const size_t o_ps = (size_t)HW * s.out_ctot;
-    size_t goff[ST_TPOS], ooff[ST_TPOS];
-    float4 prev[ST_TPOS];
-#pragma unroll
-    for (int u = 0; u < ST_TPOS; ++u) {
-      const int e = base + u * ST_THREADS;
-      const int pix = e / cq, c = (e - pix * cq) << 2;
-      goff[u] = (size_t)pix * s.g_ps + c;     // dg uses the same pixel stride as g
-      ooff[u] = (size_t)pix * s.out_ctot + c;
-      prev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int t = 0; t < s.L; ++t) {
-      float4 cur[ST_TPOS], gv[ST_TPOS];
-#pragma unroll
-      for (int u = 0; u < ST_TPOS; ++u) {
-        cur[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (base + u * ST_THREADS < npos) {
-          if (t < s.L - 1) cur[u] = ldg_stream4(ob + (size_t)t * o_ps + ooff[u]);
-          gv[u] = ldg_stream4(gb + (size_t)t * s.g_fs + goff[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < ST_TPOS; ++u)
-        if (base + u * ST_THREADS < npos) {
-          float4 r = f4sub(prev[u], cur[u]);
-          r.x = gv[u].x > 0.f ? r.x : 0.f;
-          r.y = gv[u].y > 0.f ? r.y : 0.f;
-          r.z = gv[u].z > 0.f ? r.z : 0.f;
-          r.w = gv[u].w > 0.f ? r.w : 0.f;
-          stg_stream4(dgb + (size_t)t * dg_fs + goff[u], r);
-          prev[u] = cur[u];
-        }
-    }
+  if (rel >= lv.n_sblocks) {
+    temporal_fwd(lv, rel - lv.n_sblocks, tid);
     return;
   }
-  __shared__ float ws[ST_MAX_CS * 2 * 9];
-  const uint32_t thr = drop_threshold24(s.drop_p);
-  const int cq = s.Cs >> 2;
+  // ------------------------------ spatial gradient (RGB_OFF.py:611 / Flow_OFF.py:622 / util.py:46-50) + dropout
+  const offk_stencil_t& s = lv.s;
+  const int H = s.H, W = s.W, HW = H * W, K = s.K, Cs = s.Cs, ctot = s.out_ctot, d_ps = s.d_ps;
+  const int p = rel / lv.bands, band = rel - p * lv.bands;
+  const int y0 = band * lv.band_rows;
+  const int rows = min(lv.band_rows, H - y0);
+  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq, TCP = 1 << ltcp;
+  float4* tile = st_smem;                                        // [rows+2][TCP][CQ]
+  float4* ws4 = st_smem + (((lv.band_rows + 2) << ltcp) << lq);  // [K*9][CQ]
+  float4* bs4 = ws4 + K * 9 * CQ;                                // [K][CQ]
   {
-    // ------------------------------ dD(y,x) = sum_kk sum_ab w[kk][a][b] * dS[kk](y-a+1, x-b+1)
-    for (int i = tid; i < s.Cs * s.K * 9; i += ST_THREADS) ws[i] = __ldg(w + i);
-    __syncthreads();
-    const size_t total = (size_t)s.B * s.L * HW * cq;
-    const size_t e = (size_t)(blockIdx.x - n_tblocks) * ST_THREADS + tid;
-    if (e >= total) return;
-    const int c = (int)(e % cq) << 2;
-    const int pix = (int)((e / cq) % HW);
-    const int f = (int)(e / ((size_t)cq * HW));
-    const int y = pix / s.W, x = pix - y * s.W;
-    float* ddp = dd + (size_t)f * dd_fs + (size_t)pix * s.d_ps + c;   // dd uses the same pixel stride as d
-    const int p = spatial_pair_of_frame(s, f);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p >= 0) {
-      for (int kk = 0; kk < s.K; ++kk) {
-        const int och = kk * s.Cs + c;
-        const float* w0 = ws + ((c + 0) * s.K + kk) * 9;
-        const float* w1 = ws + ((c + 1) * s.K + kk) * 9;
-        const float* w2 = ws + ((c + 2) * s.K + kk) * 9;
-        const float* w3 = ws + ((c + 3) * s.K + kk) * 9;
+    const float* dp = lv.d + (size_t)spatial_frame(s, p) * s.d_fs;
+    const int n_cells = ((rows + 2) << ltcp) << lq;
+    const uint32_t tile_s = st_smem_u32(tile);
+    for (int i = tid; i < n_cells; i += ST_THREADS) {
+      const int c4 = i & (CQ - 1), col = (i >> lq) & (TCP - 1), r = i >> (lq + ltcp);
+      if (col < W + 2) {
+        const int yy = y0 - 1 + r, xx = col - 1;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        st_cp_async16(tile_s + (uint32_t)i * 16u, in ? dp + (size_t)(yy * W + xx) * d_ps + c4 * 4 : dp, in ? 16u : 0u);
+      }
+    }
+  }
+  load_taps(lv, ws4, bs4, tid);
+  st_cp_async_wait_all();
+  __syncthreads();
+
+  const int c4 = tid & (CQ - 1), slot = tid >> lq;
+  const int XW = 1 << lv.lxw;
+  const int rpp = (ST_THREADS >> lq) >> lv.lxw;                  // rows per pass
+  const int sx = slot & (XW - 1), sy = slot >> lv.lxw;
+  const uint32_t thr = drop_threshold16(s.drop_p);
+  const float4* wk = ws4 + c4;
+  const float4 b0 = bs4[c4], b1 = K > 1 ? bs4[CQ + c4] : f4zero();
+  float* obase = lv.out + (size_t)p * HW * ctot + s.out_coff + c4 * 4;
+  for (int yb = 0; yb < rows; yb += rpp) {
+    const int y = yb + sy;
+    for (int x0 = 0; x0 < W; x0 += XW) {
+      const int x = x0 + sx;
+      if (y < rows && x < W) {
+        const float4* t0 = tile + (((y << ltcp) + x) << lq) + c4;     // halo coordinates: (y, x) = top-left neighbour
+        float4 acc0 = b0, acc1 = b1;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
           for (int bb = 0; bb < 3; ++bb) {
-            const int yy = y - a + 1, xx = x - bb + 1;
-            if (yy >= 0 && yy < s.H && xx >= 0 && xx < s.W) {
-              const int np_ = yy * s.W + xx;
-              float4 v = ldg4(dout + ((size_t)p * HW + np_) * s.out_ctot + s.out_coff + och);
-              const float4 k4 = drop_factor4(s, thr, p, och, np_);
-              acc.x = fmaf(w0[a * 3 + bb], v.x * k4.x, acc.x);
-              acc.y = fmaf(w1[a * 3 + bb], v.y * k4.y, acc.y);
-              acc.z = fmaf(w2[a * 3 + bb], v.z * k4.z, acc.z);
-              acc.w = fmaf(w3[a * 3 + bb], v.w * k4.w, acc.w);
+            const float4 nb = t0[((a << ltcp) + bb) << lq];
+            const float4 w0 = wk[(a * 3 + bb) << lq];
+            acc0.x = fmaf(w0.x, nb.x, acc0.x);
+            acc0.y = fmaf(w0.y, nb.y, acc0.y);
+            acc0.z = fmaf(w0.z, nb.z, acc0.z);
+            acc0.w = fmaf(w0.w, nb.w, acc0.w);
+            if (K > 1) {
+              const float4 w1 = wk[(9 + a * 3 + bb) << lq];
+              acc1.x = fmaf(w1.x, nb.x, acc1.x);
+              acc1.y = fmaf(w1.y, nb.y, acc1.y);
+              acc1.z = fmaf(w1.z, nb.z, acc1.z);
+              acc1.w = fmaf(w1.w, nb.w, acc1.w);
             }
           }
-      }
-    }
-    *reinterpret_cast<float4*>(ddp) = acc;   // zero for frames that feed no pair
-    return;
-  }
-}
-
-// tap / bias gradients: persistent blocks, register accumulation (separate kernel: it needs ~120 registers, the
-// streaming halves above should keep their occupancy)
-//   dw[c,kk,a,b] = sum_{p,y,x} dS[p,kk*Cs+c,y,x] * D[fs(p),c,y+a-1,x+b-1],  dbias[kk*Cs+c] = sum dS
-__global__ void __launch_bounds__(ST_THREADS)
-stencil_tapgrad_kernel(const offk_stencil_t s, const float* __restrict__ dout, const float* __restrict__ d,
-                       float* __restrict__ dw, float* __restrict__ dbias) {
-  __shared__ float acc_s[ST_MAX_CS * 2 * 10];
-  const int HW = s.H * s.W;
-  const int tid = threadIdx.x;
-  const uint32_t thr = drop_threshold24(s.drop_p);
-  const int cq = s.Cs >> 2;
-  const int n_wblocks = gridDim.x;
-  const int wb = blockIdx.x;
-  for (int i = tid; i < s.Cs * s.K * 10; i += ST_THREADS) acc_s[i] = 0.f;
-  __syncthreads();
-  const int P = s.B * (s.L - 1);
-  const int groups = ST_THREADS / cq;                 // (pair,pixel) positions handled per block iteration
-  const int c = (tid % cq) << 2;
-  const int slot = tid / cq;
-  const bool need_dw = dw != nullptr;
-  for (int kk = 0; kk < s.K; ++kk) {
-    float sums[4][10];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 10; ++j) sums[i][j] = 0.f;
-    const int och = kk * s.Cs + c;
-    if (slot < groups) {
-      for (size_t pos = (size_t)wb * groups + slot; pos < (size_t)P * HW; pos += (size_t)n_wblocks * groups) {
-        const int p = (int)(pos / HW), pix = (int)(pos - (size_t)p * HW);
-        const int y = pix / s.W, x = pix - y * s.W;
-        float4 v = ldg4(dout + ((size_t)p * HW + pix) * s.out_ctot + s.out_coff + och);
-        const float4 k4 = drop_factor4(s, thr, p, och, pix);
-        v.x *= k4.x; v.y *= k4.y; v.z *= k4.z; v.w *= k4.w;
-        sums[0][9] += v.x; sums[1][9] += v.y; sums[2][9] += v.z; sums[3][9] += v.w;
-        if (need_dw) {
-          const float* dp = d + (size_t)spatial_frame(s, p) * s.d_fs + c;
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int bb = 0; bb < 3; ++bb) {
-              const int yy = y + a - 1, xx = x + bb - 1;
-              if (yy >= 0 && yy < s.H && xx >= 0 && xx < s.W) {
-                const float4 nv = ldg4(dp + (size_t)(yy * s.W + xx) * s.d_ps);
-                sums[0][a * 3 + bb] = fmaf(v.x, nv.x, sums[0][a * 3 + bb]);
-                sums[1][a * 3 + bb] = fmaf(v.y, nv.y, sums[1][a * 3 + bb]);
-                sums[2][a * 3 + bb] = fmaf(v.z, nv.z, sums[2][a * 3 + bb]);
-                sums[3][a * 3 + bb] = fmaf(v.w, nv.w, sums[3][a * 3 + bb]);
-              }
-            }
+        const int pix = (y0 + y) * W + x;
+        float* op = obase + (size_t)pix * ctot;
+        const float4 k0 = drop_factor4(s, thr, p, c4 * 4, pix, HW);
+        stg_stream4(op, make_float4(acc0.x * k0.x, acc0.y * k0.y, acc0.z * k0.z, acc0.w * k0.w));
+        if (K > 1) {
+          const float4 k1 = drop_factor4(s, thr, p, Cs + c4 * 4, pix, HW);
+          stg_stream4(op + Cs, make_float4(acc1.x * k1.x, acc1.y * k1.y, acc1.z * k1.z, acc1.w * k1.w));
         }
       }
     }
-    // lanes l and l^cq, l^2cq, ... hold the same channels (cq is a power of two <= 32 on this path)
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 10; ++j) {
-        float v = sums[i][j];
-        for (int o = 16; o >= cq; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) < cq && slot < groups) atomicAdd(&acc_s[((c + i) * s.K + kk) * 10 + j], v);
-      }
   }
-  __syncthreads();
-  for (int i = tid; i < s.Cs * s.K * 10; i += ST_THREADS) {
-    const int ck = i / 10, j = i - ck * 10;   // ck = c*K + kk
-    if (j < 9) {
-      if (need_dw) atomicAdd(dw + (size_t)ck * 9 + j, acc_s[i]);
-    } else if (dbias) {
-      const int cc = ck / s.K, kk = ck - cc * s.K;
-      atomicAdd(dbias + kk * s.Cs + cc, acc_s[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+// dG[b,t] = (dT[b,t-1] - dT[b,t]) * (G[b,t] > 0)      (ReLU' of RGB_OFF.py:598); a streaming kernel of its own so that
+// it keeps a high occupancy (the spatial kernel below needs ~40 accumulator registers)
+__global__ void __launch_bounds__(ST_THREADS, 4)
+stencil_diff_bwd_temporal_kernel(const __grid_constant__ StBatch bt) {
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  const int r2 = (int)blockIdx.x - lv.blk0;
+  const int tid = threadIdx.x;
+  const int L = lv.s.L, Cg = lv.s.Cg, HW = lv.s.H * lv.s.W;
+  const int g_ps = lv.s.g_ps, ctot = lv.s.out_ctot;
+  const size_t g_fs = (size_t)lv.s.g_fs, dg_fs = (size_t)lv.dg_fs, o_fs = (size_t)HW * ctot;
+  const int b = r2 / lv.t_chunks, chunk = r2 - b * lv.t_chunks;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pix0 = chunk * (ST_WARPS * ST_TJ) + warp * ST_TJ;
+  bool ok[ST_TJ];
+#pragma unroll
+  for (int j = 0; j < ST_TJ; ++j) ok[j] = pix0 + j < HW;
+  for (int c = lane * 4; c < Cg; c += 128) {
+    const float* gp = lv.g + (size_t)b * L * g_fs + (size_t)pix0 * g_ps + c;
+    float* dgp = lv.dg + (size_t)b * L * dg_fs + (size_t)pix0 * g_ps + c;        // dg uses the pixel stride of g
+    const float* op = lv.dout + ((size_t)b * (L - 1) * HW + pix0) * ctot + lv.s.out_coff + lv.s.K * lv.s.Cs + c;
+    float4 prev[ST_TJ];
+#pragma unroll
+    for (int j = 0; j < ST_TJ; ++j) prev[j] = f4zero();
+    for (int t0 = 0; t0 < L; t0 += ST_BC) {
+      float4 gv[ST_BC][ST_TJ], dt[ST_BC][ST_TJ];
+#pragma unroll
+      for (int i = 0; i < ST_BC; ++i) {
+#pragma unroll
+        for (int j = 0; j < ST_TJ; ++j) {
+          gv[i][j] = (ok[j] && t0 + i < L) ? ldg_stream4(gp + j * g_ps) : f4zero();
+          dt[i][j] = (ok[j] && t0 + i < L - 1) ? ldg_stream4(op + j * ctot) : f4zero();
+        }
+        gp += g_fs;
+        op += o_fs;
+      }
+#pragma unroll
+      for (int i = 0; i < ST_BC; ++i) {
+        if (t0 + i < L) {
+#pragma unroll
+          for (int j = 0; j < ST_TJ; ++j) {
+            float4 r = f4sub(prev[j], dt[i][j]);
+            r.x = gv[i][j].x > 0.f ? r.x : 0.f;
+            r.y = gv[i][j].y > 0.f ? r.y : 0.f;
+            r.z = gv[i][j].z > 0.f ? r.z : 0.f;
+            r.w = gv[i][j].w > 0.f ? r.w : 0.f;
+            if (ok[j]) stg_stream4(dgp + j * g_ps, r);
+            prev[j] = dt[i][j];
+          }
+        }
+        dgp += dg_fs;
+      }
     }
   }
 }
 
+// spatial: dD = transposed stencil of the dropped dS; tap / bias gradients.  Persistent blocks over (frame, band) items.
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
+  extern __shared__ __align__(16) float4 st_smem[];
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  const offk_stencil_t& s = lv.s;
+  const int rel = (int)blockIdx.x - lv.blk0;
+  const int tid = threadIdx.x;
+  const int H = s.H, W = s.W, HW = H * W, K = s.K, Cs = s.Cs, ctot = s.out_ctot, d_ps = s.d_ps;
+  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq, TCP = 1 << ltcp;
+  float4* tile = st_smem;                                        // dS band + halo [rows+2][TCP][CQ]
+  float4* ws4 = st_smem + (((lv.band_rows + 2) << ltcp) << lq);  // [K*9][CQ]
+  float* red = reinterpret_cast<float*>(ws4 + K * 9 * CQ);       // [10][Cs] block reduction of the tap gradients
+  load_taps(lv, ws4, nullptr, tid);
+  const bool need_dw = lv.dw != nullptr, need_db = lv.dbias != nullptr;
+  const bool need_acc = need_dw || need_db;
+  for (int i = tid; i < 10 * Cs; i += ST_THREADS) red[i] = 0.f;
+  const int c4 = tid & (CQ - 1), slot = tid >> lq;
+  const int XW = 1 << lv.lxw;
+  const int rpp = (ST_THREADS >> lq) >> lv.lxw;
+  const int sx = slot & (XW - 1), sy = slot >> lv.lxw;
+  const uint32_t thr = drop_threshold16(s.drop_p);
+
+  for (int kk = 0; kk < K; ++kk) {
+    float4 wacc[9], bacc = f4zero();
+#pragma unroll
+    for (int j = 0; j < 9; ++j) wacc[j] = f4zero();
+    const int och = kk * Cs + c4 * 4;
+    const float4* wk = ws4 + kk * 9 * CQ + c4;
+    for (int item = rel; item < lv.n_sitems; item += lv.n_sblocks) {
+      const int f = item / lv.bands, band = item - f * lv.bands;
+      const int y0 = band * lv.band_rows;
+      const int rows = min(lv.band_rows, H - y0);
+      const int p = spatial_pair_of_frame(s, f);
+      __syncthreads();                                           // previous item's tile fully consumed (and ws4 / red ready)
+      if (p >= 0) {
+        const float* sp = lv.dout + (size_t)p * HW * ctot + s.out_coff + och;
+        const int n_cells = ((rows + 2) << ltcp) << lq;
+        for (int i = tid; i < n_cells; i += ST_THREADS) {        // (the cell's c4 equals this thread's c4: 256 % CQ == 0)
+          const int col = (i >> lq) & (TCP - 1), r = i >> (lq + ltcp);
+          if (col < W + 2) {
+            const int yy = y0 - 1 + r, xx = col - 1;
+            float4 v = f4zero();
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+              const int np_ = yy * W + xx;
+              v = ldg4(sp + (size_t)np_ * ctot);
+              const float4 k4 = drop_factor4(s, thr, p, och, np_, HW);
+              v.x *= k4.x; v.y *= k4.y; v.z *= k4.z; v.w *= k4.w;
+            }
+            tile[i] = v;
+          }
+        }
+      }
+      __syncthreads();
+      float* ddf = lv.dd + (size_t)f * lv.dd_fs + c4 * 4;          // dd uses the pixel stride of d
+      const float* dfp = (need_dw && p >= 0) ? lv.d + (size_t)spatial_frame(s, p) * s.d_fs + c4 * 4 : nullptr;
+      for (int yb = 0; yb < rows; yb += rpp) {
+        const int y = yb + sy;
+        for (int x0 = 0; x0 < W; x0 += XW) {
+          const int x = x0 + sx;
+          if (y < rows && x < W) {
+            const int pix = (y0 + y) * W + x;
+            float4 acc = f4zero();
+            if (p >= 0) {
+              float4 dv = f4zero();
+              if (dfp) dv = ldg4(dfp + (size_t)pix * d_ps);
+              // dS(y-a+1, x-b+1) sits at halo coordinates (y+2-a, x+2-b)
+              const float4* t2 = tile + ((((y + 2) << ltcp) + x + 2) << lq) + c4;
+#pragma unroll
+              for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb) {
+                  const float4 nv = *(t2 - (((a << ltcp) + bb) << lq));
+                  const float4 wv = wk[(a * 3 + bb) << lq];
+                  acc.x = fmaf(wv.x, nv.x, acc.x);
+                  acc.y = fmaf(wv.y, nv.y, acc.y);
+                  acc.z = fmaf(wv.z, nv.z, acc.z);
+                  acc.w = fmaf(wv.w, nv.w, acc.w);
+                  wacc[a * 3 + bb].x = fmaf(dv.x, nv.x, wacc[a * 3 + bb].x);
+                  wacc[a * 3 + bb].y = fmaf(dv.y, nv.y, wacc[a * 3 + bb].y);
+                  wacc[a * 3 + bb].z = fmaf(dv.z, nv.z, wacc[a * 3 + bb].z);
+                  wacc[a * 3 + bb].w = fmaf(dv.w, nv.w, wacc[a * 3 + bb].w);
+                  if (a == 1 && bb == 1) { bacc.x += nv.x; bacc.y += nv.y; bacc.z += nv.z; bacc.w += nv.w; }
+                }
+            }
+            float4* o = reinterpret_cast<float4*>(ddf + (size_t)pix * d_ps);
+            if (kk > 0) {
+              const float4 old = *o;
+              acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+            }
+            *o = acc;                                              // zero for frames that feed no pair
+          }
+        }
+      }
+    }
+    if (need_acc) {
+      // lanes l, l^CQ, l^2CQ, ... hold the same channels
+      float vals[40];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) { vals[4 * j] = wacc[j].x; vals[4 * j + 1] = wacc[j].y; vals[4 * j + 2] = wacc[j].z; vals[4 * j + 3] = wacc[j].w; }
+      vals[36] = bacc.x; vals[37] = bacc.y; vals[38] = bacc.z; vals[39] = bacc.w;
+#pragma unroll
+      for (int q = 0; q < 40; ++q) {
+        float v = vals[q];
+        for (int o = 16; o >= CQ; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) < CQ) atomicAdd(&red[(q >> 2) * Cs + c4 * 4 + (q & 3)], v);
+      }
+      __syncthreads();
+      for (int i = tid; i < 10 * Cs; i += ST_THREADS) {
+        const int j = i / Cs, c = i - j * Cs;
+        const float v = red[i];
+        red[i] = 0.f;
+        if (j < 9) {
+          if (need_dw) atomicAdd(lv.dw + ((size_t)c * K + kk) * 9 + j, v);
+        } else if (need_db) {
+          atomicAdd(lv.dbias + kk * Cs + c, v);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
 static int check_stencil(const offk_stencil_t* s) {
   OFFK_REQUIRE(s != nullptr, "stencil: null descriptor");
   OFFK_REQUIRE(s->B >= 1 && s->L >= 2, "stencil: need B >= 1 and L >= 2 (got B=%d L=%d)", s->B, s->L);
   OFFK_REQUIRE(s->Cg >= 0 && s->Cs >= 0 && s->Cg + s->Cs > 0, "stencil: bad channel counts");
   OFFK_REQUIRE(s->Cg % 4 == 0 && s->Cs % 4 == 0 && s->Cs <= ST_MAX_CS, "stencil: channels must be multiples of 4, Cs <= %d",
                ST_MAX_CS);
-  OFFK_REQUIRE(s->Cs == 0 || ((s->Cs >> 2) <= 32 && (((s->Cs >> 2) & ((s->Cs >> 2) - 1)) == 0)),
-               "stencil: Cs/4 must be a power of two <= 32");
+  OFFK_REQUIRE(s->Cs == 0 || (((s->Cs >> 2) & ((s->Cs >> 2) - 1)) == 0), "stencil: Cs/4 must be a power of two");
   OFFK_REQUIRE(s->H >= 1 && s->W >= 1 && s->H < 32768 && s->W < 32768, "stencil: plane size");
   OFFK_REQUIRE(s->K >= 1 && s->K <= 2, "stencil: K must be 1 or 2");
   OFFK_REQUIRE(s->out_coff >= 0 && s->out_coff + s->K * s->Cs + s->Cg <= s->out_ctot, "stencil: channel slice");
@@ -329,59 +444,146 @@ static int check_stencil(const offk_stencil_t* s) {
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// geometry of the spatial blocks of one level; returns the dynamic shared memory the level needs (0 if Cs == 0)
+static int plan_spatial(StLevel& lv, bool backward) {
+  const offk_stencil_t& s = lv.s;
+  lv.lq = lv.ltcp = lv.lxw = 0;
+  lv.bands = lv.band_rows = 1;
+  lv.n_sitems = lv.n_sblocks = 0;
+  if (s.Cs == 0) return 0;
+  const int CQ = s.Cs / 4;
+  lv.lq = ilog2_ceil(CQ);
+  lv.ltcp = ilog2_ceil(s.W + 2);
+  const int row_bytes = (1 << lv.ltcp) * CQ * 16;
+  int max_rows = ST_TILE_BUDGET / row_bytes - 2;
+  if (max_rows < 1) max_rows = 1;
+  lv.bands = (s.H + max_rows - 1) / max_rows;
+  lv.band_rows = (s.H + lv.bands - 1) / lv.bands;
+  lv.bands = (s.H + lv.band_rows - 1) / lv.band_rows;
+  const int slots = ST_THREADS / CQ;
+  int lxw = ilog2_ceil(s.W);
+  while ((1 << lxw) > slots) --lxw;
+  lv.lxw = lxw;
+  const long long units = backward ? (long long)s.B * s.L : (long long)s.B * (s.L - 1);
+  const long long items = units * lv.bands;
+  lv.n_sitems = (int)items;
+  lv.n_sblocks = (int)items;
+  if (backward && (lv.dw || lv.dbias)) {
+    const long long cap = 2LL * sm_count();      // persistent: register-resident tap-gradient partial sums
+    if (items > cap) lv.n_sblocks = (int)cap;
+  }
+  const int tile_bytes = (lv.band_rows + 2) * row_bytes;
+  const int tap_bytes = s.K * 9 * CQ * 16;
+  const int extra = backward ? 10 * s.Cs * 4 : s.K * CQ * 16;
+  return tile_bytes + tap_bytes + extra;
+}
+
+static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, bool backward, void* stream) {
+  OFFK_REQUIRE(n >= 1 && n <= ST_MAX_LEVELS, "stencil batch: 1 <= n <= %d (got %d)", ST_MAX_LEVELS, n);
+  OFFK_REQUIRE(s != nullptr && io != nullptr, "stencil batch: null arrays");
+  StBatch bt;
+  bt.n = n;
+  long long n_t[ST_MAX_LEVELS];
+  int smem = 0;
+  for (int i = 0; i < n; ++i) {
+    if (int e = check_stencil(&s[i])) return e;
+    StLevel& lv = bt.lv[i];
+    lv.s = s[i];
+    lv.g = io[i].g; lv.d = io[i].d; lv.w = io[i].w; lv.bias = io[i].bias; lv.out = io[i].out;
+    lv.dout = io[i].dout; lv.dg = io[i].dg; lv.dd = io[i].dd; lv.dw = io[i].dw; lv.dbias = io[i].dbias;
+    lv.dg_fs = io[i].dg_fs; lv.dd_fs = io[i].dd_fs;
+    if (!backward) {
+      OFFK_REQUIRE(lv.out != nullptr && aligned16(lv.out), "stencil_fwd: out must be non-null and 16-byte aligned");
+      OFFK_REQUIRE(s[i].Cg == 0 || (lv.g && aligned16(lv.g)), "stencil_fwd: g must be 16-byte aligned");
+      OFFK_REQUIRE(s[i].Cs == 0 || (lv.d && lv.w && aligned16(lv.d)), "stencil_fwd: d / w missing or unaligned");
+      OFFK_REQUIRE(lv.bias == nullptr || aligned16(lv.bias), "stencil_fwd: bias must be 16-byte aligned");
+    } else {
+      OFFK_REQUIRE(lv.dout != nullptr && aligned16(lv.dout), "stencil_bwd: dout must be 16-byte aligned");
+      OFFK_REQUIRE(s[i].Cg == 0 || (lv.g && lv.dg && aligned16(lv.g) && aligned16(lv.dg) && lv.dg_fs % 4 == 0), "stencil_bwd: g/dg");
+      OFFK_REQUIRE(s[i].Cs == 0 || (lv.w && lv.dd && aligned16(lv.dd) && lv.dd_fs % 4 == 0), "stencil_bwd: w/dd missing");
+      OFFK_REQUIRE(lv.dw == nullptr || (lv.d != nullptr && aligned16(lv.d)), "stencil_bwd: tap gradient needs d");
+    }
+    const int need = plan_spatial(lv, backward);
+    OFFK_REQUIRE(need <= ST_SMEM_MAX, "stencil: halo tile of %d bytes exceeds %d (W=%d, Cs=%d)", need, ST_SMEM_MAX, s[i].W, s[i].Cs);
+    if (need > smem) smem = need;
+    const int HW = s[i].H * s[i].W;
+    const int per_blk = ST_WARPS * ST_TJ;
+    lv.t_chunks = s[i].Cg > 0 ? (HW + per_blk - 1) / per_blk : 1;
+    n_t[i] = s[i].Cg > 0 ? (long long)lv.t_chunks * s[i].B : 0;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stencil_diff_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stencil_diff_bwd_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
+    if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(stencil)");
+    attr_set = true;
+  }
+  if (!backward) {
+    // one grid: per level, spatial blocks first (heavier per byte), then temporal blocks
+    long long blk = 0;
+    for (int i = 0; i < n; ++i) {
+      bt.lv[i].blk0 = (int)blk;
+      blk += bt.lv[i].n_sblocks + n_t[i];
+      OFFK_REQUIRE(blk < 2147483647LL, "stencil: grid too large");
+    }
+    if (blk == 0) return 0;
+    stencil_diff_fwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+    return OFFK_LAUNCH_CHECK("stencil_diff_fwd");
+  }
+  // backward: a streaming kernel for dG and a persistent kernel for dD + tap gradients
+  long long blk = 0;
+  for (int i = 0; i < n; ++i) {
+    bt.lv[i].blk0 = (int)blk;
+    blk += n_t[i];
+    OFFK_REQUIRE(blk < 2147483647LL, "stencil: grid too large");
+  }
+  if (blk > 0) {
+    stencil_diff_bwd_temporal_kernel<<<(unsigned)blk, ST_THREADS, 0, as_stream(stream)>>>(bt);
+    if (int e = OFFK_LAUNCH_CHECK("stencil_diff_bwd_temporal")) return e;
+  }
+  blk = 0;
+  for (int i = 0; i < n; ++i) {
+    bt.lv[i].blk0 = (int)blk;
+    blk += bt.lv[i].n_sblocks;
+  }
+  if (blk > 0) {
+    stencil_diff_bwd_spatial_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+    return OFFK_LAUNCH_CHECK("stencil_diff_bwd_spatial");
+  }
+  return 0;
+}
 
 }  // namespace offk
 
 using namespace offk;
 
+extern "C" int offk_stencil_diff_fwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream) {
+  return launch_batch(n, s, io, false, stream);
+}
+
+extern "C" int offk_stencil_diff_bwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream) {
+  return launch_batch(n, s, io, true, stream);
+}
+
 extern "C" int offk_stencil_diff_fwd(const offk_stencil_t* s, const float* g, const float* d, const float* w,
                                      const float* bias, float* out, void* stream) {
-  if (int e = check_stencil(s)) return e;
-  OFFK_REQUIRE(out != nullptr && aligned16(out), "stencil_fwd: out must be non-null and 16-byte aligned");
-  OFFK_REQUIRE(s->Cg == 0 || (g && aligned16(g)), "stencil_fwd: g must be 16-byte aligned");
-  OFFK_REQUIRE(s->Cs == 0 || (d && w && aligned16(d)), "stencil_fwd: d / w missing or unaligned");
-  const long long HW = (long long)s->H * s->W;
-  const long long npos = HW * (s->Cg / 4);
-  const int per_blk = ST_THREADS * ST_TPOS;
-  const int tb = s->Cg > 0 ? (int)((npos + per_blk - 1) / per_blk) : 0;
-  const long long n_t = (long long)tb * s->B;
-  const long long P = (long long)s->B * (s->L - 1);
-  const long long n_s = s->Cs > 0 ? (P * HW * (s->Cs / 4) + ST_THREADS - 1) / ST_THREADS : 0;
-  if (n_t + n_s == 0) return 0;
-  OFFK_REQUIRE(n_t + n_s < 2147483647LL, "stencil_fwd: grid too large");
-  stencil_diff_fwd_kernel<<<(unsigned)(n_t + n_s), ST_THREADS, 0, as_stream(stream)>>>(*s, g, d, w, bias, out,
-                                                                                      tb > 0 ? tb : 1, (int)n_t);
-  return OFFK_LAUNCH_CHECK("stencil_diff_fwd");
+  offk_stencil_io_t io = {};
+  io.g = g; io.d = d; io.w = w; io.bias = bias; io.out = out;
+  return launch_batch(1, s, &io, false, stream);
 }
 
 extern "C" int offk_stencil_diff_bwd(const offk_stencil_t* s, const float* dout, const float* g, const float* d,
                                      const float* w, float* dg, int64_t dg_fs, float* dd, int64_t dd_fs, float* dw,
                                      float* dbias, void* stream) {
-  if (int e = check_stencil(s)) return e;
-  OFFK_REQUIRE(dout != nullptr && aligned16(dout), "stencil_bwd: dout must be 16-byte aligned");
-  OFFK_REQUIRE(s->Cg == 0 || (g && dg && aligned16(g) && aligned16(dg) && dg_fs % 4 == 0), "stencil_bwd: g/dg");
-  OFFK_REQUIRE(s->Cs == 0 || (w && dd && aligned16(dd) && dd_fs % 4 == 0), "stencil_bwd: w/dd missing");
-  OFFK_REQUIRE(dw == nullptr || d != nullptr, "stencil_bwd: tap gradient needs d");
-  const long long HW = (long long)s->H * s->W;
-  const long long npos = HW * (s->Cg / 4);
-  const int per_blk = ST_THREADS * ST_TPOS;
-  const int tb = s->Cg > 0 ? (int)((npos + per_blk - 1) / per_blk) : 0;
-  const long long n_t = (long long)tb * s->B;
-  const long long n_s = s->Cs > 0 ? ((long long)s->B * s->L * HW * (s->Cs / 4) + ST_THREADS - 1) / ST_THREADS : 0;
-  long long n_w = 0;
-  if (s->Cs > 0 && (dw || dbias)) {
-    const long long groups = ST_THREADS / (s->Cs / 4);
-    const long long need = ((long long)s->B * (s->L - 1) * HW + groups - 1) / groups;
-    n_w = need < 2 * sm_count() ? need : 2 * sm_count();
-  }
-  if (n_t + n_s == 0) return 0;
-  OFFK_REQUIRE(n_t + n_s < 2147483647LL, "stencil_bwd: grid too large");
-  stencil_diff_bwd_kernel<<<(unsigned)(n_t + n_s), ST_THREADS, 0, as_stream(stream)>>>(
-      *s, dout, g, d, w, dg, (long long)dg_fs, dd, (long long)dd_fs, tb > 0 ? tb : 1, (int)n_t);
-  if (int e = OFFK_LAUNCH_CHECK("stencil_diff_bwd")) return e;
-  if (n_w > 0) {
-    stencil_tapgrad_kernel<<<(unsigned)n_w, ST_THREADS, 0, as_stream(stream)>>>(*s, dout, d, dw, dbias);
-    return OFFK_LAUNCH_CHECK("stencil_tapgrad");
-  }
-  return 0;
+  offk_stencil_io_t io = {};
+  io.g = g; io.d = d; io.w = w; io.dout = dout; io.dg = dg; io.dg_fs = dg_fs; io.dd = dd; io.dd_fs = dd_fs;
+  io.dw = dw; io.dbias = dbias;
+  return launch_batch(1, s, &io, true, stream);
 }

@@ -281,11 +281,16 @@ class OFFEngine:
 
         # ============ OFF units (RGB_OFF.py:596-616 and the eight copies)
         self._stencils = {}
-        fwd_lane = {"3a": 0, "3b": 0, "3c": 1, "4a": 1, "4b": 1, "4c": 1, "4d": 1, "5a": 2, "5b": 2}
-        self.stencil_fwd_steps = OrderedDict()
+        fwd_lane = {"28": 0, "14": 1, "7": 2}
+        self.stencil_fwd_steps = OrderedDict()        # stage -> batched stencil launch (bench.py times these)
+        stage_levels = OrderedDict((st, [t for t in S.LEVELS if S.LEVEL_STAGE[t] == st]) for st in S.STAGES)
+        n_lv = len(S.LEVELS)
+        self._st_desc = (L.OffkStencil * n_lv)()      # one contiguous array: stage batches are slices of it
+        self._st_io = (L.OffkStencilIO * n_lv)()
+        k4_steps = []
         for li, (tag, (cin, s)) in enumerate(S.LEVELS.items()):
             st = S.LEVEL_STAGE[tag]
-            fl, bl = fwd_lane[tag], li % 3
+            fl = fwd_lane[st]
             ctot, _, members = S.STAGES[st]
             coff = dict(members)[tag]
             geom = T.ConvGeom(N, cin, s, s, S.UNIT_C)
@@ -295,8 +300,8 @@ class OFFEngine:
                                 self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nchw")
             fwd.append(_on(k1, fl))
             self._tap_users[tag].append(getattr(k1, "gemm", k1))
-            # K2: fused spatial stencil + temporal difference + dropout + cat, into the stage buffer
-            sd = L.OffkStencil()
+            # K2 / K3 descriptors: fused spatial stencil + temporal difference + dropout + cat, into the stage buffer
+            sd = self._st_desc[li]
             sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, S.GEN_C, S.DOWN_C, 1, s, s
             sd.g_fs = sd.d_fs = S.UNIT_C * s * s
             sd.g_ps = sd.d_ps = S.UNIT_C
@@ -308,32 +313,45 @@ class OFFEngine:
                 dw3, db3 = gr[f"motion_spatial_grad_{tag}.weight"], gr[f"motion_spatial_grad_{tag}.bias"]
             else:
                 w3, b3, dw3, db3 = self.sobel_w, None, None, None
-            Fst, dFst = bf["F" + st], bf["dF" + st]
-            g_ptr, d_ptr = gd.data_ptr(), gd.data_ptr() + 4 * S.GEN_C     # D = channels [128,160) of every pixel
-            dg_ptr, dd_ptr = dgd.data_ptr(), dgd.data_ptr() + 4 * S.GEN_C
-            fs = S.UNIT_C * s * s
-
-            def k2(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, b3=b3, Fst=Fst, tag=tag):
-                L.check(lib.offk_stencil_diff_fwd(C.byref(sd), g_ptr, d_ptr, _ptr(w3), _ptr(b3), _ptr(Fst), stream),
-                        "stencil_fwd_" + tag)
-            fwd.append(_nm(k2, "stencil_fwd_" + tag, reads=[gd], writes=[Fst], lane=fl))
-            self.stencil_fwd_steps[tag] = k2
-
-            def k3(stream, sd=sd, g_ptr=g_ptr, d_ptr=d_ptr, w3=w3, dFst=dFst, dg_ptr=dg_ptr, dd_ptr=dd_ptr, fs=fs,
-                   dw3=dw3, db3=db3, tag=tag):
-                L.check(lib.offk_stencil_diff_bwd(C.byref(sd), _ptr(dFst), g_ptr, d_ptr, _ptr(w3), dg_ptr, fs, dd_ptr,
-                                                  fs, _ptr(dw3), _ptr(db3), stream), "stencil_bwd_" + tag)
-            _nm(k3, "stencil_bwd_" + tag, reads=[dFst, gd], writes=[dgd, dw3, db3], lane=bl)
-            k3.launches = ["stencil_bwd_" + tag] + (["stencil_tapgrad_" + tag] if self.variant == "rgb" else [])
-            bwd_units.append(k3)
+            io = self._st_io[li]
+            io.g, io.d = gd.data_ptr(), gd.data_ptr() + 4 * S.GEN_C            # D = channels [128,160) of every pixel
+            io.w, io.bias = w3.data_ptr(), (b3.data_ptr() if b3 is not None else None)
+            io.out, io.dout = bf["F" + st].data_ptr(), bf["dF" + st].data_ptr()
+            io.dg, io.dd = dgd.data_ptr(), dgd.data_ptr() + 4 * S.GEN_C
+            io.dg_fs = io.dd_fs = S.UNIT_C * s * s
+            io.dw = dw3.data_ptr() if dw3 is not None else None
+            io.dbias = db3.data_ptr() if db3 is not None else None
             # K4: weight / bias gradient of the fused 1x1 (no dX for the frozen taps unless asked, train_off.py:39-46)
             k4 = self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
                                   self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag), x_layout="nchw")
-            bwd_units.append(_on(k4, bl))
+            k4_steps.append(_on(k4, li % 3))
             self._tap_users[tag].append(k4)
             if self.tap_grads:
-                bwd_units += [_on(g, bl) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
-                                                                   self.tap_grad[tag], geom, x_layout="nchw")]
+                k4_steps += [_on(g, li % 3) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
+                                                                      self.tap_grad[tag], geom, x_layout="nchw")]
+        # K2: ONE stencil launch per stage-fusion buffer (its units' GEMMs precede it on the same lane)
+        tags = list(S.LEVELS)
+        for st, lv_tags in stage_levels.items():
+            i0, n = tags.index(lv_tags[0]), len(lv_tags)
+            assert tags[i0:i0 + n] == lv_tags
+
+            def k2(stream, i0=i0, n=n, st=st):
+                L.check(lib.offk_stencil_diff_fwd_batch(n, C.byref(self._st_desc[i0]), C.byref(self._st_io[i0]), stream),
+                        "stencil_fwd_" + st)
+            step = _nm(k2, "stencil_fwd_" + st, reads=[bf["gd_" + t] for t in lv_tags], writes=[bf["F" + st]],
+                       lane=fwd_lane[st])
+            fwd.append(step)
+            self.stencil_fwd_steps[st] = step
+        # K3: the backward of all nine units in ONE launch (every stage gradient dF* is complete by then)
+        grad3 = [gr[f"motion_spatial_grad_{t}.{k}"] for t in tags for k in ("weight", "bias")] if self.variant == "rgb" else []
+
+        def k3(stream):
+            L.check(lib.offk_stencil_diff_bwd_batch(n_lv, self._st_desc, self._st_io, stream), "stencil_bwd")
+        k3 = _nm(k3, "stencil_bwd", reads=[bf["dF" + st] for st in S.STAGES] + [bf["gd_" + t] for t in tags],
+                 writes=[bf["dgd_" + t] for t in tags] + grad3, lane=0)
+        k3.launches = ["stencil_bwd_temporal", "stencil_bwd_spatial"]
+        bwd_units.append(k3)
+        bwd_units += k4_steps
 
         # ============ stage convs
         def geom_of(name, n_img, s_in, x_ctot=0, x_coff=0, y_ctot=0, y_coff=0):
@@ -516,11 +534,8 @@ class OFFEngine:
                     _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n), "unpermute " + name,
                     reads=[self.dwp[name]], writes=[gr[name + ".weight"]], lane=1))
         self.fwd_steps = pre + fwd
-        # kernels of liboffk launched per pass (split-K forward convs = GEMM + bias/activation pass; the learned
-        # stencil's backward = data-gradient kernel + tap-gradient kernel)
-        count = lambda steps: sum(2 if getattr(st, "_split", False) else 1 for st in steps)
-        self.launches_fwd = count(self.fwd_steps)
-        self.launches_bwd = count(bwd_stage + post + bwd_units) + (len(S.LEVELS) if self.variant == "rgb" else 0)
+        # kernels of liboffk launched per pass (cudaMemsetAsync zero-fills are not kernels)
+        count = lambda steps: sum(len([n for n in _names(st) if not _is_memset(n)]) for st in steps)
         # gradient accumulators start from zero (split-K / atomic accumulation); grads_flat only when asked
         self._zero_grads = True
         gflat, dwflat = self.grads_flat, self.dwp_flat
@@ -532,6 +547,8 @@ class OFFEngine:
         self.bwd_stage_steps = zero + bwd_stage + post
         self.bwd_unit_steps = bwd_units
         self.bwd_steps = self.bwd_stage_steps + self.bwd_unit_steps
+        self.launches_fwd = count(self.fwd_steps)
+        self.launches_bwd = count(self.bwd_steps)
         # parameters and taps are read-only inside a pass: never a hazard
         ro = [self.params_flat] + [t for ts in self.tap_sets for t in ts.values()]
         if self.variant == "flow":
@@ -641,7 +658,7 @@ class OFFEngine:
         """One name per device launch of forward() + backward(), in issue order (for annotating ncu launch lists)."""
         out = [n for st in self.fwd_steps for n in _names(st)]
         out += [n for st in self.bwd_steps for n in _names(st)]    # (the d_out copies are cudaMemcpyAsync, not kernels)
-        return out
+        return [n for n in out if not _is_memset(n)]
 
     def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None):
         """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads).
@@ -691,6 +708,10 @@ def _auto_tile_n(M: int, N: int) -> int:
             if mt * (N // bn) >= 140:
                 break
     return best
+
+
+def _is_memset(name):
+    return name.endswith(".zero") or name.startswith("zero ")
 
 
 def _nm(fn, name, reads=(), writes=(), lane=0):

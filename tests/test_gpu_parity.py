@@ -147,14 +147,17 @@ def test_stencil_diff_fwd_bwd(dev, case):
     if drop == 1:
         keep = mask.double() * 5.0
     elif drop == 2:      # counter-hash dropout: regenerate on the host with the library's own hash
-        idx = np.arange(P * K * Cs * S * S, dtype=np.uint64)
-        x = np.uint64(1234) + idx * np.uint64(0x9E3779B97F4A7C15)
+        # element index = channels-last ((p*HW + pix)*K*Cs + ch); 4 consecutive elements share one splitmix64 hash
+        n_el = P * K * Cs * S * S
+        quad = np.arange(n_el // 4, dtype=np.uint64)
+        x = np.uint64(1234) + quad * np.uint64(0x9E3779B97F4A7C15)
         x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9); x ^= x >> np.uint64(27)
         x *= np.uint64(0x94D049BB133111EB); x ^= x >> np.uint64(31)
-        k24 = (x >> np.uint64(40)).astype(np.int64) >= int(0.8 * 16777216.0)
-        assert all(bool(k24[i]) == bool(lib.offk_drop_keep_host(1234, int(i), 0.8)) for i in range(0, min(4096, len(k24)), 7))
-        assert 0.15 < k24.mean() < 0.25
-        keep = torch.from_numpy(k24.astype(np.float64)).to(dev).view(P, K * Cs, S, S) * 5.0
+        fields = np.stack([(x >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], 1).reshape(-1)
+        k16 = fields.astype(np.int64) >= int(0.8 * 65536.0)
+        assert all(bool(k16[i]) == bool(lib.offk_drop_keep_host(1234, int(i), 0.8)) for i in range(0, min(4096, n_el), 7))
+        assert 0.15 < k16.mean() < 0.25
+        keep = torch.from_numpy(k16.astype(np.float64)).to(dev).view(P, S, S, K * Cs).permute(0, 3, 1, 2) * 5.0
     else:
         keep = torch.ones(P, K * Cs, S, S, device=dev, dtype=torch.float64)
     Sg = Sg * keep

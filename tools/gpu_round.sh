@@ -11,6 +11,8 @@ for w in $WHAT; do
   case $w in
     tests)
       timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_$TAG.log; tail -5 $OUT/pytest_$TAG.log;;
+    sanitize)
+      timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k stencil > $OUT/sanitize_$TAG.log 2>&1; echo "sanitize exit $?" >> $OUT/sanitize_$TAG.log; tail -8 $OUT/sanitize_$TAG.log;;
     smoke)
       timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke_$TAG.log 2>&1; echo "smoke exit $?" >> $OUT/smoke_$TAG.log; tail -3 $OUT/smoke_$TAG.log;;
     bench)
