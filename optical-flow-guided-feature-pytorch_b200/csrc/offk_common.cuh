@@ -31,17 +31,22 @@ inline int cuda_check(cudaError_t e, const char* what) {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---- counter-hash dropout (OFFK_DROP_SEED) ----------------------------------
-// One splitmix64 hash serves FOUR consecutive elements (a channel quad of a channels-last tensor):
-//   keep(idx) = 16-bit field (idx & 3) of splitmix64(seed + golden * (idx >> 2)) >= p * 2^16.
+// One 64-bit hash (two 32-bit lowbias mixers) serves FOUR consecutive elements (a channel quad of a channels-last
+// tensor): keep(idx) = 16-bit field (idx & 3) of hash(seed, idx >> 2) >= p * 2^16.
 // Same on host and device so tests can regenerate the mask and the backward kernels never need it in memory.
-__host__ __device__ __forceinline__ uint64_t drop_hash64(uint64_t seed, uint64_t quad) {
-  uint64_t x = seed + quad * 0x9E3779B97F4A7C15ull;
-  x ^= x >> 30;
-  x *= 0xBF58476D1CE4E5B9ull;
-  x ^= x >> 27;
-  x *= 0x94D049BB133111EBull;
-  x ^= x >> 31;
+__host__ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x21F0AAADu;
+  x ^= x >> 15;
+  x *= 0x735A2D97u;
+  x ^= x >> 15;
   return x;
+}
+__host__ __device__ __forceinline__ uint64_t drop_hash64(uint64_t seed, uint64_t quad) {
+  const uint32_t q = (uint32_t)quad ^ ((uint32_t)(quad >> 32) * 0x9E3779B1u);
+  const uint32_t lo = drop_mix32(q * 0x9E3779B1u + (uint32_t)seed);
+  const uint32_t hi = drop_mix32((q ^ 0x85EBCA77u) * 0xC2B2AE3Du + (uint32_t)(seed >> 32));
+  return ((uint64_t)hi << 32) | lo;
 }
 __host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
   float t = p * 65536.0f;
@@ -50,8 +55,9 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {
 // bit i = keep decision of element 4*quad + i
 __host__ __device__ __forceinline__ uint32_t drop_keep4(uint64_t seed, uint64_t quad, uint32_t thr16) {
   const uint64_t h = drop_hash64(seed, quad);
-  return ((uint32_t)(h & 0xFFFFu) >= thr16 ? 1u : 0u) | ((uint32_t)((h >> 16) & 0xFFFFu) >= thr16 ? 2u : 0u) |
-         ((uint32_t)((h >> 32) & 0xFFFFu) >= thr16 ? 4u : 0u) | ((uint32_t)(h >> 48) >= thr16 ? 8u : 0u);
+  const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+  return ((lo & 0xFFFFu) >= thr16 ? 1u : 0u) | ((lo >> 16) >= thr16 ? 2u : 0u) |
+         ((hi & 0xFFFFu) >= thr16 ? 4u : 0u) | ((hi >> 16) >= thr16 ? 8u : 0u);
 }
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thr16) {
   return (drop_keep4(seed, idx >> 2, thr16) >> (idx & 3u)) & 1u;

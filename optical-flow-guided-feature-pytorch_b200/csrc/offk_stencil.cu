@@ -2,34 +2,39 @@
 //
 // One launch serves a BATCH of OFF units (the units feeding one stage-fusion buffer, or all nine in the backward
 // pass), so the 14x14 and 7x7 levels -- a few MB each -- do not pay one launch latency apiece.  A block is either
-//   a temporal block : (clip, 32 pixels).  One warp = the 128 reduced channels of a pixel (lane = channel quad), so
-//                      there is no index arithmetic beyond pointer increments.  The warp walks t = 0..L-1 with the
-//                      loads of frame t+1 issued before the difference of frame t is stored: every G frame is read
-//                      exactly once (128-bit, 512 contiguous bytes per warp), every difference written once, and
-//                      8 independent 16-byte loads per thread are in flight.
+//   a temporal block : (clip, 64 pixels).  One warp = the 128 reduced channels of a pixel (lane = channel quad), so
+//                      there is no index arithmetic beyond pointer increments.  A warp walks 4 pixel pairs; for each
+//                      pair every frame is read exactly once (128-bit loads, 512 contiguous bytes per warp), all
+//                      frames of the pair in flight together (L = 3) or two frames ahead (general L), and every
+//                      difference G(t+1) - G(t) is written once.
 //   a spatial block  : (pair, band of rows).  The D band plus a one-pixel halo is staged in shared memory with
-//                      16-byte cp.async (zero-fill gives the conv's zero padding), then each thread produces
-//                      (pixel, 4 channels) outputs from nine LDS.128 neighbours and per-channel taps kept in
-//                      shared memory; bias, dropout and the store at the unit's channel offset of the stage buffer
-//                      follow.  K = 2 emits two maps per channel (Sobel x and y).
-// No torch.cat, no sub, no conv2d, no separate dropout launch.
+//                      16-byte cp.async (zero-fill gives the conv's zero padding); each thread then produces two
+//                      horizontally adjacent (pixel, 4 channels) outputs from twelve LDS.128 neighbours with the
+//                      per-channel taps held in registers; bias, dropout and the stores at the unit's channel offset
+//                      of the stage buffer follow.  K = 2 emits two maps per channel (Sobel x and y).
+// Spatial blocks (instruction-heavy, few bytes) are spread evenly between the temporal blocks (streaming) of their
+// level.  No torch.cat, no sub, no conv2d, no separate dropout launch.
 //
 // Backward mirrors it: dG = (dT(t-1) - dT(t)) * [G > 0]; the spatial blocks stage the DROPPED spatial gradient dS
 // (band + halo) once and use the same nine neighbours twice: dD = transposed stencil of dS, and
 // dw[a,b] += D(y,x) * dS(y-a+1, x-b+1) (the tap gradient re-indexed so that it needs D only at the centre pixel).
-// Tap / bias gradients are accumulated in registers by persistent spatial blocks, reduced with warp shuffles and
+// Tap / bias gradients are accumulated in registers over a few consecutive items, reduced with warp shuffles and
 // shared-memory atomics, then one global atomicAdd per tap and block.
 #include "offk_common.cuh"
 
 namespace offk {
 
+#ifndef ST_FWD_MINB
+#define ST_FWD_MINB 3      // resident blocks per SM the kernels are compiled for (register cap 80)
+#endif
 constexpr int ST_THREADS = 256;
 constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_MAX_LEVELS = 12;
 constexpr int ST_MAX_CS = 64;                 // spatial channels per level (32 on the path)
-constexpr int ST_TJ = 2;                      // pixels per warp of a temporal block (lane = channel quad)
-constexpr int ST_FC = 3;                      // frames loaded per chunk, forward
-constexpr int ST_BC = 2;                      // frames loaded per chunk, backward (two tensors per frame)
+constexpr int ST_TIT = 4;                     // pixel pairs per warp: a temporal block covers ST_WARPS*2*ST_TIT = 64 pixels
+constexpr int ST_TPIX = ST_WARPS * 2 * ST_TIT;
+constexpr int ST_WQ = 16;                     // channel quads per tap row in shared memory (= ST_MAX_CS / 4)
+constexpr int ST_ITEMS = 4;                   // max (frame, band) items per backward spatial block
 constexpr int ST_TILE_BUDGET = 24 * 1024;     // target size of a halo tile (bytes)
 constexpr int ST_SMEM_MAX = 64 * 1024;
 
@@ -47,11 +52,16 @@ struct StLevel {
   float* dbias;
   long long dg_fs, dd_fs;
   int blk0;            // first block of this level
-  int n_sblocks;       // spatial blocks (forward: one per item; backward: persistent over items)
+  int n_sblocks;       // spatial blocks
   int n_sitems;        // spatial items = (pair | frame) x band
+  int n_tblocks;       // temporal blocks
+  int lstride;         // log2 spacing of the spatial blocks inside the level's block range
   int bands, band_rows;
   int t_chunks;        // temporal blocks per clip
-  int lq, ltcp, lxw;   // log2: channel quads per pixel, tile column pitch, x positions per pass
+  int ipb;             // backward: (frame, band) items per spatial block
+  int lq, ltcp;        // log2: channel quads per pixel, tile column pitch
+  int lpw;             // forward: log2 pixel-PAIR slots per row and pass
+  int lxw;             // backward: log2 pixel slots per row and pass
 };
 struct StBatch {
   int n;
@@ -60,6 +70,16 @@ struct StBatch {
 
 __device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ void f4fma(float4& acc, float4 w, float4 v) {
+  acc.x = fmaf(w.x, v.x, acc.x);
+  acc.y = fmaf(w.y, v.y, acc.y);
+  acc.z = fmaf(w.z, v.z, acc.z);
+  acc.w = fmaf(w.w, v.w, acc.w);
+}
+__device__ __forceinline__ float4 relu_gate4(float4 g, float4 r) {
+  return make_float4(g.x > 0.f ? r.x : 0.f, g.y > 0.f ? r.y : 0.f, g.z > 0.f ? r.z : 0.f, g.w > 0.f ? r.w : 0.f);
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_cp_async16(uint32_t dst, const float* src, uint32_t src_bytes) {
@@ -83,16 +103,16 @@ __device__ __forceinline__ int spatial_pair_of_frame(const offk_stencil_t& s, in
 }
 // keep-factors of the 4 spatial outputs (p, och..och+3, pix).  OFFK_DROP_MASK: the mask is indexed like the
 // reference's dropout input [P, K*Cs, H, W] (RGB_OFF.py:612), so injected masks keep the reference's layout.
-// OFFK_DROP_SEED: one 64-bit hash per channel quad of the channels-last element index ((p*HW + pix)*K*Cs + och).
-__device__ __forceinline__ float4 drop_factor4(const offk_stencil_t& s, uint32_t thr, int p, int och, int pix, int HW) {
+// OFFK_DROP_SEED: one hash per channel quad; quad = channels-last element index ((p*HW + pix)*K*Cs + och) / 4.
+__device__ __forceinline__ float4 drop_factor4(const offk_stencil_t& s, uint32_t thr, int p, int och, int pix, int HW,
+                                               uint64_t quad) {
   if (s.drop_mode == OFFK_DROP_NONE) return make_float4(1.f, 1.f, 1.f, 1.f);
-  const int KC = s.K * s.Cs;
   uint32_t keep;
   if (s.drop_mode == OFFK_DROP_MASK) {
-    const uint8_t* m = s.keep_mask + ((size_t)p * KC + och) * (size_t)HW + pix;
+    const uint8_t* m = s.keep_mask + ((size_t)p * (s.K * s.Cs) + och) * (size_t)HW + pix;
     keep = (m[0] != 0 ? 1u : 0u) | (m[HW] != 0 ? 2u : 0u) | (m[2 * (size_t)HW] != 0 ? 4u : 0u) | (m[3 * (size_t)HW] != 0 ? 8u : 0u);
   } else {
-    keep = drop_keep4(s.seed, (((uint64_t)p * HW + pix) * KC + och) >> 2, thr);
+    keep = drop_keep4(s.seed, quad, thr);
   }
   const float k = s.keep_scale;
   return make_float4(keep & 1u ? k : 0.f, keep & 2u ? k : 0.f, keep & 4u ? k : 0.f, keep & 8u ? k : 0.f);
@@ -105,217 +125,292 @@ __device__ __forceinline__ const StLevel& find_level(const StBatch& bt, int blk)
   return bt.lv[li];
 }
 
-// per-channel taps and bias as float4 over 4 consecutive channels: ws4[(kk*9 + j)*CQ + c4], bs4[kk*CQ + c4]
+// Spatial blocks sit at every (1 << lstride)-th position of the level's block range until all are placed; the other
+// positions are temporal blocks.  Returns the spatial index (>= 0) or ~temporal index.
+__device__ __forceinline__ int block_role(const StLevel& lv, int rel) {
+  const int ls = lv.lstride, sidx = rel >> ls;
+  if ((rel & ((1 << ls) - 1)) == 0 && sidx < lv.n_sblocks) return sidx;
+  const int before = min(lv.n_sblocks, (rel + (1 << ls) - 1) >> ls);
+  return ~(rel - before);
+}
+
+// per-channel taps and bias as float4 over 4 consecutive channels, fixed stride so that the tap index is an immediate
+// offset: ws4[(kk*9 + j)*ST_WQ + c4], bs4[kk*ST_WQ + c4]
 __device__ __forceinline__ void load_taps(const StLevel& lv, float4* ws4, float4* bs4, int tid) {
-  const offk_stencil_t& s = lv.s;
-  const int CQ = 1 << lv.lq, K9 = s.K * 9;
-  for (int i = tid; i < K9 * CQ; i += ST_THREADS) {
-    const int c4 = i & (CQ - 1), kj = i >> lv.lq;
-    const float* b = lv.w + (size_t)(c4 * 4) * K9 + kj;          // w[c][kk][3][3]: channel stride K*9
-    ws4[i] = make_float4(__ldg(b), __ldg(b + K9), __ldg(b + 2 * K9), __ldg(b + 3 * K9));
+  const int K = lv.s.K, Cs = lv.s.Cs, K9 = K * 9, CQ = 1 << lv.lq;
+  for (int i = tid; i < K9 * ST_WQ; i += ST_THREADS) {
+    const int c4 = i & (ST_WQ - 1), kj = i / ST_WQ;
+    if (c4 < CQ) {
+      const float* b = lv.w + (size_t)(c4 * 4) * K9 + kj;          // w[c][kk][3][3]: channel stride K*9
+      ws4[i] = make_float4(__ldg(b), __ldg(b + K9), __ldg(b + 2 * K9), __ldg(b + 3 * K9));
+    }
   }
   if (bs4) {
-    for (int i = tid; i < s.K * CQ; i += ST_THREADS) {
-      const int c4 = i & (CQ - 1), kk = i >> lv.lq;
-      bs4[i] = lv.bias ? ldg4(lv.bias + kk * s.Cs + c4 * 4) : f4zero();
+    for (int i = tid; i < K * ST_WQ; i += ST_THREADS) {
+      const int c4 = i & (ST_WQ - 1), kk = i / ST_WQ;
+      if (c4 < CQ) bs4[i] = lv.bias ? ldg4(lv.bias + kk * Cs + c4 * 4) : f4zero();
+    }
+  }
+}
+
+struct StNoXform {
+  __device__ __forceinline__ float4 operator()(float4 v, int) const { return v; }
+};
+
+// Stage rows [y0-1, y0+rows] x columns [-1, W] x Cs channels of frame `src` into tile[(r*TCP + col)*CQ + c4]
+// (zero outside the plane).  RAW: 16-byte cp.async with zero-fill; otherwise through registers with `xform`.
+template <bool RAW, typename F>
+__device__ __forceinline__ void stage_tile(const StLevel& lv, float4* tile, const float* src, int src_ps, int y0, int rows,
+                                           int tid, F xform) {
+  const int H = lv.s.H, W = lv.s.W, lq = lv.lq, lcpr = lv.ltcp + lv.lq, CQ = 1 << lq;
+  const uint32_t tile_s = st_smem_u32(tile);
+  if ((1 << lcpr) <= ST_THREADS) {
+    // a thread owns one (column, channel quad) and walks the rows
+    const int rr = tid >> lcpr, within = tid & ((1 << lcpr) - 1), col = within >> lq, c4 = within & (CQ - 1);
+    const int rpi = ST_THREADS >> lcpr, xx = col - 1;
+    const bool colok = col < W + 2, xin = xx >= 0 && xx < W;
+    int off = ((y0 - 1 + rr) * W + xx) * src_ps + c4 * 4;
+    int cell = (rr << lcpr) + within;
+    const int off_step = rpi * W * src_ps, cell_step = rpi << lcpr;
+    for (int r = rr; r < rows + 2; r += rpi, off += off_step, cell += cell_step) {
+      const int yy = y0 - 1 + r;
+      const bool in = xin && yy >= 0 && yy < H;
+      if (colok) {
+        if (RAW) st_cp_async16(tile_s + (uint32_t)cell * 16u, in ? src + off : src, in ? 16u : 0u);
+        else tile[cell] = in ? xform(ldg4(src + off), yy * W + xx) : f4zero();
+      }
+    }
+  } else {
+    const int TCP = 1 << lv.ltcp;
+    const int n_cells = (rows + 2) << lcpr;
+    for (int i = tid; i < n_cells; i += ST_THREADS) {
+      const int c4 = i & (CQ - 1), col = (i >> lq) & (TCP - 1), r = i >> lcpr;
+      if (col < W + 2) {
+        const int yy = y0 - 1 + r, xx = col - 1;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const int off = (yy * W + xx) * src_ps + c4 * 4;
+        if (RAW) st_cp_async16(tile_s + (uint32_t)i * 16u, in ? src + off : src, in ? 16u : 0u);
+        else tile[i] = in ? xform(ldg4(src + off), yy * W + xx) : f4zero();
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-// temporal difference (RGB_OFF.py:599-604): thread = (ST_TJ pixels, one channel quad); frames are walked in chunks of
-// ST_FC so that ST_TJ*ST_FC independent 16-byte loads are in flight per thread at ~50 % occupancy.
+// temporal difference (RGB_OFF.py:599-604).  LT = 3: fully unrolled, the three frames of a pixel pair in flight together;
+// LT = 0: any L, frames t+1 and t+2 requested before the difference of frame t is stored.
+template <int LT>
 __device__ __forceinline__ void temporal_fwd(const StLevel& lv, int r2, int tid) {
   const int L = lv.s.L, Cg = lv.s.Cg, HW = lv.s.H * lv.s.W;
+  const size_t g_fs = (size_t)lv.s.g_fs, o_fs = (size_t)HW * lv.s.out_ctot;
   const int g_ps = lv.s.g_ps, ctot = lv.s.out_ctot;
-  const size_t g_fs = (size_t)lv.s.g_fs, o_fs = (size_t)HW * ctot;
   const int b = r2 / lv.t_chunks, chunk = r2 - b * lv.t_chunks;
   const int warp = tid >> 5, lane = tid & 31;
-  const int pix0 = chunk * (ST_WARPS * ST_TJ) + warp * ST_TJ;
-  bool ok[ST_TJ];
-#pragma unroll
-  for (int j = 0; j < ST_TJ; ++j) ok[j] = pix0 + j < HW;
+  const int pixw = chunk * ST_TPIX + warp * (2 * ST_TIT);
   for (int c = lane * 4; c < Cg; c += 128) {
-    const float* gp = lv.g + (size_t)b * L * g_fs + (size_t)pix0 * g_ps + c;
-    float* op = lv.out + ((size_t)b * (L - 1) * HW + pix0) * ctot + lv.s.out_coff + lv.s.K * lv.s.Cs + c;
-    float4 prev[ST_TJ];
-#pragma unroll
-    for (int j = 0; j < ST_TJ; ++j) prev[j] = ok[j] ? ldg_stream4(gp + j * g_ps) : f4zero();
-    for (int t0 = 1; t0 < L; t0 += ST_FC) {
-      float4 cur[ST_FC][ST_TJ];
-#pragma unroll
-      for (int i = 0; i < ST_FC; ++i) {
-        gp += g_fs;
-#pragma unroll
-        for (int j = 0; j < ST_TJ; ++j) cur[i][j] = (ok[j] && t0 + i < L) ? ldg_stream4(gp + j * g_ps) : f4zero();
-      }
-#pragma unroll
-      for (int i = 0; i < ST_FC; ++i) {
-        if (t0 + i < L) {
-#pragma unroll
-          for (int j = 0; j < ST_TJ; ++j) {
-            if (ok[j]) stg_stream4(op + j * ctot, f4sub(cur[i][j], prev[j]));
-            prev[j] = cur[i][j];
-          }
+    const float* g0 = lv.g + (size_t)b * L * g_fs + (size_t)pixw * g_ps + c;
+    float* o0 = lv.out + (size_t)b * (L - 1) * o_fs + (size_t)pixw * ctot + lv.s.out_coff + lv.s.K * lv.s.Cs + c;
+#pragma unroll 1
+    for (int it = 0; it < ST_TIT; ++it, g0 += 2 * g_ps, o0 += 2 * ctot) {
+      const int pix0 = pixw + it * 2;
+      if (pix0 >= HW) break;
+      const bool ok1 = pix0 + 1 < HW;                              // the second pixel of the pair may fall off the plane
+      const float* gp0 = g0;
+      const float* gp1 = ok1 ? g0 + g_ps : g0;                     // clamped: duplicate loads, predicated stores
+      float* op0 = o0;
+      float* op1 = o0 + ctot;
+      if (LT == 3) {
+        const float4 a0 = ldg_stream4(gp0), a1 = ldg_stream4(gp1);
+        const float4 b0 = ldg_stream4(gp0 + g_fs), b1 = ldg_stream4(gp1 + g_fs);
+        const float4 c0 = ldg_stream4(gp0 + 2 * g_fs), c1 = ldg_stream4(gp1 + 2 * g_fs);
+        stg_stream4(op0, f4sub(b0, a0));
+        if (ok1) stg_stream4(op1, f4sub(b1, a1));
+        stg_stream4(op0 + o_fs, f4sub(c0, b0));
+        if (ok1) stg_stream4(op1 + o_fs, f4sub(c1, b1));
+      } else {
+        float4 p0 = ldg_stream4(gp0), p1 = ldg_stream4(gp1);
+        gp0 += g_fs; gp1 += g_fs;
+        float4 c0 = ldg_stream4(gp0), c1 = ldg_stream4(gp1);
+        float4 n0 = f4zero(), n1 = f4zero(), m0 = f4zero(), m1 = f4zero();
+        if (L > 2) {
+          gp0 += g_fs; gp1 += g_fs;
+          n0 = ldg_stream4(gp0); n1 = ldg_stream4(gp1);
         }
-        op += o_fs;
+        for (int t = 1; t < L; ++t) {
+          if (t + 2 < L) {
+            gp0 += g_fs; gp1 += g_fs;
+            m0 = ldg_stream4(gp0); m1 = ldg_stream4(gp1);
+          }
+          stg_stream4(op0, f4sub(c0, p0));
+          if (ok1) stg_stream4(op1, f4sub(c1, p1));
+          op0 += o_fs; op1 += o_fs;
+          p0 = c0; p1 = c1; c0 = n0; c1 = n1; n0 = m0; n1 = m1;
+        }
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 4)
-stencil_diff_fwd_kernel(const __grid_constant__ StBatch bt) {
-  extern __shared__ __align__(16) float4 st_smem[];
-  const StLevel& lv = find_level(bt, (int)blockIdx.x);
-  const int rel = (int)blockIdx.x - lv.blk0;
-  const int tid = threadIdx.x;
-  if (rel >= lv.n_sblocks) {
-    temporal_fwd(lv, rel - lv.n_sblocks, tid);
-    return;
-  }
-  // ------------------------------ spatial gradient (RGB_OFF.py:611 / Flow_OFF.py:622 / util.py:46-50) + dropout
+// spatial gradient (RGB_OFF.py:611 / Flow_OFF.py:622 / util.py:46-50) + bias + dropout for one (pair, band) item
+template <int KK>
+__device__ __forceinline__ void spatial_fwd(const StLevel& lv, int item, int tid, float4* st_smem) {
   const offk_stencil_t& s = lv.s;
-  const int H = s.H, W = s.W, HW = H * W, K = s.K, Cs = s.Cs, ctot = s.out_ctot, d_ps = s.d_ps;
-  const int p = rel / lv.bands, band = rel - p * lv.bands;
+  const int H = s.H, W = s.W, HW = H * W, Cs = s.Cs, ctot = s.out_ctot;
+  const int p = item / lv.bands, band = item - p * lv.bands;
   const int y0 = band * lv.band_rows;
   const int rows = min(lv.band_rows, H - y0);
-  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq, TCP = 1 << ltcp;
+  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq;
   float4* tile = st_smem;                                        // [rows+2][TCP][CQ]
-  float4* ws4 = st_smem + (((lv.band_rows + 2) << ltcp) << lq);  // [K*9][CQ]
-  float4* bs4 = ws4 + K * 9 * CQ;                                // [K][CQ]
-  {
-    const float* dp = lv.d + (size_t)spatial_frame(s, p) * s.d_fs;
-    const int n_cells = ((rows + 2) << ltcp) << lq;
-    const uint32_t tile_s = st_smem_u32(tile);
-    for (int i = tid; i < n_cells; i += ST_THREADS) {
-      const int c4 = i & (CQ - 1), col = (i >> lq) & (TCP - 1), r = i >> (lq + ltcp);
-      if (col < W + 2) {
-        const int yy = y0 - 1 + r, xx = col - 1;
-        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-        st_cp_async16(tile_s + (uint32_t)i * 16u, in ? dp + (size_t)(yy * W + xx) * d_ps + c4 * 4 : dp, in ? 16u : 0u);
-      }
-    }
-  }
+  float4* ws4 = st_smem + ((lv.band_rows + 2) << (ltcp + lq));   // [K*9][ST_WQ]
+  float4* bs4 = ws4 + KK * 9 * ST_WQ;                            // [K][ST_WQ]
+  stage_tile<true>(lv, tile, lv.d + (size_t)spatial_frame(s, p) * s.d_fs, s.d_ps, y0, rows, tid, StNoXform());
   load_taps(lv, ws4, bs4, tid);
   st_cp_async_wait_all();
   __syncthreads();
 
   const int c4 = tid & (CQ - 1), slot = tid >> lq;
-  const int XW = 1 << lv.lxw;
-  const int rpp = (ST_THREADS >> lq) >> lv.lxw;                  // rows per pass
-  const int sx = slot & (XW - 1), sy = slot >> lv.lxw;
+  const int lpw = lv.lpw, PW = (W + 1) >> 1;                     // pixel pairs per row
+  const int rpp = (ST_THREADS >> lq) >> lpw;                     // rows per pass
+  const int sx = slot & ((1 << lpw) - 1), sy = slot >> lpw;
   const uint32_t thr = drop_threshold16(s.drop_p);
   const float4* wk = ws4 + c4;
-  const float4 b0 = bs4[c4], b1 = K > 1 ? bs4[CQ + c4] : f4zero();
+  float4 wr[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) wr[j] = wk[j * ST_WQ];             // first map's taps live in registers
+  const float4 b0 = bs4[c4], b1 = KK > 1 ? bs4[ST_WQ + c4] : f4zero();
+  const int rs = 1 << (ltcp + lq);                               // tile row stride (float4)
   float* obase = lv.out + (size_t)p * HW * ctot + s.out_coff + c4 * 4;
+  const uint32_t qbase = (uint32_t)p * (uint32_t)HW;             // dropout: quad index = ((p*HW + pix)*K*Cs + och) / 4
+  const uint32_t kcq = (uint32_t)(KK * Cs) >> 2;
   for (int yb = 0; yb < rows; yb += rpp) {
     const int y = yb + sy;
-    for (int x0 = 0; x0 < W; x0 += XW) {
-      const int x = x0 + sx;
+    for (int xp0 = 0; xp0 < PW; xp0 += 1 << lpw) {
+      const int x = (xp0 + sx) * 2;
       if (y < rows && x < W) {
-        const float4* t0 = tile + (((y << ltcp) + x) << lq) + c4;     // halo coordinates: (y, x) = top-left neighbour
-        float4 acc0 = b0, acc1 = b1;
+        const float4* r0 = tile + (((y << ltcp) + x) << lq) + c4;       // halo coordinates: (y, x) = top-left neighbour
+        float4 e0 = b0, e1 = b0, f0 = b1, f1 = b1;                      // e: map 0 at x / x+1, f: map 1
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int bb = 0; bb < 3; ++bb) {
-            const float4 nb = t0[((a << ltcp) + bb) << lq];
-            const float4 w0 = wk[(a * 3 + bb) << lq];
-            acc0.x = fmaf(w0.x, nb.x, acc0.x);
-            acc0.y = fmaf(w0.y, nb.y, acc0.y);
-            acc0.z = fmaf(w0.z, nb.z, acc0.z);
-            acc0.w = fmaf(w0.w, nb.w, acc0.w);
-            if (K > 1) {
-              const float4 w1 = wk[(9 + a * 3 + bb) << lq];
-              acc1.x = fmaf(w1.x, nb.x, acc1.x);
-              acc1.y = fmaf(w1.y, nb.y, acc1.y);
-              acc1.z = fmaf(w1.z, nb.z, acc1.z);
-              acc1.w = fmaf(w1.w, nb.w, acc1.w);
-            }
+        for (int a = 0; a < 3; ++a) {
+          const float4* ra = r0 + a * rs;
+          const float4 n0 = ra[0], n1 = ra[CQ], n2 = ra[2 * CQ], n3 = ra[3 * CQ];
+          f4fma(e0, wr[a * 3], n0); f4fma(e0, wr[a * 3 + 1], n1); f4fma(e0, wr[a * 3 + 2], n2);
+          f4fma(e1, wr[a * 3], n1); f4fma(e1, wr[a * 3 + 1], n2); f4fma(e1, wr[a * 3 + 2], n3);
+          if (KK > 1) {
+            const float4 u0 = wk[(9 + a * 3) * ST_WQ], u1 = wk[(10 + a * 3) * ST_WQ], u2 = wk[(11 + a * 3) * ST_WQ];
+            f4fma(f0, u0, n0); f4fma(f0, u1, n1); f4fma(f0, u2, n2);
+            f4fma(f1, u0, n1); f4fma(f1, u1, n2); f4fma(f1, u2, n3);
           }
+        }
         const int pix = (y0 + y) * W + x;
         float* op = obase + (size_t)pix * ctot;
-        const float4 k0 = drop_factor4(s, thr, p, c4 * 4, pix, HW);
-        stg_stream4(op, make_float4(acc0.x * k0.x, acc0.y * k0.y, acc0.z * k0.z, acc0.w * k0.w));
-        if (K > 1) {
-          const float4 k1 = drop_factor4(s, thr, p, Cs + c4 * 4, pix, HW);
-          stg_stream4(op + Cs, make_float4(acc1.x * k1.x, acc1.y * k1.y, acc1.z * k1.z, acc1.w * k1.w));
+        const uint64_t q = (uint64_t)(qbase + pix) * kcq + c4;
+        stg_stream4(op, f4mul(e0, drop_factor4(s, thr, p, c4 * 4, pix, HW, q)));
+        if (KK > 1) stg_stream4(op + Cs, f4mul(f0, drop_factor4(s, thr, p, Cs + c4 * 4, pix, HW, q + (Cs >> 2))));
+        if (x + 1 < W) {
+          stg_stream4(op + ctot, f4mul(e1, drop_factor4(s, thr, p, c4 * 4, pix + 1, HW, q + kcq)));
+          if (KK > 1)
+            stg_stream4(op + ctot + Cs, f4mul(f1, drop_factor4(s, thr, p, Cs + c4 * 4, pix + 1, HW, q + kcq + (Cs >> 2))));
         }
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS, ST_FWD_MINB)
+stencil_diff_fwd_kernel(const __grid_constant__ StBatch bt) {
+  extern __shared__ __align__(16) float4 st_smem[];
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  const int tid = threadIdx.x;
+  const int role = block_role(lv, (int)blockIdx.x - lv.blk0);
+  if (role < 0) {
+    if (lv.s.L == 3) temporal_fwd<3>(lv, ~role, tid);
+    else temporal_fwd<0>(lv, ~role, tid);
+  } else {
+    if (lv.s.K == 1) spatial_fwd<1>(lv, role, tid, st_smem);
+    else spatial_fwd<2>(lv, role, tid, st_smem);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-// dG[b,t] = (dT[b,t-1] - dT[b,t]) * (G[b,t] > 0)      (ReLU' of RGB_OFF.py:598); a streaming kernel of its own so that
-// it keeps a high occupancy (the spatial kernel below needs ~40 accumulator registers)
-__global__ void __launch_bounds__(ST_THREADS, 4)
-stencil_diff_bwd_temporal_kernel(const __grid_constant__ StBatch bt) {
-  const StLevel& lv = find_level(bt, (int)blockIdx.x);
-  const int r2 = (int)blockIdx.x - lv.blk0;
-  const int tid = threadIdx.x;
+// dG[b,t] = (dT[b,t-1] - dT[b,t]) * (G[b,t] > 0)      (ReLU' of RGB_OFF.py:598): same walk as the forward
+template <int LT>
+__device__ __forceinline__ void temporal_bwd(const StLevel& lv, int r2, int tid) {
   const int L = lv.s.L, Cg = lv.s.Cg, HW = lv.s.H * lv.s.W;
+  const size_t g_fs = (size_t)lv.s.g_fs, dg_fs = (size_t)lv.dg_fs, o_fs = (size_t)HW * lv.s.out_ctot;
   const int g_ps = lv.s.g_ps, ctot = lv.s.out_ctot;
-  const size_t g_fs = (size_t)lv.s.g_fs, dg_fs = (size_t)lv.dg_fs, o_fs = (size_t)HW * ctot;
   const int b = r2 / lv.t_chunks, chunk = r2 - b * lv.t_chunks;
   const int warp = tid >> 5, lane = tid & 31;
-  const int pix0 = chunk * (ST_WARPS * ST_TJ) + warp * ST_TJ;
-  bool ok[ST_TJ];
-#pragma unroll
-  for (int j = 0; j < ST_TJ; ++j) ok[j] = pix0 + j < HW;
+  const int pixw = chunk * ST_TPIX + warp * (2 * ST_TIT);
   for (int c = lane * 4; c < Cg; c += 128) {
-    const float* gp = lv.g + (size_t)b * L * g_fs + (size_t)pix0 * g_ps + c;
-    float* dgp = lv.dg + (size_t)b * L * dg_fs + (size_t)pix0 * g_ps + c;        // dg uses the pixel stride of g
-    const float* op = lv.dout + ((size_t)b * (L - 1) * HW + pix0) * ctot + lv.s.out_coff + lv.s.K * lv.s.Cs + c;
-    float4 prev[ST_TJ];
-#pragma unroll
-    for (int j = 0; j < ST_TJ; ++j) prev[j] = f4zero();
-    for (int t0 = 0; t0 < L; t0 += ST_BC) {
-      float4 gv[ST_BC][ST_TJ], dt[ST_BC][ST_TJ];
-#pragma unroll
-      for (int i = 0; i < ST_BC; ++i) {
-#pragma unroll
-        for (int j = 0; j < ST_TJ; ++j) {
-          gv[i][j] = (ok[j] && t0 + i < L) ? ldg_stream4(gp + j * g_ps) : f4zero();
-          dt[i][j] = (ok[j] && t0 + i < L - 1) ? ldg_stream4(op + j * ctot) : f4zero();
-        }
-        gp += g_fs;
-        op += o_fs;
-      }
-#pragma unroll
-      for (int i = 0; i < ST_BC; ++i) {
-        if (t0 + i < L) {
-#pragma unroll
-          for (int j = 0; j < ST_TJ; ++j) {
-            float4 r = f4sub(prev[j], dt[i][j]);
-            r.x = gv[i][j].x > 0.f ? r.x : 0.f;
-            r.y = gv[i][j].y > 0.f ? r.y : 0.f;
-            r.z = gv[i][j].z > 0.f ? r.z : 0.f;
-            r.w = gv[i][j].w > 0.f ? r.w : 0.f;
-            if (ok[j]) stg_stream4(dgp + j * g_ps, r);
-            prev[j] = dt[i][j];
+    const float* g0 = lv.g + (size_t)b * L * g_fs + (size_t)pixw * g_ps + c;
+    float* d0 = lv.dg + (size_t)b * L * dg_fs + (size_t)pixw * g_ps + c;                 // dg uses the pixel stride of g
+    const float* o0 = lv.dout + (size_t)b * (L - 1) * o_fs + (size_t)pixw * ctot + lv.s.out_coff + lv.s.K * lv.s.Cs + c;
+#pragma unroll 1
+    for (int it = 0; it < ST_TIT; ++it, g0 += 2 * g_ps, d0 += 2 * g_ps, o0 += 2 * ctot) {
+      const int pix0 = pixw + it * 2;
+      if (pix0 >= HW) break;
+      const bool ok1 = pix0 + 1 < HW;
+      const float* gp0 = g0;
+      const float* gp1 = ok1 ? g0 + g_ps : g0;
+      const float* op0 = o0;
+      const float* op1 = ok1 ? o0 + ctot : o0;
+      float* dp0 = d0;
+      float* dp1 = d0 + g_ps;
+      if (LT == 3) {
+        const float4 ga0 = ldg_stream4(gp0), ga1 = ldg_stream4(gp1);
+        const float4 ta0 = ldg_stream4(op0), ta1 = ldg_stream4(op1);
+        const float4 gb0 = ldg_stream4(gp0 + g_fs), gb1 = ldg_stream4(gp1 + g_fs);
+        const float4 tb0 = ldg_stream4(op0 + o_fs), tb1 = ldg_stream4(op1 + o_fs);
+        const float4 gc0 = ldg_stream4(gp0 + 2 * g_fs), gc1 = ldg_stream4(gp1 + 2 * g_fs);
+        stg_stream4(dp0, relu_gate4(ga0, f4sub(f4zero(), ta0)));
+        if (ok1) stg_stream4(dp1, relu_gate4(ga1, f4sub(f4zero(), ta1)));
+        stg_stream4(dp0 + dg_fs, relu_gate4(gb0, f4sub(ta0, tb0)));
+        if (ok1) stg_stream4(dp1 + dg_fs, relu_gate4(gb1, f4sub(ta1, tb1)));
+        stg_stream4(dp0 + 2 * dg_fs, relu_gate4(gc0, tb0));
+        if (ok1) stg_stream4(dp1 + 2 * dg_fs, relu_gate4(gc1, tb1));
+      } else {
+        float4 pv0 = f4zero(), pv1 = f4zero();
+        float4 gv0 = ldg_stream4(gp0), gv1 = ldg_stream4(gp1);
+        float4 dt0 = ldg_stream4(op0), dt1 = ldg_stream4(op1);     // L >= 2: pair 0 exists
+        float4 ng0 = f4zero(), ng1 = f4zero(), nd0, nd1;
+        for (int t = 0; t < L; ++t) {
+          if (t + 1 < L) {
+            gp0 += g_fs; gp1 += g_fs;
+            ng0 = ldg_stream4(gp0); ng1 = ldg_stream4(gp1);
           }
+          nd0 = f4zero(); nd1 = f4zero();
+          if (t + 1 < L - 1) {
+            op0 += o_fs; op1 += o_fs;
+            nd0 = ldg_stream4(op0); nd1 = ldg_stream4(op1);
+          }
+          stg_stream4(dp0, relu_gate4(gv0, f4sub(pv0, dt0)));
+          if (ok1) stg_stream4(dp1, relu_gate4(gv1, f4sub(pv1, dt1)));
+          dp0 += dg_fs; dp1 += dg_fs;
+          pv0 = dt0; pv1 = dt1; dt0 = nd0; dt1 = nd1; gv0 = ng0; gv1 = ng1;
         }
-        dgp += dg_fs;
       }
     }
   }
 }
 
-// spatial: dD = transposed stencil of the dropped dS; tap / bias gradients.  Persistent blocks over (frame, band) items.
-__global__ void __launch_bounds__(ST_THREADS, 2)
-stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
-  extern __shared__ __align__(16) float4 st_smem[];
-  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+struct StDropXform {       // staging transform of the backward pass: dS <- dS * keep-factor (dropout')
+  const offk_stencil_t* s;
+  uint32_t thr, qbase, kcq;
+  int p, och, HW;
+  __device__ __forceinline__ float4 operator()(float4 v, int pix) const {
+    return f4mul(v, drop_factor4(*s, thr, p, och, pix, HW, (uint64_t)(qbase + pix) * kcq + (och >> 2)));
+  }
+};
+
+// spatial blocks: dD = transposed stencil of the dropped dS; tap / bias gradients.  A block owns `ipb` consecutive
+// (frame, band) items and keeps the tap-gradient partial sums in registers across them.
+__device__ __forceinline__ void spatial_bwd(const StLevel& lv, int rel, int tid, float4* st_smem) {
   const offk_stencil_t& s = lv.s;
-  const int rel = (int)blockIdx.x - lv.blk0;
-  const int tid = threadIdx.x;
   const int H = s.H, W = s.W, HW = H * W, K = s.K, Cs = s.Cs, ctot = s.out_ctot, d_ps = s.d_ps;
-  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq, TCP = 1 << ltcp;
+  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq;
   float4* tile = st_smem;                                        // dS band + halo [rows+2][TCP][CQ]
-  float4* ws4 = st_smem + (((lv.band_rows + 2) << ltcp) << lq);  // [K*9][CQ]
-  float* red = reinterpret_cast<float*>(ws4 + K * 9 * CQ);       // [10][Cs] block reduction of the tap gradients
+  float4* ws4 = st_smem + ((lv.band_rows + 2) << (ltcp + lq));   // [K*9][ST_WQ]
+  float* red = reinterpret_cast<float*>(ws4 + K * 9 * ST_WQ);    // [10][Cs] block reduction of the tap gradients
   load_taps(lv, ws4, nullptr, tid);
   const bool need_dw = lv.dw != nullptr, need_db = lv.dbias != nullptr;
   const bool need_acc = need_dw || need_db;
@@ -324,37 +419,27 @@ stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
   const int XW = 1 << lv.lxw;
   const int rpp = (ST_THREADS >> lq) >> lv.lxw;
   const int sx = slot & (XW - 1), sy = slot >> lv.lxw;
-  const uint32_t thr = drop_threshold16(s.drop_p);
+  const int rs = 1 << (ltcp + lq);
+  const int item0 = rel * lv.ipb, item1 = min(item0 + lv.ipb, lv.n_sitems);
+  StDropXform xf;
+  xf.s = &s; xf.thr = drop_threshold16(s.drop_p); xf.kcq = (uint32_t)(K * Cs) >> 2; xf.HW = HW;
 
   for (int kk = 0; kk < K; ++kk) {
     float4 wacc[9], bacc = f4zero();
 #pragma unroll
     for (int j = 0; j < 9; ++j) wacc[j] = f4zero();
     const int och = kk * Cs + c4 * 4;
-    const float4* wk = ws4 + kk * 9 * CQ + c4;
-    for (int item = rel; item < lv.n_sitems; item += lv.n_sblocks) {
+    const float4* wk = ws4 + kk * 9 * ST_WQ + c4;
+    for (int item = item0; item < item1; ++item) {
       const int f = item / lv.bands, band = item - f * lv.bands;
       const int y0 = band * lv.band_rows;
       const int rows = min(lv.band_rows, H - y0);
       const int p = spatial_pair_of_frame(s, f);
       __syncthreads();                                           // previous item's tile fully consumed (and ws4 / red ready)
       if (p >= 0) {
-        const float* sp = lv.dout + (size_t)p * HW * ctot + s.out_coff + och;
-        const int n_cells = ((rows + 2) << ltcp) << lq;
-        for (int i = tid; i < n_cells; i += ST_THREADS) {        // (the cell's c4 equals this thread's c4: 256 % CQ == 0)
-          const int col = (i >> lq) & (TCP - 1), r = i >> (lq + ltcp);
-          if (col < W + 2) {
-            const int yy = y0 - 1 + r, xx = col - 1;
-            float4 v = f4zero();
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-              const int np_ = yy * W + xx;
-              v = ldg4(sp + (size_t)np_ * ctot);
-              const float4 k4 = drop_factor4(s, thr, p, och, np_, HW);
-              v.x *= k4.x; v.y *= k4.y; v.z *= k4.z; v.w *= k4.w;
-            }
-            tile[i] = v;
-          }
-        }
+        // every cell a thread stages has the thread's own channel quad (ST_THREADS and the row pitch are multiples of CQ)
+        xf.p = p; xf.och = och; xf.qbase = (uint32_t)p * (uint32_t)HW;
+        stage_tile<false>(lv, tile, lv.dout + (size_t)p * HW * ctot + s.out_coff + kk * Cs, ctot, y0, rows, tid, xf);
       }
       __syncthreads();
       float* ddf = lv.dd + (size_t)f * lv.dd_fs + c4 * 4;          // dd uses the pixel stride of d
@@ -372,21 +457,16 @@ stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
               // dS(y-a+1, x-b+1) sits at halo coordinates (y+2-a, x+2-b)
               const float4* t2 = tile + ((((y + 2) << ltcp) + x + 2) << lq) + c4;
 #pragma unroll
-              for (int a = 0; a < 3; ++a)
+              for (int a = 0; a < 3; ++a) {
+                const float4* ra = t2 - a * rs;
 #pragma unroll
                 for (int bb = 0; bb < 3; ++bb) {
-                  const float4 nv = *(t2 - (((a << ltcp) + bb) << lq));
-                  const float4 wv = wk[(a * 3 + bb) << lq];
-                  acc.x = fmaf(wv.x, nv.x, acc.x);
-                  acc.y = fmaf(wv.y, nv.y, acc.y);
-                  acc.z = fmaf(wv.z, nv.z, acc.z);
-                  acc.w = fmaf(wv.w, nv.w, acc.w);
-                  wacc[a * 3 + bb].x = fmaf(dv.x, nv.x, wacc[a * 3 + bb].x);
-                  wacc[a * 3 + bb].y = fmaf(dv.y, nv.y, wacc[a * 3 + bb].y);
-                  wacc[a * 3 + bb].z = fmaf(dv.z, nv.z, wacc[a * 3 + bb].z);
-                  wacc[a * 3 + bb].w = fmaf(dv.w, nv.w, wacc[a * 3 + bb].w);
+                  const float4 nv = *(ra - bb * CQ);
+                  f4fma(acc, wk[(a * 3 + bb) * ST_WQ], nv);
+                  f4fma(wacc[a * 3 + bb], dv, nv);
                   if (a == 1 && bb == 1) { bacc.x += nv.x; bacc.y += nv.y; bacc.z += nv.z; bacc.w += nv.w; }
                 }
+              }
             }
             float4* o = reinterpret_cast<float4*>(ddf + (size_t)pix * d_ps);
             if (kk > 0) {
@@ -425,6 +505,20 @@ stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
   }
 }
 
+__global__ void __launch_bounds__(ST_THREADS, ST_FWD_MINB)
+stencil_diff_bwd_kernel(const __grid_constant__ StBatch bt) {
+  extern __shared__ __align__(16) float4 st_smem[];
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  const int tid = threadIdx.x;
+  const int role = block_role(lv, (int)blockIdx.x - lv.blk0);
+  if (role < 0) {
+    if (lv.s.L == 3) temporal_bwd<3>(lv, ~role, tid);
+    else temporal_bwd<0>(lv, ~role, tid);
+  } else {
+    spatial_bwd(lv, role, tid, st_smem);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host
 static int check_stencil(const offk_stencil_t* s) {
   OFFK_REQUIRE(s != nullptr, "stencil: null descriptor");
@@ -453,7 +547,8 @@ static int ilog2_ceil(int v) {
 // geometry of the spatial blocks of one level; returns the dynamic shared memory the level needs (0 if Cs == 0)
 static int plan_spatial(StLevel& lv, bool backward) {
   const offk_stencil_t& s = lv.s;
-  lv.lq = lv.ltcp = lv.lxw = 0;
+  lv.lq = lv.ltcp = lv.lxw = lv.lpw = 0;
+  lv.ipb = 1;
   lv.bands = lv.band_rows = 1;
   lv.n_sitems = lv.n_sblocks = 0;
   if (s.Cs == 0) return 0;
@@ -470,17 +565,20 @@ static int plan_spatial(StLevel& lv, bool backward) {
   int lxw = ilog2_ceil(s.W);
   while ((1 << lxw) > slots) --lxw;
   lv.lxw = lxw;
+  int lpw = ilog2_ceil((s.W + 1) / 2);
+  while ((1 << lpw) > slots) --lpw;
+  lv.lpw = lpw;
   const long long units = backward ? (long long)s.B * s.L : (long long)s.B * (s.L - 1);
   const long long items = units * lv.bands;
   lv.n_sitems = (int)items;
-  lv.n_sblocks = (int)items;
-  if (backward && (lv.dw || lv.dbias)) {
-    const long long cap = 2LL * sm_count();      // persistent: register-resident tap-gradient partial sums
-    if (items > cap) lv.n_sblocks = (int)cap;
-  }
+  // backward: a block keeps the tap-gradient partial sums in registers over up to ST_ITEMS consecutive items (fewer
+  // block reductions / atomics); small levels keep one item per block so their blocks stay short
+  long long ipb = items / (2LL * sm_count());
+  lv.ipb = backward ? (int)(ipb < 1 ? 1 : (ipb > ST_ITEMS ? ST_ITEMS : ipb)) : 1;
+  lv.n_sblocks = (int)((items + lv.ipb - 1) / lv.ipb);
   const int tile_bytes = (lv.band_rows + 2) * row_bytes;
-  const int tap_bytes = s.K * 9 * CQ * 16;
-  const int extra = backward ? 10 * s.Cs * 4 : s.K * CQ * 16;
+  const int tap_bytes = s.K * 9 * ST_WQ * 16;
+  const int extra = backward ? 10 * s.Cs * 4 : s.K * ST_WQ * 16;
   return tile_bytes + tap_bytes + extra;
 }
 
@@ -489,7 +587,7 @@ static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t*
   OFFK_REQUIRE(s != nullptr && io != nullptr, "stencil batch: null arrays");
   StBatch bt;
   bt.n = n;
-  long long n_t[ST_MAX_LEVELS];
+  long long blk = 0;
   int smem = 0;
   for (int i = 0; i < n; ++i) {
     if (int e = check_stencil(&s[i])) return e;
@@ -513,51 +611,32 @@ static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t*
     OFFK_REQUIRE(need <= ST_SMEM_MAX, "stencil: halo tile of %d bytes exceeds %d (W=%d, Cs=%d)", need, ST_SMEM_MAX, s[i].W, s[i].Cs);
     if (need > smem) smem = need;
     const int HW = s[i].H * s[i].W;
-    const int per_blk = ST_WARPS * ST_TJ;
-    lv.t_chunks = s[i].Cg > 0 ? (HW + per_blk - 1) / per_blk : 1;
-    n_t[i] = s[i].Cg > 0 ? (long long)lv.t_chunks * s[i].B : 0;
+    lv.t_chunks = s[i].Cg > 0 ? (HW + ST_TPIX - 1) / ST_TPIX : 1;
+    const long long n_t = s[i].Cg > 0 ? (long long)lv.t_chunks * s[i].B : 0;
+    lv.n_tblocks = (int)n_t;
+    // spatial blocks at every 2^lstride-th position of the level's range
+    lv.lstride = 0;
+    if (lv.n_sblocks > 0)
+      while (((long long)lv.n_sblocks << (lv.lstride + 1)) <= lv.n_sblocks + n_t) ++lv.lstride;
+    lv.blk0 = (int)blk;
+    blk += lv.n_sblocks + n_t;
+    OFFK_REQUIRE(blk < 2147483647LL, "stencil: grid too large");
   }
+  if (blk == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(stencil_diff_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(stencil_diff_bwd_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
+      e = cudaFuncSetAttribute(stencil_diff_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
     if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(stencil)");
     attr_set = true;
   }
   if (!backward) {
-    // one grid: per level, spatial blocks first (heavier per byte), then temporal blocks
-    long long blk = 0;
-    for (int i = 0; i < n; ++i) {
-      bt.lv[i].blk0 = (int)blk;
-      blk += bt.lv[i].n_sblocks + n_t[i];
-      OFFK_REQUIRE(blk < 2147483647LL, "stencil: grid too large");
-    }
-    if (blk == 0) return 0;
     stencil_diff_fwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
     return OFFK_LAUNCH_CHECK("stencil_diff_fwd");
   }
-  // backward: a streaming kernel for dG and a persistent kernel for dD + tap gradients
-  long long blk = 0;
-  for (int i = 0; i < n; ++i) {
-    bt.lv[i].blk0 = (int)blk;
-    blk += n_t[i];
-    OFFK_REQUIRE(blk < 2147483647LL, "stencil: grid too large");
-  }
-  if (blk > 0) {
-    stencil_diff_bwd_temporal_kernel<<<(unsigned)blk, ST_THREADS, 0, as_stream(stream)>>>(bt);
-    if (int e = OFFK_LAUNCH_CHECK("stencil_diff_bwd_temporal")) return e;
-  }
-  blk = 0;
-  for (int i = 0; i < n; ++i) {
-    bt.lv[i].blk0 = (int)blk;
-    blk += bt.lv[i].n_sblocks;
-  }
-  if (blk > 0) {
-    stencil_diff_bwd_spatial_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
-    return OFFK_LAUNCH_CHECK("stencil_diff_bwd_spatial");
-  }
-  return 0;
+  stencil_diff_bwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+  return OFFK_LAUNCH_CHECK("stencil_diff_bwd");
 }
 
 }  // namespace offk

@@ -349,7 +349,6 @@ class OFFEngine:
             L.check(lib.offk_stencil_diff_bwd_batch(n_lv, self._st_desc, self._st_io, stream), "stencil_bwd")
         k3 = _nm(k3, "stencil_bwd", reads=[bf["dF" + st] for st in S.STAGES] + [bf["gd_" + t] for t in tags],
                  writes=[bf["dgd_" + t] for t in tags] + grad3, lane=0)
-        k3.launches = ["stencil_bwd_temporal", "stencil_bwd_spatial"]
         bwd_units.append(k3)
         bwd_units += k4_steps
 

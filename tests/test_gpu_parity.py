@@ -146,18 +146,12 @@ def test_stencil_diff_fwd_bwd(dev, case):
     Sg = torch.nn.functional.conv2d(Ds.repeat(1, K, 1, 1), wd.permute(1, 0, 2, 3).reshape(K * Cs, 1, 3, 3), bd, 1, 1, 1, K * Cs)
     if drop == 1:
         keep = mask.double() * 5.0
-    elif drop == 2:      # counter-hash dropout: regenerate on the host with the library's own hash
-        # element index = channels-last ((p*HW + pix)*K*Cs + ch); 4 consecutive elements share one splitmix64 hash
+    elif drop == 2:      # counter-hash dropout: regenerate on the host with the library's own hash (host mirror)
+        # element index = channels-last ((p*HW + pix)*K*Cs + ch); 4 consecutive elements share one hash
         n_el = P * K * Cs * S * S
-        quad = np.arange(n_el // 4, dtype=np.uint64)
-        x = np.uint64(1234) + quad * np.uint64(0x9E3779B97F4A7C15)
-        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9); x ^= x >> np.uint64(27)
-        x *= np.uint64(0x94D049BB133111EB); x ^= x >> np.uint64(31)
-        fields = np.stack([(x >> np.uint64(16 * i)) & np.uint64(0xFFFF) for i in range(4)], 1).reshape(-1)
-        k16 = fields.astype(np.int64) >= int(0.8 * 65536.0)
-        assert all(bool(k16[i]) == bool(lib.offk_drop_keep_host(1234, int(i), 0.8)) for i in range(0, min(4096, n_el), 7))
+        k16 = np.array([lib.offk_drop_keep_host(1234, i, 0.8) for i in range(n_el)], dtype=np.float64)
         assert 0.15 < k16.mean() < 0.25
-        keep = torch.from_numpy(k16.astype(np.float64)).to(dev).view(P, S, S, K * Cs).permute(0, 3, 1, 2) * 5.0
+        keep = torch.from_numpy(k16).to(dev).view(P, S, S, K * Cs).permute(0, 3, 1, 2) * 5.0
     else:
         keep = torch.ones(P, K * Cs, S, S, device=dev, dtype=torch.float64)
     Sg = Sg * keep
