@@ -292,7 +292,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 tensor-core multiply, fp32 accumulate/storage" if args.precision == "tf32" else "fp32",
+            "dtype": "tf32 (tcgen05 kind::tf32 multiply, fp32 accumulate, fp32 storage)" if args.precision == "tf32" else "fp32",
             "data": "synthetic",
             "config": {"workload": f"{args.variant.upper()}_OFF OFF sub-network fwd+bwd, {B} clips x {Lg} segments per GPU "
                                    f"(BASELINE config 2), train-mode dropout, CE loss on the 7x7 and 14x14 heads",

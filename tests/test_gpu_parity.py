@@ -192,6 +192,54 @@ def test_stencil_diff_fwd_bwd(dev, case):
     assert _rel(dw, wd.grad.cpu()) < 1e-5 and _rel(dbias, bd.grad.cpu()) < 1e-5
 
 
+def test_stencil_batch_equals_single_launches(dev):
+    """offk_stencil_diff_fwd_batch / _bwd_batch (one launch for several OFF units) write exactly what the per-unit
+    calls write: same arithmetic per element, only the block -> work mapping differs."""
+    from off_b200 import _lib as L
+    lib = L.lib()
+    B, Lg, Cg, Cs = 3, 4, 128, 32
+    N, P = B * Lg, B * (Lg - 1)
+    torch.manual_seed(3)
+    geoms = [(14, 480, 0), (14, 480, 160), (14, 480, 320)]
+    n = len(geoms)
+    descs, ios = (L.OffkStencil * n)(), (L.OffkStencilIO * n)()
+    keep = []
+    F_b, F_s = torch.zeros(P, 14, 14, 480, device=dev), torch.zeros(P, 14, 14, 480, device=dev)
+    dF = torch.randn(P, 14, 14, 480, device=dev)
+    for i, (S, ctot, coff) in enumerate(geoms):
+        gd = torch.randn(N, S, S, Cg + Cs, device=dev)
+        gd[..., :Cg].relu_()
+        w, bias = torch.randn(Cs, 1, 3, 3, device=dev), torch.randn(Cs, device=dev)
+        bufs = {k: (torch.full_like(gd, float("nan")), torch.zeros_like(w), torch.zeros_like(bias)) for k in "bs"}
+        sd = descs[i]
+        sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, Cg, Cs, 1, S, S
+        sd.g_fs = sd.d_fs = (Cg + Cs) * S * S
+        sd.g_ps = sd.d_ps = Cg + Cs
+        sd.out_ctot, sd.out_coff, sd.index_mode = ctot, coff, i % 2
+        sd.drop_mode, sd.keep_scale, sd.drop_p, sd.seed = 2, 5.0, 0.8, 40 + i
+        io = ios[i]
+        io.g, io.d, io.w, io.bias = gd.data_ptr(), gd.data_ptr() + 4 * Cg, w.data_ptr(), bias.data_ptr()
+        io.out, io.dout = F_b.data_ptr(), dF.data_ptr()
+        dgd, dw, db = bufs["b"]
+        io.dg, io.dd, io.dg_fs, io.dd_fs = dgd.data_ptr(), dgd.data_ptr() + 4 * Cg, sd.g_fs, sd.g_fs
+        io.dw, io.dbias = dw.data_ptr(), db.data_ptr()
+        keep.append((gd, w, bias, bufs))
+    L.check(lib.offk_stencil_diff_fwd_batch(n, descs, ios, None), "fwd_batch")
+    L.check(lib.offk_stencil_diff_bwd_batch(n, descs, ios, None), "bwd_batch")
+    for i in range(n):
+        gd, w, bias, bufs = keep[i]
+        dgd, dw, db = bufs["s"]
+        L.check(lib.offk_stencil_diff_fwd(C.byref(descs[i]), ios[i].g, ios[i].d, ios[i].w, ios[i].bias, F_s.data_ptr(), None), "fwd")
+        L.check(lib.offk_stencil_diff_bwd(C.byref(descs[i]), dF.data_ptr(), ios[i].g, ios[i].d, ios[i].w, dgd.data_ptr(),
+                                          descs[i].g_fs, dgd.data_ptr() + 4 * Cg, descs[i].g_fs, dw.data_ptr(), db.data_ptr(),
+                                          None), "bwd")
+    torch.cuda.synchronize()
+    assert torch.equal(F_b, F_s) and F_b.abs().sum().item() > 0
+    for gd, w, bias, bufs in keep:
+        assert torch.equal(bufs["b"][0], bufs["s"][0])                                   # dG, dD: bit-exact
+        assert _rel(bufs["b"][1], bufs["s"][1].cpu()) < 1e-5 and _rel(bufs["b"][2], bufs["s"][2].cpu()) < 1e-5  # atomics: order
+
+
 def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit, tol_grad):
     from off_b200 import engine as E
     seed = 5
@@ -224,12 +272,14 @@ def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit
 
 
 @pytest.mark.parametrize("variant,B,Lg,train", [("rgb", 2, 3, False), ("flow", 2, 3, False), ("rgb", 2, 2, True),
-                                                ("flow", 1, 4, False), ("rgb", 1, 3, False)])
+                                                ("flow", 1, 4, False), ("rgb", 1, 3, False),
+                                                ("rgb", 2, 7, False), ("flow", 1, 7, True)])   # config 4 geometry: 7 segments
 def test_engine_fp32_mode_matches_oracle(dev, variant, B, Lg, train):
     _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, 2e-5, 2e-5, 2e-3)
 
 
-@pytest.mark.parametrize("variant,B,Lg,train", [("rgb", 2, 3, False), ("flow", 2, 3, False), ("rgb", 2, 2, True)])
+@pytest.mark.parametrize("variant,B,Lg,train", [("rgb", 2, 3, False), ("flow", 2, 3, False), ("rgb", 2, 2, True),
+                                                ("rgb", 2, 7, True)])
 def test_engine_tf32_mode_matches_oracle(dev, variant, B, Lg, train):
     _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, 5e-3, 1e-2, 0.2)
 

@@ -61,9 +61,10 @@ def test_ctypes_structs_match_the_c_header():
     #include <stddef.h>
     #include "offk.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(offk_idx_t), sizeof(offk_gemm_t), offsetof(offk_gemm_t, out),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(offk_idx_t), sizeof(offk_gemm_t), offsetof(offk_gemm_t, out),
              offsetof(offk_gemm_t, split_k), sizeof(offk_stencil_t), offsetof(offk_stencil_t, seed),
-             offsetof(offk_stencil_t, keep_mask));
+             offsetof(offk_stencil_t, keep_mask), sizeof(offk_stencil_io_t), offsetof(offk_stencil_io_t, dg_fs),
+             offsetof(offk_stencil_io_t, dbias));
       return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -73,7 +74,8 @@ def test_ctypes_structs_match_the_c_header():
         out = subprocess.check_output([os.path.join(d, "t")]).split()
     got = [int(x) for x in out]
     assert got == [C.sizeof(L.OffkIdx), C.sizeof(L.OffkGemm), L.OffkGemm.out.offset, L.OffkGemm.split_k.offset,
-                   C.sizeof(L.OffkStencil), L.OffkStencil.seed.offset, L.OffkStencil.keep_mask.offset]
+                   C.sizeof(L.OffkStencil), L.OffkStencil.seed.offset, L.OffkStencil.keep_mask.offset,
+                   C.sizeof(L.OffkStencilIO), L.OffkStencilIO.dg_fs.offset, L.OffkStencilIO.dbias.offset]
 
 
 def test_cpu_calls_fail_loudly():
