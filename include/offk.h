@@ -145,6 +145,39 @@ typedef struct offk_gemm {
 int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
 
 /* ------------------------------------------------------------------------
+ * TMA-fed GEMM: the same contraction and epilogue as offk_gather_gemm (bias, ReLU prefix, ReLU' gate, residual
+ * add, split-K / atomic accumulation, output through out_row / out_col), but the operand tiles are fetched by the
+ * Tensor Memory Accelerator (cp.async.bulk.tensor) instead of index-table gathers.  Used for every conv / FC of
+ * the OFF sub-network whose input is a channels-last activation: the residual-block 1x1 convs and FC heads
+ * (RGB_OFF.py:659-685,764-780,787,793,835-847) as dense 2-D tiles, the stage-entry 7x7/5x5/3x3 convs and the
+ * bottleneck 3x3s (:657,661,672,681,762,766,775,777,833,837) through TMA im2col mode.
+ *   g.a_src / g.b_src : operand base pointers (16-byte aligned); the a_row/a_col/b_row/b_col tables are ignored
+ *   A dense  : A(m,k) = a_src[m*lda + k]
+ *   A im2col : a_src = channels-last [n_img, hin, win, ctot]; channels [a_coff, a_coff+cin) feed the conv;
+ *              K = kh*kw*cin ordered (r, q, c) -- the order of OHWI weights; cin % 32 == 0
+ *   B dense  : B(n,k) = b_src[n*ldb + k]   (weights [cout, K])
+ * offk_tma_gemm_prepare() encodes the two CUtensorMap objects into the descriptor (host only, no device memory);
+ * call it again whenever a pointer or shape changes.  precision is always OFFK_PREC_TF32.
+ * ---------------------------------------------------------------------- */
+#define OFFK_TMA_A_DENSE  0
+#define OFFK_TMA_A_IM2COL 1
+#define OFFK_TMA_B_DENSE  0
+
+typedef struct offk_tgemm {
+  offk_gemm_t g;
+  int32_t a_kind, lda, a_coff;
+  int32_t n_img, hin, win, ctot, cin, kh, kw, stride, pad, hout, wout; /* im2col geometry */
+  int32_t b_kind, ldb;
+  int32_t prepared;      /* set by offk_tma_gemm_prepare (the N tile the B tensor map was built for) */
+  int32_t reserved;
+  uint64_t tmap_a[16];   /* CUtensorMap storage */
+  uint64_t tmap_b[16];
+} offk_tgemm_t;
+
+int offk_tma_gemm_prepare(offk_tgemm_t* t);
+int offk_tma_gemm(const offk_tgemm_t* t, void* stream);
+
+/* ------------------------------------------------------------------------
  * Fused OFF stencil: spatial gradient + temporal difference + dropout +
  * both torch.cat()s in one pass.  Replaces RGB_OFF.py:599-604 (view / slice /
  * sub), :611 (depth-wise 3x3, learned weight + bias) or Flow_OFF.py:622

@@ -41,6 +41,22 @@ class OffkGemm(C.Structure):
     ]
 
 
+class OffkTGemm(C.Structure):
+    """Mirror of offk_tgemm_t."""
+    _fields_ = [
+        ("g", OffkGemm),
+        ("a_kind", C.c_int32), ("lda", C.c_int32), ("a_coff", C.c_int32),
+        ("n_img", C.c_int32), ("hin", C.c_int32), ("win", C.c_int32), ("ctot", C.c_int32), ("cin", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("hout", C.c_int32),
+        ("wout", C.c_int32),
+        ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("reserved", C.c_int32),
+        ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
+    ]
+
+
+TMA_A_DENSE, TMA_A_IM2COL, TMA_B_DENSE = 0, 1, 0
+
+
 class OffkStencil(C.Structure):
     """Mirror of offk_stencil_t."""
     _fields_ = [
@@ -70,6 +86,8 @@ _PROTOS = {
     "offk_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_longlong)]),
     "offk_gather_gemm": (C.c_int, [C.POINTER(OffkGemm), C.c_int, _P]),
+    "offk_tma_gemm_prepare": (C.c_int, [C.POINTER(OffkTGemm)]),
+    "offk_tma_gemm": (C.c_int, [C.POINTER(OffkTGemm), _P]),
     "offk_stencil_diff_fwd": (C.c_int, [C.POINTER(OffkStencil), _P, _P, _P, _P, _P, _P]),
     "offk_stencil_diff_bwd": (C.c_int, [C.POINTER(OffkStencil), _P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                         _P, _P, _P]),

@@ -10,7 +10,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v
        -I"$ROOT/include" -I"$HERE" ${OFFK_EXTRA_FLAGS:-})
 OBJS=()
-for f in offk_api offk_gemm_simt offk_gemm_tc offk_stencil offk_head; do
+for f in offk_api offk_gemm_simt offk_gemm_tc offk_gemm_tma offk_stencil offk_head; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$ODIR/$f.o" 2> "$ODIR/$f.ptxas.log" || { cat "$ODIR/$f.ptxas.log" >&2; exit 1; }
   OBJS+=("$ODIR/$f.o")
 done

@@ -1,0 +1,350 @@
+// TMA-fed tcgen05 GEMM (OFFK_PREC_TF32) for sm_100a: the dense contractions whose operands are regular enough for the
+// Tensor Memory Accelerator -- every conv / FC of the OFF sub-network that works on channels-last tensors.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 32] (tf32, smem) * B[BN x 32]^T (tf32, smem)   per K-block
+//
+// Warp roles (320 threads):
+//   warp 0     TMA producer: one elected lane waits for a free stage, posts mbarrier.arrive.expect_tx and issues
+//              cp.async.bulk.tensor loads that land directly in the canonical SWIZZLE_128B shared-memory layouts:
+//                A dense   : 2-D tile  {32 k, 128 rows}   of a row-major [M, lda] matrix (1x1 conv / FC input)
+//                A im2col  : 4-D im2col {32 c, 128 pixels} of a channels-last [n, h, w, ctot] tensor at filter offset
+//                            (q, r): the hardware walks the output pixels (stride, zero padding, image wrap) -- no index
+//                            tables, no per-element predicates, one instruction per K-block
+//                B dense   : 2-D tile  {32 k, BN rows}    of the [N, K] weight matrix (OHWI for KxK convs)
+//   warp 1     allocates TMEM; one elected lane waits on "full", issues 4 x tcgen05.mma (kind::tf32, M=128, N=BN, K=8)
+//              per stage, tcgen05.commit's to the stage's "empty" mbarrier and to "accum_full" after the last K-block
+//   warps 2-9  epilogue: tcgen05.ld the accumulator rows out of TMEM (warp w may touch TMEM lanes 32*(w%4)..+31), transpose
+//              32-column chunks through shared memory so that bias / ReLU / ReLU' gate / residual add and the float4
+//              stores (red.global.add for split-K) touch whole 128-byte lines of the channels-last output
+// One output tile per CTA; two CTAs co-reside per SM so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include "offk_tc.cuh"
+
+namespace offk {
+
+constexpr int TM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TM_EPI_PITCH = 36;          // floats per row of the epilogue staging tile (32 columns + 4 padding)
+
+struct TmGeom {        // what the producer needs to turn (tile, K-block) into TMA coordinates
+  int a_kind;
+  int a_coff;          // first channel of the A operand inside its buffer (im2col)
+  int cblocks;         // cin / 32 (im2col)
+  int kw;              // filter width (im2col)
+  int hout, wout, stride, pad;
+};
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int n,
+                                                   int woff, int hoff, uint32_t bar) {
+  const unsigned short wo = (unsigned short)woff, ho = (unsigned short)hoff;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(wo), "h"(ho)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+struct TmShared {
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
+  uint64_t accum_full;
+  uint32_t tmem_base;
+};
+
+template <int A_KIND>
+__global__ void __launch_bounds__(TM_THREADS, 2)
+tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const offk_gemm_t g,
+                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
+  const int num_kb_total = (g.K + TC_BK - 1) / TC_BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&sh->full[s]), 1);
+      mbar_init(smem_u32(&sh->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&sh->accum_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tma);
+    tma_prefetch_desc(&tmb);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&sh->tmem_base), (uint32_t)tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = sh->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer (one thread) =================
+      int w0 = 0, h0 = 0, img0 = 0;
+      if (A_KIND == OFFK_TMA_A_IM2COL) {
+        const int hw = geo.hout * geo.wout;
+        img0 = m0 / hw;
+        const int rem = m0 - img0 * hw;
+        const int oy = rem / geo.wout, ox = rem - oy * geo.wout;
+        w0 = ox * geo.stride - geo.pad;
+        h0 = oy * geo.stride - geo.pad;
+      }
+      int s = 0;
+      uint32_t parity = 1;                                       // empty-barrier parity of the current round
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb_begin + i;
+        mbar_wait(smem_u32(&sh->empty[s]), parity);              // slot free (first round passes at once)
+        const uint32_t full = smem_u32(&sh->full[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        const uint32_t a_dst = smem_base + s * stage_bytes;
+        if (A_KIND == OFFK_TMA_A_DENSE) {
+          tma_load_2d(a_dst, &tma, kb * TC_BK, m0, full);
+        } else {
+          const int tap = kb / geo.cblocks, cb = kb - tap * geo.cblocks;
+          const int r = tap / geo.kw, q = tap - r * geo.kw;
+          tma_load_im2col_4d(a_dst, &tma, geo.a_coff + cb * TC_BK, w0, h0, img0, q, r, full);
+        }
+        tma_load_2d(a_dst + TC_A_BYTES, &tmb, kb * TC_BK, n0, full);
+        if (++s == stages) { s = 0; parity ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer (one thread) =================
+      const uint32_t idesc = make_idesc_tf32(bn, false, false);
+      int s = 0;
+      uint32_t parity = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(smem_u32(&sh->full[s]), parity);
+        tc_fence_after();
+        const uint32_t a_base = smem_base + s * stage_bytes;
+        const uint64_t adesc = make_smem_desc(a_base), bdesc = make_smem_desc(a_base + TC_A_BYTES);
+#pragma unroll
+        for (int j = 0; j < TC_BK / 8; ++j)                    // +32 bytes inside the 128-byte swizzle row per K = 8
+          umma_tf32(tmem_d, adesc + 2ull * j, bdesc + 2ull * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        umma_commit(smem_u32(&sh->empty[s]));                    // frees the smem slot when these MMAs retire
+        if (++s == stages) { s = 0; parity ^= 1u; }
+      }
+      umma_commit(smem_u32(&sh->accum_full));                    // accumulator complete
+    }
+    __syncwarp();
+  } else if (nkb > 0) {
+    // ================= epilogue (warps 2-9) =================
+    mbar_wait(smem_u32(&sh->accum_full), 0u);
+    tc_fence_after();
+    const int ew = warp - 2;                                     // 0..7
+    const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                                    // which 16 columns of a 32-column chunk
+    const bool atomic = (g.split_k > 1) || g.atomic_out;
+    if (g.out_vec) {
+      // Transposed through shared memory (the pipeline stages are idle once accum_full fired) so that bias / gate /
+      // residual loads and the stores are row-contiguous: 8 lanes x 16 bytes = one 128-byte line per output row.
+      // Staging tile: 128 rows x 32 columns, row pitch 36 floats (conflict-free 128-bit accesses), double-buffered.
+      const uint32_t stg0 = smem_base;
+      const int trow = quad * 32 + lane;                         // accumulator row this thread drains
+      const int rsub = lane >> 3, cq = lane & 7;                 // read-back: 4 rows per warp pass, 8 float4 per row
+      const int nchunks = (bn + 31) >> 5;
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t stg = stg0 + (uint32_t)(c & 1) * (TC_BM * TM_EPI_PITCH * 4);
+        if (c * 32 + half * 16 < bn) {
+          float v[16];
+          tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16), v);
+          const uint32_t dst = stg + (uint32_t)(trow * TM_EPI_PITCH + half * 16) * 4;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) sts128(dst + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int n = n0 + c * 32 + cq * 4;
+        if (n < g.N && c * 32 + cq * 4 < bn) {
+#pragma unroll
+          for (int it = 0; it < TC_BM / 32; ++it) {
+            const int row = it * 32 + ew * 4 + rsub;
+            const int m = m0 + row;
+            if (m < g.M) {
+              float4 v;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                           : "r"(stg + (uint32_t)(row * TM_EPI_PITCH + cq * 4) * 4));
+              const EpiRow er = epi_row(g, m);
+              epi_store4(g, er, n, v, atomic);
+            }
+          }
+        }
+      }
+    } else {
+      const int m = m0 + quad * 32 + lane;
+      const bool mvalid = m < g.M;
+      EpiRow er = {0, 0, 0, false};
+      if (mvalid) er = epi_row(g, m);
+      const int nchunks = bn >> 4;
+      for (int c = half; c < nchunks; c += 2) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16), v);
+        if (mvalid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c * 16 + j;
+            if (n < g.N) epi_store(g, er, n, v[j], atomic);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int driver_fn(const char* name, void** fn) {
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return cuda_check(e, name);
+  if (q != cudaDriverEntryPointSuccess || *fn == nullptr) return fail(OFFK_E_NOTSM100, "%s: driver entry point unavailable", name);
+  return 0;
+}
+
+static int encode_2d(CUtensorMap* tm, const float* base, long long inner, long long rows, long long ld, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn)
+    if (int e = driver_fn("cuTensorMapEncodeTiled", (void**)&fn)) return e;
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OFFK_E_BADARG, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld ld=%lld box=%d", (int)r, inner, rows, ld, box_rows);
+  return 0;
+}
+
+static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t) {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn)
+    if (int e = driver_fn("cuTensorMapEncodeIm2col", (void**)&fn)) return e;
+  const cuuint64_t dims[4] = {(cuuint64_t)t->ctot, (cuuint64_t)t->win, (cuuint64_t)t->hin, (cuuint64_t)t->n_img};
+  const cuuint64_t strides[3] = {(cuuint64_t)t->ctot * 4, (cuuint64_t)t->win * t->ctot * 4,
+                                 (cuuint64_t)t->hin * t->win * t->ctot * 4};
+  // base pixels (top-left corner of the filter window) range over [-pad, dim + pad - (k - 1)) in steps of `stride`
+  const int lower[2] = {-t->pad, -t->pad};
+  const int upper[2] = {t->pad - (t->kw - 1), t->pad - (t->kh - 1)};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)t->stride, (cuuint32_t)t->stride, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t->g.a_src), dims, strides, lower, upper,
+                  (cuuint32_t)TC_BK, (cuuint32_t)TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(OFFK_E_BADARG, "cuTensorMapEncodeIm2col failed (%d): [n=%d h=%d w=%d c=%d] k=%dx%d s=%d p=%d", (int)r, t->n_img,
+                t->hin, t->win, t->ctot, t->kh, t->kw, t->stride, t->pad);
+  return 0;
+}
+
+template <int A_KIND>
+static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
+                       int kb_per, int tmem_cols, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = tma_gemm_kernel<A_KIND>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(tma_gemm)");
+    attr_set = true;
+  }
+  kern<<<grid, TM_THREADS, smem, st>>>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols);
+  return OFFK_LAUNCH_CHECK("tma_gemm");
+}
+
+}  // namespace offk
+
+using namespace offk;
+
+extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
+  OFFK_REQUIRE(t != nullptr, "tma_gemm: null descriptor");
+  const offk_gemm_t& g = t->g;
+  OFFK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "tma_gemm: empty problem");
+  OFFK_REQUIRE(g.a_src && g.b_src, "tma_gemm: operand pointers");
+  OFFK_REQUIRE((reinterpret_cast<uintptr_t>(g.a_src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(g.b_src) & 15u) == 0,
+               "tma_gemm: operands must be 16-byte aligned");
+  OFFK_REQUIRE(t->b_kind == OFFK_TMA_B_DENSE && t->ldb >= g.K && t->ldb % 4 == 0, "tma_gemm: B must be a dense [N, ldb] matrix, ldb %% 4 == 0");
+  int bn = g.tile_n > 0 ? g.tile_n : (g.N <= 256 ? (g.N + 15) / 16 * 16 : 256);
+  OFFK_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "tma_gemm: bad N tile %d", bn);
+  CUtensorMap ta, tb;
+  if (t->a_kind == OFFK_TMA_A_DENSE) {
+    OFFK_REQUIRE(t->lda >= g.K && t->lda % 4 == 0, "tma_gemm: dense A needs lda >= K, lda %% 4 == 0");
+    if (int e = encode_2d(&ta, g.a_src, g.K, g.M, t->lda, TC_BM)) return e;
+  } else if (t->a_kind == OFFK_TMA_A_IM2COL) {
+    OFFK_REQUIRE(t->cin % TC_BK == 0 && t->ctot % 4 == 0 && t->a_coff % 4 == 0 && t->a_coff + t->cin <= t->ctot,
+                 "tma_gemm: im2col needs cin %% 32 == 0 and a 16-byte aligned channel slice");
+    OFFK_REQUIRE(t->kh >= 1 && t->kw >= 1 && t->stride >= 1 && t->stride <= 8 && t->pad >= 0, "tma_gemm: conv geometry");
+    OFFK_REQUIRE(g.K == t->cin * t->kh * t->kw, "tma_gemm: K must equal kh*kw*cin");
+    OFFK_REQUIRE(t->hout == (t->hin + 2 * t->pad - t->kh) / t->stride + 1 && t->wout == (t->win + 2 * t->pad - t->kw) / t->stride + 1 &&
+                     g.M == t->n_img * t->hout * t->wout, "tma_gemm: output geometry");
+    if (int e = encode_im2col(&ta, t)) return e;
+  } else {
+    return fail(OFFK_E_BADARG, "tma_gemm: unknown a_kind %d", t->a_kind);
+  }
+  if (int e = encode_2d(&tb, g.b_src, g.K, g.N, t->ldb, bn)) return e;
+  memcpy(t->tmap_a, &ta, sizeof(ta));
+  memcpy(t->tmap_b, &tb, sizeof(tb));
+  t->prepared = bn;
+  return 0;
+}
+
+extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
+  OFFK_REQUIRE(t != nullptr && t->prepared > 0, "tma_gemm: descriptor not prepared (offk_tma_gemm_prepare)");
+  const offk_gemm_t& g = t->g;
+  OFFK_REQUIRE(g.out && g.out_row && g.out_col, "tma_gemm: output tables");
+  if (g.out_vec) OFFK_REQUIRE((g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15u) == 0, "tma_gemm: out_vec alignment");
+  const int bn = t->prepared;
+  const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+  const int split = g.split_k > 1 ? g.split_k : 1;
+  const int kb_per = (num_kb + split - 1) / split;
+  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)bn * 128u;
+  const int budget = 108 * 1024;                 // two CTAs per SM
+  int stages = budget / (int)stage_bytes;
+  if (stages < 2) stages = 2;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
+  const size_t smem = (size_t)stages * stage_bytes + sizeof(TmShared) + 1024;
+  int tmem_cols = 32;
+  while (tmem_cols < bn) tmem_cols <<= 1;
+  dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + bn - 1) / bn, (num_kb + kb_per - 1) / kb_per);
+  OFFK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tma_gemm: grid too large");
+  TmGeom geo;
+  geo.a_kind = t->a_kind; geo.a_coff = t->a_coff; geo.cblocks = t->cin > 0 ? t->cin / TC_BK : 1; geo.kw = t->kw > 0 ? t->kw : 1;
+  geo.hout = t->hout; geo.wout = t->wout; geo.stride = t->stride; geo.pad = t->pad;
+  alignas(64) CUtensorMap ta, tb;
+  memcpy(&ta, t->tmap_a, sizeof(ta));
+  memcpy(&tb, t->tmap_b, sizeof(tb));
+  if (t->a_kind == OFFK_TMA_A_DENSE)
+    return launch_tm_t<OFFK_TMA_A_DENSE>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, as_stream(stream));
+  return launch_tm_t<OFFK_TMA_A_IM2COL>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, as_stream(stream));
+}

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -72,6 +73,39 @@ class Gemm:
         L.check(self.eng.lib.offk_gather_gemm(C.byref(self.desc), self.eng.prec, stream), self.name)
 
 
+class TGemm(Gemm):
+    """A forward conv / FC on a channels-last input as ONE TMA-fed launch (offk_tma_gemm): A through a dense 2-D
+    tensor map (1x1, stride 1) or TMA im2col mode (KxK), B = the [cout, K] weight matrix.  Same epilogue fields and
+    output tables as the gather-GEMM it stands in for."""
+
+    @staticmethod
+    def eligible(geom: T.ConvGeom, prec, a_relu=False) -> bool:
+        return (prec == L.PREC_TF32 and not a_relu and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0 and geom.x_coff % 4 == 0
+                and geom.kdim % 4 == 0)
+
+    def __init__(self, eng, spc, key, geom: T.ConvGeom, **kw):
+        super().__init__(eng, spc, key, **kw)
+        t = L.OffkTGemm()
+        C.memmove(C.byref(t.g), C.byref(self.desc), C.sizeof(L.OffkGemm))
+        one = geom.kh == 1 and geom.kw == 1 and geom.stride == 1 and geom.pad == 0
+        if one:
+            t.a_kind, t.lda = L.TMA_A_DENSE, geom.x_ctot
+            t.g.a_src = kw["a_src"].data_ptr() + 4 * geom.x_coff
+        else:
+            t.a_kind = L.TMA_A_IM2COL
+        t.a_coff = geom.x_coff
+        t.n_img, t.hin, t.win, t.ctot, t.cin = geom.n_img, geom.hin, geom.win, geom.x_ctot, geom.cin
+        t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = geom.kh, geom.kw, geom.stride, geom.pad, geom.hout, geom.wout
+        t.b_kind, t.ldb = L.TMA_B_DENSE, geom.kdim
+        self.tdesc = t
+
+    def __call__(self, stream):
+        lib = self.eng.lib
+        if not self.tdesc.prepared:                                  # tensor maps are encoded on first use (needs a driver)
+            L.check(lib.offk_tma_gemm_prepare(C.byref(self.tdesc)), self.name + " (prepare)")
+        L.check(lib.offk_tma_gemm(C.byref(self.tdesc), stream), self.name)
+
+
 class OFFEngine:
     """Plan + buffers for one (batch, length) shape on one GPU.
 
@@ -93,6 +127,7 @@ class OFFEngine:
         self.consensus = (variant != "rgb") if consensus is None else bool(consensus)
         self.tap_grads = tap_grads
         self.single_stream = False       # True: issue every lane on the caller's stream (profiling / debugging)
+        self.use_tma = os.environ.get("OFFK_NO_TMA", "0") != "1"     # bring-up switch: gather-fed GEMMs everywhere
         self._tab_cache = {}
         self._keep = []
 
@@ -220,8 +255,10 @@ class OFFEngine:
         if self.prec == L.PREC_TF32 and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
             split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), kb // 8))
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
+        tma = self.use_tma and x_layout == "nhwc" and TGemm.eligible(geom, self.prec, a_relu)
+        mk = (lambda *a, **k: TGemm(*a, geom=geom, **k)) if tma else Gemm
         if split > 1:
-            g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
+            g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
             hw = geom.hout * geom.wout
 
             def run(stream, g=g, y=y, b=b, geom=geom, hw=hw, cols=cols):
@@ -238,8 +275,8 @@ class OFFEngine:
             run.gemm = g
             run.reads, run.writes, run.lane = g.reads, g.writes, 0
             return run
-        g = Gemm(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
-                 addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
+        g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
+               addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
         self.flops_fwd += g.flops
         return g
 
@@ -694,17 +731,18 @@ class OFFEngine:
 
 
 def _auto_tile_n(M: int, N: int) -> int:
-    """N tile of a GEMM that would otherwise launch far fewer CTAs than the GPU has SMs (the 7x7-resolution layers:
-    37 M tiles): a narrower tile multiplies the CTA count; 0 = the kernel's default (widest legal tile)."""
+    """N tile of a GEMM launched without split-K.  Two CTAs fit an SM and one CTA's epilogue should overlap another's
+    main loop, so aim for >= 2 x 148 CTAs: the widest tile (fewest re-reads of A) that gets there, else the narrowest
+    one that divides N.  0 = the kernel's default (widest legal tile)."""
     mt = math.ceil(M / 128)
     bn0 = (N + 15) // 16 * 16 if N <= 256 else 256
-    if mt * math.ceil(N / bn0) >= 120:
+    if mt * math.ceil(N / bn0) >= 2 * _SM_TARGET:
         return 0
     best = 0
     for bn in (128, 64, 32):
         if bn < bn0 and N % bn == 0:
             best = bn
-            if mt * (N // bn) >= 140:
+            if mt * (N // bn) >= 2 * _SM_TARGET:
                 break
     return best
 

@@ -105,6 +105,72 @@ def test_gather_gemm_conv_parity(dev, case, prec, tol):
     assert _rel(back(dx, xl)[:, xco:xco + cin], xs.grad.cpu()) < tol
 
 
+TMA_CASES = [
+    # n, cin, h, w, cout, k, s, p, x_ctot, x_coff, y_ctot, y_coff, split_k
+    (4, 64, 14, 14, 256, 1, 1, 0, 64, 0, 256, 0, 1),        # dense A (1x1), one N tile
+    (3, 128, 7, 7, 512, 1, 1, 0, 160, 32, 512, 0, 1),       # dense A on a channel slice, two N tiles, M = 147
+    (5, 64, 14, 14, 64, 3, 1, 1, 64, 0, 64, 0, 1),          # im2col 3x3, tiles straddle rows and images
+    (3, 32, 28, 28, 64, 7, 2, 3, 32, 0, 64, 0, 1),          # motion_conv_trans_28 geometry (7x7 stride 2)
+    (2, 96, 14, 14, 128, 5, 2, 2, 160, 32, 160, 32, 1),     # 5x5 stride 2 on channel slices, M = 98
+    (3, 128, 7, 7, 128, 3, 1, 1, 128, 0, 128, 0, 4),        # split-K accumulation
+    (8, 1024, 1, 1, 101, 1, 1, 0, 1024, 0, 101, 0, 1),      # FC head, N = 101
+]
+
+
+@pytest.mark.parametrize("case", TMA_CASES, ids=[f"{c[1]}x{c[2]}k{c[5]}s{c[6]}n{c[4]}" for c in TMA_CASES])
+def test_tma_gemm_conv_parity(dev, case):
+    """offk_tma_gemm (TMA dense / im2col operand fetch + tcgen05) against conv2d, and bit-for-bit against the gather-fed
+    tensor-core kernel on the same operands (same tf32 products, same fp32 accumulation order per K-block)."""
+    from off_b200 import _lib as L, tables as T
+    lib = L.lib()
+    n, cin, h, w, cout, k, st, p, xct, xco, yct, yco, split = case
+    g = T.ConvGeom(n, cin, h, w, cout, k, k, st, p, xct, xco, yct, yco)
+    torch.manual_seed(0)
+    x = torch.randn(n, xct, h, w, device=dev)
+    wt = torch.randn(cout, cin, k, k, device=dev) / (g.kdim ** 0.5)
+    bias = torch.randn(cout, device=dev)
+    xl = x.permute(0, 2, 3, 1).contiguous()
+    wl = wt.permute(0, 2, 3, 1).contiguous()                        # OHWI
+    spc = T.conv_fwd_spec(g, "nhwc", "nhwc")
+    tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
+    outs = []
+    for use_tma in (True, False):
+        out = torch.zeros(n, g.hout, g.wout, yct, device=dev)
+        t = L.OffkTGemm()
+        d = t.g
+        d.M, d.N, d.K = spc.M, spc.N, spc.K
+        d.a_src, d.a_row, d.a_col = xl.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
+        d.a_h, d.a_w = (spc.a_h, spc.a_w) if spc.a_h else (T.NO_BOX, T.NO_BOX)
+        d.a_ones_row, d.a_mode = -1, spc.a_mode
+        d.b_src, d.b_row, d.b_col, d.b_mode = wl.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
+        d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+        d.bias = bias.data_ptr() if split == 1 else None
+        d.split_k, d.out_vec = split, spc.out_vec
+        if use_tma:
+            one = k == 1 and st == 1 and p == 0
+            t.a_kind, t.lda, t.a_coff = (L.TMA_A_DENSE if one else L.TMA_A_IM2COL), xct, xco
+            if one:
+                d.a_src = xl.data_ptr() + 4 * xco
+            t.n_img, t.hin, t.win, t.ctot, t.cin = n, h, w, xct, cin
+            t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = k, k, st, p, g.hout, g.wout
+            t.b_kind, t.ldb = L.TMA_B_DENSE, g.kdim
+            L.check(lib.offk_tma_gemm_prepare(C.byref(t)), "prepare")
+            L.check(lib.offk_tma_gemm(C.byref(t), None), "tma_gemm")
+        else:
+            L.check(lib.offk_gather_gemm(C.byref(d), 1, None), "gather_gemm")
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = torch.nn.functional.conv2d(x[:, xco:xco + cin].double(), wt.double(), bias.double() if split == 1 else None, st, p)
+    got = outs[0].permute(0, 3, 1, 2)[:, yco:yco + cout]
+    assert _rel(got, ref.cpu()) < 3e-3
+    if yco:
+        assert outs[0][..., :yco].abs().max().item() == 0
+    if split == 1:
+        assert torch.equal(outs[0], outs[1])
+    else:
+        assert _rel(outs[0], outs[1].cpu()) < 1e-5                   # atomics: summation order differs
+
+
 STENCIL_CASES = [
     # B, L, S, K, index_mode, drop_mode
     (2, 3, 28, 1, 0, 0), (3, 4, 14, 1, 1, 1), (2, 2, 7, 1, 0, 2), (2, 3, 7, 2, 0, 0), (1, 7, 14, 1, 0, 1), (1, 2, 5, 1, 1, 0),
