@@ -288,6 +288,11 @@ int offk_add_relu_slice(const float* a, const float* b, float* dst, int dst_ctot
  * 2: dst(OIHW) += src(OHWI) (weight gradients) */
 int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi, void* stream);
 
+/* dst[i] = src[idx[i]], i < n.  One launch re-lays every conv weight of the step: OHWI copies for the forward
+ * implicit GEMMs and [cin][kh][kw][cout] copies with flipped taps for the data-gradient GEMMs (autograd of
+ * RGB_OFF.py:657-841); idx is built once on the host.  idx and dst 16-byte aligned. */
+int offk_gather_copy(const float* src, const int32_t* idx, float* dst, long long n, void* stream);
+
 /* keep decision of OFFK_DROP_SEED for element `idx` (host mirror for tests): 1 = keep */
 int offk_drop_keep_host(uint64_t seed, uint64_t idx, float drop_p);
 

@@ -106,6 +106,7 @@ _PROTOS = {
                                  C.c_int, _P]),
     "offk_bias_act": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_add_relu_slice": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "offk_gather_copy": (C.c_int, [_P, _P, _P, C.c_longlong, _P]),
     "offk_permute_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_drop_keep_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_float]),
 }

@@ -242,6 +242,28 @@ extern "C" int offk_fill_zero(float* p, long long n, void* stream) {
   return cuda_check(cudaMemsetAsync(p, 0, (size_t)n * sizeof(float), as_stream(stream)), "fill_zero");
 }
 
+// dst[i] = src[idx[i]]: all per-step weight re-layouts (OHWI forward copies, flipped / transposed data-gradient copies)
+// in one launch; idx is built once per plan on the host
+__global__ void gather_copy_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                   long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const int4 j = *reinterpret_cast<const int4*>(idx + i);
+    *reinterpret_cast<float4*>(dst + i) = make_float4(__ldg(src + j.x), __ldg(src + j.y), __ldg(src + j.z), __ldg(src + j.w));
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __ldg(src + idx[k]);
+  }
+}
+
+extern "C" int offk_gather_copy(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
+  OFFK_REQUIRE(src && idx && dst && n >= 0, "gather_copy: bad args");
+  OFFK_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0, "gather_copy: alignment");
+  if (n == 0) return 0;
+  const long long threads = (n + 3) / 4;
+  gather_copy_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(src, idx, dst, n);
+  return OFFK_LAUNCH_CHECK("gather_copy");
+}
+
 extern "C" int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi,
                                    void* stream) {
   OFFK_REQUIRE(src && dst && cout > 0 && cin > 0 && kh > 0 && kw > 0, "permute_weight: bad args");

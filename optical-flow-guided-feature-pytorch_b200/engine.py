@@ -57,7 +57,7 @@ class Gemm:
         d.relu_post, d.atomic_out = int(relu_post), int(atomic)
         d.ones_row_out = ones_out.data_ptr() if ones_out is not None else None
         if tile_n == 0 and split_k == 1:
-            tile_n = _auto_tile_n(spc.M, spc.N)
+            tile_n = _auto_tile_n(spc.M, spc.N, isinstance(self, TGemm))
         d.split_k, d.tile_n = split_k, tile_n
         d.out_vec = spc.out_vec if (gate_tabs is None or True) else 0
         T.check_modes(spc)
@@ -228,16 +228,34 @@ class OFFEngine:
         self._copy_stream = None
         if self.tap_grads:
             self.tap_grad = OrderedDict((tag, torch.zeros_like(t)) for tag, t in self.taps.items())
-        # OHWI copies of the KxK conv weights (k order of the channels-last implicit GEMM) and of their gradients
-        self.wp, self.dwp = {}, {}
+        # Per-step weight re-layouts, produced by ONE gather-copy launch (wc_flat[i] = params_flat[wc_idx[i]]):
+        #   wp[name] : OHWI [cout, kh, kw, cin] copies of the KxK conv weights (K order of the channels-last implicit GEMM)
+        #   wd[name] : [cin, kh, kw, cout] copies with flipped taps of every stride-1 conv = the B operand of its
+        #              data-gradient GEMM (dX = dY * W^T as a forward conv over dY)
+        # dwp[name]: OHWI accumulators of the KxK weight gradients (un-permuted into grads_flat after the backward)
+        self.wp, self.dwp, self.wd = {}, {}, {}
         kxk = [(name, cout, cin, k) for name, cout, cin, k, _, _ in S.STAGE_CONVS if k > 1]
         total = sum(cout * cin * k * k for _, cout, cin, k in kxk)
-        self.wp_flat = torch.zeros(total, device=self.device)
         self.dwp_flat = torch.zeros(total, device=self.device)
+        idx, off, views = [], 0, []
+        for name, cout, cin, k, stride, _ in S.STAGE_CONVS:
+            p_off = self.layout[name + ".weight"][0]
+            oihw = p_off + np.arange(cout * cin * k * k, dtype=np.int64).reshape(cout, cin, k, k)
+            if k > 1:
+                idx.append(oihw.transpose(0, 2, 3, 1).reshape(-1))
+                views.append(("wp", name, off, (cout, k, k, cin)))
+                off += oihw.size
+            if stride == 1:
+                idx.append(oihw[:, :, ::-1, ::-1].transpose(1, 2, 3, 0).reshape(-1))
+                views.append(("wd", name, off, (cin, k * k * cout)))
+                off += oihw.size
+        self.wc_idx = torch.from_numpy(np.concatenate(idx).astype(np.int32)).to(self.device)
+        self.wc_flat = torch.zeros(off, device=self.device)
+        for kind, name, o, shape in views:
+            getattr(self, kind)[name] = self.wc_flat[o:o + int(np.prod(shape))].view(shape)
         off = 0
         for name, cout, cin, k in kxk:
             n = cout * cin * k * k
-            self.wp[name] = self.wp_flat[off:off + n].view(cout, k, k, cin)
             self.dwp[name] = self.dwp_flat[off:off + n].view(cout, k, k, cin)
             off += n
         # dropout state (filled per forward call)
@@ -303,8 +321,17 @@ class OFFEngine:
                 aspec = T.conv_dgrad_specs(add_geom, "nhwc", "nhwc", "nhwc")[i]
                 t = self._tables(("dgrad", "nhwc", _gkey(add_geom), i), aspec)
                 add_tabs = (t["out_row"], t["out_col"])
-            g = Gemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), a_src=dy, b_src=w, out=dx, gate=gate, gate_col0=gate_col0,
-                     gate_first=gate_first, addend=addend, add_tabs=add_tabs, name=f"{name}.dgrad{i}")
+            kw_ = dict(a_src=dy, b_src=w, out=dx, gate=gate, gate_col0=gate_col0, gate_first=gate_first, addend=addend,
+                       add_tabs=add_tabs, name=f"{name}.dgrad{i}")
+            # dX of a stride-1 conv = a forward conv over dY with flipped taps and pad' = k-1-pad: TMA-fed
+            gd = T.ConvGeom(geom.n_img, geom.cout, geom.hout, geom.wout, geom.cin, geom.kh, geom.kw, 1,
+                            geom.kh - 1 - geom.pad, geom.y_ctot, geom.y_coff, geom.x_ctot, geom.x_coff) if geom.stride == 1 else None
+            if (self.use_tma and x_layout == "nhwc" and gd is not None and name in self.wd and geom.kh == geom.kw
+                    and TGemm.eligible(gd, self.prec) and (gd.hout, gd.wout) == (geom.hin, geom.win)):
+                kw_["b_src"] = self.wd[name]
+                g = TGemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), geom=gd, **kw_)
+            else:
+                g = Gemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), **kw_)
             self.flops_bwd += g.flops
             out.append(g)
         return out
@@ -559,13 +586,13 @@ class OFFEngine:
         back("motion_conv_trans_28", bf["F28"], d("t28"), g_t28)
         dgrad("motion_conv_trans_28", d("t28"), bf["dF28"], g_t28)
 
-        # OHWI weight copies before the forward, OHWI -> OIHW weight gradients after the backward
-        pre, post = [], []
+        # weight re-layouts before the forward (one launch), OHWI -> OIHW weight gradients after the backward
+        wc, wci, pflat = self.wc_flat, self.wc_idx, self.params_flat
+        pre = [_nm(lambda stream: L.check(lib.offk_gather_copy(_ptr(pflat), _ptr(wci), _ptr(wc), wc.numel(), stream),
+                                          "weight copies"), "weight_copies", writes=[wc])]
+        post = []
         for name, cout, cin, k, _, _ in S.STAGE_CONVS:
             if k > 1:
-                pre.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
-                    _ptr(pr[n + ".weight"]), _ptr(self.wp[n]), co, ci, k, k, 1, stream), "permute " + n), "permute " + name,
-                    writes=[self.wp[name]]))
                 post.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
                     _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n), "unpermute " + name,
                     reads=[self.dwp[name]], writes=[gr[name + ".weight"]], lane=1))
@@ -730,19 +757,22 @@ class OFFEngine:
                 streams[0].wait_stream(s_)
 
 
-def _auto_tile_n(M: int, N: int) -> int:
-    """N tile of a GEMM launched without split-K.  Two CTAs fit an SM and one CTA's epilogue should overlap another's
-    main loop, so aim for >= 2 x 148 CTAs: the widest tile (fewest re-reads of A) that gets there, else the narrowest
-    one that divides N.  0 = the kernel's default (widest legal tile)."""
+def _auto_tile_n(M: int, N: int, tma: bool = False) -> int:
+    """N tile of a GEMM launched without split-K; 0 = the kernel's default (widest legal tile).
+    TMA-fed: two CTAs fit an SM and one CTA's epilogue should overlap another's main loop, so aim for >= 2 x 148 CTAs
+    with the widest tile that gets there (re-reading A per N tile is one cheap TMA instruction).
+    Gather-fed: the A gather is the expensive part and is repeated per N tile, so only narrow the tile when the grid
+    would otherwise leave most SMs idle (the 7x7-resolution layers: 37 M tiles)."""
     mt = math.ceil(M / 128)
     bn0 = (N + 15) // 16 * 16 if N <= 256 else 256
-    if mt * math.ceil(N / bn0) >= 2 * _SM_TARGET:
+    want, enough = (2 * _SM_TARGET, 2 * _SM_TARGET) if tma else (120, 140)
+    if mt * math.ceil(N / bn0) >= want:
         return 0
     best = 0
     for bn in (128, 64, 32):
         if bn < bn0 and N % bn == 0:
             best = bn
-            if mt * (N // bn) >= 2 * _SM_TARGET:
+            if mt * (N // bn) >= enough:
                 break
     return best
 
