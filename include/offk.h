@@ -155,13 +155,24 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
  *   A dense  : A(m,k) = a_src[m*lda + k]
  *   A im2col : a_src = channels-last [n_img, hin, win, ctot]; channels [a_coff, a_coff+cin) feed the conv;
  *              K = kh*kw*cin ordered (r, q, c) -- the order of OHWI weights; cin % 32 == 0
+ *   A nchw   : a_src = NCHW [n_img, cin, hin*win] (pixels contiguous); fetched as the MN-major tcgen05 operand, so the
+ *              NCHW -> channels-last conversion of the unit's fused 1x1 conv executes no transpose
  *   B dense  : B(n,k) = b_src[n*ldb + k]   (weights [cout, K])
  * offk_tma_gemm_prepare() encodes the two CUtensorMap objects into the descriptor (host only, no device memory);
  * call it again whenever a pointer or shape changes.  precision is always OFFK_PREC_TF32.
  * ---------------------------------------------------------------------- */
 #define OFFK_TMA_A_DENSE  0
 #define OFFK_TMA_A_IM2COL 1
+#define OFFK_TMA_A_NCHW   2 /* A(m = img*hw + pix, k = c) = a_src[(img*cin + c)*hw + pix]: an NCHW tensor read in place
+                               (the BN-Inception taps of motion_conv_gen_X / motion_spatial_down_X, RGB_OFF.py:597,610);
+                               hw = hin*win, hw % 4 == 0, cin % 32 == 0; M tiles are cut per frame */
+#define OFFK_TMA_A_NCHW_T   3 /* weight gradient of the above: A(m = c, k = img*hw + pix), same NCHW tensor; M = cin (+ 1:
+                                 a_ones_row == cin gives the bias gradient); K-blocks are cut per frame */
+#define OFFK_TMA_A_IM2COL_T 4 /* weight gradient of a channels-last conv: A(m = (r,q,c), k = output pixel) = im2col(x)^T;
+                                 M = kh*kw*cin (+ 1: a_ones_row == kh*kw*cin); cin % 32 == 0 */
 #define OFFK_TMA_B_DENSE  0
+#define OFFK_TMA_B_DENSE_T 1  /* B(n,k) = b_src[k*ldb + n]: a row-major [K, ldb] matrix (the channels-last output gradient
+                                 dY[pixel, cout slice] of a weight-gradient GEMM).  Pairs with the *_T A kinds. */
 
 typedef struct offk_tgemm {
   offk_gemm_t g;

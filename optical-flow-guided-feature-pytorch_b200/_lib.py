@@ -54,7 +54,8 @@ class OffkTGemm(C.Structure):
     ]
 
 
-TMA_A_DENSE, TMA_A_IM2COL, TMA_B_DENSE = 0, 1, 0
+TMA_A_DENSE, TMA_A_IM2COL, TMA_A_NCHW, TMA_A_NCHW_T, TMA_A_IM2COL_T = 0, 1, 2, 3, 4
+TMA_B_DENSE, TMA_B_DENSE_T = 0, 1
 
 
 class OffkStencil(C.Structure):

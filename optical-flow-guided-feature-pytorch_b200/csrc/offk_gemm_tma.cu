@@ -10,7 +10,19 @@
 //                A im2col  : 4-D im2col {32 c, 128 pixels} of a channels-last [n, h, w, ctot] tensor at filter offset
 //                            (q, r): the hardware walks the output pixels (stride, zero padding, image wrap) -- no index
 //                            tables, no per-element predicates, one instruction per K-block
+//                A nchw    : 3-D tiles {32 pixels, 32 c, 1 frame} of an NCHW [n, c, hw] tensor (the BN-Inception taps of
+//                            the OFF units' fused 1x1 conv): pixels are contiguous, so the tile is the MN-major
+//                            SWIZZLE_128B_BASE32B operand (tensor-map swizzle 128B_ATOM_32B) -- the NCHW -> channels-last
+//                            conversion costs no instruction; M tiles never straddle a frame (OOB pixels zero-fill)
+//                A nchw_t  : 3-D tile  {32 pixels, 128 c, 1 frame} of the same NCHW tensor with m = channel, k = pixel
+//                            (weight gradient of the units' 1x1 conv): K-major; K-blocks are cut per frame
+//                A im2col_t: up to four 4-D im2col atoms {32 c, 32 pixels} at the filter offsets of rows m = (r, q, c)
+//                            with k = output pixel (weight gradient of a channels-last conv): MN-major
 //                B dense   : 2-D tile  {32 k, BN rows}    of the [N, K] weight matrix (OHWI for KxK convs)
+//                B dense_t : 2-D atoms {32 n, 32 k} of a row-major [K, ldb] matrix (the channels-last output gradient
+//                            dY[pixel, cout] of a weight-gradient GEMM): MN-major
+//              The all-ones A row of a weight-gradient GEMM (bias gradient, offk.h) cannot come from memory: the MMA
+//              warp writes it into the landed tile (generic proxy + fence.proxy.async) before issuing the MMAs.
 //   warp 1     allocates TMEM; one elected lane waits on "full", issues 4 x tcgen05.mma (kind::tf32, M=128, N=BN, K=8)
 //              per stage, tcgen05.commit's to the stage's "empty" mbarrier and to "accum_full" after the last K-block
 //   warps 2-9  epilogue: tcgen05.ld the accumulator rows out of TMEM (warp w may touch TMEM lanes 32*(w%4)..+31), transpose
@@ -31,6 +43,9 @@ struct TmGeom {        // what the producer needs to turn (tile, K-block) into T
   int cblocks;         // cin / 32 (im2col)
   int kw;              // filter width (im2col)
   int hout, wout, stride, pad;
+  int hw, tiles_per_img;   // nchw: pixels per frame, M tiles per frame
+  int kb_per_img;          // nchw_t: K-blocks per frame (ceil(hw / 32))
+  int kw_rows;             // im2col_t: kh*kw*cin = number of real A rows (the ones row follows)
 };
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -40,6 +55,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* tm, int c, int w, int h, int n,
@@ -62,19 +83,29 @@ struct TmShared {
   uint32_t tmem_base;
 };
 
-template <int A_KIND>
+template <int A_KIND, int B_KIND>
 __global__ void __launch_bounds__(TM_THREADS, 2)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const offk_gemm_t g,
                 const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)bn * 128u;
+  constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
+  constexpr bool B_MN = (B_KIND == OFFK_TMA_B_DENSE_T);
+  const uint32_t b_bytes = B_MN ? (((uint32_t)bn + 31u) >> 5) * 4096u : (uint32_t)bn * 128u;
   const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
   TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * bn;
-  const int num_kb_total = (g.K + TC_BK - 1) / TC_BK;
+  int m0 = blockIdx.x * TC_BM, m_lim = g.M;
+  int img_t = 0, pix0 = 0;
+  if (A_KIND == OFFK_TMA_A_NCHW) {                               // M tiles are cut per frame
+    img_t = blockIdx.x / geo.tiles_per_img;
+    pix0 = (blockIdx.x - img_t * geo.tiles_per_img) * TC_BM;
+    m0 = img_t * geo.hw + pix0;
+    m_lim = min(g.M, (img_t + 1) * geo.hw);
+  }
+  const int n0 = blockIdx.y * bn;
+  const int num_kb_total = A_KIND == OFFK_TMA_A_NCHW_T ? (g.K / geo.hw) * geo.kb_per_img : (g.K + TC_BK - 1) / TC_BK;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
   const int nkb = kb_end - kb_begin;
@@ -113,38 +144,103 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         const int kb = kb_begin + i;
         mbar_wait(smem_u32(&sh->empty[s]), parity);              // slot free (first round passes at once)
         const uint32_t full = smem_u32(&sh->full[s]);
-        mbar_arrive_expect_tx(full, stage_bytes);
         const uint32_t a_dst = smem_base + s * stage_bytes;
-        if (A_KIND == OFFK_TMA_A_DENSE) {
+        const uint32_t b_dst = a_dst + TC_A_BYTES;
+        int b_row0 = kb * TC_BK;                                 // dense_t: first k (pixel) row of this K-block
+        if (A_KIND == OFFK_TMA_A_NCHW) {
+          // four 4 KB atoms {32 pixels x 32 channels}; atoms wholly past the frame end are skipped (their
+          // accumulator rows are never stored)
+          const int n_at = min(TC_BM / 32, (geo.hw - pix0 + 31) >> 5);
+          mbar_arrive_expect_tx(full, (uint32_t)n_at * 4096u + b_bytes);
+          for (int a = 0; a < n_at; ++a) tma_load_3d(a_dst + a * 4096, &tma, pix0 + 32 * a, kb * TC_BK, img_t, full);
+        } else if (A_KIND == OFFK_TMA_A_NCHW_T) {
+          // K-block = 32 pixels of ONE frame (pixels past the frame end zero-fill, so whatever rows of dY they meet
+          // contribute nothing); rows = 128 channels (channels >= cin zero-fill; the ones row is patched in)
+          const int img = kb / geo.kb_per_img, pb = kb - img * geo.kb_per_img;
+          b_row0 = img * geo.hw + pb * TC_BK;
+          mbar_arrive_expect_tx(full, stage_bytes);
+          tma_load_3d(a_dst, &tma, pb * TC_BK, m0, img, full);
+        } else if (A_KIND == OFFK_TMA_A_IM2COL_T) {
+          // rows m = (r, q, c): each 32-row atom is one {32 channels x 32 output pixels} im2col box at its own (q, r)
+          const int at0 = m0 >> 5;
+          const int n_at = max(0, min(TC_BM / 32, (geo.kw_rows >> 5) - at0));
+          mbar_arrive_expect_tx(full, (uint32_t)n_at * 4096u + b_bytes);
+          const int hwo = geo.hout * geo.wout;
+          const int p0 = kb * TC_BK;
+          const int img = p0 / hwo, rem = p0 - img * hwo;
+          const int oy = rem / geo.wout, ox = rem - oy * geo.wout;
+          const int wb = ox * geo.stride - geo.pad, hb = oy * geo.stride - geo.pad;
+          for (int a = 0; a < n_at; ++a) {
+            const int tap = (at0 + a) / geo.cblocks, cb = (at0 + a) - tap * geo.cblocks;
+            const int r = tap / geo.kw, q = tap - r * geo.kw;
+            tma_load_im2col_4d(a_dst + a * 4096, &tma, geo.a_coff + cb * TC_BK, wb, hb, img, q, r, full);
+          }
+        } else if (A_KIND == OFFK_TMA_A_DENSE) {
+          mbar_arrive_expect_tx(full, stage_bytes);
           tma_load_2d(a_dst, &tma, kb * TC_BK, m0, full);
         } else {
+          mbar_arrive_expect_tx(full, stage_bytes);
           const int tap = kb / geo.cblocks, cb = kb - tap * geo.cblocks;
           const int r = tap / geo.kw, q = tap - r * geo.kw;
           tma_load_im2col_4d(a_dst, &tma, geo.a_coff + cb * TC_BK, w0, h0, img0, q, r, full);
         }
-        tma_load_2d(a_dst + TC_A_BYTES, &tmb, kb * TC_BK, n0, full);
+        if (B_MN) {
+          const int n_bat = (bn + 31) >> 5;
+          for (int a = 0; a < n_bat; ++a) tma_load_2d(b_dst + a * 4096, &tmb, n0 + 32 * a, b_row0, full);
+        } else {
+          tma_load_2d(b_dst, &tmb, kb * TC_BK, n0, full);
+        }
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer (one thread) =================
-      const uint32_t idesc = make_idesc_tf32(bn, false, false);
+    // ================= MMA issuer (one elected lane; the whole warp when it must patch the ones row) =================
+    // K-major: +32 bytes inside the 128-byte swizzle row per K = 8.  MN-major: 512-byte atoms of {32 m|n x 4 k}; a
+    // TMA box stacks the 8 k-groups of one 32-wide atom (SBO 512), the atoms along m|n follow at 4 KB (LBO);
+    // K = 8 advances two k-groups.
+    const uint32_t idesc = make_idesc_tf32(bn, A_MN, B_MN);
+    const uint64_t a_step = A_MN ? (uint64_t)(1024 >> 4) : 2ull, b_step = B_MN ? (uint64_t)(1024 >> 4) : 2ull;
+    constexpr bool kOnes = (A_KIND == OFFK_TMA_A_NCHW_T || A_KIND == OFFK_TMA_A_IM2COL_T);
+    const int ones_loc = g.a_ones_row - m0;                       // row of this tile that must read all-ones
+    const bool patch = kOnes && ones_loc >= 0 && ones_loc < TC_BM;
+    if (lane == 0 || patch) {
       int s = 0;
       uint32_t parity = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(smem_u32(&sh->full[s]), parity);
         tc_fence_after();
         const uint32_t a_base = smem_base + s * stage_bytes;
-        const uint64_t adesc = make_smem_desc(a_base), bdesc = make_smem_desc(a_base + TC_A_BYTES);
+        if (patch) {
+          // lane = k inside the K-block; 1 for real pixels, 0 past the end (of the frame: nchw_t; of K: im2col_t)
+          const int kb = kb_begin + i;
+          bool real;
+          uint32_t off;
+          if (A_KIND == OFFK_TMA_A_NCHW_T) {
+            const int pb = kb - (kb / geo.kb_per_img) * geo.kb_per_img;
+            real = pb * TC_BK + lane < geo.hw;
+            off = swz(ones_loc, lane >> 2) + (uint32_t)(lane & 3) * 4u;
+          } else {
+            real = kb * TC_BK + lane < g.K;
+            const int ma = ones_loc >> 5, mi = ones_loc & 31, kl = lane & 3;
+            off = (uint32_t)(ma * 4096 + (lane >> 2) * 512 + kl * 128 + ((((mi >> 3) ^ kl) << 5) | ((mi & 7) << 2)));
+          }
+          sts32(a_base + off, real ? 1.f : 0.f);
+          fence_proxy_async_smem();
+          __syncwarp();
+        }
+        if (lane == 0) {
+          const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, 4096u, 512u) : make_smem_desc(a_base);
+          const uint64_t bdesc = B_MN ? make_smem_desc_mn(a_base + TC_A_BYTES, 4096u, 512u) : make_smem_desc(a_base + TC_A_BYTES);
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j)                    // +32 bytes inside the 128-byte swizzle row per K = 8
-          umma_tf32(tmem_d, adesc + 2ull * j, bdesc + 2ull * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
-        umma_commit(smem_u32(&sh->empty[s]));                    // frees the smem slot when these MMAs retire
+          for (int j = 0; j < TC_BK / 8; ++j)
+            umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&sh->empty[s]));                  // frees the smem slot when these MMAs retire
+        }
+        if (patch) __syncwarp();
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
-      umma_commit(smem_u32(&sh->accum_full));                    // accumulator complete
+      if (lane == 0) umma_commit(smem_u32(&sh->accum_full));     // accumulator complete
     }
     __syncwarp();
   } else if (nkb > 0) {
@@ -179,7 +275,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           for (int it = 0; it < TC_BM / 32; ++it) {
             const int row = it * 32 + ew * 4 + rsub;
             const int m = m0 + row;
-            if (m < g.M) {
+            if (m < m_lim) {
               float4 v;
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                            : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
@@ -192,7 +288,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       }
     } else {
       const int m = m0 + quad * 32 + lane;
-      const bool mvalid = m < g.M;
+      const bool mvalid = m < m_lim;
       EpiRow er = {0, 0, 0, false};
       if (mvalid) er = epi_row(g, m);
       const int nchunks = bn >> 4;
@@ -233,7 +329,8 @@ static int driver_fn(const char* name, void** fn) {
   return 0;
 }
 
-static int encode_2d(CUtensorMap* tm, const float* base, long long inner, long long rows, long long ld, int box_rows) {
+static int encode_2d(CUtensorMap* tm, const float* base, long long inner, long long rows, long long ld, int box_rows,
+                     bool mn_major = false) {
   static EncodeTiledFn fn = nullptr;
   if (!fn)
     if (int e = driver_fn("cuTensorMapEncodeTiled", (void**)&fn)) return e;
@@ -242,13 +339,32 @@ static int encode_2d(CUtensorMap* tm, const float* base, long long inner, long l
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(OFFK_E_BADARG, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld ld=%lld box=%d", (int)r, inner, rows, ld, box_rows);
   return 0;
 }
 
-static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t) {
+// NCHW [n_img, cin, hw] as {hw, cin, n_img}; box {32 pixels, 32 channels, 1 frame}; 32-byte-atom 128B swizzle = the
+// MN-major SWIZZLE_128B_BASE32B operand layout of kind::tf32 (cute Swizzle<2,5,2>)
+static int encode_nchw(CUtensorMap* tm, const float* base, long long hw, long long cin, long long n_img, bool transposed) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn)
+    if (int e = driver_fn("cuTensorMapEncodeTiled", (void**)&fn)) return e;
+  const cuuint64_t dims[3] = {(cuuint64_t)hw, (cuuint64_t)cin, (cuuint64_t)n_img};
+  const cuuint64_t strides[2] = {(cuuint64_t)hw * 4, (cuuint64_t)hw * cin * 4};
+  // forward (m = pixel): {32 pixels, 32 channels} MN-major atoms; transposed (m = channel, k = pixel): one K-major
+  // {32 pixels, 128 channels} tile
+  const cuuint32_t box[3] = {32, (cuuint32_t)(transposed ? TC_BM : TC_BK), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, transposed ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OFFK_E_BADARG, "cuTensorMapEncodeTiled(nchw) failed (%d): hw=%lld cin=%lld n=%lld", (int)r, hw, cin, n_img);
+  return 0;
+}
+
+static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn)
     if (int e = driver_fn("cuTensorMapEncodeIm2col", (void**)&fn)) return e;
@@ -260,7 +376,8 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t) {
   const int upper[2] = {t->pad - (t->kw - 1), t->pad - (t->kh - 1)};
   const cuuint32_t estr[4] = {1, (cuuint32_t)t->stride, (cuuint32_t)t->stride, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t->g.a_src), dims, strides, lower, upper,
-                  (cuuint32_t)TC_BK, (cuuint32_t)TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  (cuuint32_t)TC_BK, (cuuint32_t)(transposed ? 32 : TC_BM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  transposed ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(OFFK_E_BADARG, "cuTensorMapEncodeIm2col failed (%d): [n=%d h=%d w=%d c=%d] k=%dx%d s=%d p=%d", (int)r, t->n_img,
@@ -268,10 +385,10 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t) {
   return 0;
 }
 
-template <int A_KIND>
+template <int A_KIND, int B_KIND>
 static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
                        int kb_per, int tmem_cols, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = tma_gemm_kernel<A_KIND>;
+  auto kern = tma_gemm_kernel<A_KIND, B_KIND>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -293,25 +410,50 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
   OFFK_REQUIRE(g.a_src && g.b_src, "tma_gemm: operand pointers");
   OFFK_REQUIRE((reinterpret_cast<uintptr_t>(g.a_src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(g.b_src) & 15u) == 0,
                "tma_gemm: operands must be 16-byte aligned");
-  OFFK_REQUIRE(t->b_kind == OFFK_TMA_B_DENSE && t->ldb >= g.K && t->ldb % 4 == 0, "tma_gemm: B must be a dense [N, ldb] matrix, ldb %% 4 == 0");
+  const bool wgrad = (t->a_kind == OFFK_TMA_A_NCHW_T || t->a_kind == OFFK_TMA_A_IM2COL_T);
+  OFFK_REQUIRE(wgrad == (t->b_kind == OFFK_TMA_B_DENSE_T), "tma_gemm: transposed A kinds pair with OFFK_TMA_B_DENSE_T and only with it");
   int bn = g.tile_n > 0 ? g.tile_n : (g.N <= 256 ? (g.N + 15) / 16 * 16 : 256);
   OFFK_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "tma_gemm: bad N tile %d", bn);
+  const long long hw = (long long)t->hin * t->win;
   CUtensorMap ta, tb;
   if (t->a_kind == OFFK_TMA_A_DENSE) {
     OFFK_REQUIRE(t->lda >= g.K && t->lda % 4 == 0, "tma_gemm: dense A needs lda >= K, lda %% 4 == 0");
     if (int e = encode_2d(&ta, g.a_src, g.K, g.M, t->lda, TC_BM)) return e;
-  } else if (t->a_kind == OFFK_TMA_A_IM2COL) {
+  } else if (t->a_kind == OFFK_TMA_A_IM2COL || t->a_kind == OFFK_TMA_A_IM2COL_T) {
     OFFK_REQUIRE(t->cin % TC_BK == 0 && t->ctot % 4 == 0 && t->a_coff % 4 == 0 && t->a_coff + t->cin <= t->ctot,
                  "tma_gemm: im2col needs cin %% 32 == 0 and a 16-byte aligned channel slice");
     OFFK_REQUIRE(t->kh >= 1 && t->kw >= 1 && t->stride >= 1 && t->stride <= 8 && t->pad >= 0, "tma_gemm: conv geometry");
-    OFFK_REQUIRE(g.K == t->cin * t->kh * t->kw, "tma_gemm: K must equal kh*kw*cin");
-    OFFK_REQUIRE(t->hout == (t->hin + 2 * t->pad - t->kh) / t->stride + 1 && t->wout == (t->win + 2 * t->pad - t->kw) / t->stride + 1 &&
-                     g.M == t->n_img * t->hout * t->wout, "tma_gemm: output geometry");
-    if (int e = encode_im2col(&ta, t)) return e;
+    OFFK_REQUIRE(t->hout == (t->hin + 2 * t->pad - t->kh) / t->stride + 1 && t->wout == (t->win + 2 * t->pad - t->kw) / t->stride + 1,
+                 "tma_gemm: output geometry");
+    const long long pixels = (long long)t->n_img * t->hout * t->wout, kw_rows = (long long)t->cin * t->kh * t->kw;
+    if (t->a_kind == OFFK_TMA_A_IM2COL) {
+      OFFK_REQUIRE(g.K == kw_rows && g.M == pixels, "tma_gemm: im2col needs K == kh*kw*cin, M == output pixels");
+    } else {
+      OFFK_REQUIRE(g.K == pixels && (g.M == kw_rows || (g.M == kw_rows + 1 && g.a_ones_row == kw_rows)),
+                   "tma_gemm: im2col_t needs K == output pixels, M == kh*kw*cin (+ the ones row)");
+    }
+    if (int e = encode_im2col(&ta, t, t->a_kind == OFFK_TMA_A_IM2COL_T)) return e;
+  } else if (t->a_kind == OFFK_TMA_A_NCHW) {
+    OFFK_REQUIRE(hw % 4 == 0 && t->cin % TC_BK == 0 && g.K == t->cin && g.M == (long long)t->n_img * hw && t->ctot == t->cin,
+                 "tma_gemm: nchw A needs hw %% 4 == 0, cin %% 32 == 0, K == cin, M == n_img*hw");
+    if (int e = encode_nchw(&ta, g.a_src, hw, t->cin, t->n_img, false)) return e;
+  } else if (t->a_kind == OFFK_TMA_A_NCHW_T) {
+    OFFK_REQUIRE(hw % 4 == 0 && t->ctot == t->cin && g.K == (long long)t->n_img * hw &&
+                     (g.M == t->cin || (g.M == t->cin + 1 && g.a_ones_row == t->cin)),
+                 "tma_gemm: nchw_t A needs hw %% 4 == 0, K == n_img*hw, M == cin (+ the ones row)");
+    if (int e = encode_nchw(&ta, g.a_src, hw, t->cin, t->n_img, true)) return e;
   } else {
     return fail(OFFK_E_BADARG, "tma_gemm: unknown a_kind %d", t->a_kind);
   }
-  if (int e = encode_2d(&tb, g.b_src, g.K, g.N, t->ldb, bn)) return e;
+  if (t->b_kind == OFFK_TMA_B_DENSE) {
+    OFFK_REQUIRE(t->ldb >= g.K && t->ldb % 4 == 0, "tma_gemm: B must be a dense [N, ldb] matrix, ldb %% 4 == 0");
+    if (int e = encode_2d(&tb, g.b_src, g.K, g.N, t->ldb, bn)) return e;
+  } else if (t->b_kind == OFFK_TMA_B_DENSE_T) {
+    OFFK_REQUIRE(t->ldb >= g.N && t->ldb % 4 == 0, "tma_gemm: transposed B must be a row-major [K, ldb] matrix, ldb %% 4 == 0");
+    if (int e = encode_2d(&tb, g.b_src, g.N, g.K, t->ldb, 32, true)) return e;     // {32 n, 32 k} atoms
+  } else {
+    return fail(OFFK_E_BADARG, "tma_gemm: unknown b_kind %d", t->b_kind);
+  }
   memcpy(t->tmap_a, &ta, sizeof(ta));
   memcpy(t->tmap_b, &tb, sizeof(tb));
   t->prepared = bn;
@@ -324,10 +466,19 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   OFFK_REQUIRE(g.out && g.out_row && g.out_col, "tma_gemm: output tables");
   if (g.out_vec) OFFK_REQUIRE((g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15u) == 0, "tma_gemm: out_vec alignment");
   const int bn = t->prepared;
-  const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+  TmGeom geo;
+  geo.a_kind = t->a_kind; geo.a_coff = t->a_coff; geo.cblocks = t->cin > 0 ? t->cin / TC_BK : 1; geo.kw = t->kw > 0 ? t->kw : 1;
+  geo.hout = t->hout; geo.wout = t->wout; geo.stride = t->stride; geo.pad = t->pad;
+  geo.hw = t->hin * t->win; geo.tiles_per_img = (geo.hw + TC_BM - 1) / TC_BM;
+  geo.kb_per_img = (geo.hw + TC_BK - 1) / TC_BK;
+  geo.kw_rows = t->cin * t->kh * t->kw;
+  const bool wgrad = t->b_kind == OFFK_TMA_B_DENSE_T;
+  OFFK_REQUIRE(!(wgrad && g.out_vec), "tma_gemm: weight-gradient kinds use the scalar epilogue (out_vec = 0)");
+  const int num_kb = t->a_kind == OFFK_TMA_A_NCHW_T ? t->n_img * geo.kb_per_img : (g.K + TC_BK - 1) / TC_BK;
   const int split = g.split_k > 1 ? g.split_k : 1;
   const int kb_per = (num_kb + split - 1) / split;
-  const uint32_t stage_bytes = TC_A_BYTES + (uint32_t)bn * 128u;
+  const uint32_t b_bytes = wgrad ? (uint32_t)((bn + 31) / 32) * 4096u : (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
   const int budget = 108 * 1024;                 // two CTAs per SM
   int stages = budget / (int)stage_bytes;
   if (stages < 2) stages = 2;
@@ -337,14 +488,19 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   int tmem_cols = 32;
   while (tmem_cols < bn) tmem_cols <<= 1;
   dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + bn - 1) / bn, (num_kb + kb_per - 1) / kb_per);
+  if (t->a_kind == OFFK_TMA_A_NCHW) grid.x = (unsigned)(t->n_img * geo.tiles_per_img);
   OFFK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tma_gemm: grid too large");
-  TmGeom geo;
-  geo.a_kind = t->a_kind; geo.a_coff = t->a_coff; geo.cblocks = t->cin > 0 ? t->cin / TC_BK : 1; geo.kw = t->kw > 0 ? t->kw : 1;
-  geo.hout = t->hout; geo.wout = t->wout; geo.stride = t->stride; geo.pad = t->pad;
   alignas(64) CUtensorMap ta, tb;
   memcpy(&ta, t->tmap_a, sizeof(ta));
   memcpy(&tb, t->tmap_b, sizeof(tb));
-  if (t->a_kind == OFFK_TMA_A_DENSE)
-    return launch_tm_t<OFFK_TMA_A_DENSE>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, as_stream(stream));
-  return launch_tm_t<OFFK_TMA_A_IM2COL>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+#define OFFK_TM_CASE(AK, BK) \
+  if (t->a_kind == AK && t->b_kind == BK) return launch_tm_t<AK, BK>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, st);
+  OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
+  OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
+  OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)
+  OFFK_TM_CASE(OFFK_TMA_A_NCHW_T, OFFK_TMA_B_DENSE_T)
+  OFFK_TM_CASE(OFFK_TMA_A_IM2COL_T, OFFK_TMA_B_DENSE_T)
+#undef OFFK_TM_CASE
+  return fail(OFFK_E_BADARG, "tma_gemm: unsupported operand kinds %d/%d", t->a_kind, t->b_kind);
 }

@@ -69,6 +69,9 @@ class Gemm:
         self.writes = [out, ones_out]
         self.lane = 0
 
+    def set_a_src(self, ptr):
+        self.desc.a_src = ptr
+
     def __call__(self, stream):
         L.check(self.eng.lib.offk_gather_gemm(C.byref(self.desc), self.eng.prec, stream), self.name)
 
@@ -79,16 +82,33 @@ class TGemm(Gemm):
     output tables as the gather-GEMM it stands in for."""
 
     @staticmethod
-    def eligible(geom: T.ConvGeom, prec, a_relu=False) -> bool:
+    def eligible(geom: T.ConvGeom, prec, a_relu=False, x_layout="nhwc") -> bool:
+        if x_layout == "nchw":      # the taps, read in place as an MN-major operand: 1x1 conv over whole frames
+            return (prec == L.PREC_TF32 and not a_relu and T._is1x1(geom) and geom.cin % 32 == 0 and geom.x_coff == 0
+                    and geom.x_ctot == geom.cin and (geom.hin * geom.win) % 4 == 0)
         return (prec == L.PREC_TF32 and not a_relu and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0 and geom.x_coff % 4 == 0
                 and geom.kdim % 4 == 0)
 
-    def __init__(self, eng, spc, key, geom: T.ConvGeom, **kw):
+    @staticmethod
+    def wgrad_eligible(geom: T.ConvGeom, prec, a_relu=False, x_layout="nhwc") -> bool:
+        """Weight gradient with both operands TMA-fed: A = im2col(x)^T (channels-last) or the NCHW tap, B = dY."""
+        y_ok = geom.y_ctot % 4 == 0 and geom.y_coff % 4 == 0 and geom.cout % 4 == 0
+        if x_layout == "nchw":
+            return (prec == L.PREC_TF32 and not a_relu and y_ok and T._is1x1(geom) and geom.x_coff == 0
+                    and geom.x_ctot == geom.cin and (geom.hin * geom.win) % 4 == 0)
+        return (prec == L.PREC_TF32 and not a_relu and y_ok and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0
+                and geom.x_coff % 4 == 0)
+
+    def __init__(self, eng, spc, key, geom: T.ConvGeom, x_layout="nhwc", wgrad=False, **kw):
         super().__init__(eng, spc, key, **kw)
         t = L.OffkTGemm()
         C.memmove(C.byref(t.g), C.byref(self.desc), C.sizeof(L.OffkGemm))
         one = geom.kh == 1 and geom.kw == 1 and geom.stride == 1 and geom.pad == 0
-        if one:
+        if wgrad:
+            t.a_kind = L.TMA_A_NCHW_T if x_layout == "nchw" else L.TMA_A_IM2COL_T
+        elif x_layout == "nchw":
+            t.a_kind = L.TMA_A_NCHW
+        elif one:
             t.a_kind, t.lda = L.TMA_A_DENSE, geom.x_ctot
             t.g.a_src = kw["a_src"].data_ptr() + 4 * geom.x_coff
         else:
@@ -96,8 +116,25 @@ class TGemm(Gemm):
         t.a_coff = geom.x_coff
         t.n_img, t.hin, t.win, t.ctot, t.cin = geom.n_img, geom.hin, geom.win, geom.x_ctot, geom.cin
         t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = geom.kh, geom.kw, geom.stride, geom.pad, geom.hout, geom.wout
-        t.b_kind, t.ldb = L.TMA_B_DENSE, geom.kdim
+        if wgrad:                         # B = dY[pixel, cout slice], row-major
+            t.b_kind, t.ldb = L.TMA_B_DENSE_T, geom.y_ctot
+            t.g.b_src = kw["b_src"].data_ptr() + 4 * geom.y_coff
+        else:
+            t.b_kind, t.ldb = L.TMA_B_DENSE, geom.kdim
         self.tdesc = t
+        self._by_src = {}                 # a_src pointer -> prepared descriptor (the two tap sets alternate)
+
+    def set_a_src(self, ptr):
+        if self.tdesc.g.a_src == ptr:
+            return
+        self._by_src[self.tdesc.g.a_src] = self.tdesc
+        t = self._by_src.get(ptr)
+        if t is None:
+            t = L.OffkTGemm()
+            C.memmove(C.byref(t), C.byref(self.tdesc), C.sizeof(L.OffkTGemm))
+            t.g.a_src, t.prepared = ptr, 0
+        self.tdesc = t
+        self.desc.a_src = ptr
 
     def __call__(self, stream):
         lib = self.eng.lib
@@ -128,6 +165,10 @@ class OFFEngine:
         self.tap_grads = tap_grads
         self.single_stream = False       # True: issue every lane on the caller's stream (profiling / debugging)
         self.use_tma = os.environ.get("OFFK_NO_TMA", "0") != "1"     # bring-up switch: gather-fed GEMMs everywhere
+        # weight gradients with TMA-fed operands: on for the NCHW taps (measured 81 -> 54 us at level 3a); off by default
+        # for channels-last convs, where 32-pixel im2col boxes lose to the cp.async gather on the big KxK layers
+        # (motion_conv_trans_28: 388 vs 211 us) and tie elsewhere -- OFFK_TMA_WGRAD=all forces them on, =none disables both
+        self.tma_wgrad = os.environ.get("OFFK_TMA_WGRAD", "taps")
         self._tab_cache = {}
         self._keep = []
 
@@ -273,8 +314,10 @@ class OFFEngine:
         if self.prec == L.PREC_TF32 and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
             split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), kb // 8))
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
-        tma = self.use_tma and x_layout == "nhwc" and TGemm.eligible(geom, self.prec, a_relu)
-        mk = (lambda *a, **k: TGemm(*a, geom=geom, **k)) if tma else Gemm
+        tma = self.use_tma and TGemm.eligible(geom, self.prec, a_relu, x_layout)
+        mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, **k)) if tma else Gemm
+        if tma and x_layout == "nchw":
+            split = 1                     # per-frame M tiles already fill the machine (N * ceil(hw/128) CTAs)
         if split > 1:
             g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
             hw = geom.hout * geom.wout
@@ -293,8 +336,10 @@ class OFFEngine:
             run.gemm = g
             run.reads, run.writes, run.lane = g.reads, g.writes, 0
             return run
+        # nchw TMA: one N tile (re-reading the tap per N tile would multiply the HBM traffic of an HBM-bound GEMM)
+        tn = (spc.N + 15) // 16 * 16 if (tma and x_layout == "nchw" and spc.N <= 256) else 0
         g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
-               addend=addend, add_tabs=add_tabs, relu_post=relu_post, name=name)
+               addend=addend, add_tabs=add_tabs, relu_post=relu_post, tile_n=tn, name=name)
         self.flops_fwd += g.flops
         return g
 
@@ -306,8 +351,11 @@ class OFFEngine:
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
-        g = Gemm(self, spc, ("wgrad", x_layout, _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
-                 atomic=True, split_k=split, name=name + ".wgrad")
+        tma = (self.use_tma and (self.tma_wgrad == "all" or (self.tma_wgrad == "taps" and x_layout == "nchw"))
+               and TGemm.wgrad_eligible(geom, self.prec, a_relu, x_layout))
+        mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, **k)) if tma else Gemm
+        g = mk(self, spc, ("wgrad", x_layout, _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
+               atomic=True, split_k=split, name=name + ".wgrad")
         self.flops_bwd += g.flops
         return g
 
@@ -687,7 +735,7 @@ class OFFEngine:
         for tag, users in self._tap_users.items():
             ptr = self.taps[tag].data_ptr()
             for g in users:
-                g.desc.a_src = ptr
+                g.set_a_src(ptr)
 
     def stage_taps(self, taps: dict):
         """Asynchronously copy ``taps`` (host -- ideally pinned -- or device tensors) into the IDLE input set on a

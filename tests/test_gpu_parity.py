@@ -171,6 +171,125 @@ def test_tma_gemm_conv_parity(dev, case):
         assert _rel(outs[0], outs[1].cpu()) < 1e-5                   # atomics: summation order differs
 
 
+NCHW_CASES = [
+    # n_img, cin, s, cout, relu_cols
+    (3, 256, 28, 160, 128),     # level 3a: 784 pixels = 6 full M tiles + a 16-pixel one per frame
+    (4, 320, 14, 160, 128),     # 196 pixels: 128 + 68 (the second tile skips one 32-pixel atom)
+    (2, 608, 14, 160, 128),     # 19 K-blocks: the pipeline wraps several times
+    (5, 64, 6, 48, 0),          # 36 pixels: one partial tile, partial atom, N = 48
+]
+
+
+@pytest.mark.parametrize("case", NCHW_CASES, ids=[f"n{c[0]}c{c[1]}s{c[2]}" for c in NCHW_CASES])
+def test_tma_gemm_nchw_taps(dev, case):
+    """The OFF units' fused 1x1 conv (RGB_OFF.py:597-598,610) with the NCHW tap fetched in place by TMA as the MN-major
+    tcgen05 operand (OFFK_TMA_A_NCHW): against conv2d, and bit-for-bit against the gather-fed kernel."""
+    from off_b200 import _lib as L, tables as T
+    lib = L.lib()
+    n, cin, s_, cout, relu_cols = case
+    g = T.ConvGeom(n, cin, s_, s_, cout)
+    torch.manual_seed(1)
+    x = torch.relu(torch.randn(n, cin, s_, s_, device=dev))
+    wt = torch.randn(cout, cin, device=dev) / cin ** 0.5
+    bias = torch.randn(cout, device=dev)
+    spc = T.conv_fwd_spec(g, "nchw", "nhwc")
+    tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
+    outs = []
+    for use_tma in (True, False):
+        out = torch.zeros(n, s_, s_, cout, device=dev)
+        t = L.OffkTGemm()
+        d = t.g
+        d.M, d.N, d.K = spc.M, spc.N, spc.K
+        d.a_src, d.a_row, d.a_col = x.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
+        d.a_h, d.a_w = T.NO_BOX, T.NO_BOX
+        d.a_ones_row, d.a_mode = -1, spc.a_mode
+        d.b_src, d.b_row, d.b_col, d.b_mode = wt.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
+        d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+        d.bias, d.relu_pre_cols = bias.data_ptr(), relu_cols
+        d.split_k, d.out_vec, d.tile_n = 1, spc.out_vec, (cout + 15) // 16 * 16
+        if use_tma:
+            t.a_kind = L.TMA_A_NCHW
+            t.n_img, t.hin, t.win, t.ctot, t.cin = n, s_, s_, cin, cin
+            t.kh = t.kw = t.stride = 1
+            t.hout, t.wout = s_, s_
+            t.b_kind, t.ldb = L.TMA_B_DENSE, cin
+            L.check(lib.offk_tma_gemm_prepare(C.byref(t)), "prepare")
+            L.check(lib.offk_tma_gemm(C.byref(t), None), "tma_gemm")
+        else:
+            L.check(lib.offk_gather_gemm(C.byref(d), 1, None), "gather_gemm")
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = torch.nn.functional.conv2d(x.double(), wt.double()[:, :, None, None], bias.double())
+    ref[:, :relu_cols] = torch.relu(ref[:, :relu_cols])
+    assert _rel(outs[0].permute(0, 3, 1, 2), ref.cpu()) < 3e-3
+    assert torch.equal(outs[0], outs[1])
+
+
+WGRAD_CASES = [
+    # n, cin, h, w, cout, k, s, p, x_ctot, x_coff, y_ctot, y_coff, x_layout, split_k
+    (5, 64, 14, 14, 64, 3, 1, 1, 64, 0, 64, 0, "nhwc", 1),        # 3x3; K = 980 pixels (tail K-block), M = 577
+    (3, 32, 28, 28, 64, 7, 2, 3, 32, 0, 64, 0, "nhwc", 3),        # motion_conv_trans_28 geometry, split-K
+    (4, 64, 14, 14, 256, 1, 1, 0, 96, 32, 288, 32, "nhwc", 2),    # 1x1 on channel slices, N tile 256
+    (2, 96, 14, 14, 128, 5, 2, 2, 160, 32, 160, 32, "nhwc", 1),   # 5x5 stride 2, K = 98 pixels
+    (3, 256, 28, 28, 160, 1, 1, 0, 256, 0, 160, 0, "nchw", 4),    # unit 3a: ones row opens a third M tile
+    (4, 320, 14, 14, 160, 1, 1, 0, 320, 0, 160, 0, "nchw", 1),    # 196 pixels per frame: 7 K-blocks, the last one partial
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=[f"{c[12]}{c[1]}x{c[2]}k{c[5]}s{c[6]}n{c[4]}" for c in WGRAD_CASES])
+def test_tma_gemm_weight_gradient(dev, case):
+    """Weight + bias gradient GEMMs with both operands TMA-fed (OFFK_TMA_A_IM2COL_T / _NCHW_T x OFFK_TMA_B_DENSE_T,
+    the ones row patched into the landed tile) against autograd of conv2d and against the gather-fed kernel."""
+    from off_b200 import _lib as L, tables as T
+    lib = L.lib()
+    n, cin, h, w, cout, k, st, p, xct, xco, yct, yco, xl, split = case
+    g = T.ConvGeom(n, cin, h, w, cout, k, k, st, p, xct, xco, yct, yco)
+    torch.manual_seed(2)
+    x = torch.randn(n, xct, h, w, device=dev)
+    dy = torch.randn(n, yct, g.hout, g.wout, device=dev)
+    xs = x[:, xco:xco + cin].double().requires_grad_(False)
+    wt = torch.zeros(cout, cin, k, k, device=dev, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(xs, wt, torch.zeros(cout, device=dev, dtype=torch.float64), st, p)
+    (y * dy[:, yco:yco + cout].double()).sum().backward()
+    ref_w = wt.grad.permute(0, 2, 3, 1) if xl == "nhwc" else wt.grad          # OHWI for channels-last inputs
+    ref_b = dy[:, yco:yco + cout].double().sum((0, 2, 3))
+    xb = x.permute(0, 2, 3, 1).contiguous() if xl == "nhwc" else x
+    dyb = dy.permute(0, 2, 3, 1).contiguous()
+    spc = T.conv_wgrad_spec(g, xl, "nhwc")
+    tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
+    outs = []
+    for use_tma in (True, False):
+        dw = torch.zeros(cout, g.kdim, device=dev)
+        db = torch.zeros(cout, device=dev)
+        t = L.OffkTGemm()
+        d = t.g
+        d.M, d.N, d.K = spc.M, spc.N, spc.K
+        d.a_src, d.a_row, d.a_col = xb.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
+        d.a_h, d.a_w = (spc.a_h, spc.a_w) if spc.a_h else (T.NO_BOX, T.NO_BOX)
+        d.a_ones_row, d.a_mode = spc.a_ones_row, spc.a_mode
+        d.b_src, d.b_row, d.b_col, d.b_mode = dyb.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
+        d.out, d.out_row, d.out_col = dw.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+        d.ones_row_out = db.data_ptr()
+        d.split_k, d.atomic_out, d.out_vec = split, 1, 0
+        if use_tma:
+            t.a_kind = L.TMA_A_NCHW_T if xl == "nchw" else L.TMA_A_IM2COL_T
+            t.a_coff = xco
+            t.n_img, t.hin, t.win, t.ctot, t.cin = n, h, w, xct, cin
+            t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = k, k, st, p, g.hout, g.wout
+            t.b_kind, t.ldb = L.TMA_B_DENSE_T, yct
+            d.b_src = dyb.data_ptr() + 4 * yco
+            L.check(lib.offk_tma_gemm_prepare(C.byref(t)), "prepare")
+            L.check(lib.offk_tma_gemm(C.byref(t), None), "tma_gemm")
+        else:
+            L.check(lib.offk_gather_gemm(C.byref(d), 1, None), "gather_gemm")
+        torch.cuda.synchronize()
+        outs.append((dw, db))
+    (dw_t, db_t), (dw_g, db_g) = outs
+    assert _rel(dw_t.view(ref_w.shape), ref_w.cpu()) < 3e-3
+    assert _rel(db_t, ref_b.cpu()) < 3e-3
+    assert _rel(dw_t, dw_g.cpu()) < 1e-4 and _rel(db_t, db_g.cpu()) < 1e-4      # same tf32 products, other summation order
+
+
 STENCIL_CASES = [
     # B, L, S, K, index_mode, drop_mode
     (2, 3, 28, 1, 0, 0), (3, 4, 14, 1, 1, 1), (2, 2, 7, 1, 0, 2), (2, 3, 7, 2, 0, 0), (1, 7, 14, 1, 0, 1), (1, 2, 5, 1, 1, 0),
