@@ -256,6 +256,44 @@ def run_ours(args):
             tot_ms += acc / reps
             tot_bytes += nbytes
         achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+        # backward: temporal half (streams G and dT, writes dG) and spatial half (dD, tap gradients) as two launches on
+        # two streams, as the engine schedules them; algorithmic bytes 4*S^2*(160*P + 128*N + 128*N + 32*P) per level
+        bwd_bytes = sum(4.0 * s * s * (S.UNIT_C * eng.P + 2 * S.GEN_C * eng.N + S.DOWN_C * eng.P) for _, s in S.LEVELS.values())
+        side = torch.cuda.Stream(device=dev)
+        n_lv = len(S.LEVELS)
+        eng._set_dropout(True, None, 1)
+        acc = 0.0
+        for _ in range(10):
+            flush.fill_(1)
+            flush_sink.add_(flush_r.view(torch.int64).sum())
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            main = torch.cuda.current_stream()
+            a.record(main)
+            side.wait_event(a)
+            eng.lib.offk_stencil_diff_bwd_batch_part(n_lv, eng._st_desc, eng._st_io, 1, C.c_void_p(main.cuda_stream))
+            eng.lib.offk_stencil_diff_bwd_batch_part(n_lv, eng._st_desc, eng._st_io, 2, C.c_void_p(side.cuda_stream))
+            main.wait_stream(side)
+            b.record(main)
+            torch.cuda.synchronize()
+            acc += a.elapsed_time(b)
+        bwd_us = acc / 10 * 1e3
+        acc = 0.0
+        for _ in range(10):                                  # same work as ONE launch (roles interleaved in one grid)
+            flush.fill_(1)
+            flush_sink.add_(flush_r.view(torch.int64).sum())
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.lib.offk_stencil_diff_bwd_batch(n_lv, eng._st_desc, eng._st_io, stream)
+            b.record()
+            torch.cuda.synchronize()
+            acc += a.elapsed_time(b)
+        fused_us = acc / 10 * 1e3
+        bwd = {"MB": round(bwd_bytes / 1e6, 1), "us": round(fused_us, 1), "GBs": round(bwd_bytes / (fused_us * 1e-6) / 1e9, 1),
+               "frac": round(bwd_bytes / (fused_us * 1e-6) / 1e9 / pk["hbm_gbs"], 3),
+               "two_launch_us": round(bwd_us, 1),
+               "note": "stencil_diff_bwd_kernel, all nine units in one launch (temporal and spatial blocks interleaved in one "
+                       "grid), cold L2; two_launch_us = the halves as separate launches on two streams "
+                       "(offk_stencil_diff_bwd_batch_part)"}
         # in-step: same launches timed inside full forward passes (single-stream issue so the events bracket them)
         eng.single_stream = True
         evs = []
@@ -275,7 +313,7 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "stencil_diff_fwd_kernel (3 launches per step: one per stage-fusion buffer, 9 OFF units)",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES, "bytes_per_step": tot_bytes,
-                "per_stage": per_stage,
+                "per_stage": per_stage, "backward": bwd,
                 "in_step": {"GBs": round(tot_bytes / (in_step_ms * 1e-3) / 1e9, 1), "us": round(in_step_ms * 1e3, 1),
                             "note": "same 3 launches timed inside forward passes (inputs fresh from the unit GEMMs, partly L2-resident)"},
                 "note": "algorithmic bytes 4*S^2*(128*N + 32*P + 160*P) per level (read G once, read D once, write the "

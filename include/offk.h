@@ -247,6 +247,10 @@ typedef struct offk_stencil_io {
  * host arrays of n entries; semantics per entry are those of offk_stencil_diff_fwd / _bwd. */
 int offk_stencil_diff_fwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream);
 int offk_stencil_diff_bwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream);
+/* One half of the batched backward: part = 1 the temporal half (dg: streams G and dT once), 2 the spatial half (dd, dw,
+ * dbias), 3 both (= offk_stencil_diff_bwd_batch).  The halves write disjoint elements (dg / dd may be channel slices of
+ * one buffer) and may run concurrently on two streams. */
+int offk_stencil_diff_bwd_batch_part(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, int part, void* stream);
 
 /* Backward of the above.  dout is the gradient of the stage buffer (same
  * ctot/coff addressing as `out`).  Writes
@@ -303,6 +307,11 @@ int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh,
  * implicit GEMMs and [cin][kh][kw][cout] copies with flipped taps for the data-gradient GEMMs (autograd of
  * RGB_OFF.py:657-841); idx is built once on the host.  idx and dst 16-byte aligned. */
 int offk_gather_copy(const float* src, const int32_t* idx, float* dst, long long n, void* stream);
+
+/* dst[n, hw, c] = src[n, c, hw]: channels-last copy of an NCHW tensor.  Used for the 7x7 taps (inception_5a / 5b,
+ * RGB_OFF.py:567,590): their 196-byte channel stride is not a legal TMA stride, so the unit's 1x1 conv and its weight
+ * gradient read this copy through dense / im2col tensor maps instead. */
+int offk_nchw_to_nhwc(const float* src, float* dst, int n_img, int C, int HW, void* stream);
 
 /* keep decision of OFFK_DROP_SEED for element `idx` (host mirror for tests): 1 = keep */
 int offk_drop_keep_host(uint64_t seed, uint64_t idx, float drop_p);

@@ -255,6 +255,35 @@ __global__ void gather_copy_kernel(const float* __restrict__ src, const int32_t*
   }
 }
 
+// NCHW [n, C, HW] -> channels-last [n, HW, C] through 32x32 shared-memory tiles (both sides coalesced)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const size_t img = blockIdx.z;
+  const float* s = src + img * (size_t)C * HW;
+  float* d = dst + img * (size_t)C * HW;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, p = p0 + tx;
+    if (c < C && p < HW) t[j][tx] = __ldg(s + (size_t)c * HW + p);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, c = c0 + tx;
+    if (p < HW && c < C) d[(size_t)p * C + c] = t[tx][j];
+  }
+}
+
+extern "C" int offk_nchw_to_nhwc(const float* src, float* dst, int n_img, int C, int HW, void* stream) {
+  OFFK_REQUIRE(src && dst && n_img > 0 && C > 0 && HW > 0 && n_img <= 65535, "nchw_to_nhwc: bad args");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img);
+  OFFK_REQUIRE(grid.y <= 65535, "nchw_to_nhwc: too many channels");
+  nchw_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW);
+  return OFFK_LAUNCH_CHECK("nchw_to_nhwc");
+}
+
 extern "C" int offk_gather_copy(const float* src, const int32_t* idx, float* dst, long long n, void* stream) {
   OFFK_REQUIRE(src && idx && dst && n >= 0, "gather_copy: bad args");
   OFFK_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0, "gather_copy: alignment");

@@ -20,6 +20,7 @@
 // dw[a,b] += D(y,x) * dS(y-a+1, x-b+1) (the tap gradient re-indexed so that it needs D only at the centre pixel).
 // Tap / bias gradients are accumulated in registers over a few consecutive items, reduced with warp shuffles and
 // shared-memory atomics, then one global atomicAdd per tap and block.
+#include <stdlib.h>
 #include "offk_common.cuh"
 
 namespace offk {
@@ -34,7 +35,7 @@ constexpr int ST_MAX_CS = 64;                 // spatial channels per level (32 
 constexpr int ST_TIT = 4;                     // pixel pairs per warp: a temporal block covers ST_WARPS*2*ST_TIT = 64 pixels
 constexpr int ST_TPIX = ST_WARPS * 2 * ST_TIT;
 constexpr int ST_WQ = 16;                     // channel quads per tap row in shared memory (= ST_MAX_CS / 4)
-constexpr int ST_ITEMS = 4;                   // max (frame, band) items per backward spatial block
+constexpr int ST_ITEMS = 8;                   // max (frame, band) items per backward spatial block
 constexpr int ST_TILE_BUDGET = 24 * 1024;     // target size of a halo tile (bytes)
 constexpr int ST_SMEM_MAX = 64 * 1024;
 
@@ -393,36 +394,29 @@ __device__ __forceinline__ void temporal_bwd(const StLevel& lv, int r2, int tid)
   }
 }
 
-struct StDropXform {       // staging transform of the backward pass: dS <- dS * keep-factor (dropout')
-  const offk_stencil_t* s;
-  uint32_t thr, qbase, kcq;
-  int p, och, HW;
-  __device__ __forceinline__ float4 operator()(float4 v, int pix) const {
-    return f4mul(v, drop_factor4(*s, thr, p, och, pix, HW, (uint64_t)(qbase + pix) * kcq + (och >> 2)));
-  }
-};
-
 // spatial blocks: dD = transposed stencil of the dropped dS; tap / bias gradients.  A block owns `ipb` consecutive
-// (frame, band) items and keeps the tap-gradient partial sums in registers across them.
+// (frame, band) items and keeps the tap-gradient partial sums in registers across them.  Per item, the dS band + halo
+// and the D band are staged with 16-byte cp.async (everything in flight at once: one exposed memory latency per
+// item), dropout' is applied to the staged tile in place, and the compute passes touch shared memory only.
 __device__ __forceinline__ void spatial_bwd(const StLevel& lv, int rel, int tid, float4* st_smem) {
   const offk_stencil_t& s = lv.s;
   const int H = s.H, W = s.W, HW = H * W, K = s.K, Cs = s.Cs, ctot = s.out_ctot, d_ps = s.d_ps;
-  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq;
+  const int lq = lv.lq, ltcp = lv.ltcp, CQ = 1 << lq, lcpr = ltcp + lq;
   float4* tile = st_smem;                                        // dS band + halo [rows+2][TCP][CQ]
-  float4* ws4 = st_smem + ((lv.band_rows + 2) << (ltcp + lq));   // [K*9][ST_WQ]
-  float* red = reinterpret_cast<float*>(ws4 + K * 9 * ST_WQ);    // [10][Cs] block reduction of the tap gradients
-  load_taps(lv, ws4, nullptr, tid);
+  float4* dband = st_smem + ((lv.band_rows + 2) << lcpr);        // D band [rows][W][CQ]
   const bool need_dw = lv.dw != nullptr, need_db = lv.dbias != nullptr;
   const bool need_acc = need_dw || need_db;
-  for (int i = tid; i < 10 * Cs; i += ST_THREADS) red[i] = 0.f;
+  float4* ws4 = dband + (need_dw ? (lv.band_rows * W) << lq : 0);   // [K*9][ST_WQ]  (the D band exists only with dw)
+  float* redw = reinterpret_cast<float*>(ws4 + K * 9 * ST_WQ);   // [ST_WARPS][10][Cs] per-warp tap-gradient partials
+  bool taps_loaded = false;                                      // loaded under the first item's cp.async traffic
   const int c4 = tid & (CQ - 1), slot = tid >> lq;
   const int XW = 1 << lv.lxw;
   const int rpp = (ST_THREADS >> lq) >> lv.lxw;
   const int sx = slot & (XW - 1), sy = slot >> lv.lxw;
-  const int rs = 1 << (ltcp + lq);
+  const int rs = 1 << lcpr;
   const int item0 = rel * lv.ipb, item1 = min(item0 + lv.ipb, lv.n_sitems);
-  StDropXform xf;
-  xf.s = &s; xf.thr = drop_threshold16(s.drop_p); xf.kcq = (uint32_t)(K * Cs) >> 2; xf.HW = HW;
+  const uint32_t thr = drop_threshold16(s.drop_p), kcq = (uint32_t)(K * Cs) >> 2;
+  const uint32_t dband_s = st_smem_u32(dband);
 
   for (int kk = 0; kk < K; ++kk) {
     float4 wacc[9], bacc = f4zero();
@@ -430,20 +424,48 @@ __device__ __forceinline__ void spatial_bwd(const StLevel& lv, int rel, int tid,
     for (int j = 0; j < 9; ++j) wacc[j] = f4zero();
     const int och = kk * Cs + c4 * 4;
     const float4* wk = ws4 + kk * 9 * ST_WQ + c4;
+    bool any_pair = false;
     for (int item = item0; item < item1; ++item) {
       const int f = item / lv.bands, band = item - f * lv.bands;
       const int y0 = band * lv.band_rows;
       const int rows = min(lv.band_rows, H - y0);
       const int p = spatial_pair_of_frame(s, f);
-      __syncthreads();                                           // previous item's tile fully consumed (and ws4 / red ready)
-      if (p >= 0) {
-        // every cell a thread stages has the thread's own channel quad (ST_THREADS and the row pitch are multiples of CQ)
-        xf.p = p; xf.och = och; xf.qbase = (uint32_t)p * (uint32_t)HW;
-        stage_tile<false>(lv, tile, lv.dout + (size_t)p * HW * ctot + s.out_coff + kk * Cs, ctot, y0, rows, tid, xf);
+      float* ddf = lv.dd + (size_t)f * lv.dd_fs + c4 * 4;          // dd uses the pixel stride of d
+      __syncthreads();                                           // previous item's tiles fully consumed (and ws4 ready)
+      if (p < 0) {                                               // frame feeds no pair: dD = 0 (first map only writes)
+        if (kk == 0)
+          for (int i = slot; i < rows * W; i += ST_THREADS >> lq)
+            *reinterpret_cast<float4*>(ddf + (size_t)(y0 * W + i) * d_ps) = f4zero();
+        continue;
+      }
+      any_pair = true;
+      const bool use_d = need_dw;
+      stage_tile<true>(lv, tile, lv.dout + (size_t)p * HW * ctot + s.out_coff + kk * Cs, ctot, y0, rows, tid, StNoXform());
+      if (use_d) {
+        const float* dsrc = lv.d + (size_t)spatial_frame(s, p) * s.d_fs + (size_t)(y0 * W) * d_ps + c4 * 4;
+        for (int i = slot; i < rows * W; i += ST_THREADS >> lq)
+          st_cp_async16(dband_s + (uint32_t)((i << lq) + c4) * 16u, dsrc + (size_t)i * d_ps, 16u);
+      }
+      if (!taps_loaded) {
+        load_taps(lv, ws4, nullptr, tid);
+        taps_loaded = true;
+      }
+      st_cp_async_wait_all();
+      if (s.drop_mode != OFFK_DROP_NONE) {
+        // dropout' in place on the landed tile: cell i = tid + k*ST_THREADS is exactly the set of cells this thread
+        // staged itself (stage_tile's three index walks all reduce to it), so its own wait_group is enough -- no barrier
+        const int n_cells = (rows + 2) << lcpr;
+        const uint32_t qbase = (uint32_t)p * (uint32_t)HW;
+        for (int i = tid; i < n_cells; i += ST_THREADS) {         // ST_THREADS % CQ == 0: i & (CQ-1) == c4
+          const int col = (i >> lq) & ((1 << ltcp) - 1), r = i >> lcpr;
+          const int yy = y0 - 1 + r, xx = col - 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const int pix = yy * W + xx;
+            tile[i] = f4mul(tile[i], drop_factor4(s, thr, p, och, pix, HW, (uint64_t)(qbase + pix) * kcq + (och >> 2)));
+          }
+        }
       }
       __syncthreads();
-      float* ddf = lv.dd + (size_t)f * lv.dd_fs + c4 * 4;          // dd uses the pixel stride of d
-      const float* dfp = (need_dw && p >= 0) ? lv.d + (size_t)spatial_frame(s, p) * s.d_fs + c4 * 4 : nullptr;
       for (int yb = 0; yb < rows; yb += rpp) {
         const int y = yb + sy;
         for (int x0 = 0; x0 < W; x0 += XW) {
@@ -451,21 +473,19 @@ __device__ __forceinline__ void spatial_bwd(const StLevel& lv, int rel, int tid,
           if (y < rows && x < W) {
             const int pix = (y0 + y) * W + x;
             float4 acc = f4zero();
-            if (p >= 0) {
-              float4 dv = f4zero();
-              if (dfp) dv = ldg4(dfp + (size_t)pix * d_ps);
-              // dS(y-a+1, x-b+1) sits at halo coordinates (y+2-a, x+2-b)
-              const float4* t2 = tile + ((((y + 2) << ltcp) + x + 2) << lq) + c4;
+            float4 dv = f4zero();
+            if (use_d) dv = dband[((y * W + x) << lq) + c4];
+            // dS(y-a+1, x-b+1) sits at halo coordinates (y+2-a, x+2-b)
+            const float4* t2 = tile + ((((y + 2) << ltcp) + x + 2) << lq) + c4;
 #pragma unroll
-              for (int a = 0; a < 3; ++a) {
-                const float4* ra = t2 - a * rs;
+            for (int a = 0; a < 3; ++a) {
+              const float4* ra = t2 - a * rs;
 #pragma unroll
-                for (int bb = 0; bb < 3; ++bb) {
-                  const float4 nv = *(ra - bb * CQ);
-                  f4fma(acc, wk[(a * 3 + bb) * ST_WQ], nv);
-                  f4fma(wacc[a * 3 + bb], dv, nv);
-                  if (a == 1 && bb == 1) { bacc.x += nv.x; bacc.y += nv.y; bacc.z += nv.z; bacc.w += nv.w; }
-                }
+              for (int bb = 0; bb < 3; ++bb) {
+                const float4 nv = *(ra - bb * CQ);
+                f4fma(acc, wk[(a * 3 + bb) * ST_WQ], nv);
+                f4fma(wacc[a * 3 + bb], dv, nv);
+                if (a == 1 && bb == 1) { bacc.x += nv.x; bacc.y += nv.y; bacc.z += nv.z; bacc.w += nv.w; }
               }
             }
             float4* o = reinterpret_cast<float4*>(ddf + (size_t)pix * d_ps);
@@ -473,28 +493,46 @@ __device__ __forceinline__ void spatial_bwd(const StLevel& lv, int rel, int tid,
               const float4 old = *o;
               acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
             }
-            *o = acc;                                              // zero for frames that feed no pair
+            *o = acc;
           }
         }
       }
     }
-    if (need_acc) {
-      // lanes l, l^CQ, l^2CQ, ... hold the same channels
+    if (need_acc && any_pair) {                                  // block-uniform: items are per block
+      // lanes l, l^CQ, l^2CQ, ... hold the same channels: butterfly over them, then one slot per warp (no atomics)
+      const int warp = tid >> 5, lane = tid & 31;
       float vals[40];
 #pragma unroll
       for (int j = 0; j < 9; ++j) { vals[4 * j] = wacc[j].x; vals[4 * j + 1] = wacc[j].y; vals[4 * j + 2] = wacc[j].z; vals[4 * j + 3] = wacc[j].w; }
       vals[36] = bacc.x; vals[37] = bacc.y; vals[38] = bacc.z; vals[39] = bacc.w;
+      float* mine = redw + (size_t)warp * 10 * Cs + c4 * 4;
+      if (lq == 3) {                                             // Cs = 32 (every OFF unit): two butterfly steps, unrolled
 #pragma unroll
-      for (int q = 0; q < 40; ++q) {
-        float v = vals[q];
-        for (int o = 16; o >= CQ; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) < CQ) atomicAdd(&red[(q >> 2) * Cs + c4 * 4 + (q & 3)], v);
+        for (int q = 0; q < 40; ++q) {
+          float v = vals[q];
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          vals[q] = v;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 40; ++q) {
+          float v = vals[q];
+          for (int o = 16; o >= CQ; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          vals[q] = v;
+        }
+      }
+      if (lane < CQ) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          *reinterpret_cast<float4*>(mine + j * Cs) = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
       }
       __syncthreads();
       for (int i = tid; i < 10 * Cs; i += ST_THREADS) {
         const int j = i / Cs, c = i - j * Cs;
-        const float v = red[i];
-        red[i] = 0.f;
+        float v = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < ST_WARPS; ++w8) v += redw[w8 * 10 * Cs + i];
         if (j < 9) {
           if (need_dw) atomicAdd(lv.dw + ((size_t)c * K + kk) * 9 + j, v);
         } else if (need_db) {
@@ -517,6 +555,23 @@ stencil_diff_bwd_kernel(const __grid_constant__ StBatch bt) {
   } else {
     spatial_bwd(lv, role, tid, st_smem);
   }
+}
+
+// The two halves of the backward as separate launches (offk_stencil_diff_bwd_batch_part): the temporal half is a pure
+// stream (64 registers, 4 blocks per SM), the spatial half is instruction-heavy and moves a tenth of the bytes; on two
+// streams the block scheduler mixes them instead of spatial blocks holding a third of the resident-block slots.
+__global__ void __launch_bounds__(ST_THREADS, 4)
+stencil_diff_bwd_temporal_kernel(const __grid_constant__ StBatch bt) {
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  const int r2 = (int)blockIdx.x - lv.blk0;
+  if (lv.s.L == 3) temporal_bwd<3>(lv, r2, threadIdx.x);
+  else temporal_bwd<0>(lv, r2, threadIdx.x);
+}
+__global__ void __launch_bounds__(ST_THREADS, ST_FWD_MINB)
+stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
+  extern __shared__ __align__(16) float4 st_smem[];
+  const StLevel& lv = find_level(bt, (int)blockIdx.x);
+  spatial_bwd(lv, (int)blockIdx.x - lv.blk0, threadIdx.x, st_smem);
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -573,16 +628,27 @@ static int plan_spatial(StLevel& lv, bool backward) {
   lv.n_sitems = (int)items;
   // backward: a block keeps the tap-gradient partial sums in registers over up to ST_ITEMS consecutive items (fewer
   // block reductions / atomics); small levels keep one item per block so their blocks stay short
-  long long ipb = items / (2LL * sm_count());
-  lv.ipb = backward ? (int)(ipb < 1 ? 1 : (ipb > ST_ITEMS ? ST_ITEMS : ipb)) : 1;
+  // measured at config 2 (B200): items / (0.5 * SMs) capped at 8 -> 121 us; 2.0 / 4 -> 149 us; 0.2 / 32 -> 250 us (tail)
+  static int div10 = 0, cap = 0;                                   // bring-up knobs (environment)
+  if (!div10) {
+    const char* e = getenv("OFFK_ST_IPB_DIV10");
+    div10 = e ? atoi(e) : 5;
+    const char* c = getenv("OFFK_ST_IPB_CAP");
+    cap = c ? atoi(c) : ST_ITEMS;
+  }
+  long long ipb = items * 10 / ((long long)div10 * sm_count());
+  lv.ipb = backward ? (int)(ipb < 1 ? 1 : (ipb > cap ? cap : ipb)) : 1;
   lv.n_sblocks = (int)((items + lv.ipb - 1) / lv.ipb);
   const int tile_bytes = (lv.band_rows + 2) * row_bytes;
   const int tap_bytes = s.K * 9 * ST_WQ * 16;
-  const int extra = backward ? 10 * s.Cs * 4 : s.K * ST_WQ * 16;
+  // backward: + the D band (no halo) and one tap-gradient partial slot per warp
+  const int extra = backward ? (lv.dw ? lv.band_rows * s.W * CQ * 16 : 0) + ((lv.dw || lv.dbias) ? ST_WARPS * 10 * s.Cs * 4 : 0)
+                             : s.K * ST_WQ * 16;
   return tile_bytes + tap_bytes + extra;
 }
 
-static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, bool backward, void* stream) {
+static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, bool backward, void* stream, int part = 3) {
+  OFFK_REQUIRE(part >= 1 && part <= 3 && (backward || part == 3), "stencil batch: part must be 1 (temporal), 2 (spatial) or 3 (both)");
   OFFK_REQUIRE(n >= 1 && n <= ST_MAX_LEVELS, "stencil batch: 1 <= n <= %d (got %d)", ST_MAX_LEVELS, n);
   OFFK_REQUIRE(s != nullptr && io != nullptr, "stencil batch: null arrays");
   StBatch bt;
@@ -607,12 +673,13 @@ static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t*
       OFFK_REQUIRE(s[i].Cs == 0 || (lv.w && lv.dd && aligned16(lv.dd) && lv.dd_fs % 4 == 0), "stencil_bwd: w/dd missing");
       OFFK_REQUIRE(lv.dw == nullptr || (lv.d != nullptr && aligned16(lv.d)), "stencil_bwd: tap gradient needs d");
     }
-    const int need = plan_spatial(lv, backward);
+    int need = plan_spatial(lv, backward);
+    if (!(part & 2)) { lv.n_sblocks = 0; need = 0; }               // temporal half only
     OFFK_REQUIRE(need <= ST_SMEM_MAX, "stencil: halo tile of %d bytes exceeds %d (W=%d, Cs=%d)", need, ST_SMEM_MAX, s[i].W, s[i].Cs);
     if (need > smem) smem = need;
     const int HW = s[i].H * s[i].W;
     lv.t_chunks = s[i].Cg > 0 ? (HW + ST_TPIX - 1) / ST_TPIX : 1;
-    const long long n_t = s[i].Cg > 0 ? (long long)lv.t_chunks * s[i].B : 0;
+    const long long n_t = (s[i].Cg > 0 && (part & 1)) ? (long long)lv.t_chunks * s[i].B : 0;
     lv.n_tblocks = (int)n_t;
     // spatial blocks at every 2^lstride-th position of the level's range
     lv.lstride = 0;
@@ -628,6 +695,8 @@ static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t*
     cudaError_t e = cudaFuncSetAttribute(stencil_diff_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(stencil_diff_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stencil_diff_bwd_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_MAX);
     if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(stencil)");
     attr_set = true;
   }
@@ -635,7 +704,9 @@ static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t*
     stencil_diff_fwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
     return OFFK_LAUNCH_CHECK("stencil_diff_fwd");
   }
-  stencil_diff_bwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+  if (part == 1) stencil_diff_bwd_temporal_kernel<<<(unsigned)blk, ST_THREADS, 0, as_stream(stream)>>>(bt);
+  else if (part == 2) stencil_diff_bwd_spatial_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+  else stencil_diff_bwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
   return OFFK_LAUNCH_CHECK("stencil_diff_bwd");
 }
 
@@ -649,6 +720,10 @@ extern "C" int offk_stencil_diff_fwd_batch(int n, const offk_stencil_t* s, const
 
 extern "C" int offk_stencil_diff_bwd_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, void* stream) {
   return launch_batch(n, s, io, true, stream);
+}
+
+extern "C" int offk_stencil_diff_bwd_batch_part(int n, const offk_stencil_t* s, const offk_stencil_io_t* io, int part, void* stream) {
+  return launch_batch(n, s, io, true, stream, part);
 }
 
 extern "C" int offk_stencil_diff_fwd(const offk_stencil_t* s, const float* g, const float* d, const float* w,

@@ -306,7 +306,7 @@ class OFFEngine:
 
     # ------------------------------------------------------------------ plan
     def _conv_fwd(self, name, x, y, geom, w, b, *, relu=False, relu_cols=None, a_relu=False, addend=None,
-                  add_tabs=None, relu_post=False, x_layout="nhwc"):
+                  add_tabs=None, relu_post=False, x_layout="nhwc", no_split=False):
         spc = T.conv_fwd_spec(geom, x_layout, "nhwc")
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
@@ -316,7 +316,7 @@ class OFFEngine:
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
         tma = self.use_tma and TGemm.eligible(geom, self.prec, a_relu, x_layout)
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, **k)) if tma else Gemm
-        if tma and x_layout == "nchw":
+        if (tma and x_layout == "nchw") or no_split:
             split = 1                     # per-frame M tiles already fill the machine (N * ceil(hw/128) CTAs)
         if split > 1:
             g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
@@ -343,7 +343,7 @@ class OFFEngine:
         self.flops_fwd += g.flops
         return g
 
-    def _conv_wgrad(self, name, x, dy, geom, dw, db, *, a_relu=False, x_layout="nhwc"):
+    def _conv_wgrad(self, name, x, dy, geom, dw, db, *, a_relu=False, x_layout="nhwc", force_tma=False):
         # dW is accumulated in the k order of the implicit GEMM (OHWI: consecutive accumulator rows = consecutive
         # addresses, so the split-K reductions coalesce) and un-permuted once at the end; writing OIHW directly
         # (dw_layout="oihw") was measured slower: the strided atomics cost more than the permute pass
@@ -351,7 +351,7 @@ class OFFEngine:
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
-        tma = (self.use_tma and (self.tma_wgrad == "all" or (self.tma_wgrad == "taps" and x_layout == "nchw"))
+        tma = (self.use_tma and (self.tma_wgrad == "all" or (self.tma_wgrad == "taps" and (x_layout == "nchw" or force_tma)))
                and TGemm.wgrad_eligible(geom, self.prec, a_relu, x_layout))
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, **k)) if tma else Gemm
         g = mk(self, spc, ("wgrad", x_layout, _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
@@ -408,10 +408,23 @@ class OFFEngine:
             geom = T.ConvGeom(N, cin, s, s, S.UNIT_C)
             gd, dgd = bf["gd_" + tag], bf["dgd_" + tag]
             # K1: gen (ReLU) and down (linear) 1x1 convs as ONE GEMM with 160 output channels
-            k1 = self._conv_fwd("unit_" + tag, self.taps[tag], gd, geom, self._unit_w(self.params_flat, tag),
-                                self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nchw")
+            # 7x7 taps: a 196-byte channel stride is not a legal TMA stride -> one channels-last copy of the tap per
+            # step feeds both the forward GEMM (dense tensor map) and the weight gradient (im2col_t), all TMA-fed
+            via_copy = (self.prec == L.PREC_TF32 and self.use_tma and (s * s) % 4 != 0 and cin % 32 == 0
+                        and os.environ.get("OFFK_NO_TAP_COPY", "0") != "1")
+            if via_copy:
+                tapT = self._buf("tapT_" + tag, N, s, s, cin)
+
+                def kt(stream, tag=tag, tapT=tapT, cin=cin, hw=s * s):
+                    L.check(lib.offk_nchw_to_nhwc(_ptr(self.taps[tag]), _ptr(tapT), N, cin, hw, stream), "tapT_" + tag)
+                fwd.append(_nm(kt, "tapT_" + tag, writes=[tapT], lane=fl))
+                k1 = self._conv_fwd("unit_" + tag, tapT, gd, geom, self._unit_w(self.params_flat, tag),
+                                    self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nhwc", no_split=True)
+            else:
+                k1 = self._conv_fwd("unit_" + tag, self.taps[tag], gd, geom, self._unit_w(self.params_flat, tag),
+                                    self._unit_b(self.params_flat, tag), relu_cols=S.GEN_C, x_layout="nchw")
+                self._tap_users[tag].append(getattr(k1, "gemm", k1))
             fwd.append(_on(k1, fl))
-            self._tap_users[tag].append(getattr(k1, "gemm", k1))
             # K2 / K3 descriptors: fused spatial stencil + temporal difference + dropout + cat, into the stage buffer
             sd = self._st_desc[li]
             sd.B, sd.L, sd.Cg, sd.Cs, sd.K, sd.H, sd.W = B, Lg, S.GEN_C, S.DOWN_C, 1, s, s
@@ -434,10 +447,14 @@ class OFFEngine:
             io.dw = dw3.data_ptr() if dw3 is not None else None
             io.dbias = db3.data_ptr() if db3 is not None else None
             # K4: weight / bias gradient of the fused 1x1 (no dX for the frozen taps unless asked, train_off.py:39-46)
-            k4 = self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
-                                  self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag), x_layout="nchw")
+            if via_copy:
+                k4 = self._conv_wgrad("unit_" + tag, tapT, dgd, geom, self._unit_w(self.grads_flat, tag),
+                                      self._unit_b(self.grads_flat, tag), x_layout="nhwc", force_tma=True)
+            else:
+                k4 = self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
+                                      self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag), x_layout="nchw")
+                self._tap_users[tag].append(k4)
             k4_steps.append(_on(k4, li % 3))
-            self._tap_users[tag].append(k4)
             if self.tap_grads:
                 k4_steps += [_on(g, li % 3) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
                                                                       self.tap_grad[tag], geom, x_layout="nchw")]
@@ -457,11 +474,22 @@ class OFFEngine:
         # K3: the backward of all nine units in ONE launch (every stage gradient dF* is complete by then)
         grad3 = [gr[f"motion_spatial_grad_{t}.{k}"] for t in tags for k in ("weight", "bias")] if self.variant == "rgb" else []
 
+        # two launches on two lanes: the temporal half streams (dG), the spatial half (dD, tap gradients) is
+        # instruction-heavy; they write disjoint channels of dgd_X, so the pair is exempt from the hazard analysis
+        def k3t(stream):
+            L.check(lib.offk_stencil_diff_bwd_batch_part(n_lv, self._st_desc, self._st_io, 1, stream), "stencil_bwd_temporal")
+
+        def k3s(stream):
+            L.check(lib.offk_stencil_diff_bwd_batch_part(n_lv, self._st_desc, self._st_io, 2, stream), "stencil_bwd_spatial")
+        rd3 = [bf["dF" + st] for st in S.STAGES] + [bf["gd_" + t] for t in tags]
+        k3t = _nm(k3t, "stencil_bwd_temporal", reads=rd3, writes=[bf["dgd_" + t] for t in tags], lane=0)
+        k3s = _nm(k3s, "stencil_bwd_spatial", reads=rd3, writes=[bf["dgd_" + t] for t in tags] + grad3, lane=1)
+        k3s.independent_of = (k3t,)
+
         def k3(stream):
             L.check(lib.offk_stencil_diff_bwd_batch(n_lv, self._st_desc, self._st_io, stream), "stencil_bwd")
-        k3 = _nm(k3, "stencil_bwd", reads=[bf["dF" + st] for st in S.STAGES] + [bf["gd_" + t] for t in tags],
-                 writes=[bf["dgd_" + t] for t in tags] + grad3, lane=0)
-        bwd_units.append(k3)
+        k3 = _nm(k3, "stencil_bwd", reads=rd3, writes=[bf["dgd_" + t] for t in tags] + grad3, lane=0)
+        bwd_units += [k3t, k3s] if os.environ.get("OFFK_STENCIL_BWD_SPLIT", "0") == "1" else [k3]
         bwd_units += k4_steps
 
         # ============ stage convs
@@ -881,6 +909,8 @@ class Schedule:
             for j in range(i):
                 if lanes[j] == lanes[i] or j <= covered[lanes[i]][lanes[j]]:
                     continue
+                if self.steps[j] in getattr(self.steps[i], "independent_of", ()):
+                    continue                      # declared to touch disjoint elements of the same buffers
                 if hit(wr[j], rd[i]) or hit(wr[j], wr[i]) or hit(rd[j], wr[i]):
                     need[lanes[j]] = j
             for lane_j, j in need.items():
