@@ -174,12 +174,18 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
 #define OFFK_TMA_B_DENSE_T 1  /* B(n,k) = b_src[k*ldb + n]: a row-major [K, ldb] matrix (the channels-last output gradient
                                  dY[pixel, cout slice] of a weight-gradient GEMM).  Pairs with the *_T A kinds. */
 
+#define OFFK_TGEMM_FREE_GEOM 1
+
 typedef struct offk_tgemm {
   offk_gemm_t g;
   int32_t a_kind, lda, a_coff;
   int32_t n_img, hin, win, ctot, cin, kh, kw, stride, pad, hout, wout; /* im2col geometry */
   int32_t b_kind, ldb;
   int32_t prepared;      /* set by offk_tma_gemm_prepare (the N tile the B tensor map was built for) */
+  int32_t geom_flags;    /* OFFK_TGEMM_FREE_GEOM: hout / wout are given (not derived), pad = top rows, pad_w = left columns,
+                            kh != kw allowed -- the data gradient of a strided conv, one stride-parity class at a time, is
+                            such a stride-1 correlation over dY (autograd of RGB_OFF.py:657,762) */
+  int32_t pad_w;
   int32_t reserved;
   uint64_t tmap_a[16];   /* CUtensorMap storage */
   uint64_t tmap_b[16];

@@ -49,13 +49,15 @@ class OffkTGemm(C.Structure):
         ("n_img", C.c_int32), ("hin", C.c_int32), ("win", C.c_int32), ("ctot", C.c_int32), ("cin", C.c_int32),
         ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("hout", C.c_int32),
         ("wout", C.c_int32),
-        ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("reserved", C.c_int32),
+        ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("geom_flags", C.c_int32),
+        ("pad_w", C.c_int32), ("reserved", C.c_int32),
         ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
     ]
 
 
 TMA_A_DENSE, TMA_A_IM2COL, TMA_A_NCHW, TMA_A_NCHW_T, TMA_A_IM2COL_T = 0, 1, 2, 3, 4
 TMA_B_DENSE, TMA_B_DENSE_T = 0, 1
+TGEMM_FREE_GEOM = 1
 
 
 class OffkStencil(C.Structure):

@@ -42,7 +42,7 @@ struct TmGeom {        // what the producer needs to turn (tile, K-block) into T
   int a_coff;          // first channel of the A operand inside its buffer (im2col)
   int cblocks;         // cin / 32 (im2col)
   int kw;              // filter width (im2col)
-  int hout, wout, stride, pad;
+  int hout, wout, stride, pad, pad_w;   // pad = top rows, pad_w = left columns (equal unless OFFK_TGEMM_FREE_GEOM)
   int hw, tiles_per_img;   // nchw: pixels per frame, M tiles per frame
   int kb_per_img;          // nchw_t: K-blocks per frame (ceil(hw / 32))
   int kw_rows;             // im2col_t: kh*kw*cin = number of real A rows (the ones row follows)
@@ -135,7 +135,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         img0 = m0 / hw;
         const int rem = m0 - img0 * hw;
         const int oy = rem / geo.wout, ox = rem - oy * geo.wout;
-        w0 = ox * geo.stride - geo.pad;
+        w0 = ox * geo.stride - geo.pad_w;
         h0 = oy * geo.stride - geo.pad;
       }
       int s = 0;
@@ -169,7 +169,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           const int p0 = kb * TC_BK;
           const int img = p0 / hwo, rem = p0 - img * hwo;
           const int oy = rem / geo.wout, ox = rem - oy * geo.wout;
-          const int wb = ox * geo.stride - geo.pad, hb = oy * geo.stride - geo.pad;
+          const int wb = ox * geo.stride - geo.pad_w, hb = oy * geo.stride - geo.pad;
           for (int a = 0; a < n_at; ++a) {
             const int tap = (at0 + a) / geo.cblocks, cb = (at0 + a) - tap * geo.cblocks;
             const int r = tap / geo.kw, q = tap - r * geo.kw;
@@ -372,8 +372,15 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
   const cuuint64_t strides[3] = {(cuuint64_t)t->ctot * 4, (cuuint64_t)t->win * t->ctot * 4,
                                  (cuuint64_t)t->hin * t->win * t->ctot * 4};
   // base pixels (top-left corner of the filter window) range over [-pad, dim + pad - (k - 1)) in steps of `stride`
-  const int lower[2] = {-t->pad, -t->pad};
-  const int upper[2] = {t->pad - (t->kw - 1), t->pad - (t->kh - 1)};
+  int lower[2] = {-t->pad, -t->pad};
+  int upper[2] = {t->pad - (t->kw - 1), t->pad - (t->kh - 1)};
+  if (t->geom_flags & OFFK_TGEMM_FREE_GEOM) {
+    // caller-given output grid and top / left padding (data gradient of a strided conv as a stride-1 correlation over
+    // dY): base pixels run from -pad to -pad + (n_out - 1) * stride, whatever that implies for the bottom / right edge
+    lower[0] = -t->pad_w; lower[1] = -t->pad;
+    upper[0] = (t->wout - 1) * t->stride - t->pad_w - (t->win - 1);
+    upper[1] = (t->hout - 1) * t->stride - t->pad - (t->hin - 1);
+  }
   const cuuint32_t estr[4] = {1, (cuuint32_t)t->stride, (cuuint32_t)t->stride, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t->g.a_src), dims, strides, lower, upper,
                   (cuuint32_t)TC_BK, (cuuint32_t)(transposed ? 32 : TC_BM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -423,8 +430,12 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
     OFFK_REQUIRE(t->cin % TC_BK == 0 && t->ctot % 4 == 0 && t->a_coff % 4 == 0 && t->a_coff + t->cin <= t->ctot,
                  "tma_gemm: im2col needs cin %% 32 == 0 and a 16-byte aligned channel slice");
     OFFK_REQUIRE(t->kh >= 1 && t->kw >= 1 && t->stride >= 1 && t->stride <= 8 && t->pad >= 0, "tma_gemm: conv geometry");
-    OFFK_REQUIRE(t->hout == (t->hin + 2 * t->pad - t->kh) / t->stride + 1 && t->wout == (t->win + 2 * t->pad - t->kw) / t->stride + 1,
-                 "tma_gemm: output geometry");
+    if (t->geom_flags & OFFK_TGEMM_FREE_GEOM) {
+      OFFK_REQUIRE(t->a_kind == OFFK_TMA_A_IM2COL && t->pad_w >= 0 && t->hout >= 1 && t->wout >= 1, "tma_gemm: free geometry is for im2col A");
+    } else {
+      OFFK_REQUIRE(t->hout == (t->hin + 2 * t->pad - t->kh) / t->stride + 1 && t->wout == (t->win + 2 * t->pad - t->kw) / t->stride + 1,
+                   "tma_gemm: output geometry");
+    }
     const long long pixels = (long long)t->n_img * t->hout * t->wout, kw_rows = (long long)t->cin * t->kh * t->kw;
     if (t->a_kind == OFFK_TMA_A_IM2COL) {
       OFFK_REQUIRE(g.K == kw_rows && g.M == pixels, "tma_gemm: im2col needs K == kh*kw*cin, M == output pixels");
@@ -469,6 +480,7 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   TmGeom geo;
   geo.a_kind = t->a_kind; geo.a_coff = t->a_coff; geo.cblocks = t->cin > 0 ? t->cin / TC_BK : 1; geo.kw = t->kw > 0 ? t->kw : 1;
   geo.hout = t->hout; geo.wout = t->wout; geo.stride = t->stride; geo.pad = t->pad;
+  geo.pad_w = (t->geom_flags & OFFK_TGEMM_FREE_GEOM) ? t->pad_w : t->pad;
   geo.hw = t->hin * t->win; geo.tiles_per_img = (geo.hw + TC_BM - 1) / TC_BM;
   geo.kb_per_img = (geo.hw + TC_BK - 1) / TC_BK;
   geo.kw_rows = t->cin * t->kh * t->kw;

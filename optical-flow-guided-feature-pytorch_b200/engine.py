@@ -30,6 +30,23 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _FreeGeom:
+    """im2col geometry with a caller-given output grid and separate top / left padding (OFFK_TGEMM_FREE_GEOM)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _pick_tile_n(M: int, N: int) -> int:
+    """Widest N tile (multiple of 16, <= 256, dividing N) that still gives about two CTAs per SM."""
+    mt = math.ceil(M / 128)
+    cands = [bn for bn in range(256, 15, -16) if N % bn == 0]
+    for bn in cands:
+        if mt * (N // bn) >= 280:
+            return bn
+    return cands[-1] if cands else 0
+
+
 class Gemm:
     """One bound gather-GEMM launch (descriptor + device tables kept alive)."""
 
@@ -116,6 +133,8 @@ class TGemm(Gemm):
         t.a_coff = geom.x_coff
         t.n_img, t.hin, t.win, t.ctot, t.cin = geom.n_img, geom.hin, geom.win, geom.x_ctot, geom.cin
         t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = geom.kh, geom.kw, geom.stride, geom.pad, geom.hout, geom.wout
+        if isinstance(geom, _FreeGeom):
+            t.geom_flags, t.pad_w = L.TGEMM_FREE_GEOM, geom.pad_w
         if wgrad:                         # B = dY[pixel, cout slice], row-major
             t.b_kind, t.ldb = L.TMA_B_DENSE_T, geom.y_ctot
             t.g.b_src = kw["b_src"].data_ptr() + 4 * geom.y_coff
@@ -169,6 +188,7 @@ class OFFEngine:
         # for channels-last convs, where 32-pixel im2col boxes lose to the cp.async gather on the big KxK layers
         # (motion_conv_trans_28: 388 vs 211 us) and tie elsewhere -- OFFK_TMA_WGRAD=all forces them on, =none disables both
         self.tma_wgrad = os.environ.get("OFFK_TMA_WGRAD", "taps")
+        self.tma_strided_dgrad = os.environ.get("OFFK_NO_TMA_SDGRAD", "0") != "1"
         self._tab_cache = {}
         self._keep = []
 
@@ -279,7 +299,7 @@ class OFFEngine:
         total = sum(cout * cin * k * k for _, cout, cin, k in kxk)
         self.dwp_flat = torch.zeros(total, device=self.device)
         idx, off, views = [], 0, []
-        for name, cout, cin, k, stride, _ in S.STAGE_CONVS:
+        for name, cout, cin, k, stride, pad in S.STAGE_CONVS:
             p_off = self.layout[name + ".weight"][0]
             oihw = p_off + np.arange(cout * cin * k * k, dtype=np.int64).reshape(cout, cin, k, k)
             if k > 1:
@@ -290,6 +310,17 @@ class OFFEngine:
                 idx.append(oihw[:, :, ::-1, ::-1].transpose(1, 2, 3, 0).reshape(-1))
                 views.append(("wd", name, off, (cin, k * k * cout)))
                 off += oihw.size
+            else:
+                # one [cin, R, Q, cout] block per stride-parity class (a, b) of the input pixel: the taps r = r0 + s*i
+                # that reach the class, walked in reverse (tables.conv_dgrad_specs)
+                for a in range(stride):
+                    for b in range(stride):
+                        rs = np.arange((a + pad) % stride, k, stride)[::-1]
+                        qs = np.arange((b + pad) % stride, k, stride)[::-1]
+                        sub = oihw[:, :, rs][:, :, :, qs].transpose(1, 2, 3, 0)
+                        idx.append(sub.reshape(-1))
+                        views.append(("wd", (name, a, b), off, (cin, len(rs) * len(qs) * cout)))
+                        off += sub.size
         self.wc_idx = torch.from_numpy(np.concatenate(idx).astype(np.int32)).to(self.device)
         self.wc_flat = torch.zeros(off, device=self.device)
         for kind, name, o, shape in views:
@@ -374,10 +405,22 @@ class OFFEngine:
             # dX of a stride-1 conv = a forward conv over dY with flipped taps and pad' = k-1-pad: TMA-fed
             gd = T.ConvGeom(geom.n_img, geom.cout, geom.hout, geom.wout, geom.cin, geom.kh, geom.kw, 1,
                             geom.kh - 1 - geom.pad, geom.y_ctot, geom.y_coff, geom.x_ctot, geom.x_coff) if geom.stride == 1 else None
+            ex = spc.extra
             if (self.use_tma and x_layout == "nhwc" and gd is not None and name in self.wd and geom.kh == geom.kw
                     and TGemm.eligible(gd, self.prec) and (gd.hout, gd.wout) == (geom.hin, geom.win)):
                 kw_["b_src"] = self.wd[name]
                 g = TGemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), geom=gd, **kw_)
+            elif (self.use_tma and self.tma_strided_dgrad and x_layout == "nhwc" and geom.stride > 1
+                  and (name, ex["a"], ex["b"]) in self.wd and self.prec == L.PREC_TF32 and geom.cout % 32 == 0
+                  and geom.y_ctot % 4 == 0 and geom.y_coff % 4 == 0 and ex["pad_h"] >= 0 and ex["pad_w"] >= 0):
+                # one stride-parity class = a stride-1 correlation over dY with the class's R x Q taps (free geometry)
+                R, Q = len(ex["rs"]), len(ex["qs"])
+                fg = _FreeGeom(n_img=geom.n_img, cin=geom.cout, hin=geom.hout, win=geom.wout, cout=geom.cin, kh=R, kw=Q,
+                               stride=1, pad=ex["pad_h"], pad_w=ex["pad_w"], x_ctot=geom.y_ctot, x_coff=geom.y_coff,
+                               hout=ex["hc"], wout=ex["wc"], kdim=R * Q * geom.cout)
+                kw_["b_src"] = self.wd[(name, ex["a"], ex["b"])]
+                kw_["tile_n"] = _pick_tile_n(spc.M, spc.N)
+                g = TGemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), geom=fg, **kw_)
             else:
                 g = Gemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), **kw_)
             self.flops_bwd += g.flops

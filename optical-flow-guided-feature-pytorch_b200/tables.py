@@ -232,7 +232,10 @@ def conv_dgrad_specs(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw"
             specs.append(GemmSpec(
                 M=g.n_img * hc * wc, N=g.cin, K=g.cout * len(rs) * len(qs), a_row=a_row, a_col=a_col,
                 b_row=_i32(b_row), b_col=_i32(b_col), out_row=_i32(out_row), out_col=_i32(out_col),
-                a_h=g.hout, a_w=g.wout, a_mode=a_mode, b_mode=b_mode, out_vec=out_vec, kind=f"dgrad[{a},{b}]"))
+                a_h=g.hout, a_w=g.wout, a_mode=a_mode, b_mode=b_mode, out_vec=out_vec, kind=f"dgrad[{a},{b}]",
+                # the same class as a stride-1 correlation over dY (TMA im2col form): output grid hc x wc, filter
+                # len(rs) x len(qs) with taps walked in reverse, top / left padding len(rs)-1-dh / len(qs)-1-dw
+                extra=dict(a=a, b=b, rs=rs, qs=qs, hc=hc, wc=wc, pad_h=len(rs) - 1 - dh, pad_w=len(qs) - 1 - dw)))
     return specs
 
 

@@ -290,6 +290,65 @@ def test_tma_gemm_weight_gradient(dev, case):
     assert _rel(dw_t, dw_g.cpu()) < 1e-4 and _rel(db_t, db_g.cpu()) < 1e-4      # same tf32 products, other summation order
 
 
+SDGRAD_CASES = [
+    # n, cin, h, w, cout, k, s, p, x_ctot, x_coff
+    (3, 64, 28, 28, 64, 7, 2, 3, 64, 0),          # motion_conv_trans_28 geometry: classes with 3 or 4 taps per axis
+    (4, 96, 14, 14, 128, 5, 2, 2, 128, 32),       # motion_conv_trans_14 geometry, dX into a channel slice
+]
+
+
+@pytest.mark.parametrize("case", SDGRAD_CASES, ids=[f"{c[1]}x{c[2]}k{c[5]}s{c[6]}" for c in SDGRAD_CASES])
+def test_tma_gemm_strided_data_gradient(dev, case):
+    """Data gradient of a stride-2 conv, one stride-parity class at a time, as a TMA-im2col stride-1 correlation over dY
+    (OFFK_TGEMM_FREE_GEOM) against autograd of conv2d and bit-for-bit against the gather-fed kernel."""
+    from off_b200 import _lib as L, tables as T
+    lib = L.lib()
+    n, cin, h, w, cout, k, st, p, xct, xco = case
+    g = T.ConvGeom(n, cin, h, w, cout, k, k, st, p, xct, xco)
+    torch.manual_seed(3)
+    x = torch.zeros(n, cin, h, w, device=dev, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(cout, cin, k, k, device=dev) / (g.kdim ** 0.5)
+    dy = torch.randn(n, cout, g.hout, g.wout, device=dev)
+    (torch.nn.functional.conv2d(x, wt.double(), None, st, p) * dy.double()).sum().backward()
+    dyb = dy.permute(0, 2, 3, 1).contiguous()
+    w_ohwi = wt.permute(0, 2, 3, 1).contiguous()
+    outs = []
+    for use_tma in (True, False):
+        dx = torch.zeros(n, h, w, xct, device=dev)
+        for spc in T.conv_dgrad_specs(g, "nhwc", "nhwc", "nhwc"):
+            ex = spc.extra
+            tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
+            t = L.OffkTGemm()
+            d = t.g
+            d.M, d.N, d.K = spc.M, spc.N, spc.K
+            d.a_src, d.a_row, d.a_col = dyb.data_ptr(), tabs["a_row"].data_ptr(), tabs["a_col"].data_ptr()
+            d.a_h, d.a_w, d.a_ones_row, d.a_mode = spc.a_h, spc.a_w, -1, spc.a_mode
+            d.b_src, d.b_row, d.b_col, d.b_mode = w_ohwi.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
+            d.out, d.out_row, d.out_col = dx.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+            d.split_k, d.out_vec, d.tile_n = 1, spc.out_vec, 32
+            if use_tma:
+                rs, qs = ex["rs"][::-1].copy(), ex["qs"][::-1].copy()
+                wsub = wt[:, :, torch.as_tensor(rs, device=dev)][:, :, :, torch.as_tensor(qs, device=dev)]
+                wcls = wsub.permute(1, 2, 3, 0).contiguous()                   # [cin, R, Q, cout]
+                t.a_kind, t.a_coff = L.TMA_A_IM2COL, 0
+                t.n_img, t.hin, t.win, t.ctot, t.cin = n, g.hout, g.wout, cout, cout
+                t.kh, t.kw, t.stride, t.pad, t.pad_w = len(rs), len(qs), 1, ex["pad_h"], ex["pad_w"]
+                t.hout, t.wout, t.geom_flags = ex["hc"], ex["wc"], L.TGEMM_FREE_GEOM
+                t.b_kind, t.ldb = L.TMA_B_DENSE, len(rs) * len(qs) * cout
+                d.b_src = wcls.data_ptr()
+                L.check(lib.offk_tma_gemm_prepare(C.byref(t)), "prepare")
+                L.check(lib.offk_tma_gemm(C.byref(t), None), "tma_gemm")
+            else:
+                L.check(lib.offk_gather_gemm(C.byref(d), 1, None), "gather_gemm")
+            torch.cuda.synchronize()
+        outs.append(dx)
+    got = outs[0].permute(0, 3, 1, 2)[:, xco:xco + cin]
+    assert _rel(got, x.grad.cpu()) < 3e-3
+    assert _rel(outs[0], outs[1].cpu()) < 1e-5           # same products; the K order (tap walk) differs
+    if xco:
+        assert outs[0][..., :xco].abs().max().item() == 0
+
+
 STENCIL_CASES = [
     # B, L, S, K, index_mode, drop_mode
     (2, 3, 28, 1, 0, 0), (3, 4, 14, 1, 1, 1), (2, 2, 7, 1, 0, 2), (2, 3, 7, 2, 0, 0), (1, 7, 14, 1, 0, 1), (1, 2, 5, 1, 1, 0),
