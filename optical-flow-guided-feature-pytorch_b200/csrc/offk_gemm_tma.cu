@@ -30,6 +30,7 @@
 //              stores (red.global.add for split-K) touch whole 128-byte lines of the channels-last output
 // One output tile per CTA; two CTAs co-reside per SM so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 #include "offk_tc.cuh"
 
 namespace offk {
@@ -125,6 +126,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = sh->tmem_base;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) may overlap
+  // the tail of the previous kernel in the stream; nothing below runs before that kernel's memory is visible.  The
+  // next kernel may begin ITS prologue once every CTA of this grid got past the wait.  (No-ops without the attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -402,7 +408,16 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
     if (e != cudaSuccess) return cuda_check(e, "cudaFuncSetAttribute(tma_gemm)");
     attr_set = true;
   }
-  kern<<<grid, TM_THREADS, smem, st>>>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols);
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("OFFK_NO_PDL"); pdl = (e && e[0] == '1') ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols);
+  if (e != cudaSuccess) return cuda_check(e, "tma_gemm launch");
   return OFFK_LAUNCH_CHECK("tma_gemm");
 }
 

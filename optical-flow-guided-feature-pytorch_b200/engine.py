@@ -443,6 +443,7 @@ class OFFEngine:
         self._st_desc = (L.OffkStencil * n_lv)()      # one contiguous array: stage batches are slices of it
         self._st_io = (L.OffkStencilIO * n_lv)()
         k4_steps = []
+        k4_by_stage = {st: [] for st in S.STAGES}
         for li, (tag, (cin, s)) in enumerate(S.LEVELS.items()):
             st = S.LEVEL_STAGE[tag]
             fl = fwd_lane[st]
@@ -497,10 +498,12 @@ class OFFEngine:
                 k4 = self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
                                       self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag), x_layout="nchw")
                 self._tap_users[tag].append(k4)
-            k4_steps.append(_on(k4, li % 3))
+            grp = [_on(k4, li % 3)]
             if self.tap_grads:
-                k4_steps += [_on(g, li % 3) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
-                                                                      self.tap_grad[tag], geom, x_layout="nchw")]
+                grp += [_on(g, li % 3) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
+                                                                  self.tap_grad[tag], geom, x_layout="nchw")]
+            k4_steps += grp
+            k4_by_stage[st] += grp
         # K2: ONE stencil launch per stage-fusion buffer (its units' GEMMs precede it on the same lane)
         tags = list(S.LEVELS)
         for st, lv_tags in stage_levels.items():
@@ -532,8 +535,32 @@ class OFFEngine:
         def k3(stream):
             L.check(lib.offk_stencil_diff_bwd_batch(n_lv, self._st_desc, self._st_io, stream), "stencil_bwd")
         k3 = _nm(k3, "stencil_bwd", reads=rd3, writes=[bf["dgd_" + t] for t in tags] + grad3, lane=0)
-        bwd_units += [k3t, k3s] if os.environ.get("OFFK_STENCIL_BWD_SPLIT", "0") == "1" else [k3]
-        bwd_units += k4_steps
+        # Early unit backward (optional): dF7[:, :320] is final right after motion_conv_trans' data gradient and
+        # dF14[:, :800] after motion_conv_trans_14's, so the 7- and 14-stage units' stencil backward + weight gradients
+        # can run on side lanes under the rest of the stage chain.  Measured at config 2: 2.90 ms/step vs 2.84 ms with
+        # all nine units at the tail -- the HBM-bound unit kernels slow the chain more than the overlap saves -- so off.
+        self.unit_bwd_early = os.environ.get("OFFK_UNIT_BWD_EARLY", "0") == "1"
+        unit_bwd = {}
+        for st, lv_tags in stage_levels.items():
+            i0, n = tags.index(lv_tags[0]), len(lv_tags)
+            g3 = [gr[f"motion_spatial_grad_{t}.{k}"] for t in lv_tags for k in ("weight", "bias")] if self.variant == "rgb" else []
+
+            def k3st(stream, i0=i0, n=n, st=st):
+                L.check(lib.offk_stencil_diff_bwd_batch(n, C.byref(self._st_desc[i0]), C.byref(self._st_io[i0]), stream),
+                        "stencil_bwd_" + st)
+            lane3 = 0 if st == "28" else 2
+            stp = _nm(k3st, "stencil_bwd_" + st, reads=[bf["dF" + st]] + [bf["gd_" + t] for t in lv_tags],
+                      writes=[bf["dgd_" + t] for t in lv_tags] + g3, lane=lane3)
+            grp = list(k4_by_stage[st])
+            if self.unit_bwd_early:
+                for j, g_ in enumerate(grp):                       # early groups stay off lane 0 (the dgrad chain)
+                    g_.lane = (2, 1)[j % 2] if st != "28" else (0, 2, 1)[j % 3]
+            unit_bwd[st] = [stp] + grp
+        if self.unit_bwd_early:
+            bwd_units += unit_bwd["28"]
+        else:
+            bwd_units += [k3t, k3s] if os.environ.get("OFFK_STENCIL_BWD_SPLIT", "0") == "1" else [k3]
+            bwd_units += k4_steps
 
         # ============ stage convs
         def geom_of(name, n_img, s_in, x_ctot=0, x_coff=0, y_ctot=0, y_coff=0):
@@ -652,6 +679,8 @@ class OFFEngine:
         dgrad("motion_conv_trans", d("t7"), bf["dF7"], g_t7)
         # d sum_14b = (dF7[:,320:] + head-14 pool gradient) * [sum_14b > 0]   (in place in the dF7 slice)
         bs.append(self._pool_bwd("14", bf["dF7"], 512, 832, 320, act=bf["F7"], accumulate=True))
+        if self.unit_bwd_early:          # after the in-place update of dF7[:, 320:], so the main lane never waits on these
+            bs.extend(unit_bwd["7"])
         # ---- 14b:  sum_14b = relu(s14a + relu(conv3_14b(h2b)))
         bs.append(_nm(lambda stream: L.check(lib.offk_gate_copy(_ptr(bf["dF7"]), 832, 320, _ptr(bf["h3_14b"]), 512, 0,
                                                                 _ptr(d("h3_14b")), 512, 0, P, 512, 49, stream), "gate_h3b"),
@@ -676,6 +705,8 @@ class OFFEngine:
         back("motion_conv_trans_14", bf["F14"], d("t14"), g_t14)
         # dF14; channels >= 800 are sum_28c = relu(.) -> gate them here (fc28 contributes nothing)
         dgrad("motion_conv_trans_14", d("t14"), bf["dF14"], g_t14, gate=bf["F14"], gate_col0=800)
+        if self.unit_bwd_early:
+            bs.extend(unit_bwd["14"])
         # ---- 28c / 28b (identity residuals): the incoming gradient of 28c is the dF14 slice [800,1056)
         g_dy_c3c = g_c3c
         back("motion_conv3_trans_28c", bf["h2_28c"], bf["dF14"], g_dy_c3c)
