@@ -84,4 +84,25 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// ---- programmatic dependent launch ---------------------------------------------
+// Kernels call pdl_sync() before their first global access: it waits until the previous kernel in the stream has
+// completed and its writes are visible, then lets the NEXT kernel be scheduled (whose own pdl_sync() blocks until this
+// grid is done).  Launch latency and kernel prologues thereby overlap the predecessor's tail.  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();  // OFFK_NO_PDL=1 turns the launch attribute off
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace offk

@@ -16,6 +16,7 @@ __device__ __forceinline__ float keep_factor(int mode, const uint8_t* mask, uint
 __global__ void avgpool_drop_fwd_kernel(const float* __restrict__ x, int P, int C, int HW, int ctot, int coff, int mode,
                                         const uint8_t* __restrict__ mask, uint64_t seed, float drop_p, float scale,
                                         float* __restrict__ out) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * C) return;
   const int p = i / C, c = i - p * C;
@@ -30,6 +31,7 @@ __global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P
                                         int mode, const uint8_t* __restrict__ mask, uint64_t seed, float drop_p,
                                         float scale, const float* __restrict__ act, int accumulate,
                                         float* __restrict__ dx) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
@@ -46,6 +48,7 @@ __global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P
 
 __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C, int H, int W, int ctot, int coff,
                                       int Ho, int Wo, float* __restrict__ out) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * Ho * Wo;
   if (i >= total) return;
@@ -68,6 +71,7 @@ __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C,
 }
 
 __global__ void segment_mean_fwd_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
@@ -76,6 +80,7 @@ __global__ void segment_mean_fwd_kernel(const float* __restrict__ x, int B, int 
   out[i] = s / (float)T;
 }
 __global__ void segment_mean_bwd_kernel(const float* __restrict__ dout, int B, int T, int C, float* __restrict__ dx) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T * C) return;
   const int c = i % C, b = i / (T * C);
@@ -83,6 +88,7 @@ __global__ void segment_mean_bwd_kernel(const float* __restrict__ dout, int B, i
 }
 __global__ void relu_gate_kernel(const float* __restrict__ grad, const float* __restrict__ act, long long n,
                                  float* __restrict__ out) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __ldg(act + i) > 0.f ? __ldg(grad + i) : 0.f;
 }
@@ -90,6 +96,7 @@ __global__ void relu_gate_kernel(const float* __restrict__ grad, const float* __
 __global__ void gate_copy_kernel(const float* __restrict__ src, int sctot, int scoff, const float* __restrict__ act,
                                  int actot, int acoff, float* __restrict__ dst, int dctot, int dcoff, int P, int C,
                                  int HW) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
@@ -102,6 +109,7 @@ __global__ void gate_copy_kernel(const float* __restrict__ src, int sctot, int s
 // dst[p, coff+c, :] = (relu ? max(.,0) : .)(a[p,c,:] + b[p,c,:])
 __global__ void add_relu_slice_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst,
                                       int ctot, int coff, int P, int C, int HW, int relu) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
@@ -113,6 +121,7 @@ __global__ void add_relu_slice_kernel(const float* __restrict__ a, const float* 
 }
 __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, int P, int C, int HW, int ctot,
                                 int coff, int relu_cols) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
@@ -129,6 +138,7 @@ __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__
 // side (32*rq contiguous floats) and the OHWI side (32 contiguous channels per tap) are accessed coalesced.
 __global__ void __launch_bounds__(256)
 permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int rq, int to_ohwi) {
+  pdl_sync();
   extern __shared__ float tile[];                       // [32][rq] in OIHW order (rq is odd on this path: no conflicts)
   const int o = blockIdx.y, c0 = blockIdx.x * 32;
   const int n = min(32, cin - c0), cnt = n * rq;
@@ -165,7 +175,7 @@ extern "C" int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x
                                      float* out, void* stream) {
   OFFK_REQUIRE(x && out && P > 0 && C > 0 && HW > 0 && x_coff >= 0 && x_coff + C <= x_ctot, "avgpool_fwd: bad args");
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_fwd: mask missing");
-  avgpool_drop_fwd_kernel<<<blocks_for((size_t)P * C, 128), 128, 0, as_stream(stream)>>>(
+  (void)launch_pdl(avgpool_drop_fwd_kernel, dim3(blocks_for((size_t)P * C, 128)), dim3(128), 0, as_stream(stream), 
       x, P, C, HW, x_ctot, x_coff, drop_mode, keep_mask, seed, drop_p, keep_scale, out);
   return OFFK_LAUNCH_CHECK("avgpool_drop_fwd");
 }
@@ -176,7 +186,7 @@ extern "C" int offk_avgpool_drop_bwd(const float* dpooled, int P, int C, int HW,
   OFFK_REQUIRE(dx && P > 0 && C > 0 && HW > 0 && coff >= 0 && coff + C <= ctot, "avgpool_bwd: bad args");
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_bwd: mask missing");
   const size_t total = (size_t)P * C * HW;
-  avgpool_drop_bwd_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(
+  (void)launch_pdl(avgpool_drop_bwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, as_stream(stream), 
       dpooled, P, C, HW, ctot, coff, drop_mode, keep_mask, seed, drop_p, keep_scale, act, accumulate, dx);
   return OFFK_LAUNCH_CHECK("avgpool_drop_bwd");
 }
@@ -189,30 +199,30 @@ extern "C" int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, i
   if ((Ho - 1) * 2 >= H) --Ho;                             // ... and the last window must start inside the input
   if ((Wo - 1) * 2 >= W) --Wo;
   const size_t total = (size_t)P * C * Ho * Wo;
-  maxpool3s2_fwd_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(x, P, C, H, W, x_ctot, x_coff, Ho, Wo,
+  (void)launch_pdl(maxpool3s2_fwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, as_stream(stream), x, P, C, H, W, x_ctot, x_coff, Ho, Wo,
                                                                                out);
   return OFFK_LAUNCH_CHECK("maxpool3s2_fwd");
 }
 
 extern "C" int offk_segment_mean_fwd(const float* x, int B, int T, int C, float* out, void* stream) {
   OFFK_REQUIRE(x && out && B > 0 && T > 0 && C > 0, "segment_mean_fwd: bad args");
-  segment_mean_fwd_kernel<<<blocks_for((size_t)B * C, 256), 256, 0, as_stream(stream)>>>(x, B, T, C, out);
+  (void)launch_pdl(segment_mean_fwd_kernel, dim3(blocks_for((size_t)B * C, 256)), dim3(256), 0, as_stream(stream), x, B, T, C, out);
   return OFFK_LAUNCH_CHECK("segment_mean_fwd");
 }
 extern "C" int offk_segment_mean_bwd(const float* dout, int B, int T, int C, float* dx, void* stream) {
   OFFK_REQUIRE(dout && dx && B > 0 && T > 0 && C > 0, "segment_mean_bwd: bad args");
-  segment_mean_bwd_kernel<<<blocks_for((size_t)B * T * C, 256), 256, 0, as_stream(stream)>>>(dout, B, T, C, dx);
+  (void)launch_pdl(segment_mean_bwd_kernel, dim3(blocks_for((size_t)B * T * C, 256)), dim3(256), 0, as_stream(stream), dout, B, T, C, dx);
   return OFFK_LAUNCH_CHECK("segment_mean_bwd");
 }
 extern "C" int offk_relu_gate(const float* grad, const float* act, long long n, float* out, void* stream) {
   OFFK_REQUIRE(grad && act && out && n > 0, "relu_gate: bad args");
-  relu_gate_kernel<<<blocks_for((size_t)n, 256), 256, 0, as_stream(stream)>>>(grad, act, n, out);
+  (void)launch_pdl(relu_gate_kernel, dim3(blocks_for((size_t)n, 256)), dim3(256), 0, as_stream(stream), grad, act, n, out);
   return OFFK_LAUNCH_CHECK("relu_gate");
 }
 extern "C" int offk_bias_act(float* y, const float* bias, int P, int C, int HW, int ctot, int coff, int relu_cols,
                              void* stream) {
   OFFK_REQUIRE(y && P > 0 && C > 0 && HW > 0 && coff >= 0 && coff + C <= ctot, "bias_act: bad args");
-  bias_act_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(y, bias, P, C, HW, ctot, coff,
+  (void)launch_pdl(bias_act_kernel, dim3(blocks_for((size_t)P * C * HW, 256)), dim3(256), 0, as_stream(stream), y, bias, P, C, HW, ctot, coff,
                                                                                      relu_cols);
   return OFFK_LAUNCH_CHECK("bias_act");
 }
@@ -222,7 +232,7 @@ extern "C" int offk_gate_copy(const float* src, int src_ctot, int src_coff, cons
                               void* stream) {
   OFFK_REQUIRE(src && act && dst && P > 0 && C > 0 && HW > 0, "gate_copy: bad args");
   OFFK_REQUIRE(src_coff + C <= src_ctot && act_coff + C <= act_ctot && dst_coff + C <= dst_ctot, "gate_copy: slices");
-  gate_copy_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(
+  (void)launch_pdl(gate_copy_kernel, dim3(blocks_for((size_t)P * C * HW, 256)), dim3(256), 0, as_stream(stream), 
       src, src_ctot, src_coff, act, act_ctot, act_coff, dst, dst_ctot, dst_coff, P, C, HW);
   return OFFK_LAUNCH_CHECK("gate_copy");
 }
@@ -231,7 +241,7 @@ extern "C" int offk_add_relu_slice(const float* a, const float* b, float* dst, i
                                    int C, int HW, int relu, void* stream) {
   OFFK_REQUIRE(a && b && dst && P > 0 && C > 0 && HW > 0 && dst_coff >= 0 && dst_coff + C <= dst_ctot,
                "add_relu_slice: bad args");
-  add_relu_slice_kernel<<<blocks_for((size_t)P * C * HW, 256), 256, 0, as_stream(stream)>>>(a, b, dst, dst_ctot,
+  (void)launch_pdl(add_relu_slice_kernel, dim3(blocks_for((size_t)P * C * HW, 256)), dim3(256), 0, as_stream(stream), a, b, dst, dst_ctot,
                                                                                            dst_coff, P, C, HW, relu);
   return OFFK_LAUNCH_CHECK("add_relu_slice");
 }
@@ -246,6 +256,7 @@ extern "C" int offk_fill_zero(float* p, long long n, void* stream) {
 // in one launch; idx is built once per plan on the host
 __global__ void gather_copy_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ dst,
                                    long long n) {
+  pdl_sync();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const int4 j = *reinterpret_cast<const int4*>(idx + i);
@@ -257,6 +268,7 @@ __global__ void gather_copy_kernel(const float* __restrict__ src, const int32_t*
 
 // NCHW [n, C, HW] -> channels-last [n, HW, C] through 32x32 shared-memory tiles (both sides coalesced)
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  pdl_sync();
   __shared__ float t[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -280,7 +292,7 @@ extern "C" int offk_nchw_to_nhwc(const float* src, float* dst, int n_img, int C,
   OFFK_REQUIRE(src && dst && n_img > 0 && C > 0 && HW > 0 && n_img <= 65535, "nchw_to_nhwc: bad args");
   dim3 grid((HW + 31) / 32, (C + 31) / 32, n_img);
   OFFK_REQUIRE(grid.y <= 65535, "nchw_to_nhwc: too many channels");
-  nchw_to_nhwc_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, C, HW);
+  (void)launch_pdl(nchw_to_nhwc_kernel, dim3(grid), dim3(256), 0, as_stream(stream), src, dst, C, HW);
   return OFFK_LAUNCH_CHECK("nchw_to_nhwc");
 }
 
@@ -289,7 +301,7 @@ extern "C" int offk_gather_copy(const float* src, const int32_t* idx, float* dst
   OFFK_REQUIRE((reinterpret_cast<uintptr_t>(idx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0, "gather_copy: alignment");
   if (n == 0) return 0;
   const long long threads = (n + 3) / 4;
-  gather_copy_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, as_stream(stream)>>>(src, idx, dst, n);
+  (void)launch_pdl(gather_copy_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, as_stream(stream), src, idx, dst, n);
   return OFFK_LAUNCH_CHECK("gather_copy");
 }
 
@@ -298,7 +310,7 @@ extern "C" int offk_permute_weight(const float* src, float* dst, int cout, int c
   OFFK_REQUIRE(src && dst && cout > 0 && cin > 0 && kh > 0 && kw > 0, "permute_weight: bad args");
   OFFK_REQUIRE(kh * kw <= 256 && cout <= 65535, "permute_weight: filter too large");
   dim3 grid((cin + 31) / 32, cout);
-  permute_weight_kernel<<<grid, 256, (size_t)32 * kh * kw * sizeof(float), as_stream(stream)>>>(src, dst, cout, cin,
+  (void)launch_pdl(permute_weight_kernel, dim3(grid), dim3(256), (size_t)32 * kh * kw * sizeof(float), as_stream(stream), src, dst, cout, cin,
                                                                                                  kh * kw, to_ohwi);
   return OFFK_LAUNCH_CHECK("permute_weight");
 }

@@ -319,6 +319,7 @@ __device__ __forceinline__ void spatial_fwd(const StLevel& lv, int item, int tid
 
 __global__ void __launch_bounds__(ST_THREADS, ST_FWD_MINB)
 stencil_diff_fwd_kernel(const __grid_constant__ StBatch bt) {
+  pdl_sync();
   extern __shared__ __align__(16) float4 st_smem[];
   const StLevel& lv = find_level(bt, (int)blockIdx.x);
   const int tid = threadIdx.x;
@@ -545,6 +546,7 @@ __device__ __forceinline__ void spatial_bwd(const StLevel& lv, int rel, int tid,
 
 __global__ void __launch_bounds__(ST_THREADS, ST_FWD_MINB)
 stencil_diff_bwd_kernel(const __grid_constant__ StBatch bt) {
+  pdl_sync();
   extern __shared__ __align__(16) float4 st_smem[];
   const StLevel& lv = find_level(bt, (int)blockIdx.x);
   const int tid = threadIdx.x;
@@ -562,6 +564,7 @@ stencil_diff_bwd_kernel(const __grid_constant__ StBatch bt) {
 // streams the block scheduler mixes them instead of spatial blocks holding a third of the resident-block slots.
 __global__ void __launch_bounds__(ST_THREADS, 4)
 stencil_diff_bwd_temporal_kernel(const __grid_constant__ StBatch bt) {
+  pdl_sync();
   const StLevel& lv = find_level(bt, (int)blockIdx.x);
   const int r2 = (int)blockIdx.x - lv.blk0;
   if (lv.s.L == 3) temporal_bwd<3>(lv, r2, threadIdx.x);
@@ -569,6 +572,7 @@ stencil_diff_bwd_temporal_kernel(const __grid_constant__ StBatch bt) {
 }
 __global__ void __launch_bounds__(ST_THREADS, ST_FWD_MINB)
 stencil_diff_bwd_spatial_kernel(const __grid_constant__ StBatch bt) {
+  pdl_sync();
   extern __shared__ __align__(16) float4 st_smem[];
   const StLevel& lv = find_level(bt, (int)blockIdx.x);
   spatial_bwd(lv, (int)blockIdx.x - lv.blk0, threadIdx.x, st_smem);
@@ -701,12 +705,12 @@ static int launch_batch(int n, const offk_stencil_t* s, const offk_stencil_io_t*
     attr_set = true;
   }
   if (!backward) {
-    stencil_diff_fwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+    (void)launch_pdl(stencil_diff_fwd_kernel, dim3((unsigned)blk), dim3(ST_THREADS), (size_t)smem, as_stream(stream), bt);
     return OFFK_LAUNCH_CHECK("stencil_diff_fwd");
   }
-  if (part == 1) stencil_diff_bwd_temporal_kernel<<<(unsigned)blk, ST_THREADS, 0, as_stream(stream)>>>(bt);
-  else if (part == 2) stencil_diff_bwd_spatial_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
-  else stencil_diff_bwd_kernel<<<(unsigned)blk, ST_THREADS, smem, as_stream(stream)>>>(bt);
+  if (part == 1) (void)launch_pdl(stencil_diff_bwd_temporal_kernel, dim3((unsigned)blk), dim3(ST_THREADS), (size_t)0, as_stream(stream), bt);
+  else if (part == 2) (void)launch_pdl(stencil_diff_bwd_spatial_kernel, dim3((unsigned)blk), dim3(ST_THREADS), (size_t)smem, as_stream(stream), bt);
+  else (void)launch_pdl(stencil_diff_bwd_kernel, dim3((unsigned)blk), dim3(ST_THREADS), (size_t)smem, as_stream(stream), bt);
   return OFFK_LAUNCH_CHECK("stencil_diff_bwd");
 }
 
