@@ -28,7 +28,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 METRIC = "off_unit_clips_per_sec_fwd_bwd"
 # dram__bytes_read.sum + dram__bytes_write.sum of the three stencil_diff_fwd launches of one step, from the committed
 # ncu --set full capture (profiles/); None until measured for the current kernel
-NCU_TRAFFIC_BYTES = 288.1e6   # profiles/ncu_full_r01l_stencil_summary.txt: read 227.8 MB + write 60.3 MB (156 MB are written; the rest is still dirty in L2 at kernel end)
+NCU_TRAFFIC_BYTES = 286.8e6   # profiles/ncu_full_r01t_stencil_summary.txt: read 227.8 MB + write 59.0 MB (156 MB are written; the rest is still dirty in L2 at kernel end)
 UNIT = "clips/s"
 
 

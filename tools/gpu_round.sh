@@ -34,7 +34,7 @@ for w in $WHAT; do
       ncu -i /tmp/all_$TAG.ncu-rep --page raw --csv > $OUT/full_all_$TAG.csv 2>/dev/null; ls -la /tmp/all_$TAG.ncu-rep;;
     full_gemm)
       OFFK_SINGLE_STREAM=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-        -k regex:gather_gemm_tc -c 12 -f -o $OUT/gemm_$TAG python tools/prof_step.py 48 3 tf32 2 > $OUT/full_gemm_$TAG.log 2>&1; tail -2 $OUT/full_gemm_$TAG.log;;
+        -k regex:tma_gemm_kernel -c 9 -f -o $OUT/gemm_$TAG python tools/prof_step.py 48 3 tf32 2 > $OUT/full_gemm_$TAG.log 2>&1; tail -2 $OUT/full_gemm_$TAG.log;;
   esac
 done
 ls -la $OUT
