@@ -308,6 +308,14 @@ int offk_add_relu_slice(const float* a, const float* b, float* dst, int dst_ctot
  * implicit GEMM.  to_ohwi = 1: dst(OHWI) = src(OIHW) (before forward); 0: dst(OIHW) = src(OHWI);
  * 2: dst(OIHW) += src(OHWI) (weight gradients) */
 int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi, void* stream);
+/* n (<= 16) weights in ONE launch, same to_ohwi for all (the OHWI -> OIHW accumulation of every KxK weight gradient
+ * after the backward pass) */
+typedef struct offk_permute {
+  const float* src;
+  float* dst;
+  int32_t cout, cin, kh, kw;
+} offk_permute_t;
+int offk_permute_weight_batch(int n, const offk_permute_t* items, int to_ohwi, void* stream);
 
 /* dst[i] = src[idx[i]], i < n.  One launch re-lays every conv weight of the step: OHWI copies for the forward
  * implicit GEMMs and [cin][kh][kw][cout] copies with flipped taps for the data-gradient GEMMs (autograd of

@@ -82,6 +82,12 @@ class OffkStencilIO(C.Structure):
     ]
 
 
+class OffkPermute(C.Structure):
+    """Mirror of offk_permute_t."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32),
+                ("kw", C.c_int32)]
+
+
 _P = C.c_void_p
 _PROTOS = {
     "offk_version": (C.c_int, []),
@@ -112,6 +118,7 @@ _PROTOS = {
     "offk_add_relu_slice": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_nchw_to_nhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "offk_gather_copy": (C.c_int, [_P, _P, _P, C.c_longlong, _P]),
+    "offk_permute_weight_batch": (C.c_int, [C.c_int, C.POINTER(OffkPermute), C.c_int, _P]),
     "offk_permute_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_drop_keep_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_float]),
 }

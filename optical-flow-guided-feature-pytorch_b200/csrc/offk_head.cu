@@ -136,11 +136,8 @@ __global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__
 // the channels-last implicit GEMM).  to_ohwi != 0: dst(OHWI) = src(OIHW); else dst(OIHW) = src(OHWI).
 // One block = one output channel x 32 input channels x all taps, staged through shared memory so that both the OIHW
 // side (32*rq contiguous floats) and the OHWI side (32 contiguous channels per tap) are accessed coalesced.
-__global__ void __launch_bounds__(256)
-permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int rq, int to_ohwi) {
-  pdl_sync();
-  extern __shared__ float tile[];                       // [32][rq] in OIHW order (rq is odd on this path: no conflicts)
-  const int o = blockIdx.y, c0 = blockIdx.x * 32;
+__device__ __forceinline__ void permute_weight_block(const float* __restrict__ src, float* __restrict__ dst, int cin, int rq,
+                                                     int to_ohwi, int o, int c0, float* tile) {
   const int n = min(32, cin - c0), cnt = n * rq;
   const size_t oihw = ((size_t)o * cin + c0) * rq;      // start of the contiguous OIHW chunk
   const size_t ohwi = (size_t)o * rq * cin + c0;        // element (tap t, channel ci) at ohwi + t*cin + ci
@@ -162,6 +159,30 @@ permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, in
       else dst[oihw + i] += tile[i];                    // 2: accumulate into the OIHW gradient
     }
   }
+}
+__global__ void __launch_bounds__(256)
+permute_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int rq, int to_ohwi) {
+  pdl_sync();
+  extern __shared__ float tile[];                       // [32][rq] in OIHW order (rq is odd on this path: no conflicts)
+  permute_weight_block(src, dst, cin, rq, to_ohwi, blockIdx.y, blockIdx.x * 32, tile);
+}
+// several weights in one launch: block -> (weight, output channel, 32-channel group)
+constexpr int PW_MAX = 16;
+struct PermuteBatch {
+  int n;
+  const float* src[PW_MAX];
+  float* dst[PW_MAX];
+  int cin[PW_MAX], rq[PW_MAX], cgroups[PW_MAX], blk0[PW_MAX + 1];
+};
+__global__ void __launch_bounds__(256) permute_weight_batch_kernel(const __grid_constant__ PermuteBatch pb, int to_ohwi) {
+  pdl_sync();
+  extern __shared__ float tile[];
+  int w = 0;
+#pragma unroll 1
+  while (w + 1 < pb.n && (int)blockIdx.x >= pb.blk0[w + 1]) ++w;
+  const int rel = (int)blockIdx.x - pb.blk0[w];
+  const int o = rel / pb.cgroups[w], cg = rel - o * pb.cgroups[w];
+  permute_weight_block(pb.src[w], pb.dst[w], pb.cin[w], pb.rq[w], to_ohwi, o, cg * 32, tile);
 }
 
 static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -303,6 +324,27 @@ extern "C" int offk_gather_copy(const float* src, const int32_t* idx, float* dst
   const long long threads = (n + 3) / 4;
   (void)launch_pdl(gather_copy_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, as_stream(stream), src, idx, dst, n);
   return OFFK_LAUNCH_CHECK("gather_copy");
+}
+
+extern "C" int offk_permute_weight_batch(int n, const offk_permute_t* items, int to_ohwi, void* stream) {
+  OFFK_REQUIRE(n >= 1 && n <= PW_MAX && items != nullptr, "permute_weight_batch: 1 <= n <= %d", PW_MAX);
+  PermuteBatch pb;
+  pb.n = n;
+  long long blk = 0;
+  int rq_max = 0;
+  for (int i = 0; i < n; ++i) {
+    const offk_permute_t& it = items[i];
+    OFFK_REQUIRE(it.src && it.dst && it.cout > 0 && it.cin > 0 && it.kh > 0 && it.kw > 0 && it.kh * it.kw <= 256, "permute_weight_batch: item %d", i);
+    pb.src[i] = it.src; pb.dst[i] = it.dst; pb.cin[i] = it.cin; pb.rq[i] = it.kh * it.kw;
+    pb.cgroups[i] = (it.cin + 31) / 32;
+    pb.blk0[i] = (int)blk;
+    blk += (long long)pb.cgroups[i] * it.cout;
+    if (pb.rq[i] > rq_max) rq_max = pb.rq[i];
+  }
+  pb.blk0[n] = (int)blk;
+  OFFK_REQUIRE(blk < 2147483647LL, "permute_weight_batch: grid too large");
+  (void)launch_pdl(permute_weight_batch_kernel, dim3((unsigned)blk), dim3(256), (size_t)32 * rq_max * sizeof(float), as_stream(stream), pb, to_ohwi);
+  return OFFK_LAUNCH_CHECK("permute_weight_batch");
 }
 
 extern "C" int offk_permute_weight(const float* src, float* dst, int cout, int cin, int kh, int kw, int to_ohwi,

@@ -740,12 +740,15 @@ class OFFEngine:
         wc, wci, pflat = self.wc_flat, self.wc_idx, self.params_flat
         pre = [_nm(lambda stream: L.check(lib.offk_gather_copy(_ptr(pflat), _ptr(wci), _ptr(wc), wc.numel(), stream),
                                           "weight copies"), "weight_copies", writes=[wc])]
-        post = []
-        for name, cout, cin, k, _, _ in S.STAGE_CONVS:
-            if k > 1:
-                post.append(_nm(lambda stream, n=name, co=cout, ci=cin, k=k: L.check(lib.offk_permute_weight(
-                    _ptr(self.dwp[n]), _ptr(gr[n + ".weight"]), co, ci, k, k, 2, stream), "unpermute " + n), "unpermute " + name,
-                    reads=[self.dwp[name]], writes=[gr[name + ".weight"]], lane=1))
+        # OHWI -> OIHW accumulation of every KxK weight gradient: one launch
+        kxk = [(name, cout, cin, k) for name, cout, cin, k, _, _ in S.STAGE_CONVS if k > 1]
+        self._unperm = (L.OffkPermute * len(kxk))()
+        for i, (name, cout, cin, k) in enumerate(kxk):
+            it = self._unperm[i]
+            it.src, it.dst = self.dwp[name].data_ptr(), gr[name + ".weight"].data_ptr()
+            it.cout, it.cin, it.kh, it.kw = cout, cin, k, k
+        post = [_nm(lambda stream: L.check(lib.offk_permute_weight_batch(len(kxk), self._unperm, 2, stream), "unpermute"),
+                    "unpermute_kxk_weight_grads", reads=[self.dwp_flat], writes=[gr[n + ".weight"] for n, _, _, _ in kxk], lane=1)]
         self.fwd_steps = pre + fwd
         # kernels of liboffk launched per pass (cudaMemsetAsync zero-fills are not kernels)
         count = lambda steps: sum(len([n for n in _names(st) if not _is_memset(n)]) for st in steps)
