@@ -251,8 +251,6 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     __syncwarp();
   } else if (nkb > 0) {
     // ================= epilogue (warps 2-9) =================
-    mbar_wait(smem_u32(&sh->accum_full), 0u);
-    tc_fence_after();
     const int ew = warp - 2;                                     // 0..7
     const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
     const int half = ew >> 2;                                    // which 16 columns of a 32-column chunk
@@ -265,8 +263,32 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       const int trow = quad * 32 + lane;                         // accumulator row this thread drains
       const int rsub = lane >> 3, cq = lane & 7;                 // read-back: 4 rows per warp pass, 8 float4 per row
       const int nchunks = (bn + 31) >> 5;
+      // The four output rows this thread stores, their table entries and the column bases are fetched while the main
+      // loop still runs (they sat on the critical path of every chunk before).  out_vec contract: the column tables are
+      // contiguous, col[n] = col[0] + n.
+      int r_out[TC_BM / 32], r_gate[TC_BM / 32], r_add[TC_BM / 32];
+      bool r_ok[TC_BM / 32];
+#pragma unroll
+      for (int it = 0; it < TC_BM / 32; ++it) {
+        const int m = m0 + it * 32 + ew * 4 + rsub;
+        r_ok[it] = m < m_lim;
+        r_out[it] = r_gate[it] = r_add[it] = 0;
+        if (r_ok[it]) {
+          const EpiRow er = epi_row(g, m);
+          r_out[it] = er.out; r_gate[it] = er.gate; r_add[it] = er.add;
+        }
+      }
+      const int oc0 = __ldg(g.out_col);
+      const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
+      const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
+      mbar_wait(smem_u32(&sh->accum_full), 0u);
+      tc_fence_after();
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t stg = stg0 + (uint32_t)(c & 1) * (TC_BM * TM_EPI_PITCH * 4);
+        const int n = n0 + c * 32 + cq * 4;
+        const bool nvalid = n < g.N && c * 32 + cq * 4 < bn;
+        float4 bias4 = f4zero();
+        if (nvalid && g.bias && !atomic) bias4 = ldg128(g.bias + n);      // in flight across the TMEM drain below
         if (c * 32 + half * 16 < bn) {
           float v[16];
           tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16), v);
@@ -275,20 +297,44 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           for (int j = 0; j < 16; j += 4) sts128(dst + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int n = n0 + c * 32 + cq * 4;
-        if (n < g.N && c * 32 + cq * 4 < bn) {
+        if (nvalid) {
+          const bool gated = g.gate && n >= g.gate_col0;
+          // all global operands of the four rows first (independent loads in flight together), then the math + stores
+          float4 gt[TC_BM / 32], ad[TC_BM / 32];
 #pragma unroll
           for (int it = 0; it < TC_BM / 32; ++it) {
-            const int row = it * 32 + ew * 4 + rsub;
-            const int m = m0 + row;
-            if (m < m_lim) {
-              float4 v;
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                           : "r"(stg + (uint32_t)(row * TM_EPI_PITCH + cq * 4) * 4));
-              const EpiRow er = epi_row(g, m);
-              epi_store4(g, er, n, v, atomic);
+            gt[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+            ad[it] = f4zero();
+            if (r_ok[it] && !atomic) {
+              if (gated) gt[it] = ldg128(g.gate + (r_gate[it] + gc0 + n));
+              if (g.addend) ad[it] = ldg128(g.addend + (r_add[it] + ac0 + n));
             }
+          }
+#pragma unroll
+          for (int it = 0; it < TC_BM / 32; ++it) {
+            if (!r_ok[it]) continue;
+            const int row = it * 32 + ew * 4 + rsub;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stg + (uint32_t)(row * TM_EPI_PITCH + cq * 4) * 4));
+            float* o = g.out + (r_out[it] + oc0 + n);
+            if (atomic) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+              continue;
+            }
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (n < g.relu_pre_cols) v = f4relu(v);             // relu_pre_cols is a multiple of 4 on this path
+            const float4 t = gt[it];
+            if (gated && g.gate_first) {
+              v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+            }
+            v.x += ad[it].x; v.y += ad[it].y; v.z += ad[it].z; v.w += ad[it].w;
+            if (gated && !g.gate_first) {
+              v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+            }
+            if (g.relu_post) v = f4relu(v);
+            *reinterpret_cast<float4*>(o) = v;
           }
         }
       }
@@ -297,6 +343,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       const bool mvalid = m < m_lim;
       EpiRow er = {0, 0, 0, false};
       if (mvalid) er = epi_row(g, m);
+      mbar_wait(smem_u32(&sh->accum_full), 0u);
+      tc_fence_after();
       const int nchunks = bn >> 4;
       for (int c = half; c < nchunks; c += 2) {
         float v[16];
