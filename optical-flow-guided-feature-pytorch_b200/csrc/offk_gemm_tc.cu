@@ -440,29 +440,81 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
 
   // ================= epilogue (warps 0-7) =================
   if (warp < 8 && nkb > 0) {
-    mbar_wait(smem_u32(&sh->accum_full), 0u);
-    tc_fence_after();
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
     const int m = m0 + quad * 32 + lane;
     const bool mvalid = m < g.M;
+    // table entries first: they are in flight while the last MMAs retire
     EpiRow er = {0, 0, 0, false};
     if (mvalid) er = epi_row(g, m);
     const bool atomic = (g.split_k > 1) || g.atomic_out;
+    const bool vec = g.out_vec && !er.ones;
+    // out_vec contract: column tables are contiguous (col[n] = col[0] + n)
+    const int oc0 = __ldg(g.out_col);
+    const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
+    const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
+    mbar_wait(smem_u32(&sh->accum_full), 0u);
+    tc_fence_after();
     const int nchunks = bn >> 4;
     for (int c = (warp >> 2); c < nchunks; c += 2) {  // warps 0-3 even 16-column chunks, 4-7 odd ones
+      const int nb = n0 + c * 16;
+      // Operands first (independent loads in flight), then the TMEM drain -- tcgen05.ld is .sync.aligned, so it is issued
+      // by the whole warp outside any lane-divergent branch -- then math + stores.
+      float4 gt[4], ad[4];
+      int oc[16];
+      const bool lane_vec = mvalid && vec;
+      if (lane_vec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = nb + 4 * j;
+          ad[j] = f4zero(); gt[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (n < g.N && !atomic) {
+            if (g.gate && n >= g.gate_col0) gt[j] = ldg128(g.gate + (er.gate + gc0 + n));
+            if (g.addend) ad[j] = ldg128(g.addend + (er.add + ac0 + n));
+          }
+        }
+      } else if (mvalid) {            // scalar path (weight gradients: out_col is a stride table)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) oc[j] = (nb + j < g.N) ? __ldg(g.out_col + nb + j) : 0;
+      }
       float v[16];
       tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16), v);
-      if (mvalid) {
-        if (g.out_vec && !er.ones) {
+      if (lane_vec) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const int n = n0 + c * 16 + j;
-            if (n < g.N) epi_store4(g, er, n, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), atomic);
+        for (int j = 0; j < 4; ++j) {
+          const int n = nb + 4 * j;
+          if (n >= g.N) continue;
+          float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          float* o = g.out + (er.out + oc0 + n);
+          if (atomic) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+            continue;
           }
+          const bool gated = g.gate && n >= g.gate_col0;
+          if (g.bias) {
+            const float4 b = ldg128(g.bias + n);
+            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+          }
+          if (n < g.relu_pre_cols) x = f4relu(x);
+          const float4 t = gt[j];
+          if (gated && g.gate_first) {
+            x.x = t.x > 0.f ? x.x : 0.f; x.y = t.y > 0.f ? x.y : 0.f; x.z = t.z > 0.f ? x.z : 0.f; x.w = t.w > 0.f ? x.w : 0.f;
+          }
+          x.x += ad[j].x; x.y += ad[j].y; x.z += ad[j].z; x.w += ad[j].w;
+          if (gated && !g.gate_first) {
+            x.x = t.x > 0.f ? x.x : 0.f; x.y = t.y > 0.f ? x.y : 0.f; x.z = t.z > 0.f ? x.z : 0.f; x.w = t.w > 0.f ? x.w : 0.f;
+          }
+          if (g.relu_post) x = f4relu(x);
+          *reinterpret_cast<float4*>(o) = x;
+        }
+      } else if (mvalid) {
+        if (atomic && !er.ones) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < g.N) atomicAdd(g.out + (er.out + oc[j]), v[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c * 16 + j;
+            const int n = nb + j;
             if (n < g.N) epi_store(g, er, n, v[j], atomic);
           }
         }
