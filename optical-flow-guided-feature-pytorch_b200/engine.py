@@ -739,7 +739,8 @@ class OFFEngine:
         # weight re-layouts before the forward (one launch), OHWI -> OIHW weight gradients after the backward
         wc, wci, pflat = self.wc_flat, self.wc_idx, self.params_flat
         pre = [_nm(lambda stream: L.check(lib.offk_gather_copy(_ptr(pflat), _ptr(wci), _ptr(wc), wc.numel(), stream),
-                                          "weight copies"), "weight_copies", writes=[wc])]
+                                          "weight copies"), "weight_copies", writes=[wc],
+                   lane=int(os.environ.get("OFFK_WC_LANE", "2")))]
         # OHWI -> OIHW accumulation of every KxK weight gradient: one launch
         kxk = [(name, cout, cin, k) for name, cout, cin, k, _, _ in S.STAGE_CONVS if k > 1]
         self._unperm = (L.OffkPermute * len(kxk))()
