@@ -482,6 +482,46 @@ def test_stencil_batch_equals_single_launches(dev):
     for gd, w, bias, bufs in keep:
         assert torch.equal(bufs["b"][0], bufs["s"][0])                                   # dG, dD: bit-exact
         assert _rel(bufs["b"][1], bufs["s"][1].cpu()) < 1e-5 and _rel(bufs["b"][2], bufs["s"][2].cpu()) < 1e-5  # atomics: order
+    # the two halves as separate launches (offk_stencil_diff_bwd_batch_part) = the one-launch backward
+    parts = []
+    for i in range(n):
+        gd, w, bias, bufs = keep[i]
+        dgd, dw, db = torch.full_like(gd, float("nan")), torch.zeros_like(w), torch.zeros_like(bias)
+        ios[i].dg, ios[i].dd, ios[i].dw, ios[i].dbias = dgd.data_ptr(), dgd.data_ptr() + 4 * Cg, dw.data_ptr(), db.data_ptr()
+        parts.append((dgd, dw, db))
+    L.check(lib.offk_stencil_diff_bwd_batch_part(n, descs, ios, 2, None), "bwd spatial half")
+    L.check(lib.offk_stencil_diff_bwd_batch_part(n, descs, ios, 1, None), "bwd temporal half")
+    torch.cuda.synchronize()
+    for (gd, w, bias, bufs), (dgd, dw, db) in zip(keep, parts):
+        assert torch.equal(dgd, bufs["b"][0])
+        assert _rel(dw, bufs["b"][1].cpu()) < 1e-5 and _rel(db, bufs["b"][2].cpu()) < 1e-5
+
+
+def test_layout_helpers(dev):
+    """offk_nchw_to_nhwc (the 7x7 tap copy) and offk_permute_weight_batch (all KxK weight-gradient un-permutes in one
+    launch) against torch permutes: pure data movement, bit-exact."""
+    from off_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(5)
+    for n, c, hw in ((5, 1024, 49), (3, 70, 36), (2, 33, 1)):
+        x = torch.randn(n, c, hw, device=dev)
+        y = torch.full((n, hw, c), float("nan"), device=dev)
+        L.check(lib.offk_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), n, c, hw, None), "nchw_to_nhwc")
+        torch.cuda.synchronize()
+        assert torch.equal(y, x.permute(0, 2, 1).contiguous())
+    shapes = [(64, 320, 7), (128, 96, 5), (40, 33, 3), (16, 64, 1)]
+    items = (L.OffkPermute * len(shapes))()
+    keep = []
+    for it, (co, ci, k) in zip(items, shapes):
+        src = torch.randn(co, k, k, ci, device=dev)                 # OHWI accumulator
+        dst = torch.randn(co, ci, k, k, device=dev)                 # OIHW gradient, accumulated into
+        want = dst + src.permute(0, 3, 1, 2)
+        it.src, it.dst, it.cout, it.cin, it.kh, it.kw = src.data_ptr(), dst.data_ptr(), co, ci, k, k
+        keep.append((src, dst, want))
+    L.check(lib.offk_permute_weight_batch(len(shapes), items, 2, None), "permute_weight_batch")
+    torch.cuda.synchronize()
+    for src, dst, want in keep:
+        assert torch.equal(dst, want)
 
 
 def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit, tol_grad):
