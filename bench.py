@@ -233,7 +233,7 @@ def run_ours(args):
         flush_r = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
         flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        stage_levels = {st: [t for t in S.LEVELS if S.LEVEL_STAGE[t] == st] for st in S.STAGES}
+        stage_levels = eng.stencil_fwd_tags                  # launch name -> the OFF units it serves
         lvl_bytes = {t: 4.0 * s * s * (S.GEN_C * eng.N + S.DOWN_C * eng.P + S.UNIT_C * eng.P)     # read G, read D, write M
                      for t, (cin, s) in S.LEVELS.items()}
         tot_ms, tot_bytes, per_stage = 0.0, 0.0, {}
@@ -310,15 +310,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         eng.single_stream = False
         in_step_ms = sum(a.elapsed_time(b) for a, b in evs) / 5
-        roof = {"bound": "hbm", "kernel": "stencil_diff_fwd_kernel (3 launches per step: one per stage-fusion buffer, 9 OFF units)",
+        roof = {"bound": "hbm", "kernel": f"stencil_diff_fwd_kernel ({len(per_stage)} launches per step: {' | '.join(per_stage)} stage units; 9 OFF units)",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES, "bytes_per_step": tot_bytes,
                 "per_stage": per_stage, "backward": bwd,
                 "in_step": {"GBs": round(tot_bytes / (in_step_ms * 1e-3) / 1e9, 1), "us": round(in_step_ms * 1e3, 1),
-                            "note": "same 3 launches timed inside forward passes (inputs fresh from the unit GEMMs, partly L2-resident)"},
+                            "note": "same launches timed inside forward passes (inputs fresh from the unit GEMMs, partly L2-resident)"},
                 "note": "algorithmic bytes 4*S^2*(128*N + 32*P + 160*P) per level (read G once, read D once, write the "
                         "160-channel slice once); `achieved` = cold launches, L2 flushed before each; traffic = ncu "
-                        "dram__bytes_read+write summed over the same 3 launches (profiles/)"}
+                        "dram__bytes_read+write summed over the forward stencil launches of one step (profiles/)"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

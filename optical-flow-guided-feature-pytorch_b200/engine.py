@@ -506,17 +506,24 @@ class OFFEngine:
             k4_by_stage[st] += grp
         # K2: ONE stencil launch per stage-fusion buffer (its units' GEMMs precede it on the same lane)
         tags = list(S.LEVELS)
-        for st, lv_tags in stage_levels.items():
+        # forward stencil launches: the 28-stage units on their own (they open the critical path); the 14- and 7-stage
+        # units together (the 7x7 levels are 7 MB each: on their own they run at a fifth of the bandwidth)
+        merge = os.environ.get("OFFK_STENCIL_FWD_MERGE", "1") == "1"
+        groups = [("28", ["28"]), ("14+7", ["14", "7"])] if merge else [(st, [st]) for st in S.STAGES]
+        self.stencil_fwd_tags = OrderedDict()         # launch name -> level tags (bench.py: algorithmic bytes)
+        for gname, sts in groups:
+            lv_tags = [t for st in sts for t in stage_levels[st]]
             i0, n = tags.index(lv_tags[0]), len(lv_tags)
             assert tags[i0:i0 + n] == lv_tags
 
-            def k2(stream, i0=i0, n=n, st=st):
+            def k2(stream, i0=i0, n=n, gname=gname):
                 L.check(lib.offk_stencil_diff_fwd_batch(n, C.byref(self._st_desc[i0]), C.byref(self._st_io[i0]), stream),
-                        "stencil_fwd_" + st)
-            step = _nm(k2, "stencil_fwd_" + st, reads=[bf["gd_" + t] for t in lv_tags], writes=[bf["F" + st]],
-                       lane=fwd_lane[st])
+                        "stencil_fwd_" + gname)
+            step = _nm(k2, "stencil_fwd_" + gname, reads=[bf["gd_" + t] for t in lv_tags], writes=[bf["F" + st] for st in sts],
+                       lane=fwd_lane[sts[0]])
             fwd.append(step)
-            self.stencil_fwd_steps[st] = step
+            self.stencil_fwd_steps[gname] = step
+            self.stencil_fwd_tags[gname] = lv_tags
         # K3: the backward of all nine units in ONE launch (every stage gradient dF* is complete by then)
         grad3 = [gr[f"motion_spatial_grad_{t}.{k}"] for t in tags for k in ("weight", "bias")] if self.variant == "rgb" else []
 
