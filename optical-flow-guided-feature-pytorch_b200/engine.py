@@ -307,19 +307,16 @@ class OFFEngine:
                 views.append(("wp", name, off, (cout, k, k, cin)))
                 off += oihw.size
             if stride == 1:
-                idx.append(oihw[:, :, ::-1, ::-1].transpose(1, 2, 3, 0).reshape(-1))
+                idx.append(p_off + T.dgrad_class_weight_index(cout, cin, k, 1, pad, 0, 0))
                 views.append(("wd", name, off, (cin, k * k * cout)))
                 off += oihw.size
             else:
-                # one [cin, R, Q, cout] block per stride-parity class (a, b) of the input pixel: the taps r = r0 + s*i
-                # that reach the class, walked in reverse (tables.conv_dgrad_specs)
+                # one [cin, R, Q, cout] block per stride-parity class (a, b) of the input pixel
                 for a in range(stride):
                     for b in range(stride):
-                        rs = np.arange((a + pad) % stride, k, stride)[::-1]
-                        qs = np.arange((b + pad) % stride, k, stride)[::-1]
-                        sub = oihw[:, :, rs][:, :, :, qs].transpose(1, 2, 3, 0)
-                        idx.append(sub.reshape(-1))
-                        views.append(("wd", (name, a, b), off, (cin, len(rs) * len(qs) * cout)))
+                        sub = p_off + T.dgrad_class_weight_index(cout, cin, k, stride, pad, a, b)
+                        idx.append(sub)
+                        views.append(("wd", (name, a, b), off, (cin, sub.size // cin)))
                         off += sub.size
         self.wc_idx = torch.from_numpy(np.concatenate(idx).astype(np.int32)).to(self.device)
         self.wc_flat = torch.zeros(off, device=self.device)

@@ -239,6 +239,35 @@ def conv_dgrad_specs(g: ConvGeom, x_layout: str = "nchw", y_layout: str = "nchw"
     return specs
 
 
+def dgrad_class_weight_index(cout: int, cin: int, k: int, stride: int, pad: int, a: int, b: int) -> np.ndarray:
+    """Element indices into an OIHW weight [cout, cin, k, k] that lay out the B operand of the data-gradient GEMM of
+    stride-parity class (a, b) as [cin, R, Q, cout]: only the taps r = r0 + stride*i (r0 = (a + pad) % stride) reach
+    input rows of parity a, and the im2col form of that class walks them in reverse (``conv_dgrad_specs`` ``extra``).
+    For stride 1 this is the whole filter flipped: dX = conv(dY, flip(W)^T)."""
+    oihw = np.arange(cout * cin * k * k, dtype=np.int64).reshape(cout, cin, k, k)
+    rs = np.arange((a + pad) % stride, k, stride)[::-1]
+    qs = np.arange((b + pad) % stride, k, stride)[::-1]
+    return oihw[:, :, rs][:, :, :, qs].transpose(1, 2, 3, 0).reshape(-1)
+
+
+def emulate_dgrad_class(g: ConvGeom, spec: GemmSpec, dy_nhwc: np.ndarray, w_oihw: np.ndarray) -> np.ndarray:
+    """numpy mirror of what the TMA-im2col kernel computes for one stride-parity class of the data gradient
+    (OFFK_TGEMM_FREE_GEOM): a stride-1 correlation over dY [n, hout, wout, cout] with the class's R x Q taps, output
+    grid hc x wc, zero padding pad_h rows above / pad_w columns left.  Returns D[M = n*hc*wc, N = cin] (float64)."""
+    ex = spec.extra
+    R, Q, hc, wc = len(ex["rs"]), len(ex["qs"]), ex["hc"], ex["wc"]
+    idx = dgrad_class_weight_index(g.cout, g.cin, g.kh, g.stride, g.pad, ex["a"], ex["b"])
+    wcls = w_oihw.reshape(-1).astype(np.float64)[idx].reshape(g.cin, R, Q, g.cout)
+    dy = dy_nhwc.astype(np.float64)
+    pad = np.zeros((g.n_img, hc + R - 1 + g.hout, wc + Q - 1 + g.wout, g.cout))
+    pad[:, ex["pad_h"]:ex["pad_h"] + g.hout, ex["pad_w"]:ex["pad_w"] + g.wout] = dy
+    out = np.zeros((g.n_img, hc, wc, g.cin))
+    for r in range(R):
+        for q in range(Q):
+            out += pad[:, r:r + hc, q:q + wc] @ wcls[:, r, q].T
+    return out.reshape(-1, g.cin)
+
+
 def check_modes(spec: GemmSpec):
     """Assert the promises behind the vector load / store modes (contiguity, alignment, shared validity)."""
     def quads(tab, n):

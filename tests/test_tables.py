@@ -113,3 +113,28 @@ def test_tables_match_conv(case):
     assert not np.isnan(got).any()
     np.testing.assert_allclose(got, x.grad.numpy(), atol=1e-9)
     assert np.isnan(np.delete(dxbuf, np.s_[xco:xco + cin], axis=1)).all()
+
+
+@pytest.mark.parametrize("n,cin,h,cout,k,st,p", [(2, 8, 28, 4, 7, 2, 3), (3, 6, 14, 8, 5, 2, 2), (2, 4, 9, 3, 3, 1, 1), (1, 5, 11, 2, 4, 3, 1)])
+def test_dgrad_class_as_stride1_correlation(n, cin, h, cout, k, st, p):
+    """Host logic behind the TMA data gradients (OFFK_TGEMM_FREE_GEOM): every stride-parity class of dX equals a
+    stride-1 correlation over dY with the class's taps in reverse order, the padding / output grid that
+    conv_dgrad_specs records in ``extra`` and the weights gathered by dgrad_class_weight_index -- checked against
+    autograd of conv2d."""
+    g = T.ConvGeom(n, cin, h, h, cout, k, k, st, p)
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((cout, cin, k, k))
+    dy = rng.standard_normal((n, cout, g.hout, g.wout))
+    x = torch.zeros(n, cin, h, h, dtype=torch.float64, requires_grad=True)
+    (torch.nn.functional.conv2d(x, torch.from_numpy(w), None, st, p) * torch.from_numpy(dy)).sum().backward()
+    want = x.grad.numpy()
+    got = np.zeros_like(want)
+    seen = np.zeros((h, h), bool)
+    for spc in T.conv_dgrad_specs(g, "nhwc", "nhwc", "nhwc"):
+        ex = spc.extra
+        assert ex["pad_h"] >= 0 and ex["pad_w"] >= 0
+        D = T.emulate_dgrad_class(g, spc, dy.transpose(0, 2, 3, 1), w).reshape(n, ex["hc"], ex["wc"], cin)
+        got[:, :, ex["a"]::st, ex["b"]::st] = D.transpose(0, 3, 1, 2)
+        seen[ex["a"]::st, ex["b"]::st] = True
+    assert seen.all()
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-10)
