@@ -65,6 +65,9 @@ def test_ctypes_structs_match_the_c_header():
              offsetof(offk_gemm_t, split_k), sizeof(offk_stencil_t), offsetof(offk_stencil_t, seed),
              offsetof(offk_stencil_t, keep_mask), sizeof(offk_stencil_io_t), offsetof(offk_stencil_io_t, dg_fs),
              offsetof(offk_stencil_io_t, dbias));
+      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(offk_tgemm_t), offsetof(offk_tgemm_t, a_kind), offsetof(offk_tgemm_t, wout),
+             offsetof(offk_tgemm_t, geom_flags), offsetof(offk_tgemm_t, pad_w), offsetof(offk_tgemm_t, tmap_a),
+             sizeof(offk_permute_t));
       return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -75,7 +78,9 @@ def test_ctypes_structs_match_the_c_header():
     got = [int(x) for x in out]
     assert got == [C.sizeof(L.OffkIdx), C.sizeof(L.OffkGemm), L.OffkGemm.out.offset, L.OffkGemm.split_k.offset,
                    C.sizeof(L.OffkStencil), L.OffkStencil.seed.offset, L.OffkStencil.keep_mask.offset,
-                   C.sizeof(L.OffkStencilIO), L.OffkStencilIO.dg_fs.offset, L.OffkStencilIO.dbias.offset]
+                   C.sizeof(L.OffkStencilIO), L.OffkStencilIO.dg_fs.offset, L.OffkStencilIO.dbias.offset,
+                   C.sizeof(L.OffkTGemm), L.OffkTGemm.a_kind.offset, L.OffkTGemm.wout.offset, L.OffkTGemm.geom_flags.offset,
+                   L.OffkTGemm.pad_w.offset, L.OffkTGemm.tmap_a.offset, C.sizeof(L.OffkPermute)]
 
 
 def test_cpu_calls_fail_loudly():
@@ -101,3 +106,16 @@ def test_engine_plan_builds_without_a_gpu():
     assert abs(eng.flops_fwd / 1e9 - gf) / gf < 0.01
     flow = E.OFFEngine(1, 4, "flow", "cpu", "fp32", tap_grads=True)
     assert flow.consensus and "motion_spatial_grad_3a.weight" not in flow.params
+    # tf32 plan: the 7x7 taps go through a channels-last copy, every stride-2 data-gradient class has its own weight
+    # block, the forward stencil is two launches and all KxK weight gradients are un-permuted by one
+    names = eng.launch_names()
+    assert "tapT_5a" in names and "tapT_5b" in names and "tapT_3a" not in names
+    assert [n for n in names if n.startswith("stencil_fwd_")] == ["stencil_fwd_28", "stencil_fwd_14+7"]
+    assert names.count("unpermute_kxk_weight_grads") == 1 and "stencil_bwd" in names
+    for conv in ("motion_conv_trans_28", "motion_conv_trans_14"):
+        assert all((conv, a, b) in eng.wd for a in (0, 1) for b in (0, 1))
+    assert "tapT_5a" not in flow.launch_names()          # fp32 exact mode reads the NCHW taps through the gather kernel
+    # hazard analysis: a step never waits on its own lane, and every cross-lane wait points backwards
+    for sched in (eng.fwd_sched, eng.bwd_sched):
+        for i, ws in enumerate(sched.waits):
+            assert all(j < i and sched.lanes[j] != sched.lanes[i] for j in ws)
