@@ -94,8 +94,9 @@ int offk_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* l2_
 #define OFFK_LOAD_SCALAR_ROW 0 /* 4-byte loads, lanes walk rows (source contiguous along m / n)                 */
 #define OFFK_LOAD_SCALAR_K   1 /* 4-byte loads, lanes walk k    (source contiguous along k)                     */
 #define OFFK_LOAD_VEC_K      2 /* 16-byte loads of 4 consecutive k (K % 4 == 0): NHWC activations, dense weights */
-#define OFFK_LOAD_VEC_ROW    3 /* 16-byte loads of 4 consecutive rows, 4x4 register transpose into the K-major
-                                  tile: NCHW taps as A(m = pixel), NHWC tensors in weight-gradient GEMMs       */
+#define OFFK_LOAD_VEC_ROW    3 /* 16-byte cp.async of 4 consecutive rows straight into the MN-major swizzled tile (the
+                                  operand is then marked MN-major for tcgen05.mma; nothing is transposed): NCHW taps
+                                  as A(m = pixel), channels-last tensors in weight- and data-gradient GEMMs        */
 
 typedef struct offk_idx {
   int32_t off; /* element offset contribution                        */
@@ -147,10 +148,13 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
 /* ------------------------------------------------------------------------
  * TMA-fed GEMM: the same contraction and epilogue as offk_gather_gemm (bias, ReLU prefix, ReLU' gate, residual
  * add, split-K / atomic accumulation, output through out_row / out_col), but the operand tiles are fetched by the
- * Tensor Memory Accelerator (cp.async.bulk.tensor) instead of index-table gathers.  Used for every conv / FC of
- * the OFF sub-network whose input is a channels-last activation: the residual-block 1x1 convs and FC heads
- * (RGB_OFF.py:659-685,764-780,787,793,835-847) as dense 2-D tiles, the stage-entry 7x7/5x5/3x3 convs and the
- * bottleneck 3x3s (:657,661,672,681,762,766,775,777,833,837) through TMA im2col mode.
+ * Tensor Memory Accelerator (cp.async.bulk.tensor) instead of index-table gathers.  Used for the fused 1x1 conv of the
+ * nine OFF units on the NCHW taps (RGB_OFF.py:597-598,609-610 and the eight copies) and its weight gradient, for every
+ * conv / FC of the OFF sub-network whose input is a channels-last activation -- the residual-block 1x1 convs and FC
+ * heads (:659-685,764-780,787,793,835-847) as dense 2-D tiles, the stage-entry 7x7/5x5/3x3 convs and the bottleneck
+ * 3x3s (:657,661,672,681,762,766,775,777,833,837) through TMA im2col mode -- and for their data gradients (autograd,
+ * train_off.py:136-146): a stride-1 conv's dX is a conv over dY with flipped weights, a stride-2 conv's dX is one
+ * OFFK_TGEMM_FREE_GEOM correlation over dY per stride-parity class of the input pixel.
  *   g.a_src / g.b_src : operand base pointers (16-byte aligned); the a_row/a_col/b_row/b_col tables are ignored
  *   A dense  : A(m,k) = a_src[m*lda + k]
  *   A im2col : a_src = channels-last [n_img, hin, win, ctot]; channels [a_coff, a_coff+cin) feed the conv;
@@ -158,6 +162,9 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
  *   A nchw   : a_src = NCHW [n_img, cin, hin*win] (pixels contiguous); fetched as the MN-major tcgen05 operand, so the
  *              NCHW -> channels-last conversion of the unit's fused 1x1 conv executes no transpose
  *   B dense  : B(n,k) = b_src[n*ldb + k]   (weights [cout, K])
+ *   weight-gradient kinds (A nchw_t / im2col_t with B dense_t): see the OFFK_TMA_* definitions below; the all-ones
+ *   row g.a_ones_row (bias gradient) is synthesised inside the kernel; out_vec must be 0
+ *   with out_vec = 1 the out / gate / addend column tables must be contiguous (col[n] = col[0] + n)
  * offk_tma_gemm_prepare() encodes the two CUtensorMap objects into the descriptor (host only, no device memory);
  * call it again whenever a pointer or shape changes.  precision is always OFFK_PREC_TF32.
  * ---------------------------------------------------------------------- */
