@@ -1,13 +1,14 @@
 """OFFEngine: the OFF sub-network (RGB_OFF.py:596-860 / Flow_OFF.py:606-884) as a static plan of
 liboffk kernel launches over preallocated fp32 buffers.
 
-Layout: the taps arrive NCHW (the reference's layout); the unit's fused 1x1 GEMM converts to channels-last in
-its epilogue and everything downstream (reduced features, stage-fusion buffers, residual blocks, gradients) is
-NHWC, so that every implicit-GEMM operand is fetched with 16-byte loads.
+Layout: the taps arrive NCHW (the reference's layout); the unit's fused 1x1 GEMM reads them in place through a TMA
+tensor map (MN-major operand), converts to channels-last in its epilogue, and everything downstream (reduced
+features, stage-fusion buffers, residual blocks, gradients) is NHWC, so that every operand tile is a TMA box or a
+16-byte cp.async gather.
 
-Every step is one C-ABI call with a descriptor bound at plan-build time, so a forward or backward
-pass is a flat list of launches on one stream: cheap to issue and capturable in a CUDA graph.
-PyTorch supplies device memory and streams only.
+Every step is one C-ABI call with a descriptor bound at plan-build time; a forward or backward pass is a flat list of
+launches spread over up to three streams by a hazard-derived schedule (class Schedule).  PyTorch supplies device
+memory and streams only.
 """
 from __future__ import annotations
 
@@ -76,7 +77,7 @@ class Gemm:
         if tile_n == 0 and split_k == 1:
             tile_n = _auto_tile_n(spc.M, spc.N, isinstance(self, TGemm))
         d.split_k, d.tile_n = split_k, tile_n
-        d.out_vec = spc.out_vec if (gate_tabs is None or True) else 0
+        d.out_vec = spc.out_vec
         T.check_modes(spc)
         self.desc = d
         self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out)
