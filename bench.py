@@ -321,7 +321,7 @@ def run_ours(args):
                         "dram__bytes_read+write summed over the forward stencil launches of one step (profiles/)"}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is timed at N = 1 only
         rate, sec, threads = cpu_oracle_rate(args.cpu_clips, Lg, args.variant, 3, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.cpu_clips} clips x {Lg} segments, fwd+bwd, fp32, 3 timed steps ({sec:.2f} s/step)"}
