@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--length", type=int, default=3, help="segments per clip")
     ap.add_argument("--variant", default="rgb", choices=["rgb", "flow"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
-    ap.add_argument("--cpu-clips", type=int, default=4, help="clips per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips per CPU-baseline step (0 = --batch: the same batch as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -88,15 +88,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    rate, sec, threads = cpu_oracle_rate(args.cpu_clips, args.length, args.variant, steps, warmup)
-    sample = f"{args.cpu_clips} clips x {args.length} segments per step (same shapes per clip as the GPU workload), fp32"
+    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    clips = args.cpu_clips or args.batch
+    rate, sec, threads = cpu_oracle_rate(clips, args.length, args.variant, steps, warmup)
+    sample = (f"{clips} clips x {args.length} segments per step (one GPU's batch), fp32, {steps} timed steps after {warmup} "
+              f"warm-up ({sec:.2f} s/step)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
         "config": {"workload": f"{args.variant.upper()}_OFF OFF sub-network fwd+bwd, {args.batch} clips x {args.length} "
-                               f"segments per GPU (BASELINE config 2); CPU arm timed on a bounded sample",
+                               f"segments per GPU (BASELINE config 2); CPU arm: the same batch per step, a bounded number of steps",
                    "sample": sample},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -322,9 +324,11 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is timed at N = 1 only
-        rate, sec, threads = cpu_oracle_rate(args.cpu_clips, Lg, args.variant, 3, 1)
+        clips = args.cpu_clips or B
+        rate, sec, threads = cpu_oracle_rate(clips, Lg, args.variant, 6, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_clips} clips x {Lg} segments, fwd+bwd, fp32, 3 timed steps ({sec:.2f} s/step)"}
+               "sample": f"{clips} clips x {Lg} segments (the GPU arm's batch), fwd+bwd, fp32, 6 timed steps after 1 warm-up "
+                         f"({sec:.2f} s/step)"}
 
     if rank == 0:
         line = {
