@@ -165,3 +165,44 @@ def test_bad_arguments_raise(dev):
     x = torch.zeros(4, device=dev)
     with pytest.raises(RuntimeError):
         L.check(lib.offk_avgpool_drop_fwd(x.data_ptr(), 1, 8, 49, 4, 0, 0, None, 0, 0.0, 1.0, x.data_ptr(), None), "pool")
+
+
+def test_reference_model_classes(dev):
+    """BNInception_OFF / bninception_off under the reference's module names: RGB_OFF_forward returns the per-pair tuple of
+    RGB_OFF.py:860, Flow_OFF.forward the consensus tuple of Flow_OFF.py:884 or the modality_fuse sum (:881); the OFF
+    outputs equal OFFSubNetwork's (same engine), the backbone score goes through the segment consensus."""
+    from off_b200 import RGB_OFF, Flow_OFF
+    from off_b200.modules import OFFSubNetwork
+    B, Lg, NC = 2, 3, 101
+    taps = {k: v.to(dev) for k, v in O.make_taps(4, B, Lg).items()}
+    score = torch.randn(B * Lg, NC, device=dev)
+
+    class Backbone(torch.nn.Module):
+        def forward(self, x):
+            return taps, score
+
+    for mod, variant in ((RGB_OFF, "rgb"), (Flow_OFF, "flow")):
+        prm = O.make_params(4, variant)
+        ref = OFFSubNetwork(B, Lg, variant, device=dev).eval()
+        ref.load_state_dict(prm, strict=False)                    # (the frozen Sobel taps are not in make_params)
+        want7, _, want14 = [t.clone() for t in ref(taps)]
+        m = mod.bninception_off(NC, B, Lg, backbone=Backbone(), device=dev).eval()
+        m.load_state_dict(prm, strict=False)                      # strict=False: the stub backbone has no entries
+        x = torch.zeros(B * Lg, 3, 8, 8, device=dev)
+        if variant == "rgb":
+            fc7, sc, fc14 = m.RGB_OFF_forward(x)
+            assert fc7.shape == (B * (Lg - 1), NC) and sc is score
+        else:
+            fc7, sc, fc14 = m(x)
+            assert fc7.shape == (B, NC)
+            assert torch.allclose(sc, score.view(B, Lg, NC).mean(1), atol=1e-6)
+        # same plan, same weights; split-K partial sums land in atomic order, hence not bit-for-bit
+        assert torch.allclose(fc7, want7, rtol=1e-3, atol=1e-4) and torch.allclose(fc14, want14, rtol=1e-3, atol=1e-4)
+        if variant == "flow":
+            m.modality_fuse = True
+            fused = m(x)
+            assert torch.allclose(fused, want7 + score.view(B, Lg, NC).mean(1) + want14, rtol=1e-3, atol=1e-3)
+    # without a backbone the taps are the input
+    m = RGB_OFF.bninception_off(NC, B, Lg, device=dev).eval()
+    fc7, sc, fc14 = m.RGB_OFF_forward(taps)
+    assert sc is None and fc7.shape == (B * (Lg - 1), NC)

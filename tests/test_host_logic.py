@@ -119,3 +119,59 @@ def test_engine_plan_builds_without_a_gpu():
     for sched in (eng.fwd_sched, eng.bwd_sched):
         for i, ws in enumerate(sched.waits):
             assert all(j < i and sched.lanes[j] != sched.lanes[i] for j in ws)
+
+
+def test_reference_model_surface_builds_without_a_gpu():
+    """BNInception_OFF(num_classes, batch, length) / bninception_off(num_classes, batch, num_seg) under the reference's
+    module names (RGB_OFF.py:30-36,1346-1377; Flow_OFF.py:38-51,1371-1385; RGB_OFF_v2.py:43-58,1378-1392): constructor
+    signature, attributes, state_dict keys of the OFF section, the 'motion' parameter filter of train_off.py:40."""
+    import inspect
+    import torch
+    from off_b200 import RGB_OFF, Flow_OFF, RGB_OFF_v2
+    gold = os.path.join(ROOT, "tests", "golden")
+    keys = lambda v: {l.split()[0]: tuple(int(x) for x in l.split()[1:]) for l in open(os.path.join(gold, f"state_dict_keys_{v}.txt"))}
+    for mod, gv in ((RGB_OFF, "rgb"), (Flow_OFF, "flow"), (RGB_OFF_v2, "flow")):
+        assert list(inspect.signature(mod.bninception_off).parameters)[:3] == ["num_classes", "batch", "num_seg"]
+        assert list(inspect.signature(mod.BNInception_OFF.__init__).parameters)[1:4] == ["num_classes", "batch", "length"]
+        m = mod.bninception_off(101, 2, 3, device="cpu")
+        assert isinstance(m, mod.BNInception_OFF) and (m.batch, m.length) == (2, 3) and m.modality_fuse is False
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == keys(gv)
+        assert all("motion" in n for n, p in m.named_parameters() if p.requires_grad)
+        assert m.consensus.consensus_type == "avg"
+        m.eval()
+        assert not m.off.training
+        with pytest.raises(RuntimeError):
+            m.forward(torch.zeros(6, 3, 8, 8)) if gv != "rgb" else m.RGB_OFF_forward(torch.zeros(6, 3, 8, 8))
+    assert RGB_OFF.bninception_off_sobel(101, 1, 3, device="cpu").variant == "rgb"
+    # data flow of the three forwards with the device work stubbed out (shapes and return structure of
+    # RGB_OFF.py:860, Flow_OFF.py:879-884, RGB_OFF_v2.py:891)
+    B, Lg, NC = 2, 3, 101
+
+    class Backbone(torch.nn.Module):
+        def forward(self, x):
+            return {"taps": x.shape[0]}, torch.arange(B * Lg * NC, dtype=torch.float32).reshape(B * Lg, NC), "conv2"
+
+    class Mean(torch.nn.Module):
+        def forward(self, t):
+            return t.mean(dim=1, keepdim=True)
+
+    for mod, per_pair in ((RGB_OFF, True), (Flow_OFF, False), (RGB_OFF_v2, False)):
+        m = mod.bninception_off(NC, B, Lg, device="cpu", backbone=Backbone())
+        n_out = B * (Lg - 1) if per_pair else B
+        object.__setattr__(m, "off", lambda taps, n_out=n_out: (torch.ones(n_out, NC), torch.zeros(n_out, NC), 2 * torch.ones(n_out, NC)))
+        m.consensus = Mean()                                       # CPU stand-in for offk_segment_mean (basic_ops.py:22)
+        x = torch.zeros(B * Lg, 3, 8, 8)
+        if per_pair:
+            fc7, score, fc14 = m.RGB_OFF_forward(x)
+            assert fc7.shape == (B * (Lg - 1), NC) and score.shape == (B * Lg, NC) and fc14[0, 0] == 2
+            assert m(x).shape == (B * Lg, NC)                      # RGB_OFF.forward = backbone classifier (:1340-1344)
+        else:
+            out = m(x)
+            assert len(out) == (4 if mod is RGB_OFF_v2 else 3)
+            fc7, score, fc14 = out[:3]
+            want = torch.arange(B * Lg * NC, dtype=torch.float32).reshape(B, Lg, NC).mean(1)
+            assert fc7.shape == (B, NC) and torch.equal(score, want)
+            if mod is RGB_OFF_v2:
+                assert out[3] == "conv2"
+            m.modality_fuse = True
+            assert torch.equal(m(x), 1 + want + 2)
