@@ -175,3 +175,32 @@ def test_reference_model_surface_builds_without_a_gpu():
                 assert out[3] == "conv2"
             m.modality_fuse = True
             assert torch.equal(m(x), 1 + want + 2)
+
+
+def test_checkpoint_compatibility(tmp_path):
+    """Reference-style checkpoints: plain state_dict files (train_off.py:155-156), 'module.' / 'base_model.' prefixes
+    (test_flow_off.py:52-58, Flow_OFF.py:1399), key-filtered partial merges (model_utils.py:200,240)."""
+    import torch
+    from off_b200 import RGB_OFF, checkpoint as CK
+    a = RGB_OFF.bninception_off(101, 1, 3, device="cpu")
+    b = RGB_OFF.bninception_off(101, 1, 3, device="cpu")
+    assert not torch.equal(a.off.engine.params_flat, b.off.engine.params_flat)
+    path = str(tmp_path / "2019-01-08_22-42-50.pth")
+    keys = CK.save_checkpoint(a, path, data_parallel_prefix=True)
+    assert all(k.startswith("module.") for k in keys) and len(keys) == 108
+    loaded, missing, ignored = CK.load_checkpoint(b, path)
+    assert len(loaded) == 108 and not missing and not ignored
+    assert torch.equal(a.off.engine.params_flat, b.off.engine.params_flat)
+    # partial merge: keep b's own FC heads, take the rest (the 'fc-action' / 'motion' style filters of model_utils.py)
+    c = RGB_OFF.bninception_off(101, 1, 3, device="cpu")
+    fc_before = c.fc_action_motion.weight.detach().clone()
+    ck = {"module.base_model." + k: v for k, v in a.state_dict().items()}
+    ck["module.base_model.conv1_7x7_s2.weight"] = torch.zeros(64, 3, 7, 7)        # a backbone entry the OFF module lacks
+    loaded, missing, ignored = CK.merge_state_dict(c, ck, keep=lambda k: "fc_action" not in k)
+    assert torch.equal(c.fc_action_motion.weight, fc_before)
+    assert torch.equal(c.motion_conv_trans_28.weight, a.motion_conv_trans_28.weight)
+    assert set(missing) == {k for k in a.state_dict() if "fc_action" in k} and "conv1_7x7_s2.weight" in ignored
+    bad = dict(a.state_dict())
+    bad["motion_conv_trans.weight"] = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError):
+        CK.merge_state_dict(c, bad)
