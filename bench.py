@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=48, help="clips per GPU")
     ap.add_argument("--length", type=int, default=3, help="segments per clip")
     ap.add_argument("--variant", default="rgb", choices=["rgb", "flow"])
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"],
+                    help="fp32 = fp32-parity mode on the tensor cores (3xTF32, the BASELINE config-2 arithmetic); tf32 = one "
+                         "kind::tf32 MMA per product (stated separately)")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips per CPU-baseline step (0 = --batch: the same batch as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -334,7 +336,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 (tcgen05 kind::tf32 multiply, fp32 accumulate, fp32 storage)" if args.precision == "tf32" else "fp32",
+            "dtype": ("tf32 (tcgen05 kind::tf32 multiply, fp32 accumulate, fp32 storage)" if args.precision == "tf32" else
+                      "fp32 (3xTF32: error-compensated tcgen05 kind::tf32 MMAs, fp32 accumulate, fp32 storage)"),
             "data": "synthetic",
             "config": {"workload": f"{args.variant.upper()}_OFF OFF sub-network fwd+bwd, {B} clips x {Lg} segments per GPU "
                                    f"(BASELINE config 2), train-mode dropout, CE loss on the 7x7 and 14x14 heads",

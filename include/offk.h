@@ -35,8 +35,12 @@ extern "C" {
 #define OFFK_E_LIMIT    (-3)  /* size beyond what the kernel supports        */
 
 /* arithmetic of the dense contractions */
-#define OFFK_PREC_FP32 0  /* CUDA-core FFMA, fp32 accumulate (exact mode)              */
-#define OFFK_PREC_TF32 1  /* tcgen05.mma kind::tf32, operands in smem, fp32 accum TMEM */
+#define OFFK_PREC_FP32   0 /* CUDA-core FFMA, fp32 accumulate: slow cross-check of the tensor-core modes (tests)       */
+#define OFFK_PREC_TF32   1 /* tcgen05.mma kind::tf32, operands in smem, fp32 accumulate in TMEM                        */
+#define OFFK_PREC_TF32X3 2 /* fp32-parity mode on the tensor cores (the reference computes in fp32, RGB_OFF.py:597):
+                              every operand tile x is used as hi = trunc_tf32(x) (what kind::tf32 reads anyway) plus a
+                              residual tile lo = tf32(x - hi) produced in shared memory, and three MMAs
+                              A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulate into the same fp32 TMEM tile ("3xTF32") */
 
 /* which frame feeds the spatial branch of pair p=(b,t) */
 #define OFFK_INDEX_REFERENCE_FLAT 0 /* flat frame p, as RGB_OFF.py:609 literally does */
@@ -166,7 +170,7 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
  *   row g.a_ones_row (bias gradient) is synthesised inside the kernel; out_vec must be 0
  *   with out_vec = 1 the out / gate / addend column tables must be contiguous (col[n] = col[0] + n)
  * offk_tma_gemm_prepare() encodes the two CUtensorMap objects into the descriptor (host only, no device memory);
- * call it again whenever a pointer or shape changes.  precision is always OFFK_PREC_TF32.
+ * call it again whenever a pointer or shape changes.  t->precision selects OFFK_PREC_TF32 or OFFK_PREC_TF32X3.
  * ---------------------------------------------------------------------- */
 #define OFFK_TMA_A_DENSE  0
 #define OFFK_TMA_A_IM2COL 1
@@ -193,7 +197,7 @@ typedef struct offk_tgemm {
                             kh != kw allowed -- the data gradient of a strided conv, one stride-parity class at a time, is
                             such a stride-1 correlation over dY (autograd of RGB_OFF.py:657,762) */
   int32_t pad_w;
-  int32_t reserved;
+  int32_t precision;     /* OFFK_PREC_TF32 (or 0) / OFFK_PREC_TF32X3 */
   uint64_t tmap_a[16];   /* CUtensorMap storage */
   uint64_t tmap_b[16];
 } offk_tgemm_t;

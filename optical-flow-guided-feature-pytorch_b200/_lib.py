@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OFFK_LIB") or os.path.join(_HERE, "liboffk.so")   # OFFK_LIB: bring-up builds only
 
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 INDEX_REFERENCE_FLAT, INDEX_ALIGNED = 0, 1
 DROP_NONE, DROP_MASK, DROP_SEED = 0, 1, 2
 LOAD_SCALAR_ROW, LOAD_SCALAR_K, LOAD_VEC_K, LOAD_VEC_ROW = 0, 1, 2, 3
@@ -50,7 +50,7 @@ class OffkTGemm(C.Structure):
         ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("hout", C.c_int32),
         ("wout", C.c_int32),
         ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("geom_flags", C.c_int32),
-        ("pad_w", C.c_int32), ("reserved", C.c_int32),
+        ("pad_w", C.c_int32), ("precision", C.c_int32),
         ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
     ]
 

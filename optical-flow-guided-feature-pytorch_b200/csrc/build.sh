@@ -9,10 +9,22 @@ mkdir -p "$ODIR"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v
        -I"$ROOT/include" -I"$HERE" ${OFFK_EXTRA_FLAGS:-})
+SRCS=(offk_api offk_gemm_simt offk_gemm_tc offk_gemm_tma offk_stencil offk_head offk_train)
 OBJS=()
-for f in offk_api offk_gemm_simt offk_gemm_tc offk_gemm_tma offk_stencil offk_head; do
-  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$ODIR/$f.o" 2> "$ODIR/$f.ptxas.log" || { cat "$ODIR/$f.ptxas.log" >&2; exit 1; }
+PIDS=()
+for f in "${SRCS[@]}"; do
+  [ -f "$HERE/$f.cu" ] || continue
+  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$ODIR/$f.o" 2> "$ODIR/$f.ptxas.log" &      # one nvcc per translation unit, in parallel
+  PIDS+=("$!:$f")
   OBJS+=("$ODIR/$f.o")
 done
+FAILED=0
+for pf in "${PIDS[@]}"; do
+  if ! wait "${pf%%:*}"; then
+    cat "$ODIR/${pf##*:}.ptxas.log" >&2
+    FAILED=1
+  fi
+done
+[ "$FAILED" = 0 ] || exit 1
 "$NVCC" -shared -o "$OUT" "${OBJS[@]}" -gencode arch=compute_100a,code=sm_100a -lcudart
 echo "built $OUT"

@@ -58,6 +58,7 @@ extern "C" int offk_gather_gemm(const offk_gemm_t* g, int precision, void* strea
   if (g->a_mode == OFFK_LOAD_VEC_K || g->b_mode == OFFK_LOAD_VEC_K) OFFK_REQUIRE((g->K & 3) == 0, "gather_gemm: VEC_K needs K %% 4 == 0");
   if (g->out_vec) OFFK_REQUIRE((g->N & 3) == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15u) == 0, "gather_gemm: out_vec alignment");
   if (precision == OFFK_PREC_FP32) return launch_gemm_simt(*g, as_stream(stream));
-  if (precision == OFFK_PREC_TF32) return launch_gemm_tc(*g, as_stream(stream));
+  if (precision == OFFK_PREC_TF32) return launch_gemm_tc(*g, as_stream(stream), false);
+  if (precision == OFFK_PREC_TF32X3) return launch_gemm_tc(*g, as_stream(stream), true);
   return fail(OFFK_E_BADARG, "gather_gemm: unknown precision %d", precision);
 }

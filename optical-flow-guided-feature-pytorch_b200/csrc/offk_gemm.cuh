@@ -55,6 +55,6 @@ __device__ __forceinline__ void epi_store(const offk_gemm_t& g, const EpiRow& r,
 }
 
 int launch_gemm_simt(const offk_gemm_t& g, cudaStream_t st);
-int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st);
+int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st, bool x3);
 
 }  // namespace offk

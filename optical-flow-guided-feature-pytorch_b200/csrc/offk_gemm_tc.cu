@@ -128,7 +128,8 @@ struct LoaderA {
       for (int i = 0; i < 4; ++i) v[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
     }
   }
-  __device__ __forceinline__ void store(const offk_gemm_t& g, uint32_t tile, int tid, float4 (&v)[4]) const {
+  // lo_off != 0 (3xTF32): the tf32 residual of every element goes to the twin tile lo_off bytes further
+  __device__ __forceinline__ void store(const offk_gemm_t& g, uint32_t tile, int tid, float4 (&v)[4], uint32_t lo_off) const {
     if (g.a_relu) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = f4relu(v[i]);
@@ -136,14 +137,27 @@ struct LoaderA {
     if (MODE == OFFK_LOAD_SCALAR_ROW) {
       const int tr = tid & 127, half = tid >> 7;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sts128(tile + swz(tr, half * 4 + c), v[c].x, v[c].y, v[c].z, v[c].w);
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t d = tile + swz(tr, half * 4 + c);
+        sts128(d, v[c].x, v[c].y, v[c].z, v[c].w);
+        if (lo_off) sts128(d + lo_off, tf32_lo(v[c].x), tf32_lo(v[c].y), tf32_lo(v[c].z), tf32_lo(v[c].w));
+      }
     } else if (MODE == OFFK_LOAD_SCALAR_K) {
       const int warp = tid >> 5, lane = tid & 31;
       const float t[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
                            v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
 #pragma unroll
-      for (int i = 0; i < 16; ++i) sts32(tile + swz(warp + 8 * i, lane >> 2) + (lane & 3) * 4, t[i]);
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t d = tile + swz(warp + 8 * i, lane >> 2) + (lane & 3) * 4;
+        sts32(d, t[i]);
+        if (lo_off) sts32(d + lo_off, tf32_lo(t[i]));
+      }
     }
+  }
+  // 3xTF32, cp.async modes: residuals of the chunks THIS thread copied (they have landed: cp.async.wait_group)
+  __device__ __forceinline__ void split_async(uint32_t tile, uint32_t lo_off) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_chunk(tile + dst[i], lo_off);
   }
   // VEC_K / VEC_ROW: straight to shared memory.  Returns true when st.shared was used (ones row).
   __device__ __forceinline__ bool issue_async(const offk_gemm_t& g, const Idx2 (&c)[4], uint32_t tile) const {
@@ -194,12 +208,12 @@ struct LoaderA {
       if (kVec) fetch_cols(g, k0 + 2 * TC_BK, tid, c_nxt);
     }
   }
-  __device__ __forceinline__ bool post_wait(const offk_gemm_t& g, uint32_t tile, int tid) {
+  __device__ __forceinline__ bool post_wait(const offk_gemm_t& g, uint32_t tile, int tid, uint32_t lo_off = 0) {
     bool stored;
     if (kAsync) {
       stored = issue_async(g, c_cur, tile);
     } else {
-      store(g, tile, tid, d_cur);
+      store(g, tile, tid, d_cur, lo_off);
       stored = true;
 #pragma unroll
       for (int q = 0; q < 4; ++q) d_cur[q] = d_nxt[q];
@@ -274,12 +288,16 @@ struct LoaderB {
       for (int i = 0; i < 4; ++i) v[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
     }
   }
-  __device__ __forceinline__ void store(uint32_t tile, int tid, int pass, const float4 (&v)[4]) const {
+  __device__ __forceinline__ void store(uint32_t tile, int tid, int pass, const float4 (&v)[4], uint32_t lo_off) const {
     if (MODE == OFFK_LOAD_SCALAR_ROW) {
       const int tr = 128 * pass + (tid & 127), half = tid >> 7;
       if (tr < bn) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sts128(tile + swz(tr, half * 4 + c), v[c].x, v[c].y, v[c].z, v[c].w);
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t d = tile + swz(tr, half * 4 + c);
+          sts128(d, v[c].x, v[c].y, v[c].z, v[c].w);
+          if (lo_off) sts128(d + lo_off, tf32_lo(v[c].x), tf32_lo(v[c].y), tf32_lo(v[c].z), tf32_lo(v[c].w));
+        }
       }
     } else if (MODE == OFFK_LOAD_SCALAR_K) {
       const int warp = tid >> 5, lane = tid & 31;
@@ -288,8 +306,28 @@ struct LoaderB {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int tr = 128 * pass + warp + 8 * i;
-        if (tr < bn) sts32(tile + swz(tr, lane >> 2) + (lane & 3) * 4, t[i]);
+        if (tr < bn) {
+          const uint32_t d = tile + swz(tr, lane >> 2) + (lane & 3) * 4;
+          sts32(d, t[i]);
+          if (lo_off) sts32(d + lo_off, tf32_lo(t[i]));
+        }
       }
+    }
+  }
+  // 3xTF32, cp.async modes: residuals of the chunks THIS thread copied (same predicates as post_wait)
+  __device__ __forceinline__ void split_async(uint32_t tile, int tid, uint32_t lo_off) const {
+    if (MODE == OFFK_LOAD_VEC_K) {
+      const int nrow = (bn + 31) >> 5;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nrow && (tid >> 3) + 32 * i < bn) split_chunk(tile + dst[i], lo_off);
+    } else if (MODE == OFFK_LOAD_VEC_ROW) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+        if (128 * p + 4 * (tid & 31) < bn) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_chunk(tile + dst[p] + i * dst[2], lo_off);
+        }
     }
   }
   static constexpr bool kAsync = (MODE == OFFK_LOAD_VEC_K || MODE == OFFK_LOAD_VEC_ROW);
@@ -310,7 +348,7 @@ struct LoaderB {
       if (kVec) fetch_cols(g, k0 + 2 * TC_BK, tid, c_nxt);
     }
   }
-  __device__ __forceinline__ void post_wait(const offk_gemm_t& g, uint32_t tile, int n0, int k0, int tid) {
+  __device__ __forceinline__ void post_wait(const offk_gemm_t& g, uint32_t tile, int n0, int k0, int tid, uint32_t lo_off = 0) {
     if (MODE == OFFK_LOAD_VEC_K) {
       const int nrow = (bn + 31) >> 5;          // 32 rows per i
 #pragma unroll
@@ -324,13 +362,13 @@ struct LoaderB {
           for (int i = 0; i < 4; ++i) cp_async16_cg(tile + dst[p] + i * dst[2], g.b_src + (r[p] + c_cur[i]), 16u);
         }
     } else {
-      store(tile, tid, 0, d_cur);
+      store(tile, tid, 0, d_cur, lo_off);
       if (bn > 128) {   // second pass of a wide tile: not prefetched (only gradient GEMMs wider than 128)
         int ct[4];
         float4 vt[4];
         if (kVec) fetch_cols(g, k0, tid, ct);
         load(g, ct, n0, k0, tid, 1, vt);
-        store(tile, tid, 1, vt);
+        store(tile, tid, 1, vt, lo_off);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) d_cur[q] = d_nxt[q];
@@ -347,14 +385,18 @@ __device__ float* g_offk_dump = nullptr;   // bring-up only: CTA (0,0,0) copies 
 #endif
 
 // ---------------------------------------------------------------------------- kernel
-template <int A_MODE, int B_MODE>
+// X3 = OFFK_PREC_TF32X3: every stage holds [A | B | A_lo | B_lo].  Each producer thread turns the chunks it copied itself
+// into their tf32 residuals (offk_tc.cuh) once its cp.async groups have landed -- `la` K-blocks behind the issue front --
+// and only then arrives on "full"; the MMA thread issues three MMAs per K = 8 step.
+template <int A_MODE, int B_MODE, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split, int tmem_cols) {
+gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split, int tmem_cols, int la) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16 KB | B bn*128)] then the barrier block
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = ((uint32_t)(bn + 31) >> 5) << 12;      // whole 32-row groups (MN-major atoms are 32 wide)
-  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const uint32_t hi_bytes = TC_A_BYTES + b_bytes;
+  const uint32_t stage_bytes = X3 ? 2u * hi_bytes : hi_bytes;
   TcShared* sh = reinterpret_cast<TcShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -395,6 +437,33 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
     }
     int s = 0;
     uint32_t parity = 1;                                       // empty-barrier parity of the current round
+    if (X3) {
+      // issue front at K-block `it`, residual + hand-over `la` K-blocks behind it (la < stages, so the empty-wait of
+      // iteration `it` only ever needs hand-overs of earlier iterations)
+      int s2 = 0;
+      for (int it = 0; it < nkb + la; ++it) {
+        if (it < nkb) {
+          const int k0 = (kb_begin + it) * TC_BK;
+          const uint32_t a_base = smem_base + s * stage_bytes;
+          pa.pre_wait(g, m0, k0, tid, it + 1 < nkb);
+          pb.pre_wait(g, n0, k0, tid, it + 1 < nkb);
+          mbar_wait(smem_u32(&sh->empty[s]), parity);
+          pa.post_wait(g, a_base, tid, hi_bytes);
+          pb.post_wait(g, a_base + TC_A_BYTES, n0, k0, tid, hi_bytes);
+          if (++s == stages) { s = 0; parity ^= 1u; }
+        }
+        cp_async_commit();                                     // one group per iteration (empty past the last K-block)
+        if (it >= la) {
+          if (la == 1) cp_async_wait_group<1>(); else if (la == 2) cp_async_wait_group<2>(); else cp_async_wait_group<3>();
+          const uint32_t a_base = smem_base + s2 * stage_bytes;
+          if (LoaderA<A_MODE>::kAsync) pa.split_async(a_base, hi_bytes);
+          if (LoaderB<B_MODE>::kAsync) pb.split_async(a_base + TC_A_BYTES, tid, hi_bytes);
+          fence_proxy_async_smem();                            // generic-proxy st.shared -> visible to the tensor core
+          mbar_arrive(smem_u32(&sh->full[s2]));
+          if (++s2 == stages) s2 = 0;
+        }
+      }
+    } else
     for (int i = 0; i < nkb; ++i) {
       const int k0 = (kb_begin + i) * TC_BK;
       const uint32_t a_base = smem_base + s * stage_bytes;
@@ -427,9 +496,15 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
         const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, 512u, 2048u) : make_smem_desc(a_base);
         const uint64_t bdesc = B_MN ? make_smem_desc_mn(b_base, 512u, b_kgroup >> 1) : make_smem_desc(b_base);
         const uint64_t a_step = A_MN ? (uint64_t)(4096 >> 4) : 2ull, b_step = B_MN ? (uint64_t)(b_kgroup >> 4) : 2ull;
+        const uint64_t lo_step = (uint64_t)(hi_bytes >> 4);   // residual tiles sit hi_bytes further (start-address field)
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j)
-          umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        for (int j = 0; j < TC_BK / 8; ++j) {
+          if (X3) {                                           // small terms first
+            umma_tf32(tmem_d, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
+          }
+          umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (X3 || i > 0 || j > 0) ? 1u : 0u);
+        }
         umma_commit(smem_u32(&sh->empty[s]));          // frees the smem slot when these MMAs retire
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
@@ -548,10 +623,11 @@ static int pick_bn(int N) {
   return best;
 }
 
-template <int A_MODE, int B_MODE>
+template <int A_MODE, int B_MODE, bool X3>
 static int launch_tc_t(const offk_gemm_t& g, int bn, int stages, int kb_per, int tmem_cols, dim3 grid, size_t smem,
                        cudaStream_t st) {
-  auto kern = gather_gemm_tc_kernel<A_MODE, B_MODE>;
+  auto kern = gather_gemm_tc_kernel<A_MODE, B_MODE, X3>;
+  const int la = stages - 1 < 3 ? stages - 1 : 3;      // X3: residual pass trails the cp.async issue front by `la` K-blocks
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -566,21 +642,22 @@ static int launch_tc_t(const offk_gemm_t& g, int bn, int stages, int kb_per, int
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, bn, stages, kb_per, tmem_cols);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, bn, stages, kb_per, tmem_cols, la);
   if (e != cudaSuccess) return cuda_check(e, "gather_gemm_tc launch");
   return OFFK_LAUNCH_CHECK("gather_gemm_tc");
 }
 
-int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st) {
+int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st, bool x3) {
   int bn = g.tile_n > 0 ? g.tile_n : pick_bn(g.N);
   if (bn % 16 != 0 || bn < 16 || bn > 256) return fail(OFFK_E_BADARG, "gather_gemm: bad N tile %d", bn);
   const int num_kb = (g.K + TC_BK - 1) / TC_BK;
   const int split = g.split_k > 1 ? g.split_k : 1;
   const int kb_per = (num_kb + split - 1) / split;
-  const uint32_t stage_bytes = TC_A_BYTES + (((bn + 31) >> 5) << 12);
-  const long long ctas = (long long)((g.M + TC_BM - 1) / TC_BM) * ((g.N + bn - 1) / bn) * ((num_kb + kb_per - 1) / kb_per);
-  (void)ctas;
-  const int budget = 108 * 1024;   // two CTAs per SM: tiles of the same or of a concurrent kernel (another lane) co-reside
+  const uint32_t stage_bytes = (TC_A_BYTES + (((bn + 31) >> 5) << 12)) * (x3 ? 2u : 1u);
+  // two CTAs per SM: tiles of the same or of a concurrent kernel (another lane) co-reside; the 3xTF32 stages (twice the
+  // bytes: residual tiles) of the wide tiles need the whole SM
+  int budget = 108 * 1024;
+  if (x3 && 3 * stage_bytes > (uint32_t)budget) budget = 216 * 1024;
   int stages = budget / (int)stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -592,8 +669,10 @@ int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st) {
   if (grid.y > 65535 || grid.z > 65535) return fail(OFFK_E_LIMIT, "gather_gemm: grid too large");
   // cp.async cannot apply ReLU-on-load: such operands (one small 1x1 conv) take the scalar register path
   const int a_mode = (g.a_relu && g.a_mode >= OFFK_LOAD_VEC_K) ? OFFK_LOAD_SCALAR_ROW : g.a_mode;
-#define OFFK_TC_CASE(AM, BM) \
-  if (a_mode == AM && g.b_mode == BM) return launch_tc_t<AM, BM>(g, bn, stages, kb_per, tmem_cols, grid, smem, st);
+#define OFFK_TC_CASE(AM, BM)                                                                        \
+  if (a_mode == AM && g.b_mode == BM)                                                               \
+    return x3 ? launch_tc_t<AM, BM, true>(g, bn, stages, kb_per, tmem_cols, grid, smem, st)         \
+              : launch_tc_t<AM, BM, false>(g, bn, stages, kb_per, tmem_cols, grid, smem, st);
   OFFK_TC_CASE(0, 0) OFFK_TC_CASE(0, 1) OFFK_TC_CASE(0, 2) OFFK_TC_CASE(0, 3)
   OFFK_TC_CASE(1, 0) OFFK_TC_CASE(1, 1) OFFK_TC_CASE(1, 2) OFFK_TC_CASE(1, 3)
   OFFK_TC_CASE(2, 0) OFFK_TC_CASE(2, 1) OFFK_TC_CASE(2, 2) OFFK_TC_CASE(2, 3)

@@ -81,10 +81,13 @@ struct TmShared {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t accum_full;
+  uint64_t split[TC_MAX_STAGES];   // X3: the residual ("lo") tiles of the stage are written (256 epilogue threads)
   uint32_t tmem_base;
 };
 
-template <int A_KIND, int B_KIND>
+// X3 = OFFK_PREC_TF32X3: every stage holds [A | B | A_lo | B_lo]; the epilogue warps, otherwise idle during the main loop,
+// turn each landed [A | B] into its tf32 residual (offk_tc.cuh) and the MMA warp issues three MMAs per K = 8 step.
+template <int A_KIND, int B_KIND, bool X3>
 __global__ void __launch_bounds__(TM_THREADS, 2)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const offk_gemm_t g,
                 const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols) {
@@ -93,7 +96,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
   constexpr bool B_MN = (B_KIND == OFFK_TMA_B_DENSE_T);
   const uint32_t b_bytes = B_MN ? (((uint32_t)bn + 31u) >> 5) * 4096u : (uint32_t)bn * 128u;
-  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+  const uint32_t hi_bytes = TC_A_BYTES + b_bytes;               // one landed [A | B] pair
+  const uint32_t stage_bytes = X3 ? 2u * hi_bytes : hi_bytes;
   TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -115,6 +119,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&sh->full[s]), 1);
       mbar_init(smem_u32(&sh->empty[s]), 1);
+      if (X3) mbar_init(smem_u32(&sh->split[s]), TM_THREADS - 64);
     }
     mbar_init(smem_u32(&sh->accum_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,7 +169,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           // contribute nothing); rows = 128 channels (channels >= cin zero-fill; the ones row is patched in)
           const int img = kb / geo.kb_per_img, pb = kb - img * geo.kb_per_img;
           b_row0 = img * geo.hw + pb * TC_BK;
-          mbar_arrive_expect_tx(full, stage_bytes);
+          mbar_arrive_expect_tx(full, hi_bytes);
           tma_load_3d(a_dst, &tma, pb * TC_BK, m0, img, full);
         } else if (A_KIND == OFFK_TMA_A_IM2COL_T) {
           // rows m = (r, q, c): each 32-row atom is one {32 channels x 32 output pixels} im2col box at its own (q, r)
@@ -182,10 +187,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
             tma_load_im2col_4d(a_dst + a * 4096, &tma, geo.a_coff + cb * TC_BK, wb, hb, img, q, r, full);
           }
         } else if (A_KIND == OFFK_TMA_A_DENSE) {
-          mbar_arrive_expect_tx(full, stage_bytes);
+          mbar_arrive_expect_tx(full, hi_bytes);
           tma_load_2d(a_dst, &tma, kb * TC_BK, m0, full);
         } else {
-          mbar_arrive_expect_tx(full, stage_bytes);
+          mbar_arrive_expect_tx(full, hi_bytes);
           const int tap = kb / geo.cblocks, cb = kb - tap * geo.cblocks;
           const int r = tap / geo.kw, q = tap - r * geo.kw;
           tma_load_im2col_4d(a_dst, &tma, geo.a_coff + cb * TC_BK, w0, h0, img0, q, r, full);
@@ -214,7 +219,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       int s = 0;
       uint32_t parity = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(smem_u32(&sh->full[s]), parity);
+        mbar_wait(smem_u32(X3 ? &sh->split[s] : &sh->full[s]), parity);
         tc_fence_after();
         const uint32_t a_base = smem_base + s * stage_bytes;
         if (patch) {
@@ -232,15 +237,22 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
             off = (uint32_t)(ma * 4096 + (lane >> 2) * 512 + kl * 128 + ((((mi >> 3) ^ kl) << 5) | ((mi & 7) << 2)));
           }
           sts32(a_base + off, real ? 1.f : 0.f);
+          if (X3) sts32(a_base + hi_bytes + off, 0.f);           // 1 and 0 are exact in tf32: no residual
           fence_proxy_async_smem();
           __syncwarp();
         }
         if (lane == 0) {
           const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, 4096u, 512u) : make_smem_desc(a_base);
           const uint64_t bdesc = B_MN ? make_smem_desc_mn(a_base + TC_A_BYTES, 4096u, 512u) : make_smem_desc(a_base + TC_A_BYTES);
+          const uint64_t lo_step = (uint64_t)(hi_bytes >> 4);    // residual tiles sit hi_bytes further (start-address field)
 #pragma unroll
-          for (int j = 0; j < TC_BK / 8; ++j)
-            umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+          for (int j = 0; j < TC_BK / 8; ++j) {
+            if (X3) {                                            // small terms first
+              umma_tf32(tmem_d, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+              umma_tf32(tmem_d, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
+            }
+            umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (X3 || i > 0 || j > 0) ? 1u : 0u);
+          }
           umma_commit(smem_u32(&sh->empty[s]));                  // frees the smem slot when these MMAs retire
         }
         if (patch) __syncwarp();
@@ -255,6 +267,23 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
     const int half = ew >> 2;                                    // which 16 columns of a 32-column chunk
     const bool atomic = (g.split_k > 1) || g.atomic_out;
+    // X3 main-loop duty of these 256 threads: residual tiles.  Stage s = [A | B | A_lo | B_lo]; the first half is what
+    // the TMA delivered, the second half is written here, element for element at the same swizzled offset.
+    auto split_loop = [&]() {
+      if (!X3) return;
+      const uint32_t e16 = (uint32_t)(tid - 64) * 16u;
+      int s = 0;
+      uint32_t parity = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(smem_u32(&sh->full[s]), parity);
+        const uint32_t base = smem_base + s * stage_bytes;
+#pragma unroll 4
+        for (uint32_t off = e16; off < hi_bytes; off += (TM_THREADS - 64) * 16u) split_chunk(base + off, hi_bytes);
+        fence_proxy_async_smem();                                // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(smem_u32(&sh->split[s]));
+        if (++s == stages) { s = 0; parity ^= 1u; }
+      }
+    };
     if (g.out_vec) {
       // Transposed through shared memory (the pipeline stages are idle once accum_full fired) so that bias / gate /
       // residual loads and the stores are row-contiguous: 8 lanes x 16 bytes = one 128-byte line per output row.
@@ -281,6 +310,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       const int oc0 = __ldg(g.out_col);
       const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
       const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
+      split_loop();
       mbar_wait(smem_u32(&sh->accum_full), 0u);
       tc_fence_after();
       for (int c = 0; c < nchunks; ++c) {
@@ -343,6 +373,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       const bool mvalid = m < m_lim;
       EpiRow er = {0, 0, 0, false};
       if (mvalid) er = epi_row(g, m);
+      split_loop();
       mbar_wait(smem_u32(&sh->accum_full), 0u);
       tc_fence_after();
       const int nchunks = bn >> 4;
@@ -446,10 +477,10 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
   return 0;
 }
 
-template <int A_KIND, int B_KIND>
+template <int A_KIND, int B_KIND, bool X3>
 static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
                        int kb_per, int tmem_cols, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kern = tma_gemm_kernel<A_KIND, B_KIND>;
+  auto kern = tma_gemm_kernel<A_KIND, B_KIND, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -553,8 +584,14 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   const int split = g.split_k > 1 ? g.split_k : 1;
   const int kb_per = (num_kb + split - 1) / split;
   const uint32_t b_bytes = wgrad ? (uint32_t)((bn + 31) / 32) * 4096u : (uint32_t)bn * 128u;
-  const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
-  const int budget = 108 * 1024;                 // two CTAs per SM
+  OFFK_REQUIRE(t->precision == 0 || t->precision == OFFK_PREC_TF32 || t->precision == OFFK_PREC_TF32X3,
+               "tma_gemm: precision must be OFFK_PREC_TF32 (or 0) or OFFK_PREC_TF32X3");
+  const bool x3 = t->precision == OFFK_PREC_TF32X3;
+  const uint32_t stage_bytes = (TC_A_BYTES + b_bytes) * (x3 ? 2u : 1u);   // x3: the residual tiles double a stage
+  // two CTAs per SM (one CTA's epilogue overlaps the other's main loop) when that still leaves a pipeline; the 3xTF32
+  // stages of the wide tiles need the whole SM
+  int budget = 108 * 1024;
+  if (x3 && 3 * stage_bytes > (uint32_t)budget) budget = 216 * 1024;
   int stages = budget / (int)stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -569,8 +606,10 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   memcpy(&ta, t->tmap_a, sizeof(ta));
   memcpy(&tb, t->tmap_b, sizeof(tb));
   cudaStream_t st = as_stream(stream);
-#define OFFK_TM_CASE(AK, BK) \
-  if (t->a_kind == AK && t->b_kind == BK) return launch_tm_t<AK, BK>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, st);
+#define OFFK_TM_CASE(AK, BK)                                                                                          \
+  if (t->a_kind == AK && t->b_kind == BK)                                                                             \
+    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, st)              \
+              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, st);
   OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)

@@ -139,6 +139,36 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
 }
 
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------- 3xTF32 (OFFK_PREC_TF32X3)
+// tcgen05.mma kind::tf32 reads the top 19 bits of each fp32 operand word (sign, 8 exponent, 10 mantissa bits: the low
+// 13 mantissa bits are ignored).  The error-compensated mode therefore keeps the operand tile as it landed ("hi": the
+// tensor core truncates it by itself) and adds a second tile "lo" = tf32(x - trunc(x)) -- the part the truncation
+// dropped, rounded to nearest so that its own 11 significant bits are unbiased -- and issues
+//   D += A_lo * B_hi + A_hi * B_lo + A_hi * B_hi
+// into the same fp32 TMEM accumulator: per-product relative error ~2^-21 instead of tf32's 2^-10 (fp32: 2^-24).
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x - hi));
+  return __uint_as_float(r);
+}
+// lo tile of 4 consecutive operand words: read the hi tile at `addr`, write the residual `lo_off` bytes further
+__device__ __forceinline__ void split_chunk(uint32_t addr, uint32_t lo_off) {
+  const float4 v = lds128(addr);
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr + lo_off), "f"(tf32_lo(v.x)), "f"(tf32_lo(v.y)),
+               "f"(tf32_lo(v.z)), "f"(tf32_lo(v.w))
+               : "memory");
+}
+
 __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float4 f4relu(float4 v) {

@@ -25,6 +25,7 @@ from . import spec as S
 from . import tables as T
 
 _SM_TARGET = 148
+_TC_PRECS = (L.PREC_TF32, L.PREC_TF32X3)      # tcgen05 modes: 1 MMA per product / error-compensated 3xTF32
 
 
 def _ptr(t):
@@ -102,9 +103,9 @@ class TGemm(Gemm):
     @staticmethod
     def eligible(geom: T.ConvGeom, prec, a_relu=False, x_layout="nhwc") -> bool:
         if x_layout == "nchw":      # the taps, read in place as an MN-major operand: 1x1 conv over whole frames
-            return (prec == L.PREC_TF32 and not a_relu and T._is1x1(geom) and geom.cin % 32 == 0 and geom.x_coff == 0
+            return (prec in _TC_PRECS and not a_relu and T._is1x1(geom) and geom.cin % 32 == 0 and geom.x_coff == 0
                     and geom.x_ctot == geom.cin and (geom.hin * geom.win) % 4 == 0)
-        return (prec == L.PREC_TF32 and not a_relu and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0 and geom.x_coff % 4 == 0
+        return (prec in _TC_PRECS and not a_relu and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0 and geom.x_coff % 4 == 0
                 and geom.kdim % 4 == 0)
 
     @staticmethod
@@ -112,9 +113,9 @@ class TGemm(Gemm):
         """Weight gradient with both operands TMA-fed: A = im2col(x)^T (channels-last) or the NCHW tap, B = dY."""
         y_ok = geom.y_ctot % 4 == 0 and geom.y_coff % 4 == 0 and geom.cout % 4 == 0
         if x_layout == "nchw":
-            return (prec == L.PREC_TF32 and not a_relu and y_ok and T._is1x1(geom) and geom.x_coff == 0
+            return (prec in _TC_PRECS and not a_relu and y_ok and T._is1x1(geom) and geom.x_coff == 0
                     and geom.x_ctot == geom.cin and (geom.hin * geom.win) % 4 == 0)
-        return (prec == L.PREC_TF32 and not a_relu and y_ok and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0
+        return (prec in _TC_PRECS and not a_relu and y_ok and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0
                 and geom.x_coff % 4 == 0)
 
     def __init__(self, eng, spc, key, geom: T.ConvGeom, x_layout="nhwc", wgrad=False, **kw):
@@ -132,6 +133,7 @@ class TGemm(Gemm):
         else:
             t.a_kind = L.TMA_A_IM2COL
         t.a_coff = geom.x_coff
+        t.precision = eng.prec
         t.n_img, t.hin, t.win, t.ctot, t.cin = geom.n_img, geom.hin, geom.win, geom.x_ctot, geom.cin
         t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = geom.kh, geom.kw, geom.stride, geom.pad, geom.hout, geom.wout
         if isinstance(geom, _FreeGeom):
@@ -168,7 +170,9 @@ class OFFEngine:
 
     variant: 'rgb'  learned depth-wise 3x3 spatial gradient + bias, per-pair logits (RGB_OFF.py)
              'flow' fixed diagonal Sobel, segment consensus over the L-1 pairs (Flow_OFF.py / RGB_OFF_v2.py)
-    precision: 'tf32' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (CUDA-core FFMA, exact mode)
+    precision: 'fp32' = fp32-parity mode ON THE TENSOR CORES (OFFK_PREC_TF32X3: error-compensated 3xTF32 tcgen05 MMAs,
+               fp32 accumulate; the reference's arithmetic is fp32, RGB_OFF.py:597), 'tf32' = one kind::tf32 MMA per
+               product (the fast mode, tolerance stated separately), 'fp32_simt' = CUDA-core FFMA cross-check (tests only)
     """
 
     def __init__(self, batch: int, length: int, variant: str = "rgb", device="cuda", precision: str = "tf32",
@@ -178,7 +182,8 @@ class OFFEngine:
         self.B, self.Lseg, self.variant = batch, length, variant
         self.N, self.P = batch * length, batch * (length - 1)
         self.device = torch.device(device)
-        self.prec = {"fp32": L.PREC_FP32, "tf32": L.PREC_TF32}[precision]
+        self.prec = {"fp32": L.PREC_TF32X3, "tf32": L.PREC_TF32, "fp32_simt": L.PREC_FP32}[precision]
+        self.tc = self.prec in _TC_PRECS
         self.precision = precision
         self.index_mode = {"reference_flat": L.INDEX_REFERENCE_FLAT, "aligned": L.INDEX_ALIGNED}[index_mode]
         self.consensus = (variant != "rgb") if consensus is None else bool(consensus)
@@ -340,7 +345,7 @@ class OFFEngine:
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = 1
-        if self.prec == L.PREC_TF32 and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
+        if self.tc and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
             split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), kb // 8))
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
         tma = self.use_tma and TGemm.eligible(geom, self.prec, a_relu, x_layout)
@@ -409,7 +414,7 @@ class OFFEngine:
                 kw_["b_src"] = self.wd[name]
                 g = TGemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), geom=gd, **kw_)
             elif (self.use_tma and self.tma_strided_dgrad and x_layout == "nhwc" and geom.stride > 1
-                  and (name, ex["a"], ex["b"]) in self.wd and self.prec == L.PREC_TF32 and geom.cout % 32 == 0
+                  and (name, ex["a"], ex["b"]) in self.wd and self.tc and geom.cout % 32 == 0
                   and geom.y_ctot % 4 == 0 and geom.y_coff % 4 == 0 and ex["pad_h"] >= 0 and ex["pad_w"] >= 0):
                 # one stride-parity class = a stride-1 correlation over dY with the class's R x Q taps (free geometry)
                 R, Q = len(ex["rs"]), len(ex["qs"])
@@ -452,7 +457,7 @@ class OFFEngine:
             # K1: gen (ReLU) and down (linear) 1x1 convs as ONE GEMM with 160 output channels
             # 7x7 taps: a 196-byte channel stride is not a legal TMA stride -> one channels-last copy of the tap per
             # step feeds both the forward GEMM (dense tensor map) and the weight gradient (im2col_t), all TMA-fed
-            via_copy = (self.prec == L.PREC_TF32 and self.use_tma and (s * s) % 4 != 0 and cin % 32 == 0
+            via_copy = (self.tc and self.use_tma and (s * s) % 4 != 0 and cin % 32 == 0
                         and os.environ.get("OFFK_NO_TAP_COPY", "0") != "1")
             if via_copy:
                 tapT = self._buf("tapT_" + tag, N, s, s, cin)

@@ -176,6 +176,50 @@ def make_dropout_masks(seed: int, batch: int, length: int, p_drop: float = 0.8):
 
 
 # ---------------------------------------------------------------------------
+# tf32 operand emulation (for pinning the product's OFFK_PREC_TF32 mode)
+# ---------------------------------------------------------------------------
+# tcgen05.mma kind::tf32 reads the top 19 bits of every fp32 operand word (the low 13 mantissa bits are ignored) and
+# accumulates the exact products in fp32.  ``mm="tf32_trunc"`` makes every dense contraction of the restatement (1x1 /
+# KxK convs, FC heads and their autograd: data gradient = dY x W, weight gradient = X x dY, bias gradient = sum of the
+# truncated dY because the product folds it into the weight-gradient GEMM as an all-ones operand row) consume operands
+# truncated the same way, everything else unchanged.  The depth-wise stencil, pools and dropout are not contractions.
+def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
+    b = x.detach().to(torch.float32).contiguous().view(torch.int32) & -8192          # 0xFFFFE000
+    return b.view(torch.float32).to(x.dtype)
+
+
+class _Tf32Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad):
+        ctx.save_for_backward(x, w)
+        ctx.geom = (stride, pad, b is not None)
+        return F.conv2d(trunc_tf32(x), trunc_tf32(w), b, stride, pad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, pad, has_b = ctx.geom
+        dyt = trunc_tf32(dy)
+        dx = torch.nn.grad.conv2d_input(x.shape, trunc_tf32(w), dyt, stride, pad) if ctx.needs_input_grad[0] else None
+        dw = torch.nn.grad.conv2d_weight(trunc_tf32(x), w.shape, dyt, stride, pad)
+        db = dyt.sum((0, 2, 3)) if has_b else None
+        return dx, dw, db, None, None
+
+
+def _conv2d(x, w, b, stride=1, pad=0, mm="exact"):
+    if mm == "exact":
+        return F.conv2d(x, w, b, stride, pad)
+    return _Tf32Conv.apply(x, w, b, stride, pad)
+
+
+def _linear(x, w, b, mm="exact"):
+    if mm == "exact":
+        return F.linear(x, w, b)
+    y = _Tf32Conv.apply(x.reshape(-1, x.shape[-1], 1, 1), w[:, :, None, None], b, 1, 0)
+    return y.reshape(*x.shape[:-1], w.shape[0])
+
+
+# ---------------------------------------------------------------------------
 # The restatement
 # ---------------------------------------------------------------------------
 def consensus_avg(x: torch.Tensor, dim: int = 1) -> torch.Tensor:
@@ -205,13 +249,13 @@ def _drop(x, mask, p_drop):
     return x * mask.to(x.dtype).reshape(x.shape) * (1.0 / (1.0 - p_drop))
 
 
-def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index_mode="reference_flat"):
+def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index_mode="reference_flat", mm="exact"):
     """One OFF unit, e.g. RGB_OFF.py:596-616 for level 3a.
 
     Returns (motion [P,160,S,S], gen_relu [N,128,S,S], down [P,32,S,S]).
     """
     s = tap.shape[-1]
-    g = F.relu(F.conv2d(tap, prm[f"motion_conv_gen_{tag}.weight"], prm[f"motion_conv_gen_{tag}.bias"]))  # :597-598
+    g = F.relu(_conv2d(tap, prm[f"motion_conv_gen_{tag}.weight"], prm[f"motion_conv_gen_{tag}.bias"], mm=mm))  # :597-598
     ch = g.shape[1]
     r = g.view(batch, -1, s, s)                       # :600
     temporal = (r[:, ch:] - r[:, :-ch]).reshape(-1, ch, s, s)  # :601-604
@@ -220,7 +264,7 @@ def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index
         spatial_frames = tap[:pairs]                  # :609  (flat-index quirk)
     else:                                             # 'aligned': frame (b,t) for pair (b,t)
         spatial_frames = tap.view(batch, length, *tap.shape[1:])[:, :-1].reshape(pairs, *tap.shape[1:])
-    d = F.conv2d(spatial_frames, prm[f"motion_spatial_down_{tag}.weight"], prm[f"motion_spatial_down_{tag}.bias"])  # :610
+    d = _conv2d(spatial_frames, prm[f"motion_spatial_down_{tag}.weight"], prm[f"motion_spatial_down_{tag}.bias"], mm=mm)  # :610
     if variant == "rgb":
         sg = F.conv2d(d, prm[f"motion_spatial_grad_{tag}.weight"], prm[f"motion_spatial_grad_{tag}.bias"], 1, 1, 1, DOWN_C)  # :611
     else:
@@ -230,7 +274,7 @@ def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index
 
 
 def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
-                consensus=None, index_mode="reference_flat"):
+                consensus=None, index_mode="reference_flat", mm="exact"):
     """OFF sub-network forward, RGB_OFF.py:596-860 / Flow_OFF.py:606-884.
 
     ``consensus``: None -> follow the variant (rgb: per-pair logits as in
@@ -242,11 +286,11 @@ def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
     mk = (lambda k: masks[k]) if masks is not None else (lambda k: None)
     w = lambda n: prm[n + ".weight"]
     b = lambda n: prm[n + ".bias"]
-    conv = lambda x, n, stride=1, pad=0: F.conv2d(x, w(n), b(n), stride, pad)
+    conv = lambda x, n, stride=1, pad=0: _conv2d(x, w(n), b(n), stride, pad, mm)
     relu = F.relu
     out = {}
 
-    m = {t: off_unit(taps[t], prm, t, batch, length, variant, mk(t), p_drop, index_mode)[0] for t in LEVELS}
+    m = {t: off_unit(taps[t], prm, t, batch, length, variant, mk(t), p_drop, index_mode, mm)[0] for t in LEVELS}
 
     # ---- resolution 28 (RGB_OFF.py:655-685)
     f28 = torch.cat((m["3a"], m["3b"]), 1)                               # :656
@@ -279,7 +323,7 @@ def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
         pooled = F.avg_pool2d(x, 7, stride=1, padding=0, ceil_mode=True, count_include_pad=True)  # global_pool :262
         pooled = _drop(pooled, mk(key), p_drop)
         pooled = torch.squeeze(pooled)                                   # :786 (drops the batch dim too when P == 1)
-        return F.linear(pooled, w(fc), b(fc))
+        return _linear(pooled, w(fc), b(fc), mm)
 
     p28 = F.max_pool2d(s28, 3, stride=2, dilation=1, ceil_mode=True)     # :353,:783
     fc28 = head(p28, "fc_action_motion_28", "fc28")
@@ -308,7 +352,7 @@ def to_dtype(d, dtype):
 
 
 def off_forward_backward(taps, prm, batch, length, variant="rgb", masks=None, dtype=torch.float32,
-                         tap_grads=False, loss="sum"):
+                         tap_grads=False, loss="sum", mm="exact"):
     """Forward + backward with ``loss = fc7.sum() + fc14.sum()``.
 
     Returns (outputs dict, grads dict name->tensor [, tap grads dict]).
@@ -316,7 +360,7 @@ def off_forward_backward(taps, prm, batch, length, variant="rgb", masks=None, dt
     """
     prm = OrderedDict((k, v.detach().to(dtype).requires_grad_(True)) for k, v in prm.items())
     taps = OrderedDict((k, v.detach().to(dtype).requires_grad_(tap_grads)) for k, v in taps.items())
-    out = off_forward(taps, prm, batch, length, variant, masks)
+    out = off_forward(taps, prm, batch, length, variant, masks, mm=mm)
     if loss == "sum":
         l = out["fc7"].sum() + out["fc14"].sum()
     else:

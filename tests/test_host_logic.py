@@ -66,7 +66,7 @@ def test_ctypes_structs_match_the_c_header():
              offsetof(offk_stencil_t, keep_mask), sizeof(offk_stencil_io_t), offsetof(offk_stencil_io_t, dg_fs),
              offsetof(offk_stencil_io_t, dbias));
       printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(offk_tgemm_t), offsetof(offk_tgemm_t, a_kind), offsetof(offk_tgemm_t, wout),
-             offsetof(offk_tgemm_t, geom_flags), offsetof(offk_tgemm_t, pad_w), offsetof(offk_tgemm_t, tmap_a),
+             offsetof(offk_tgemm_t, geom_flags), offsetof(offk_tgemm_t, precision), offsetof(offk_tgemm_t, tmap_a),
              sizeof(offk_permute_t));
       return 0;
     }'''
@@ -80,7 +80,7 @@ def test_ctypes_structs_match_the_c_header():
                    C.sizeof(L.OffkStencil), L.OffkStencil.seed.offset, L.OffkStencil.keep_mask.offset,
                    C.sizeof(L.OffkStencilIO), L.OffkStencilIO.dg_fs.offset, L.OffkStencilIO.dbias.offset,
                    C.sizeof(L.OffkTGemm), L.OffkTGemm.a_kind.offset, L.OffkTGemm.wout.offset, L.OffkTGemm.geom_flags.offset,
-                   L.OffkTGemm.pad_w.offset, L.OffkTGemm.tmap_a.offset, C.sizeof(L.OffkPermute)]
+                   L.OffkTGemm.precision.offset, L.OffkTGemm.tmap_a.offset, C.sizeof(L.OffkPermute)]
 
 
 def test_cpu_calls_fail_loudly():
@@ -104,7 +104,7 @@ def test_engine_plan_builds_without_a_gpu():
     # forward FLOPs follow the survey's scaling law 0.28897*N + 1.29305*P GFLOP (+ the down rows of the N-P extra frames)
     gf = 0.28897 * eng.N + 1.29305 * eng.P + 0.07235 * (eng.N - eng.P)
     assert abs(eng.flops_fwd / 1e9 - gf) / gf < 0.01
-    flow = E.OFFEngine(1, 4, "flow", "cpu", "fp32", tap_grads=True)
+    flow = E.OFFEngine(1, 4, "flow", "cpu", "fp32_simt", tap_grads=True)
     assert flow.consensus and "motion_spatial_grad_3a.weight" not in flow.params
     # tf32 plan: the 7x7 taps go through a channels-last copy, every stride-2 data-gradient class has its own weight
     # block, the forward stencil is two launches and all KxK weight gradients are un-permuted by one
@@ -114,7 +114,10 @@ def test_engine_plan_builds_without_a_gpu():
     assert names.count("unpermute_kxk_weight_grads") == 1 and "stencil_bwd" in names
     for conv in ("motion_conv_trans_28", "motion_conv_trans_14"):
         assert all((conv, a, b) in eng.wd for a in (0, 1) for b in (0, 1))
-    assert "tapT_5a" not in flow.launch_names()          # fp32 exact mode reads the NCHW taps through the gather kernel
+    assert "tapT_5a" not in flow.launch_names()          # the CUDA-core cross-check mode reads the NCHW taps through the gather kernel
+    # precision='fp32' is the 3xTF32 tensor-core mode: the same TMA-fed plan as 'tf32', launch for launch
+    x3 = E.OFFEngine(2, 3, "rgb", "cpu", "fp32")
+    assert x3.prec == L.PREC_TF32X3 and x3.launch_names() == names
     # hazard analysis: a step never waits on its own lane, and every cross-lane wait points backwards
     for sched in (eng.fwd_sched, eng.bwd_sched):
         for i, ws in enumerate(sched.waits):
