@@ -9,6 +9,7 @@ OFF ``state_dict`` keys equal the reference's.  Pure host code: no kernel is inv
 """
 from __future__ import annotations
 
+import warnings
 from collections import OrderedDict
 from typing import Callable, Iterable, Optional
 
@@ -36,6 +37,14 @@ def merge_state_dict(model: torch.nn.Module, checkpoint, keep: Optional[Callable
     state = model.state_dict()
     keep = keep or (lambda k: True)
     take = OrderedDict((k, v) for k, v in ckpt.items() if k in state and keep(k))
+    wanted = [k for k in ckpt if keep(k)]
+    if wanted and not take:
+        raise RuntimeError(f"checkpoint merge loaded nothing: {len(wanted)} checkpoint keys pass the filter (e.g. "
+                           f"{wanted[0]!r}) but none of them exists in the model (model keys look like {next(iter(state))!r})")
+    absent = [k for k in wanted if k not in state]
+    if absent:
+        warnings.warn(f"{len(absent)} checkpoint keys pass the filter but are not in the model and were ignored "
+                      f"(first: {absent[0]!r}); construct the model with its feature extractor (backbone=...) to load them")
     if strict_shapes:
         bad = [(k, tuple(v.shape), tuple(state[k].shape)) for k, v in take.items() if tuple(v.shape) != tuple(state[k].shape)]
         if bad:

@@ -43,9 +43,14 @@ __host__ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
   return x;
 }
 __host__ __device__ __forceinline__ uint64_t drop_hash64(uint64_t seed, uint64_t quad) {
+  // fold the whole 64-bit seed into BOTH 32-bit keys (a multiply carries the low seed bits into the high word, the
+  // xor-shift brings the high word down): small seeds (1, 2, 3, ...) must change all four keep decisions of a quad
+  uint64_t k = (seed + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+  k ^= k >> 31;
+  const uint32_t k0 = (uint32_t)k, k1 = (uint32_t)(k >> 32);
   const uint32_t q = (uint32_t)quad ^ ((uint32_t)(quad >> 32) * 0x9E3779B1u);
-  const uint32_t lo = drop_mix32(q * 0x9E3779B1u + (uint32_t)seed);
-  const uint32_t hi = drop_mix32((q ^ 0x85EBCA77u) * 0xC2B2AE3Du + (uint32_t)(seed >> 32));
+  const uint32_t lo = drop_mix32(q * 0x9E3779B1u + k0);
+  const uint32_t hi = drop_mix32((q ^ 0x85EBCA77u) * 0xC2B2AE3Du + k1);
   return ((uint64_t)hi << 32) | lo;
 }
 __host__ __device__ __forceinline__ uint32_t drop_threshold16(float p) {

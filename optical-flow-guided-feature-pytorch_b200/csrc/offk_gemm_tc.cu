@@ -390,7 +390,7 @@ __device__ float* g_offk_dump = nullptr;   // bring-up only: CTA (0,0,0) copies 
 // and only then arrives on "full"; the MMA thread issues three MMAs per K = 8 step.
 template <int A_MODE, int B_MODE, bool X3>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split, int tmem_cols, int la) {
+gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split, int tmem_cols, int la, int n_main) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16 KB | B bn*128)] then the barrier block
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -497,13 +497,18 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
         const uint64_t bdesc = B_MN ? make_smem_desc_mn(b_base, 512u, b_kgroup >> 1) : make_smem_desc(b_base);
         const uint64_t a_step = A_MN ? (uint64_t)(4096 >> 4) : 2ull, b_step = B_MN ? (uint64_t)(b_kgroup >> 4) : 2ull;
         const uint64_t lo_step = (uint64_t)(hi_bytes >> 4);   // residual tiles sit hi_bytes further (start-address field)
+        // X3: both corrections accumulate in accumulator 0, hi*hi of K-block i in main accumulator 1 + i % n_main
+        // (tmem_ld16_sum in offk_tc.cuh says why)
+        const uint32_t acc_stride = ((uint32_t)bn + 31u) & ~31u;
+        const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + i % n_main) * acc_stride : tmem_d;
+        const bool main_started = X3 ? i >= n_main : i > 0;
 #pragma unroll
         for (int j = 0; j < TC_BK / 8; ++j) {
-          if (X3) {                                           // small terms first
+          if (X3) {
             umma_tf32(tmem_d, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
             umma_tf32(tmem_d, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
           }
-          umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (X3 || i > 0 || j > 0) ? 1u : 0u);
+          umma_tf32(d_main, adesc + a_step * j, bdesc + b_step * j, idesc, (main_started || j > 0) ? 1u : 0u);
         }
         umma_commit(smem_u32(&sh->empty[s]));          // frees the smem slot when these MMAs retire
         if (++s == stages) { s = 0; parity ^= 1u; }
@@ -552,7 +557,8 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
         for (int j = 0; j < 16; ++j) oc[j] = (nb + j < g.N) ? __ldg(g.out_col + nb + j) : 0;
       }
       float v[16];
-      tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16), v);
+      tmem_ld16_sum(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16), X3 ? 1 + min(n_main, nkb) : 1,
+                    ((uint32_t)bn + 31u) & ~31u, v);
       if (lane_vec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -628,6 +634,11 @@ static int launch_tc_t(const offk_gemm_t& g, int bn, int stages, int kb_per, int
                        cudaStream_t st) {
   auto kern = gather_gemm_tc_kernel<A_MODE, B_MODE, X3>;
   const int la = stages - 1 < 3 ? stages - 1 : 3;      // X3: residual pass trails the cp.async issue front by `la` K-blocks
+  int n_main = 1;
+  if (X3) {   // (n_main + 1) accumulators of bn columns (32-column granules) in the allocated tensor memory, <= 4 mains
+    n_main = tmem_cols / ((bn + 31) / 32 * 32) - 1;
+    if (n_main > 4) n_main = 4;
+  }
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -642,7 +653,7 @@ static int launch_tc_t(const offk_gemm_t& g, int bn, int stages, int kb_per, int
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, bn, stages, kb_per, tmem_cols, la);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, bn, stages, kb_per, tmem_cols, la, n_main);
   if (e != cudaSuccess) return cuda_check(e, "gather_gemm_tc launch");
   return OFFK_LAUNCH_CHECK("gather_gemm_tc");
 }
@@ -665,6 +676,14 @@ int launch_gemm_tc(const offk_gemm_t& g, cudaStream_t st, bool x3) {
   const size_t smem = (size_t)stages * stage_bytes + sizeof(TcShared) + 1024;
   int tmem_cols = 32;
   while (tmem_cols < bn) tmem_cols <<= 1;
+  if (x3) {   // room for the correction accumulator and up to 4 main ones: 256 columns while two CTAs share the SM, else 512
+    const int cap = budget > 108 * 1024 ? 512 : 256, stride = (bn + 31) / 32 * 32;
+    if (cap / stride < 2) return fail(OFFK_E_LIMIT, "gather_gemm: no room in tensor memory for the 3xTF32 accumulators (N tile %d)", bn);
+    int want = (cap / stride > 5 ? 5 : cap / stride) * stride;
+    tmem_cols = 32;
+    while (tmem_cols < want) tmem_cols <<= 1;
+    if (tmem_cols > cap) tmem_cols = cap;
+  }
   dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + bn - 1) / bn, (num_kb + kb_per - 1) / kb_per);
   if (grid.y > 65535 || grid.z > 65535) return fail(OFFK_E_LIMIT, "gather_gemm: grid too large");
   // cp.async cannot apply ReLU-on-load: such operands (one small 1x1 conv) take the scalar register path

@@ -90,7 +90,7 @@ struct TmShared {
 template <int A_KIND, int B_KIND, bool X3>
 __global__ void __launch_bounds__(TM_THREADS, 2)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const offk_gemm_t g,
-                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols) {
+                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
@@ -245,13 +245,18 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, 4096u, 512u) : make_smem_desc(a_base);
           const uint64_t bdesc = B_MN ? make_smem_desc_mn(a_base + TC_A_BYTES, 4096u, 512u) : make_smem_desc(a_base + TC_A_BYTES);
           const uint64_t lo_step = (uint64_t)(hi_bytes >> 4);    // residual tiles sit hi_bytes further (start-address field)
+          // X3: both corrections accumulate in accumulator 0, hi*hi of K-block i in main accumulator 1 + i % n_main
+          const uint32_t acc_stride = ((uint32_t)bn + 31u) & ~31u;
+          const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + i % n_main) * acc_stride : tmem_d;
+          const uint32_t d_corr = tmem_d;
+          const bool main_started = X3 ? i >= n_main : i > 0;
 #pragma unroll
           for (int j = 0; j < TC_BK / 8; ++j) {
-            if (X3) {                                            // small terms first
-              umma_tf32(tmem_d, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
-              umma_tf32(tmem_d, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
+            if (X3) {
+              umma_tf32(d_corr, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+              umma_tf32(d_corr, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
             }
-            umma_tf32(tmem_d, adesc + a_step * j, bdesc + b_step * j, idesc, (X3 || i > 0 || j > 0) ? 1u : 0u);
+            umma_tf32(d_main, adesc + a_step * j, bdesc + b_step * j, idesc, (main_started || j > 0) ? 1u : 0u);
           }
           umma_commit(smem_u32(&sh->empty[s]));                  // frees the smem slot when these MMAs retire
         }
@@ -267,6 +272,9 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
     const int half = ew >> 2;                                    // which 16 columns of a 32-column chunk
     const bool atomic = (g.split_k > 1) || g.atomic_out;
+    // accumulators to add up in the epilogue (X3: the correction accumulator + the main ones that received a K-block)
+    const int n_acc = X3 ? 1 + min(n_main, nkb) : 1;
+    const uint32_t acc_stride = ((uint32_t)bn + 31u) & ~31u;
     // X3 main-loop duty of these 256 threads: residual tiles.  Stage s = [A | B | A_lo | B_lo]; the first half is what
     // the TMA delivered, the second half is written here, element for element at the same swizzled offset.
     auto split_loop = [&]() {
@@ -321,7 +329,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         if (nvalid && g.bias && !atomic) bias4 = ldg128(g.bias + n);      // in flight across the TMEM drain below
         if (c * 32 + half * 16 < bn) {
           float v[16];
-          tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16), v);
+          const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16);
+          tmem_ld16_sum(ta, n_acc, acc_stride, v);
           const uint32_t dst = stg + (uint32_t)(trow * TM_EPI_PITCH + half * 16) * 4;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) sts128(dst + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -379,7 +388,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       const int nchunks = bn >> 4;
       for (int c = half; c < nchunks; c += 2) {
         float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16), v);
+        const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 16);
+        tmem_ld16_sum(ta, n_acc, acc_stride, v);
         if (mvalid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -479,7 +489,7 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
 
 template <int A_KIND, int B_KIND, bool X3>
 static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
-                       int kb_per, int tmem_cols, dim3 grid, size_t smem, cudaStream_t st) {
+                       int kb_per, int tmem_cols, int n_main, dim3 grid, size_t smem, cudaStream_t st) {
   auto kern = tma_gemm_kernel<A_KIND, B_KIND, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -495,7 +505,7 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main);
   if (e != cudaSuccess) return cuda_check(e, "tma_gemm launch");
   return OFFK_LAUNCH_CHECK("tma_gemm");
 }
@@ -597,8 +607,18 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
   const size_t smem = (size_t)stages * stage_bytes + sizeof(TmShared) + 1024;
+  int n_main = 1, tmem_need = bn;
+  if (x3) {
+    // TMEM columns: 256 per CTA while two CTAs share the SM, all 512 otherwise; (n_main + 1) accumulators of bn columns
+    // (32-column granules), at most 4 mains (see tmem_ld16_sum)
+    const int cap = budget > 108 * 1024 ? 512 : 256, stride = (bn + 31) / 32 * 32;
+    n_main = cap / stride - 1;
+    if (n_main > 4) n_main = 4;
+    OFFK_REQUIRE(n_main >= 1, "tma_gemm: no room in tensor memory for the 3xTF32 accumulators (N tile %d)", bn);
+    tmem_need = (n_main + 1) * stride;
+  }
   int tmem_cols = 32;
-  while (tmem_cols < bn) tmem_cols <<= 1;
+  while (tmem_cols < tmem_need) tmem_cols <<= 1;
   dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + bn - 1) / bn, (num_kb + kb_per - 1) / kb_per);
   if (t->a_kind == OFFK_TMA_A_NCHW) grid.x = (unsigned)(t->n_img * geo.tiles_per_img);
   OFFK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tma_gemm: grid too large");
@@ -608,8 +628,8 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   cudaStream_t st = as_stream(stream);
 #define OFFK_TM_CASE(AK, BK)                                                                                          \
   if (t->a_kind == AK && t->b_kind == BK)                                                                             \
-    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, st)              \
-              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, grid, smem, st);
+    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, grid, smem, st)      \
+              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, grid, smem, st);
   OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)

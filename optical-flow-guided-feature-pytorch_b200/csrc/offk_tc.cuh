@@ -76,6 +76,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Sum of `n_acc` accumulators that sit `stride` TMEM columns apart (3xTF32: the hi*hi products of K-block i go to "main"
+// accumulator i % n_main, the two correction products to one more accumulator behind them).  The tensor core adds into
+// its fp32 accumulator with truncation, so the error of a chain grows with its length and with the magnitude of the
+// running sum: short chains for the large terms and a chain of their own for the ~2^-11 times smaller corrections keep
+// the 3xTF32 result at fp32 level; the partial accumulators are added here in round-to-nearest fp32.
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, int n_acc, uint32_t stride, float (&v)[16]) {
+  tmem_ld16(taddr, v);
+  for (int a = 1; a < n_acc; ++a) {
+    float t[16];
+    tmem_ld16(taddr + (uint32_t)a * stride, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += t[i];
+  }
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2

@@ -197,6 +197,7 @@ class OFFEngine:
         self.tma_strided_dgrad = os.environ.get("OFFK_NO_TMA_SDGRAD", "0") != "1"
         self._tab_cache = {}
         self._keep = []
+        self.generation = 0
 
         # ---- parameters: one flat buffer, reference-named views
         self.layout, self.n_flat = S.flat_layout(variant)
@@ -796,7 +797,13 @@ class OFFEngine:
                                                                    stream), "sum_14b"), "sum_14b", reads=[a, b], writes=[dst])
 
     def _site_seed(self, site):
-        return (self.drop_seed * 64 + site) & 0xFFFFFFFFFFFFFFFF
+        """64-bit seed of dropout call site ``site`` (12 per forward, RGB_OFF.py:612..:845) for this step: splitmix64 over
+        (step seed, site), so that every bit of the step seed reaches every keep decision."""
+        m = 0xFFFFFFFFFFFFFFFF
+        z = (self.drop_seed * 0x9E3779B97F4A7C15 + (site + 1) * 0xD1B54A32D192ED03) & m
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+        return z ^ (z >> 31)
 
     def _pool_fwd(self, k, x, c, ctot, coff):
         lib, P = self.lib, self.P
@@ -875,6 +882,7 @@ class OFFEngine:
         if taps is not None:
             self.set_taps(taps)
         self._set_dropout(train, masks, seed)
+        self.generation += 1            # backward() consumes the activations of THIS forward (one set of static buffers)
         streams = self._fork()
         self.fwd_sched.run(streams)
         self._join(streams)

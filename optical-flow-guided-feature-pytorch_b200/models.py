@@ -47,12 +47,50 @@ class BNInception_OFF(nn.Module):
                                                       tap_grads=tap_grads, device=device))
         for name, mod in self.off.named_children():
             setattr(self, name, mod)                  # motion_conv_gen_3a ... fc_action_motion_14 (+ sobel_edge_diagonal)
-        self.backbone = backbone
+        self._off_children = tuple(n for n, _ in self.off.named_children())
+        self._attach_backbone(backbone)
 
     # ------------------------------------------------------------------ helpers
+    def _attach_backbone(self, backbone):
+        """The reference keeps the BN-Inception layers at the TOP level of the class (``conv1_7x7_s2.weight``, ...,
+        RGB_OFF.py:43-263), so its checkpoints carry top-level keys.  The feature extractor's layers (and its direct
+        parameters / buffers) are therefore registered here under their own names -- ``state_dict()`` / ``load_state_dict``
+        / ``.to()`` see them exactly as the reference's do -- while the extractor object itself is a plain attribute."""
+        object.__setattr__(self, "backbone", backbone)
+        if backbone is None:
+            return
+        taken = set(self._off_children) | {"consensus"}
+        for name, child in backbone.named_children():
+            if name in taken:
+                raise ValueError(f"backbone layer name {name!r} collides with an OFF module of the same name")
+            setattr(self, name, child)
+        for name, p in backbone.named_parameters(recurse=False):
+            self.register_parameter(name, p)
+        for name, b in backbone.named_buffers(recurse=False):
+            self.register_buffer(name, b)
+
     def train(self, mode=True):
         super().train(mode)
         self.off.train(mode)                          # dropout of the OFF section follows the model (RGB_OFF.py:356)
+        if self.backbone is not None:
+            self.backbone.training = mode             # its layers are children of this class and were switched above
+        return self
+
+    def _apply(self, fn, recurse=True):
+        """``.cuda()`` / ``.to()`` / ``.float()`` place the feature extractor; the OFF parameters are views of the engine's
+        flat CUDA buffer and must not be replaced by moved / cast copies (the kernels would keep reading the buffer):
+        they are routed through ``OFFSubNetwork._apply`` (a no-op on the right device / dtype, an error otherwise)."""
+        self.off._apply(fn)
+        order = list(self._modules.items())
+        for n in self._off_children:
+            self._modules.pop(n)
+        try:
+            super()._apply(fn)
+        finally:
+            held = dict(order)
+            self._modules.clear()
+            for n, m in order:
+                self._modules[n] = held[n]
         return self
 
     def _taps_and_score(self, input):

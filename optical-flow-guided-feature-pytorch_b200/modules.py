@@ -34,6 +34,18 @@ class _Prefetched:
         self.index, self.event = index, event
 
 
+_NO_GRAD = ("fc_action_motion_28.weight", "fc_action_motion_28.bias")
+
+
+def _step_seed():
+    """Dropout seed of one training forward: drawn from torch's default CPU generator (so torch.manual_seed reproduces a
+    run and a resumed run does not replay the masks of step 1), offset per rank so data-parallel replicas differ."""
+    s = int(torch.randint(0, 1 << 62, (1,)).item())
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        s = (s + 0x9E3779B97F4A7C15 * (torch.distributed.get_rank() + 1)) & ((1 << 63) - 1)
+    return s
+
+
 class _OFFFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, train, masks, seed, n_taps, *tensors):
@@ -54,6 +66,7 @@ class _OFFFunction(torch.autograd.Function):
                 for buf, t in zip(eng.taps.values(), taps):
                     buf.copy_(t, non_blocking=True)
         fc7, fc28, fc14 = eng.forward(train=train, masks=masks, seed=seed)
+        ctx.generation = eng.generation                 # the engine keeps ONE set of activations: see backward()
         ctx.net = net
         ctx.n_taps = n_taps
         ctx.tap_needs = [t.requires_grad for t in taps]
@@ -64,21 +77,30 @@ class _OFFFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g7, g28, g14):
         net, eng = ctx.net, ctx.net.engine
+        if ctx.generation != eng.generation:
+            raise RuntimeError(
+                "OFFSubNetwork.backward: the module ran another forward since the one this graph belongs to. The "
+                "engine keeps one set of static activation buffers (no per-call saved tensors), so each backward must "
+                "follow its own forward: run forward -> backward per input, or use one module per concurrent graph.")
         if any(ctx.tap_needs) and not eng.tap_grads:
             raise RuntimeError("tap gradients requested but the module was built with tap_grads=False "
                                "(the reference freezes the backbone, train_off.py:39-46)")
         params = net._flat_params
         views = [eng.grads[n] for n in eng.grads]
-        aliased = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views)]
+        # parameters the backward plan never writes get NO gradient, as in the reference, where fc_action_motion_28 is
+        # not part of any returned output (RGB_OFF.py:787,860): .grad stays None, optimizers skip them (no weight decay)
+        live = [n not in _NO_GRAD for n in eng.grads]
+        aliased = [p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v, l in zip(params, views, live) if l]
         in_place = all(aliased)                          # .grad already lives in the flat buffer: accumulate there
         if any(aliased) and not in_place:
-            for p, a in zip(params, aliased):
+            for p, a in zip([p for p, l in zip(params, live) if l], aliased):
                 if a:
                     p.grad = p.grad.clone()
         g7 = torch.zeros_like(eng.d_out7) if g7 is None else g7
         g14 = torch.zeros_like(eng.d_out14) if g14 is None else g14
         eng.backward(g7.contiguous(), g14.contiguous(), zero_grads=not in_place)
-        pgrads = [None] * len(params) if in_place else [eng._view(eng.grads_flat, n) for n in eng.grads]
+        pgrads = [None] * len(params) if in_place else [eng._view(eng.grads_flat, n) if l else None
+                                                        for n, l in zip(eng.grads, live)]
         tgrads = [eng.tap_grad[tag].clone() if need else None
                   for tag, need in zip(eng.taps, ctx.tap_needs)] if eng.tap_grads else [None] * ctx.n_taps
         return (None, None, None, None, None, *tgrads, *pgrads)
@@ -149,5 +171,5 @@ class OFFSubNetwork(nn.Module):
         if isinstance(taps, dict):
             taps = [taps[t] for t in S.LEVELS]
         train = self.training
-        self._seed += 1
+        self._seed = _step_seed() if (train and masks is None) else 0
         return _OFFFunction.apply(self, train, masks, self._seed, len(taps), *taps, *self._flat_params)

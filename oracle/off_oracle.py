@@ -249,13 +249,26 @@ def _drop(x, mask, p_drop):
     return x * mask.to(x.dtype).reshape(x.shape) * (1.0 / (1.0 - p_drop))
 
 
-def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index_mode="reference_flat", mm="exact"):
+def _act(x, gates, site):
+    """ReLU (RGB_OFF.py:340).  With ``gates`` (site -> bool tensor, e.g. the product's own activation signs) the ReLU is
+    replaced by a multiplication with the given 0/1 pattern: identical wherever the pattern equals (x > 0), and at the
+    rare element whose pre-activation sits within round-off of zero the forward changes by O(round-off) while the
+    BACKWARD gate follows the supplied pattern.  This takes ReLU-gate flips -- a discontinuity, not an arithmetic
+    error -- out of a gradient comparison."""
+    if gates is None:
+        return F.relu(x)
+    return x * gates[site].to(x.dtype).reshape(x.shape)
+
+
+def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index_mode="reference_flat", mm="exact",
+             gates=None):
     """One OFF unit, e.g. RGB_OFF.py:596-616 for level 3a.
 
     Returns (motion [P,160,S,S], gen_relu [N,128,S,S], down [P,32,S,S]).
     """
     s = tap.shape[-1]
-    g = F.relu(_conv2d(tap, prm[f"motion_conv_gen_{tag}.weight"], prm[f"motion_conv_gen_{tag}.bias"], mm=mm))  # :597-598
+    g = _act(_conv2d(tap, prm[f"motion_conv_gen_{tag}.weight"], prm[f"motion_conv_gen_{tag}.bias"], mm=mm),
+             gates, "gen_" + tag)                                                                        # :597-598
     ch = g.shape[1]
     r = g.view(batch, -1, s, s)                       # :600
     temporal = (r[:, ch:] - r[:, :-ch]).reshape(-1, ch, s, s)  # :601-604
@@ -274,7 +287,7 @@ def off_unit(tap, prm, tag, batch, length, variant, mask=None, p_drop=0.8, index
 
 
 def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
-                consensus=None, index_mode="reference_flat", mm="exact"):
+                consensus=None, index_mode="reference_flat", mm="exact", gates=None):
     """OFF sub-network forward, RGB_OFF.py:596-860 / Flow_OFF.py:606-884.
 
     ``consensus``: None -> follow the variant (rgb: per-pair logits as in
@@ -287,36 +300,36 @@ def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
     w = lambda n: prm[n + ".weight"]
     b = lambda n: prm[n + ".bias"]
     conv = lambda x, n, stride=1, pad=0: _conv2d(x, w(n), b(n), stride, pad, mm)
-    relu = F.relu
+    relu = lambda x, site: _act(x, gates, site)          # ``site`` names the activation (see GATE_SITES)
     out = {}
 
-    m = {t: off_unit(taps[t], prm, t, batch, length, variant, mk(t), p_drop, index_mode, mm)[0] for t in LEVELS}
+    m = {t: off_unit(taps[t], prm, t, batch, length, variant, mk(t), p_drop, index_mode, mm, gates)[0] for t in LEVELS}
 
     # ---- resolution 28 (RGB_OFF.py:655-685)
     f28 = torch.cat((m["3a"], m["3b"]), 1)                               # :656
     t28 = conv(f28, "motion_conv_trans_28", 2, 3)                        # :657 (pre-ReLU kept for the branch, :665)
-    r28 = relu(t28)                                                      # :658
-    h = relu(conv(r28, "motion_conv1_trans_28a"))                        # :659-660
-    h = relu(conv(h, "motion_conv2_trans_28a", 1, 1))                    # :661-662
+    r28 = relu(t28, "t28")                                               # :658
+    h = relu(conv(r28, "motion_conv1_trans_28a"), "h1_28a")              # :659-660
+    h = relu(conv(h, "motion_conv2_trans_28a", 1, 1), "h2_28a")          # :661-662
     h = conv(h, "motion_conv3_trans_28a")                                # :663
-    s28 = relu(h + conv(t28, "motion_conv_branch_28a"))                  # :665-667
+    s28 = relu(h + conv(t28, "motion_conv_branch_28a"), "s28a")          # :665-667
     for blk in ("28b", "28c"):                                           # :670-685
-        h = relu(conv(s28, "motion_conv1_trans_" + blk))
-        h = relu(conv(h, "motion_conv2_trans_" + blk, 1, 1))
+        h = relu(conv(s28, "motion_conv1_trans_" + blk), "h1_" + blk)
+        h = relu(conv(h, "motion_conv2_trans_" + blk, 1, 1), "h2_" + blk)
         h = conv(h, "motion_conv3_trans_" + blk)
-        s28 = relu(h + s28)
+        s28 = relu(h + s28, "s" + blk)
 
     # ---- resolution 14 (RGB_OFF.py:759-780)
     f14 = torch.cat((m["3c"], m["4a"], m["4b"], m["4c"], m["4d"], s28), 1)  # :760
-    t14 = relu(conv(f14, "motion_conv_trans_14", 2, 2))                  # :762-763
-    h = relu(conv(t14, "motion_conv1_trans_14a"))
-    h = relu(conv(h, "motion_conv2_trans_14a", 1, 1))
+    t14 = relu(conv(f14, "motion_conv_trans_14", 2, 2), "t14")           # :762-763
+    h = relu(conv(t14, "motion_conv1_trans_14a"), "h1_14a")
+    h = relu(conv(h, "motion_conv2_trans_14a", 1, 1), "h2_14a")
     h = conv(h, "motion_conv3_trans_14a")
-    s14 = relu(h + conv(t14, "motion_conv_expand_trans_14a"))           # :769-771
-    h = relu(conv(s14, "motion_conv1_trans_14b"))
-    h = relu(conv(h, "motion_conv2_trans_14b", 1, 1))
-    h = relu(conv(h, "motion_conv3_trans_14b", 1, 1))                    # 3x3 (:316) + ReLU before the add (:778)
-    s14 = relu(s14 + h)                                                  # :779-780
+    s14 = relu(h + conv(t14, "motion_conv_expand_trans_14a"), "s14a")    # :769-771
+    h = relu(conv(s14, "motion_conv1_trans_14b"), "h1_14b")
+    h = relu(conv(h, "motion_conv2_trans_14b", 1, 1), "h2_14b")
+    h = relu(conv(h, "motion_conv3_trans_14b", 1, 1), "h3_14b")          # 3x3 (:316) + ReLU before the add (:778)
+    s14 = relu(s14 + h, "s14b")                                          # :779-780
 
     # ---- heads 28 / 14 (RGB_OFF.py:783-793)
     def head(x, fc, key):
@@ -331,9 +344,9 @@ def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
 
     # ---- resolution 7 (RGB_OFF.py:831-847)
     f7 = torch.cat((m["5a"], m["5b"], s14), 1)                           # :832
-    t7 = relu(conv(f7, "motion_conv_trans", 1, 1))                       # :833-834
-    h = relu(conv(t7, "motion_conv1_trans"))
-    h = relu(conv(h, "motion_conv2_trans", 1, 1))
+    t7 = relu(conv(f7, "motion_conv_trans", 1, 1), "t7")                 # :833-834
+    h = relu(conv(t7, "motion_conv1_trans"), "h1_7")
+    h = relu(conv(h, "motion_conv2_trans", 1, 1), "h2_7")
     h = conv(h, "motion_conv3_trans")
     s7 = h + conv(t7, "motion_conv_branch_trans")                        # :840-841 (no final ReLU)
     fc7 = head(s7, "fc_action_motion", "fc7")
@@ -347,12 +360,18 @@ def off_forward(taps, prm, batch, length, variant="rgb", masks=None, p_drop=0.8,
     return out
 
 
+# ReLU sites of the path, in forward order (the names off_forward passes to _act)
+GATE_SITES = (["gen_" + t for t in LEVELS] +
+              ["t28", "h1_28a", "h2_28a", "s28a", "h1_28b", "h2_28b", "s28b", "h1_28c", "h2_28c", "s28c",
+               "t14", "h1_14a", "h2_14a", "s14a", "h1_14b", "h2_14b", "h3_14b", "s14b", "t7", "h1_7", "h2_7"])
+
+
 def to_dtype(d, dtype):
     return OrderedDict((k, v.to(dtype)) for k, v in d.items())
 
 
 def off_forward_backward(taps, prm, batch, length, variant="rgb", masks=None, dtype=torch.float32,
-                         tap_grads=False, loss="sum", mm="exact"):
+                         tap_grads=False, loss="sum", mm="exact", gates=None):
     """Forward + backward with ``loss = fc7.sum() + fc14.sum()``.
 
     Returns (outputs dict, grads dict name->tensor [, tap grads dict]).
@@ -360,7 +379,7 @@ def off_forward_backward(taps, prm, batch, length, variant="rgb", masks=None, dt
     """
     prm = OrderedDict((k, v.detach().to(dtype).requires_grad_(True)) for k, v in prm.items())
     taps = OrderedDict((k, v.detach().to(dtype).requires_grad_(tap_grads)) for k, v in taps.items())
-    out = off_forward(taps, prm, batch, length, variant, masks, mm=mm)
+    out = off_forward(taps, prm, batch, length, variant, masks, mm=mm, gates=gates)
     if loss == "sum":
         l = out["fc7"].sum() + out["fc14"].sum()
     else:

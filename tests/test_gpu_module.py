@@ -50,7 +50,22 @@ def test_autograd_accumulates_like_torch(dev):
     fc7, _, fc14 = net(taps)
     (fc7.sum() + fc14.sum()).backward()
     assert torch.allclose(net.motion_conv_trans.weight.grad, g1, rtol=1e-4, atol=1e-6)
-    assert net.fc_action_motion_28.weight.grad is None or net.fc_action_motion_28.weight.grad.abs().max() == 0
+    # fc_action_motion_28 is not part of any returned output (RGB_OFF.py:787,860): no gradient at all, as in the reference
+    assert net.fc_action_motion_28.weight.grad is None and net.fc_action_motion_28.bias.grad is None
+
+
+def test_backward_must_follow_its_own_forward(dev):
+    """the engine keeps one set of activation buffers, so a backward whose forward has been
+    overwritten by a later forward raises instead of silently using the wrong activations."""
+    from off_b200.modules import OFFSubNetwork
+    net = OFFSubNetwork(1, 3, "rgb", precision="tf32", device=dev).eval()
+    taps = {k: v.to(dev) for k, v in O.make_taps(3, 1, 3).items()}
+    fc7_a, _, _ = net(taps)
+    fc7_b, _, _ = net(taps)
+    with pytest.raises(RuntimeError, match="another forward"):
+        fc7_a.sum().backward()
+    fc7_b.sum().backward()                                   # the latest forward is fine
+    assert net.motion_conv_trans.weight.grad is not None
 
 
 def test_tap_gradients_when_requested(dev):
@@ -63,10 +78,13 @@ def test_tap_gradients_when_requested(dev):
     tg = {k: v.to(dev).requires_grad_(True) for k, v in taps.items()}
     fc7, _, fc14 = net(tg)
     (fc7.sum() + fc14.sum()).backward()
-    _, _, tref = O.off_forward_backward(taps, prm, B, Lg, "rgb", None, torch.float64, tap_grads=True)
+    # the oracle follows the engine's ReLU gates (helpers.engine_gates): arithmetic only, no gate flips
+    from helpers import engine_gates
+    _, _, tref = O.off_forward_backward(taps, prm, B, Lg, "rgb", None, torch.float64, tap_grads=True,
+                                        gates=engine_gates(net.engine))
     for k in taps:
         err = (tg[k].grad.double().cpu() - tref[k]).norm() / tref[k].norm()
-        assert err < 2e-3, (k, float(err))
+        assert err < 2e-4, (k, float(err))
 
 
 def test_consensus_module(dev):

@@ -533,6 +533,16 @@ def test_layout_helpers(dev):
 
 import functools
 
+# ---- tolerances of the whole-section comparisons: (stage-fusion tensors, logits: max-abs / tensor max; gradients: worst
+# relative L2 over the parameters).
+# fp32 mode vs the fp64 oracle.  Forward: fp32 level.  Gradients against the oracle's OWN ReLU gates are dominated by
+# gate flips, not arithmetic: an element whose pre-activation sits within round-off of zero takes either sign, and each
+# flipped gate moves a weight gradient by O(1/sqrt(#elements)).  The reference's own fp32 CPU arithmetic shows the same
+# against fp64 (B=1, L=3: worst relative L2 1.4e-2; 1.8e-6 once the gates are matched -- measured with oracle/off_oracle.py),
+# so the exact-oracle gate only bounds the flip rate and the arithmetic is pinned by the gate-matched run.
+TOL_FP32 = (2e-5, 5e-5, 5e-2)
+TOL_FP32_GATED = (2e-5, 5e-5, 2e-4)
+
 
 @functools.lru_cache(maxsize=2)
 def _taps_cached(seed, B, Lg):
@@ -554,12 +564,23 @@ def _oracle_cached(variant, B, Lg, train, mm):
     return taps, prm, masks, r7, r14, keep, gref
 
 
-def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit, tol_grad, mm="exact"):
+from helpers import engine_gates as _engine_gates  # noqa: E402
+
+
+def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit, tol_grad, mm="exact", gate_matched=False):
+    """gate_matched: the oracle is re-run with the ENGINE's ReLU sign patterns (off_oracle._act), so that the gradient
+    comparison measures arithmetic only -- a pre-activation within round-off of zero may take either sign, and one
+    flipped gate moves a weight gradient by ~1/sqrt(#elements) in relative L2, far above fp32 round-off."""
     from off_b200 import engine as E
     taps, prm, masks, r7, r14, ref, gref = _oracle_cached(variant, B, Lg, train, mm)
     eng = E.OFFEngine(B, Lg, variant, dev, precision)
     eng.load_params(prm)
     fc7, fc28, fc14 = eng.forward({k: v.to(dev) for k, v in taps.items()}, train=train, masks=masks)
+    torch.cuda.synchronize()
+    if gate_matched:
+        lossf = lambda o: (o["fc7"].reshape(r7.shape) * r7).sum() + (o["fc14"].reshape(r14.shape) * r14).sum()
+        ref, gref = O.off_forward_backward(taps, prm, B, Lg, variant, masks, torch.float64, loss=lossf, mm=mm,
+                                           gates=_engine_gates(eng))
     report, bad = {}, []
     for k, st in (("fusion28", "F28"), ("fusion14", "F14"), ("fusion7", "F7")):      # per-level error (channels-last -> NCHW)
         report[k] = _rel(eng.buf[st].permute(0, 3, 1, 2), ref[k])
@@ -582,7 +603,7 @@ def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit
             worst, worst_name = e, n
     if not worst < tol_grad:
         bad.append(("grad " + worst_name, worst, tol_grad))
-    print(f"[parity {precision} vs {mm} oracle, {variant} B{B} L{Lg} train={train}] " +
+    print(f"[parity {precision} vs {mm}{'+gates' if gate_matched else ''} oracle, {variant} B{B} L{Lg} train={train}] " +
           " ".join(f"{k}={v:.2e}" for k, v in report.items()) + f" grad_rel_l2_worst={worst:.2e} ({worst_name})")
     assert not bad, bad
     return report, worst
@@ -593,13 +614,15 @@ def _engine_vs_oracle(dev, precision, variant, B, Lg, train, tol_fuse, tol_logit
                                                 ("rgb", 2, 7, False), ("flow", 1, 7, True)])   # config 4 geometry: 7 segments
 def test_engine_fp32_mode_matches_oracle(dev, variant, B, Lg, train):
     """precision='fp32' = the fp32-parity mode on the tensor cores (3xTF32 tcgen05, OFFK_PREC_TF32X3)."""
-    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, 2e-5, 2e-5, 2e-3)
+    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, *TOL_FP32)
+    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, *TOL_FP32_GATED, gate_matched=True)
 
 
 @pytest.mark.parametrize("variant,B,Lg,train", [("rgb", 2, 3, False), ("flow", 1, 4, True)])
 def test_engine_fp32_simt_cross_check(dev, variant, B, Lg, train):
     """The CUDA-core FFMA twin of every contraction (OFFK_PREC_FP32): an independent check of the index tables."""
-    _engine_vs_oracle(dev, "fp32_simt", variant, B, Lg, train, 2e-5, 2e-5, 2e-3)
+    _engine_vs_oracle(dev, "fp32_simt", variant, B, Lg, train, *TOL_FP32)
+    _engine_vs_oracle(dev, "fp32_simt", variant, B, Lg, train, *TOL_FP32_GATED, gate_matched=True)
 
 
 TF32_CASES = [("rgb", 2, 3, False), ("flow", 2, 3, False), ("rgb", 2, 2, True), ("rgb", 2, 7, True)]
@@ -615,12 +638,12 @@ def test_engine_tf32_mode_matches_oracle(dev, variant, B, Lg, train):
 # is fp32 accumulation order plus the rare operand whose fp32 value (GPU) and fp64 value (oracle) straddle a tf32
 # truncation boundary.  This pins the tensor-core path itself: a wrong tap, stride-parity class or table entry moves a
 # gradient by O(1), two orders of magnitude above these gates.
-TOL_TF32_EMU = (5e-4, 1e-3, 1e-2)      # stage-fusion tensors, logits (max-abs / max), gradients (relative L2)
+TOL_TF32_EMU = (5e-4, 1e-3, 5e-3)      # + the oracle follows the engine's ReLU gates (gate_matched)
 
 
 @pytest.mark.parametrize("variant,B,Lg,train", TF32_CASES)
 def test_engine_tf32_mode_matches_truncated_operand_oracle(dev, variant, B, Lg, train):
-    _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, *TOL_TF32_EMU, mm="tf32_trunc")
+    _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, *TOL_TF32_EMU, mm="tf32_trunc", gate_matched=True)
 
 
 # BASELINE.json's own shapes (config 2: RGB 48 x 3, config 3: Flow 48 x 3, config 4 per GPU at 8 ranks: RGB 16 x 7):
@@ -631,9 +654,10 @@ BENCH_SHAPES = [("rgb", 48, 3, True), ("flow", 48, 3, False), ("rgb", 16, 7, Fal
 
 @pytest.mark.parametrize("variant,B,Lg,train", BENCH_SHAPES, ids=["cfg2_rgb48x3_train", "cfg3_flow48x3", "cfg4_rgb16x7"])
 def test_benchmark_shapes_match_oracle(dev, variant, B, Lg, train):
-    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, 2e-5, 2e-5, 2e-3)
+    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, *TOL_FP32)
+    _engine_vs_oracle(dev, "fp32", variant, B, Lg, train, *TOL_FP32_GATED, gate_matched=True)
     _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, 5e-3, 1e-2, 0.2)
-    _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, *TOL_TF32_EMU, mm="tf32_trunc")
+    _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, *TOL_TF32_EMU, mm="tf32_trunc", gate_matched=True)
 
 
 @pytest.mark.parametrize("name", ["rgb_b1_l3", "rgb_b2_l3", "flow_b2_l3", "rgb_b2_l2_train", "flow_b1_l4"])
@@ -649,7 +673,7 @@ def test_module_matches_reference_golden(dev, name):
     fc7, fc28, fc14 = net({k: v.to(dev) for k, v in O.make_taps(seed, B, Lg).items()}, masks=masks)
     for k, got in (("fc7", fc7), ("fc28", fc28), ("fc14", fc14)):
         want = torch.from_numpy(fix[k]).reshape(got.shape)
-        assert _rel(got, want) < 2e-5, k
+        assert _rel(got, want) < 5e-5, k
     (fc7.sum() + fc14.sum()).backward()
     for n, p in net.named_parameters():
         if not p.requires_grad:
@@ -660,5 +684,7 @@ def test_module_matches_reference_golden(dev, name):
             continue
         idx, val = torch.from_numpy(fix[f"grad.{n}.idx"]), torch.from_numpy(fix[f"grad.{n}.val"])
         got = p.grad.reshape(-1)[idx.to(dev)].double().cpu()
-        assert abs(p.grad.double().norm().item() - l2) / l2 < 2e-3, n
-        assert (got - val).norm().item() <= 5e-3 * max(val.norm().item(), 1e-3 * l2), n
+        # gradients: flip-level tolerance (TOL_FP32 above says why); the arithmetic itself is pinned by the gate-matched
+        # oracle tests, the fixture pins that the oracle is the reference
+        assert abs(p.grad.double().norm().item() - l2) / l2 < 5e-2, n
+        assert (got - val).norm().item() <= 5e-2 * max(val.norm().item(), 1e-2 * l2), n

@@ -207,3 +207,78 @@ def test_checkpoint_compatibility(tmp_path):
     bad["motion_conv_trans.weight"] = torch.zeros(3, 3)
     with pytest.raises(RuntimeError):
         CK.merge_state_dict(c, bad)
+
+
+def test_seeded_dropout_uses_every_seed_bit():
+    """the keep decisions of ALL four elements of a channel quad must change with the seed, also for
+    small seeds and for seeds that differ only in their low or only in their high word; the keep rate stays 1 - p."""
+    lib = L.lib()
+    n = 4096
+
+    def mask(seed):
+        return [[lib.offk_drop_keep_host(seed, 4 * q + lane, 0.8) for q in range(n // 4)] for lane in range(4)]
+
+    base = mask(1)
+    for other in (2, 3, 1 + (1 << 32), 1 + (5 << 40), 73, 137, 4928):
+        m = mask(other)
+        for lane in range(4):
+            same = sum(a == b for a, b in zip(base[lane], m[lane])) / len(m[lane])
+            assert same < 0.80, (other, lane, same)          # independent masks agree on 0.8^2 + 0.2^2 = 0.68 of the elements
+    rate = sum(sum(r) for r in base) / n
+    assert 0.17 < rate < 0.23
+    # the engine's per-site seeds: 12 sites x consecutive step seeds are all distinct 64-bit values
+    from off_b200 import engine as E
+    eng = E.OFFEngine(1, 3, "rgb", "cpu", "tf32")
+    seen = set()
+    for step in (0, 1, 2, 3):
+        eng.drop_seed = step
+        seen |= {eng._site_seed(i) for i in range(12)}
+    assert len(seen) == 48 and all(0 <= v < 1 << 64 for v in seen)
+
+
+def test_backbone_layers_live_at_the_top_level_like_the_reference(tmp_path):
+    """the reference's checkpoints carry the BN-Inception layers at the top level
+    (``conv1_7x7_s2.weight``, RGB_OFF.py:43); a model built with a feature extractor must expose, load and save them under
+    exactly those keys, and a merge that would load nothing must not pass silently.  ``.to()`` / ``.float()`` move the
+    extractor only: the OFF parameters stay views of the engine's flat buffer."""
+    import torch
+    import warnings
+    from off_b200 import RGB_OFF, checkpoint as CK
+
+    class Backbone(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1_7x7_s2 = torch.nn.Conv2d(3, 64, 7, 2, 3)
+            self.conv1_7x7_s2_bn = torch.nn.BatchNorm2d(64)
+
+        def forward(self, x):
+            return {}, None
+
+    m = RGB_OFF.bninception_off(101, 1, 3, device="cpu", backbone=Backbone())
+    keys = list(m.state_dict())
+    assert "conv1_7x7_s2.weight" in keys and "conv1_7x7_s2_bn.num_batches_tracked" in keys
+    assert not any(k.startswith("backbone.") for k in keys)
+    assert sum("motion" in k for k in keys) == 108
+    # model_utils.py:240 style merge: everything but the OFF branch comes from the checkpoint
+    ck = {"module." + k: torch.full_like(v, 0.5) for k, v in m.state_dict().items()}
+    off_before = m.motion_conv_trans.weight.detach().clone()
+    loaded, missing, ignored = CK.merge_state_dict(m, ck, keep=lambda k: "motion" not in k)
+    assert "conv1_7x7_s2.weight" in loaded and float(m.backbone.conv1_7x7_s2.weight.mean()) == 0.5
+    assert torch.equal(m.motion_conv_trans.weight, off_before)
+    path = str(tmp_path / "full.pth")
+    assert "conv1_7x7_s2.weight" in CK.save_checkpoint(m, path)
+    # a backbone-only checkpoint into a model WITHOUT a backbone: nothing would be loaded -> error, not silence
+    bare = RGB_OFF.bninception_off(101, 1, 3, device="cpu")
+    with pytest.raises(RuntimeError, match="loaded nothing"):
+        CK.merge_state_dict(bare, {"conv1_7x7_s2.weight": torch.zeros(64, 3, 7, 7)})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        CK.merge_state_dict(bare, ck)                       # OFF keys load, backbone keys are reported
+        assert any("not in the model" in str(x.message) for x in w)
+    # placement / casting
+    m.float().to("cpu")
+    assert m.motion_conv_trans.weight.data_ptr() == m.off.engine.params["motion_conv_trans.weight"].data_ptr()
+    with pytest.raises(RuntimeError, match="flat"):
+        m.double()
+    assert m.motion_conv_trans.weight.dtype == torch.float32
+    assert list(m._modules)[:3] == list(RGB_OFF.bninception_off(101, 1, 3, device="cpu", backbone=Backbone())._modules)[:3]
