@@ -502,6 +502,7 @@ class OFFEngine:
                 k4 = self._conv_wgrad("unit_" + tag, self.taps[tag], dgd, geom,
                                       self._unit_w(self.grads_flat, tag), self._unit_b(self.grads_flat, tag), x_layout="nchw")
                 self._tap_users[tag].append(k4)
+            k4.unit_tag = tag                       # data parallelism: this unit's gradients are final once k4 is done
             grp = [_on(k4, li % 3)]
             if self.tap_grads:
                 grp += [_on(g, li % 3) for g in self._conv_dgrad("unit_" + tag, dgd, self._unit_w(self.params_flat, tag),
@@ -788,6 +789,9 @@ class OFFEngine:
         unit_end = max(self.layout[f"motion_{k}_{t}.bias"][0] + (S.GEN_C if k == "conv_gen" else S.DOWN_C)
                        for t in S.LEVELS for k in (("conv_gen", "spatial_down") + (("spatial_grad",) if self.variant == "rgb" else ())))
         self.unit_range = (0, (unit_end + 3) // 4 * 4)          # flat offsets of the nine units' parameters
+        # per unit: [first parameter of the level, first parameter of the next level) -- contiguous, 16-byte aligned
+        starts = [self.layout[f"motion_conv_gen_{t}.weight"][0] for t in S.LEVELS] + [self.unit_range[1]]
+        self.unit_ranges = OrderedDict((t, (starts[i], starts[i + 1])) for i, t in enumerate(S.LEVELS))
         self.stage_range = (self.unit_range[1], self.n_flat)    # stage convs + FC heads
 
     # ------------------------------------------------------------------ small step factories
@@ -895,10 +899,12 @@ class OFFEngine:
         out += [n for st in self.bwd_steps for n in _names(st)]    # (the d_out copies are cudaMemcpyAsync, not kernels)
         return [n for n in out if not _is_memset(n)]
 
-    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None):
+    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None, after_unit=None):
         """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads).
         ``after_stage()`` is called once the stage/head gradients (flat range ``stage_range``) are final and
-        before the unit gradients are computed (used to overlap their all-reduce)."""
+        before the unit gradients are computed (used to overlap their all-reduce); ``after_unit(tag, stream)`` right
+        after the last kernel that writes unit ``tag``'s gradients (flat range ``unit_ranges[tag]``) was issued on
+        ``stream``."""
         self.d_out7.copy_(g7.reshape(self.d_out7.shape))
         self.d_out14.copy_(g14.reshape(self.d_out14.shape))
         self._zero_grads = bool(zero_grads)
@@ -908,7 +914,13 @@ class OFFEngine:
         if after_stage is not None:
             self._join(streams)                      # the caller's stream now trails every stage-gradient kernel
             after_stage()
-        self.bwd_sched.run(streams, n_stage)
+        on_step = None
+        if after_unit is not None:
+            def on_step(step, stream):
+                tag = getattr(step, "unit_tag", None)
+                if tag is not None:
+                    after_unit(tag, stream)
+        self.bwd_sched.run(streams, n_stage, on_step=on_step)
         self._join(streams)
         return self.grads
 
@@ -1016,8 +1028,9 @@ class Schedule:
         self.record = record
         self.events = {j: torch.cuda.Event() for j in record}
 
-    def run(self, streams, lo=0, hi=None):
-        """Issue steps [lo, hi) on ``streams`` (torch.cuda.Stream per lane; lane 0 = the caller's stream)."""
+    def run(self, streams, lo=0, hi=None, on_step=None):
+        """Issue steps [lo, hi) on ``streams`` (torch.cuda.Stream per lane; lane 0 = the caller's stream).
+        ``on_step(step, stream)`` is called after each step has been issued."""
         hi = len(self.steps) if hi is None else hi
         handles = [C.c_void_p(st.cuda_stream) for st in streams]
         for i in range(lo, hi):
@@ -1027,6 +1040,8 @@ class Schedule:
             self.steps[i](handles[lane])
             if i in self.record:
                 self.events[i].record(streams[lane])
+            if on_step is not None:
+                on_step(self.steps[i], streams[lane])
 
 
 def _names(step):

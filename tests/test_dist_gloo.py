@@ -24,8 +24,8 @@ def _worker(rank, world, port, n, ranges, out):
     g = torch.Generator().manual_seed(100 + rank)
     flat = torch.randn(n, generator=g)
     red = GradAllReducer(flat, ranges)
-    red.launch(0)          # stage/head bucket goes first (overlaps the unit backward on the GPU path)
-    red.launch(1)
+    for i in range(len(ranges)):   # stage/head bucket first, then one bucket per OFF unit (the order the backward finishes them)
+        red.launch(i)
     red.finish()
     if rank == 0:
         torch.save(flat, out)
@@ -33,10 +33,15 @@ def _worker(rank, world, port, n, ranges, out):
 
 
 def test_bucketed_allreduce_averages_across_ranks(tmp_path):
-    from off_b200 import spec as S
-    _, n = S.flat_layout("rgb")
-    unit_end = 895200
-    ranges = [(unit_end, n), (0, unit_end)]
+    from off_b200 import engine as E
+    eng = E.OFFEngine(2, 3, "rgb", "cpu", "tf32")             # the plan (and its bucket layout) is pure host logic
+    n = eng.n_flat
+    ranges = [eng.stage_range] + list(eng.unit_ranges.values())
+    # the buckets tile the flat gradient buffer exactly once, on 16-byte boundaries
+    cover = sorted(ranges)
+    assert cover[0][0] == 0 and cover[-1][1] == n and all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    assert all(lo % 4 == 0 for lo, _ in ranges) and list(eng.unit_ranges) == ["3a", "3b", "3c", "4a", "4b", "4c", "4d", "5a", "5b"]
+    assert eng.unit_ranges["3a"][1] - eng.unit_ranges["3a"][0] >= 160 * 256 + 160 + 32 * 9 + 32
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(2, _free_port(), n, ranges, out), nprocs=2, join=True)
     want = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(2)) / 2
