@@ -338,6 +338,29 @@ int offk_gather_copy(const float* src, const int32_t* idx, float* dst, long long
  * gradient read this copy through dense / im2col tensor maps instead. */
 int offk_nchw_to_nhwc(const float* src, float* dst, int n_img, int C, int HW, void* stream);
 
+/* ------------------------------------------------------------------------
+ * The training step around the path (train_off.py:72,133-151), on the flat parameter / gradient buffers.
+ * ---------------------------------------------------------------------- */
+/* nn.CrossEntropyLoss (mean over the P rows) of logits [P, C] against the clip labels repeated per frame pair
+ * (train_off.py:133: target.unsqueeze(1).repeat(1, num_seg-1).view(-1)): label of row p = target[p / repeat].
+ * loss_accum (may be NULL) += the loss; dlogits (may be NULL) = grad_scale * dLoss/dlogits.  Several heads may
+ * accumulate into the same loss_accum (train_off.py:136-146 sums three CE terms by calling backward three times). */
+int offk_ce_loss_fwd_bwd(const float* logits, const long long* target, int P, int C, int repeat, float grad_scale,
+                         float* loss_accum, float* dlogits, void* stream);
+/* sumsq_accum += sum_i g[i]^2 (double; the caller zeroes it): the squared global norm of clip_grad_norm (train_off.py:149) */
+int offk_grad_sumsq(const float* g, long long n, double* sumsq_accum, void* stream);
+/* clip_grad_norm(params, max_norm) + optim.Adam(lr, betas, weight_decay).step() (train_off.py:72,149-151) in ONE pass over
+ * the element ranges [range_lo[k], range_hi[k]) (multiples of 4) of the flat buffers p, g, m (exp_avg), v (exp_avg_sq):
+ *   coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6))     (sumsq == NULL or max_norm <= 0: no clipping)
+ *   g' = coef * g + weight_decay * p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2
+ *   p -= lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)                      (step counts from 1)
+ * The norm is read from device memory: no host synchronisation between backward and the update.  Ranges let the caller
+ * skip parameters that have no gradient in the reference (fc_action_motion_28, RGB_OFF.py:787,860). */
+#define OFFK_ADAM_MAX_RANGES 8
+int offk_clip_adam_step(float* p, const float* g, float* m, float* v, const long long* range_lo, const long long* range_hi,
+                        int n_ranges, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        float max_norm, const double* sumsq, void* stream);
+
 /* keep decision of OFFK_DROP_SEED for element `idx` (host mirror for tests): 1 = keep */
 int offk_drop_keep_host(uint64_t seed, uint64_t idx, float drop_p);
 

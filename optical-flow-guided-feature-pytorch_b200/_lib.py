@@ -121,6 +121,10 @@ _PROTOS = {
     "offk_permute_weight_batch": (C.c_int, [C.c_int, C.POINTER(OffkPermute), C.c_int, _P]),
     "offk_permute_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_drop_keep_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_float]),
+    "offk_ce_loss_fwd_bwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
+    "offk_grad_sumsq": (C.c_int, [_P, C.c_longlong, _P, _P]),
+    "offk_clip_adam_step": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, _P, _P]),
 }
 
 _lib = None

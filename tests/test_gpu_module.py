@@ -224,3 +224,46 @@ def test_reference_model_classes(dev):
     m = RGB_OFF.bninception_off(NC, B, Lg, device=dev).eval()
     fc7, sc, fc14 = m.RGB_OFF_forward(taps)
     assert sc is None and fc7.shape == (B * (Lg - 1), NC)
+
+
+@pytest.mark.parametrize("variant,max_norm", [("rgb", 20.0), ("flow", 0.05)])
+def test_fused_training_step_matches_torch(dev, variant, max_norm):
+    """fused CE (labels repeated per pair, train_off.py:133-146) + clip_grad_norm (:149) + Adam (:72,151) on the
+    flat buffers against F.cross_entropy + torch.nn.utils.clip_grad_norm_ + torch.optim.Adam on per-parameter tensors."""
+    import torch.nn.functional as F
+    from off_b200.modules import OFFSubNetwork
+    from off_b200.train import FusedOFFTrainer
+    B, Lg = 2, 3
+    net = OFFSubNetwork(B, Lg, variant, precision="tf32", device=dev).eval()
+    net.load_state_dict(O.make_params(4, variant), strict=(variant == "rgb"))
+    eng = net.engine
+    tr = FusedOFFTrainer(net, lr=1e-3, betas=(0.9, 0.99), weight_decay=5e-4, max_norm=max_norm)
+    names = [n for n in eng.params if not n.startswith("fc_action_motion_28")]
+    ref_p = [eng.params[n].detach().clone().requires_grad_(True) for n in names]
+    fc28_before = eng.params["fc_action_motion_28.weight"].clone()
+    opt = torch.optim.Adam(ref_p, lr=1e-3, betas=(0.9, 0.99), weight_decay=5e-4)
+    target = torch.tensor([3, 77], device=dev)
+    taps = {k: v.to(dev) for k, v in O.make_taps(4, B, Lg).items()}
+    clipped = False
+    for it in range(3):
+        with torch.no_grad():
+            fc7, _, fc14 = eng.forward(taps, train=False)
+        loss = tr.loss_backward(fc7, fc14, target)
+        # loss and dL/dlogits of the fused kernel
+        t_rows = target.unsqueeze(1).repeat(1, tr.repeat).view(-1)               # train_off.py:133
+        l7, l14 = fc7.clone().requires_grad_(True), fc14.clone().requires_grad_(True)
+        want = F.cross_entropy(l7, t_rows) + F.cross_entropy(l14, t_rows)
+        want.backward()
+        assert abs(loss.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+        assert torch.allclose(tr.g7, l7.grad, atol=1e-7, rtol=1e-5) and torch.allclose(tr.g14, l14.grad, atol=1e-7, rtol=1e-5)
+        for p, n in zip(ref_p, names):
+            p.grad = eng.grads[n].detach().clone()
+        total = torch.nn.utils.clip_grad_norm_(ref_p, max_norm)
+        clipped |= bool(total > max_norm)
+        opt.step()
+        tr.step()
+        assert abs(tr.grad_norm() - total.item()) < 1e-5 * total.item()
+        for p, n in zip(ref_p, names):
+            assert torch.allclose(eng.params[n], p.detach(), atol=2e-7, rtol=1e-5), (it, n)
+    assert clipped == (max_norm < 1.0)
+    assert torch.equal(eng.params["fc_action_motion_28.weight"], fc28_before)   # no gradient in the reference: Adam skips it
