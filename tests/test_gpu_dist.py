@@ -84,6 +84,6 @@ def test_data_parallel_matches_per_rank_oracle(tmp_path, variant, b_local, lengt
     fwd_err, worst = torch.load(out).tolist()
     print(f"[dp parity {precision} {variant} {world} ranks x {b_local} clips] fwd={fwd_err:.2e} allreduced_grad_rel_l2={worst:.2e}")
     if precision == "fp32":
-        assert fwd_err < 5e-5 and worst < 2e-4, (fwd_err, worst)
+        assert fwd_err < 1e-5 and worst < 2e-5, (fwd_err, worst)
     else:
         assert fwd_err < 1e-2 and worst < 0.2, (fwd_err, worst)

@@ -84,7 +84,7 @@ def test_tap_gradients_when_requested(dev):
                                         gates=engine_gates(net.engine))
     for k in taps:
         err = (tg[k].grad.double().cpu() - tref[k]).norm() / tref[k].norm()
-        assert err < 2e-4, (k, float(err))
+        assert err < 2e-5, (k, float(err))
 
 
 def test_consensus_module(dev):

@@ -69,7 +69,7 @@ GEMM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec,tol", [(0, 5e-6), (1, 3e-3), (2, 2e-5)], ids=["fp32simt", "tf32", "tf32x3"])
+@pytest.mark.parametrize("prec,tol", [(0, 5e-6), (1, 3e-3), (2, 1e-5)], ids=["fp32simt", "tf32", "tf32x3"])
 @pytest.mark.parametrize("case", GEMM_CASES, ids=[f"{c[1]}x{c[2]}k{c[5]}s{c[6]}{c[12]}" for c in GEMM_CASES])
 def test_gather_gemm_conv_parity(dev, case, prec, tol):
     from off_b200 import tables as T
@@ -117,7 +117,7 @@ TMA_CASES = [
 ]
 
 
-PRECS = pytest.mark.parametrize("prec,tol", [(1, 3e-3), (2, 2e-5)], ids=["tf32", "tf32x3"])
+PRECS = pytest.mark.parametrize("prec,tol", [(1, 3e-3), (2, 1e-5)], ids=["tf32", "tf32x3"])
 
 
 @PRECS
@@ -540,8 +540,10 @@ import functools
 # flipped gate moves a weight gradient by O(1/sqrt(#elements)).  The reference's own fp32 CPU arithmetic shows the same
 # against fp64 (B=1, L=3: worst relative L2 1.4e-2; 1.8e-6 once the gates are matched -- measured with oracle/off_oracle.py),
 # so the exact-oracle gate only bounds the flip rate and the arithmetic is pinned by the gate-matched run.
-TOL_FP32 = (2e-5, 5e-5, 5e-2)
-TOL_FP32_GATED = (2e-5, 5e-5, 2e-4)
+# Measured on the B200 (profiles/parity_r02b.txt): fp32 mode forward 4e-7 .. 2.5e-6 (the CUDA-core FFMA twin: 4e-7 .. 9e-7),
+# gate-matched gradients 3.5e-6 .. 5.1e-6 (FFMA twin 1.7e-6), exact-oracle gradients 3.5e-6 (no flip) .. 3.7e-3 (B = 48).
+TOL_FP32 = (5e-6, 1e-5, 5e-2)
+TOL_FP32_GATED = (5e-6, 1e-5, 2e-5)
 
 
 @functools.lru_cache(maxsize=2)
@@ -638,7 +640,9 @@ def test_engine_tf32_mode_matches_oracle(dev, variant, B, Lg, train):
 # is fp32 accumulation order plus the rare operand whose fp32 value (GPU) and fp64 value (oracle) straddle a tf32
 # truncation boundary.  This pins the tensor-core path itself: a wrong tap, stride-parity class or table entry moves a
 # gradient by O(1), two orders of magnitude above these gates.
-TOL_TF32_EMU = (5e-4, 1e-3, 5e-3)      # + the oracle follows the engine's ReLU gates (gate_matched)
+# Measured (profiles/parity_r02b.txt): stage-fusion tensors 7e-7 (first stage: accumulation order only) .. 5.4e-5, logits
+# <= 1.6e-4, gradients 5e-4 .. 1.1e-3 -- against 8e-4 / 2e-3 / 6e-2 for the same mode vs the exact oracle.
+TOL_TF32_EMU = (2e-4, 5e-4, 3e-3)      # + the oracle follows the engine's ReLU gates (gate_matched)
 
 
 @pytest.mark.parametrize("variant,B,Lg,train", TF32_CASES)
@@ -673,7 +677,7 @@ def test_module_matches_reference_golden(dev, name):
     fc7, fc28, fc14 = net({k: v.to(dev) for k, v in O.make_taps(seed, B, Lg).items()}, masks=masks)
     for k, got in (("fc7", fc7), ("fc28", fc28), ("fc14", fc14)):
         want = torch.from_numpy(fix[k]).reshape(got.shape)
-        assert _rel(got, want) < 5e-5, k
+        assert _rel(got, want) < 1e-5, k
     (fc7.sum() + fc14.sum()).backward()
     for n, p in net.named_parameters():
         if not p.requires_grad:
