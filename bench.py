@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager CUDA baseline legs")
     ap.add_argument("--no-families", action="store_true", help="skip the per-kernel-family roofline pass")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every kernel from the host instead of replaying CUDA graphs")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.config == 4:
@@ -387,9 +388,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, Lg = args.batch, args.length
-    net = OFFSubNetwork(B, Lg, args.variant, precision=args.precision, device=dev).train()
+    graphs = not args.no_graphs
+    net = OFFSubNetwork(B, Lg, args.variant, precision=args.precision, device=dev, use_graphs=graphs).train()
     eng = net.engine
-    dp = DataParallelOFF(eng)
+    dp = DataParallelOFF(eng, use_graphs=graphs)
     dp.broadcast_parameters()
     torch.manual_seed(1234 + rank)
     taps_dev = net.tap_buffers()
@@ -488,11 +490,11 @@ def run_ours(args):
     if rank == 0 and world == 1:
         oprec = "tf32" if args.precision == "fp32" else "fp32"
         del step
-        net2 = OFFSubNetwork(B, Lg, args.variant, precision=oprec, device=dev).train()
+        net2 = OFFSubNetwork(B, Lg, args.variant, precision=oprec, device=dev, use_graphs=graphs).train()
         net2.engine.params_flat.copy_(eng.params_flat)
         for k, t in net2.tap_buffers().items():
             t.copy_(taps_dev[k])
-        step2 = make_step(net2, DataParallelOFF(net2.engine))
+        step2 = make_step(net2, DataParallelOFF(net2.engine, use_graphs=graphs))
         for _ in range(3):
             step2()
         ms2 = timed(step2, net2, 10, False) / 10
@@ -533,7 +535,10 @@ def run_ours(args):
                        "global_clips": B * world,
                        "l2": f"inputs larger than L2: {tap_bytes / 1e6:.0f} MB of taps per step vs 126 MB L2",
                        "parallelism": f"dp{world} (clip-sharded, NCCL all-reduce of {eng.n_flat} fp32 gradients)",
-                       "numa": numa},
+                       "numa": numa,
+                       "issue": ("forward and backward replayed as one captured CUDA graph each (multi-stream capture of the plan)"
+                                 if graphs else "every kernel issued from the host") + ("; gradient all-reduce buckets issued eagerly "
+                                 "between the unit weight-gradient kernels" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": tap_bytes, "d2h_bytes_per_step": 4,
                     "note": "taps copied from pinned host memory every step (copy of step i+1 overlaps compute of step i: "
                             "two input sets), loss read back every step"},

@@ -237,6 +237,9 @@ typedef struct offk_stencil {
   float drop_p;            /* p, used by OFFK_DROP_SEED */
   uint64_t seed;
   const uint8_t* keep_mask; /* [P, K*Cs, H, W] (NCHW order) for OFFK_DROP_MASK */
+  const uint64_t* seed_dev; /* OFFK_DROP_SEED: NULL, or a device word added to `seed` when the kernel runs -- the per-step
+                               part of the seed then lives in device memory (offk_seed_set / offk_seed_advance), so a
+                               captured CUDA graph draws fresh masks on every replay while `seed` stays the call site's salt */
 } offk_stencil_t;
 
 int offk_stencil_diff_fwd(const offk_stencil_t* s, const float* g, const float* d, const float* w,
@@ -285,13 +288,18 @@ int offk_stencil_diff_bwd(const offk_stencil_t* s, const float* dout, const floa
 /* All head tensors are channels-last: x[P, HW, ctot], slices are channel ranges [coff, coff+C).
  * out[p,c] = drop( mean_{hw} x[p, hw, x_coff+c] )   (global_pool RGB_OFF.py:262 + dropout :356) */
 int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode,
-                          const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
+                          const uint8_t* keep_mask, uint64_t seed, const uint64_t* seed_dev, float drop_p, float keep_scale,
                           float* out, void* stream);
 /* dx[p, coff+c, :] = gate( dx_in + drop'(dpooled[p,c]) / HW ) ; dx_in = dx itself when accumulate != 0,
  * gate = (act[p, coff+c, :] > 0) when act != NULL (ReLU' of the producer). dpooled may be NULL (gate only). */
 int offk_avgpool_drop_bwd(const float* dpooled, int P, int C, int HW, int ctot, int coff, int drop_mode,
-                          const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
+                          const uint8_t* keep_mask, uint64_t seed, const uint64_t* seed_dev, float drop_p, float keep_scale,
                           const float* act, int accumulate, float* dx, void* stream);
+/* seed_dev (may be NULL) as in offk_stencil_t: the effective seed is seed + *seed_dev, read when the kernel runs.
+ * offk_seed_set stores `value` into the device word; offk_seed_advance replaces it by the next value of a splitmix64
+ * sequence (the first node of a captured training step: every replay gets its own dropout masks). */
+int offk_seed_set(uint64_t* state, uint64_t value, void* stream);
+int offk_seed_advance(uint64_t* state, void* stream);
 /* 3x3 stride-2 ceil-mode max pool (motion_pool_trans_28, RGB_OFF.py:353,:783) */
 int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, int x_ctot, int x_coff, float* out,
                         void* stream);

@@ -69,7 +69,7 @@ class OffkStencil(C.Structure):
         ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
         ("index_mode", C.c_int32), ("drop_mode", C.c_int32),
         ("keep_scale", C.c_float), ("drop_p", C.c_float),
-        ("seed", C.c_uint64), ("keep_mask", C.c_void_p),
+        ("seed", C.c_uint64), ("keep_mask", C.c_void_p), ("seed_dev", C.c_void_p),
     ]
 
 
@@ -103,10 +103,12 @@ _PROTOS = {
     "offk_stencil_diff_fwd_batch": (C.c_int, [C.c_int, C.POINTER(OffkStencil), C.POINTER(OffkStencilIO), _P]),
     "offk_stencil_diff_bwd_batch": (C.c_int, [C.c_int, C.POINTER(OffkStencil), C.POINTER(OffkStencilIO), _P]),
     "offk_stencil_diff_bwd_batch_part": (C.c_int, [C.c_int, C.POINTER(OffkStencil), C.POINTER(OffkStencilIO), C.c_int, _P]),
-    "offk_avgpool_drop_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64,
+    "offk_avgpool_drop_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, _P,
                                         C.c_float, C.c_float, _P, _P]),
-    "offk_avgpool_drop_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64,
+    "offk_avgpool_drop_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, _P,
                                         C.c_float, C.c_float, _P, C.c_int, _P, _P]),
+    "offk_seed_set": (C.c_int, [_P, C.c_uint64, _P]),
+    "offk_seed_advance": (C.c_int, [_P, _P]),
     "offk_maxpool3s2_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "offk_segment_mean_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "offk_segment_mean_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -12,11 +12,18 @@ __device__ __forceinline__ float keep_factor(int mode, const uint8_t* mask, uint
   return keep ? scale : 0.f;
 }
 
+// the per-step word of the dropout seed lives in device memory (offk.h: seed_dev)
+__global__ void seed_update_kernel(uint64_t* state, uint64_t value, int advance) {
+  pdl_sync();
+  *state = advance ? *state + 0x9E3779B97F4A7C15ull : value;   // a Weyl sequence; drop_hash64 does the mixing
+}
+
 // thread per (p, c); x is channels-last [P, HW, ctot]: consecutive threads read consecutive channels
 __global__ void avgpool_drop_fwd_kernel(const float* __restrict__ x, int P, int C, int HW, int ctot, int coff, int mode,
-                                        const uint8_t* __restrict__ mask, uint64_t seed, float drop_p, float scale,
-                                        float* __restrict__ out) {
+                                        const uint8_t* __restrict__ mask, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                                        float drop_p, float scale, float* __restrict__ out) {
   pdl_sync();
+  if (seed_dev) seed += __ldg(seed_dev);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * C) return;
   const int p = i / C, c = i - p * C;
@@ -28,10 +35,12 @@ __global__ void avgpool_drop_fwd_kernel(const float* __restrict__ x, int P, int 
 }
 
 __global__ void avgpool_drop_bwd_kernel(const float* __restrict__ dpooled, int P, int C, int HW, int ctot, int coff,
-                                        int mode, const uint8_t* __restrict__ mask, uint64_t seed, float drop_p,
+                                        int mode, const uint8_t* __restrict__ mask, uint64_t seed,
+                                        const uint64_t* __restrict__ seed_dev, float drop_p,
                                         float scale, const float* __restrict__ act, int accumulate,
                                         float* __restrict__ dx) {
   pdl_sync();
+  if (seed_dev) seed += __ldg(seed_dev);
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)P * C * HW;
   if (i >= total) return;
@@ -191,24 +200,35 @@ static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 
 
 using namespace offk;
 
+extern "C" int offk_seed_set(uint64_t* state, uint64_t value, void* stream) {
+  OFFK_REQUIRE(state != nullptr, "seed_set: null state");
+  (void)launch_pdl(seed_update_kernel, dim3(1), dim3(1), 0, as_stream(stream), state, value, 0);
+  return OFFK_LAUNCH_CHECK("seed_set");
+}
+extern "C" int offk_seed_advance(uint64_t* state, void* stream) {
+  OFFK_REQUIRE(state != nullptr, "seed_advance: null state");
+  (void)launch_pdl(seed_update_kernel, dim3(1), dim3(1), 0, as_stream(stream), state, (uint64_t)0, 1);
+  return OFFK_LAUNCH_CHECK("seed_advance");
+}
+
 extern "C" int offk_avgpool_drop_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode,
-                                     const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
-                                     float* out, void* stream) {
+                                     const uint8_t* keep_mask, uint64_t seed, const uint64_t* seed_dev, float drop_p,
+                                     float keep_scale, float* out, void* stream) {
   OFFK_REQUIRE(x && out && P > 0 && C > 0 && HW > 0 && x_coff >= 0 && x_coff + C <= x_ctot, "avgpool_fwd: bad args");
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_fwd: mask missing");
   (void)launch_pdl(avgpool_drop_fwd_kernel, dim3(blocks_for((size_t)P * C, 128)), dim3(128), 0, as_stream(stream), 
-      x, P, C, HW, x_ctot, x_coff, drop_mode, keep_mask, seed, drop_p, keep_scale, out);
+      x, P, C, HW, x_ctot, x_coff, drop_mode, keep_mask, seed, seed_dev, drop_p, keep_scale, out);
   return OFFK_LAUNCH_CHECK("avgpool_drop_fwd");
 }
 
 extern "C" int offk_avgpool_drop_bwd(const float* dpooled, int P, int C, int HW, int ctot, int coff, int drop_mode,
-                                     const uint8_t* keep_mask, uint64_t seed, float drop_p, float keep_scale,
-                                     const float* act, int accumulate, float* dx, void* stream) {
+                                     const uint8_t* keep_mask, uint64_t seed, const uint64_t* seed_dev, float drop_p,
+                                     float keep_scale, const float* act, int accumulate, float* dx, void* stream) {
   OFFK_REQUIRE(dx && P > 0 && C > 0 && HW > 0 && coff >= 0 && coff + C <= ctot, "avgpool_bwd: bad args");
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "avgpool_bwd: mask missing");
   const size_t total = (size_t)P * C * HW;
   (void)launch_pdl(avgpool_drop_bwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, as_stream(stream), 
-      dpooled, P, C, HW, ctot, coff, drop_mode, keep_mask, seed, drop_p, keep_scale, act, accumulate, dx);
+      dpooled, P, C, HW, ctot, coff, drop_mode, keep_mask, seed, seed_dev, drop_p, keep_scale, act, accumulate, dx);
   return OFFK_LAUNCH_CHECK("avgpool_drop_bwd");
 }
 

@@ -113,7 +113,7 @@ __device__ __forceinline__ float4 drop_factor4(const offk_stencil_t& s, uint32_t
     const uint8_t* m = s.keep_mask + ((size_t)p * (s.K * s.Cs) + och) * (size_t)HW + pix;
     keep = (m[0] != 0 ? 1u : 0u) | (m[HW] != 0 ? 2u : 0u) | (m[2 * (size_t)HW] != 0 ? 4u : 0u) | (m[3 * (size_t)HW] != 0 ? 8u : 0u);
   } else {
-    keep = drop_keep4(s.seed, quad, thr);
+    keep = drop_keep4(s.seed + (s.seed_dev ? __ldg(s.seed_dev) : 0ull), quad, thr);
   }
   const float k = s.keep_scale;
   return make_float4(keep & 1u ? k : 0.f, keep & 2u ? k : 0.f, keep & 4u ? k : 0.f, keep & 8u ? k : 0.f);

@@ -100,8 +100,9 @@ class DataParallelOFF:
     the plan's order; the unit's stencil gradients are complete by then).  Every bucket is reduced on a communication
     stream behind an event, so only the last unit's small all-reduce is exposed."""
 
-    def __init__(self, engine, group=None, per_unit_buckets: bool = True):
+    def __init__(self, engine, group=None, per_unit_buckets: bool = True, use_graphs: bool = False):
         self.engine = engine
+        self.use_graphs = use_graphs          # single rank: replay the backward pass as one CUDA graph
         self.per_unit = per_unit_buckets
         self.tags = list(engine.unit_ranges)
         ranges = [engine.stage_range] + ([engine.unit_ranges[t] for t in self.tags] if per_unit_buckets else [engine.unit_range])
@@ -122,7 +123,7 @@ class DataParallelOFF:
     def backward(self, g7, g14):
         eng, red = self.engine, self.reducer
         if red.world == 1:
-            eng.backward(g7, g14)
+            eng.backward(g7, g14, graph=self.use_graphs)
             return eng.grads
 
         def after_stage():

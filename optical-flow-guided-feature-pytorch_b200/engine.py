@@ -338,6 +338,9 @@ class OFFEngine:
         self.drop_mode = L.DROP_NONE
         self.drop_seed = 0
         self.masks = None
+        self.seed_state = torch.zeros(1, dtype=torch.int64, device=self.device)   # per-step dropout seed (device word)
+        self._graphs = {}                # (pass, tap set, dropout mode) -> torch.cuda.CUDAGraph
+        self._cap_stream = None
 
     # ------------------------------------------------------------------ plan
     def _conv_fwd(self, name, x, y, geom, w, b, *, relu=False, relu_cols=None, a_relu=False, addend=None,
@@ -800,14 +803,20 @@ class OFFEngine:
         return _nm(lambda stream: L.check(lib.offk_add_relu_slice(_ptr(a), _ptr(b), _ptr(dst), ctot, coff, P, c, hw, 1,
                                                                    stream), "sum_14b"), "sum_14b", reads=[a, b], writes=[dst])
 
-    def _site_seed(self, site):
-        """64-bit seed of dropout call site ``site`` (12 per forward, RGB_OFF.py:612..:845) for this step: splitmix64 over
-        (step seed, site), so that every bit of the step seed reaches every keep decision."""
+    @staticmethod
+    def _site_salt(site):
+        """Constant 64-bit salt of dropout call site ``site`` (12 per forward, RGB_OFF.py:612..:845): splitmix64(site).
+        The kernels add the step seed, which lives in device memory (``seed_state``; offk.h: seed_dev), and hash the sum
+        with the element index, so every bit of both reaches every keep decision -- and a captured CUDA graph, whose
+        kernel arguments are frozen, still draws new masks whenever the device word changes."""
         m = 0xFFFFFFFFFFFFFFFF
-        z = (self.drop_seed * 0x9E3779B97F4A7C15 + (site + 1) * 0xD1B54A32D192ED03) & m
+        z = ((site + 1) * 0xD1B54A32D192ED03) & m
         z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
         z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
         return z ^ (z >> 31)
+
+    def _seed_dev(self):
+        return _ptr(self.seed_state) if self.drop_mode == L.DROP_SEED else None
 
     def _pool_fwd(self, k, x, c, ctot, coff):
         lib, P = self.lib, self.P
@@ -816,7 +825,7 @@ class OFFEngine:
         def run(stream):
             m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
             L.check(lib.offk_avgpool_drop_fwd(_ptr(x), P, c, 49, ctot, coff, self.drop_mode, _ptr(m),
-                                              self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
+                                              self._site_salt(site), self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
                                               _ptr(self.buf["pool" + k]), stream), "pool" + k)
         return _nm(run, "pool_fwd" + k, reads=[x], writes=[self.buf["pool" + k]])
 
@@ -827,7 +836,7 @@ class OFFEngine:
         def run(stream):
             m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
             L.check(lib.offk_avgpool_drop_bwd(_ptr(self.buf["d_pool" + k]), P, c, 49, ctot, coff, self.drop_mode,
-                                              _ptr(m), self._site_seed(site), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
+                                              _ptr(m), self._site_salt(site), self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
                                               _ptr(act), int(accumulate), _ptr(dx), stream), "pool_bwd" + k)
         return _nm(run, "pool_bwd" + k, reads=[self.buf["d_pool" + k], act, dx if accumulate else None], writes=[dx])
 
@@ -848,7 +857,8 @@ class OFFEngine:
             self.drop_seed = int(seed)
         for i, (tag, sd) in enumerate(self._stencils.items()):
             sd.drop_mode = self.drop_mode
-            sd.seed = self._site_seed(i)
+            sd.seed = self._site_salt(i)
+            sd.seed_dev = self.seed_state.data_ptr() if self.drop_mode == L.DROP_SEED else None
             sd.keep_mask = self.masks[tag].data_ptr() if self.drop_mode == L.DROP_MASK else None
 
     def set_taps(self, taps: dict):
@@ -881,17 +891,56 @@ class OFFEngine:
             ev.record(self._copy_stream)
         return idx, ev
 
-    def forward(self, taps: dict = None, train: bool = False, masks: dict = None, seed: int = 0):
-        """Run the forward plan.  Returns (fc7, fc28, fc14): [P,101] each, or [B,101] with consensus."""
+    def forward(self, taps: dict = None, train: bool = False, masks: dict = None, seed: int = 0, graph: bool = False):
+        """Run the forward plan.  Returns (fc7, fc28, fc14): [P,101] each, or [B,101] with consensus.
+        graph=True replays the plan as ONE captured CUDA graph (captured on first use per input set and dropout mode):
+        the same kernels, bit for bit, without the ~60 host-side launches."""
         if taps is not None:
             self.set_taps(taps)
         self._set_dropout(train, masks, seed)
         self.generation += 1            # backward() consumes the activations of THIS forward (one set of static buffers)
-        streams = self._fork()
-        self.fwd_sched.run(streams)
-        self._join(streams)
+        if self.drop_mode == L.DROP_SEED:
+            main = torch.cuda.current_stream(self.device)
+            L.check(self.lib.offk_seed_set(_ptr(self.seed_state), self.drop_seed & 0xFFFFFFFFFFFFFFFF,
+                                           C.c_void_p(main.cuda_stream)), "seed_set")
+        if graph:
+            self._replay("fwd")
+        else:
+            self._issue("fwd")
         pre = "cfc" if self.consensus else "fc"
         return self.buf[pre + "7"], self.buf[pre + "28"], self.buf[pre + "14"]
+
+    # ------------------------------------------------------------------ CUDA graphs (SURVEY 8f-1)
+    def _issue(self, which):
+        streams = self._fork()
+        (self.fwd_sched if which == "fwd" else self.bwd_sched).run(streams)
+        self._join(streams)
+
+    def _replay(self, which):
+        if self.drop_mode == L.DROP_MASK:
+            raise RuntimeError("graph replay supports eval mode and seeded dropout; injected masks are an eager-only test facility")
+        key = (which, self._tap_set, self.drop_mode)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = self._capture(which)
+        g.replay()
+
+    def _capture(self, which):
+        """Capture one pass (all lanes: the side streams fork from and join the capturing stream through the schedule's
+        events, so the graph keeps the multi-stream concurrency of the eager plan)."""
+        main = torch.cuda.current_stream(self.device)
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(device=self.device)
+        cap = self._cap_stream
+        cap.wait_stream(main)
+        with torch.cuda.stream(cap):
+            self._issue(which)          # eager once on this stream: tensor maps encoded, kernel attributes set
+        cap.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=cap):
+            self._issue(which)
+        main.wait_stream(cap)
+        return g
 
     def launch_names(self):
         """One name per device launch of forward() + backward(), in issue order (for annotating ncu launch lists)."""
@@ -899,7 +948,8 @@ class OFFEngine:
         out += [n for st in self.bwd_steps for n in _names(st)]    # (the d_out copies are cudaMemcpyAsync, not kernels)
         return [n for n in out if not _is_memset(n)]
 
-    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None, after_unit=None):
+    def backward(self, g7: torch.Tensor, g14: torch.Tensor, zero_grads: bool = True, after_stage=None, after_unit=None,
+                 graph: bool = False):
         """Run the backward plan for dL/dfc7 and dL/dfc14; fills grads_flat (views in self.grads).
         ``after_stage()`` is called once the stage/head gradients (flat range ``stage_range``) are final and
         before the unit gradients are computed (used to overlap their all-reduce); ``after_unit(tag, stream)`` right
@@ -907,6 +957,12 @@ class OFFEngine:
         ``stream``."""
         self.d_out7.copy_(g7.reshape(self.d_out7.shape))
         self.d_out14.copy_(g14.reshape(self.d_out14.shape))
+        if graph:
+            if not zero_grads or after_stage is not None or after_unit is not None:
+                raise RuntimeError("graph replay of the backward pass zeroes the gradient buffers and takes no hooks")
+            self._zero_grads = True
+            self._replay("bwd")
+            return self.grads
         self._zero_grads = bool(zero_grads)
         streams = self._fork()
         n_stage = len(self.bwd_stage_steps)

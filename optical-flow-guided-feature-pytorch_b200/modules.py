@@ -7,6 +7,7 @@ parameter buffer, and runs forward/backward through liboffk via one ``torch.auto
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 
 import torch
@@ -65,7 +66,8 @@ class _OFFFunction(torch.autograd.Function):
             else:
                 for buf, t in zip(eng.taps.values(), taps):
                     buf.copy_(t, non_blocking=True)
-        fc7, fc28, fc14 = eng.forward(train=train, masks=masks, seed=seed)
+        fc7, fc28, fc14 = eng.forward(train=train, masks=masks, seed=seed, graph=net.use_graphs and masks is None)
+        ctx.graph = net.use_graphs and masks is None
         ctx.generation = eng.generation                 # the engine keeps ONE set of activations: see backward()
         ctx.net = net
         ctx.n_taps = n_taps
@@ -98,7 +100,7 @@ class _OFFFunction(torch.autograd.Function):
                     p.grad = p.grad.clone()
         g7 = torch.zeros_like(eng.d_out7) if g7 is None else g7
         g14 = torch.zeros_like(eng.d_out14) if g14 is None else g14
-        eng.backward(g7.contiguous(), g14.contiguous(), zero_grads=not in_place)
+        eng.backward(g7.contiguous(), g14.contiguous(), zero_grads=not in_place, graph=ctx.graph and not in_place)
         pgrads = [None] * len(params) if in_place else [eng._view(eng.grads_flat, n) if l else None
                                                         for n, l in zip(eng.grads, live)]
         tgrads = [eng.tap_grad[tag].clone() if need else None
@@ -113,12 +115,18 @@ class OFFSubNetwork(nn.Module):
     ``[batch*length, C, S, S]`` (fp32, NCHW, CUDA).  variant='rgb': learned depth-wise 3x3 spatial gradient, per-pair
     logits ``[batch*(length-1), 101]``; variant='flow' (also RGB_OFF_v2): fixed diagonal Sobel and segment consensus
     ``[batch, 101]``.  Dropout follows ``self.training`` (p = 0.8, RGB_OFF.py:356); pass ``masks`` to inject keep-masks.
+    ``precision``: 'fp32' = fp32-parity arithmetic on the tensor cores (3xTF32), 'tf32' = single-MMA tf32 (the default here,
+    the fast mode), 'fp32_simt' = CUDA-core cross-check.  ``use_graphs``: replay each pass as one captured CUDA graph.
     """
 
     def __init__(self, batch: int, length: int, variant: str = "rgb", precision: str = "tf32",
-                 index_mode: str = "reference_flat", consensus=None, tap_grads: bool = False, device="cuda"):
+                 index_mode: str = "reference_flat", consensus=None, tap_grads: bool = False, device="cuda",
+                 use_graphs=None):
         super().__init__()
         self.batch, self.length, self.variant = batch, length, variant
+        # forward / backward as one captured CUDA graph each (same kernels, no per-launch host cost); OFFK_GRAPHS=1 turns it
+        # on for modules that do not say
+        self.use_graphs = (os.environ.get("OFFK_GRAPHS", "0") == "1") if use_graphs is None else bool(use_graphs)
         self.engine = OFFEngine(batch, length, variant, device, precision, index_mode, consensus, tap_grads)
         self._seed = 0
         groups = OrderedDict()

@@ -182,7 +182,7 @@ def test_bad_arguments_raise(dev):
         L.check(lib.offk_stencil_diff_fwd(C.byref(s), None, None, None, None, None, None), "stencil")
     x = torch.zeros(4, device=dev)
     with pytest.raises(RuntimeError):
-        L.check(lib.offk_avgpool_drop_fwd(x.data_ptr(), 1, 8, 49, 4, 0, 0, None, 0, 0.0, 1.0, x.data_ptr(), None), "pool")
+        L.check(lib.offk_avgpool_drop_fwd(x.data_ptr(), 1, 8, 49, 4, 0, 0, None, 0, None, 0.0, 1.0, x.data_ptr(), None), "pool")
 
 
 def test_reference_model_classes(dev):
@@ -267,3 +267,58 @@ def test_fused_training_step_matches_torch(dev, variant, max_norm):
             assert torch.allclose(eng.params[n], p.detach(), atol=2e-7, rtol=1e-5), (it, n)
     assert clipped == (max_norm < 1.0)
     assert torch.equal(eng.params["fc_action_motion_28.weight"], fc28_before)   # no gradient in the reference: Adam skips it
+
+
+@pytest.mark.parametrize("B,Lg,precision", [(2, 3, "fp32"), (48, 3, "tf32"), (1, 3, "tf32")])
+def test_cuda_graph_replay_is_bit_identical_to_eager_issue(dev, B, Lg, precision):
+    """SURVEY 8f-1 / offk.h "safe under CUDA-graph capture": forward and backward captured as one CUDA graph each (all
+    lanes, programmatic dependent launch included) replay the very kernels of the eager plan.  Everything that is not an
+    atomic accumulation must be bit-identical; split-K outputs and weight gradients are fp32 atomics (order-dependent in the
+    last bits) in BOTH modes, so they are compared against the run-to-run spread of the eager path itself."""
+    from off_b200.engine import OFFEngine
+    eng = OFFEngine(B, Lg, "rgb", dev, precision)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for n, v in eng.params.items():
+            v.uniform_(-0.05, 0.05)
+    for t in eng.taps.values():
+        t.copy_(torch.relu(torch.randn_like(t)))
+    g7, g14 = torch.randn(eng.P, 101, device=dev), torch.randn(eng.P, 101, device=dev)
+
+    def run(graph, seed):
+        out = [x.clone() for x in eng.forward(train=True, seed=seed, graph=graph)]
+        f28 = eng.buf["F28"].clone()
+        grads = eng.backward(g7, g14, graph=graph)
+        return out, f28, eng.grads_flat.clone()
+
+    e1, e2 = run(False, 11), run(False, 11)
+    g1, g2 = run(True, 11), run(True, 11)            # first call captures, second replays
+    g3 = run(True, 12)                                # another seed through the SAME graph: new dropout masks
+    torch.cuda.synchronize()
+    assert torch.equal(e1[1], g1[1]) and torch.equal(g1[1], g2[1])          # unit GEMM + stencil: no atomics -> bit-exact
+    assert not torch.equal(g3[1], g1[1])                                      # the device-resident seed reached the kernels
+    spread = lambda a, b: max((x - y).abs().max().item() / max(x.abs().max().item(), 1e-30) for x, y in zip(a, b))
+    tol = 10 * max(spread(e1[0], e2[0]), 1e-6)
+    assert spread(e1[0], g1[0]) <= tol and spread(g1[0], g2[0]) <= tol
+    gs = lambda a, b: ((a - b).norm() / a.norm()).item()
+    assert gs(e1[2], g2[2]) <= 10 * max(gs(e1[2], e2[2]), 1e-6)
+    assert eng.grads["fc_action_motion_28.weight"].abs().max().item() == 0
+    # the nn.Module surface with use_graphs=True trains like the eager one
+    from off_b200.modules import OFFSubNetwork
+    if B == 2:
+        prm = O.make_params(3, "rgb")
+        taps = {k: v.to(dev) for k, v in O.make_taps(3, B, Lg).items()}
+        outs = []
+        for use in (False, True):
+            net = OFFSubNetwork(B, Lg, "rgb", precision=precision, device=dev, use_graphs=use).eval()
+            net.load_state_dict(prm)
+            for _ in range(2):
+                net.zero_grad(set_to_none=True)
+                fc7, _, fc14 = net(taps)
+                (fc7.sum() + fc14.sum()).backward()
+            outs.append((fc7.detach().clone(), net.motion_conv_trans_28.weight.grad.clone()))
+        assert _close(outs[0][0], outs[1][0], 1e-5) and _close(outs[0][1], outs[1][1], 1e-4)
+
+
+def _close(a, b, rel):
+    return ((a - b).norm() / a.norm()).item() <= rel

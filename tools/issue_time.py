@@ -26,16 +26,16 @@ g7 = torch.randn(eng.P, 101, device="cuda") * 0.01
 g14 = torch.randn(eng.P, 101, device="cuda") * 0.01
 
 
-def run(n, what):
+def run(n, what, graph=False):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     a.record()
     for i in range(n):
         if what in ("both", "fwd"):
-            eng.forward(train=True, seed=i + 1)
+            eng.forward(train=True, seed=i + 1, graph=graph)
         if what in ("both", "bwd"):
-            eng.backward(g7, g14)
+            eng.backward(g7, g14, graph=graph)
     b.record()
     t1 = time.perf_counter()
     torch.cuda.synchronize()
@@ -49,3 +49,9 @@ for single in (False, True):
         cpu, gpu = run(10, what)
         print(f"B={B} L={Lg} {prec} single_stream={single} {what:4s}: host issue {cpu:7.3f} ms/step, device {gpu:7.3f} ms/step "
               f"({eng.launches_fwd}+{eng.launches_bwd} launches)")
+
+eng.single_stream = False
+run(3, "both", True)                      # captures
+for what in ("fwd", "bwd", "both"):
+    cpu, gpu = run(10, what, True)
+    print(f"B={B} L={Lg} {prec} CUDA GRAPH replay {what:4s}: host issue {cpu:7.3f} ms/step, device {gpu:7.3f} ms/step")
