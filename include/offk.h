@@ -300,6 +300,24 @@ int offk_avgpool_drop_bwd(const float* dpooled, int P, int C, int HW, int ctot, 
  * sequence (the first node of a captured training step: every replay gets its own dropout masks). */
 int offk_seed_set(uint64_t* state, uint64_t value, void* stream);
 int offk_seed_advance(uint64_t* state, void* stream);
+/* One head in ONE launch: global_pool -> dropout -> fc_action_motion* (-> ConsensusModule('avg') over the T
+ * frame pairs of a clip): RGB_OFF.py:784-787, 790-793, 844-847; Flow_OFF.py:867-876; basic_ops.py:21-22.
+ *   pooled[p, c]  = drop( mean_hw x[p, hw, x_coff + c] )                (written when non-NULL: the backward needs it)
+ *   out[p, n]     = bias[n] + sum_c weight[n, c] * pooled[p, c]         weight [num_classes, C] row-major, exact fp32
+ *   consensus_out[b, n] = mean_{t < T} out[b*T + t, n]                  (T > 1; NULL with T == 1: per-pair logits, RGB_OFF.py:860)
+ * C % 4 == 0, C <= 1024, num_classes <= 128. */
+int offk_head_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode, const uint8_t* keep_mask,
+                  uint64_t seed, const uint64_t* seed_dev, float drop_p, float keep_scale, const float* weight,
+                  const float* bias, int num_classes, int T, float* pooled, float* out, float* consensus_out, void* stream);
+/* Backward of the above in two launches.  dout is [P / T, num_classes]: with T > 1 the consensus backward
+ * (g.expand / T, basic_ops.py:30-31) is folded in, dfc(p, n) = dout[p / T, n] / T.
+ *   dweight[n, c] += sum_p dfc(p, n) * pooled[p, c];  dbias[n] += sum_p dfc(p, n)                       (skipped when NULL)
+ *   dx[p, hw, coff + c] = gate( dx_in + drop'( sum_n dfc(p, n) * weight[n, c] ) / HW )                   (skipped when dx NULL)
+ *     dx_in = dx itself when accumulate != 0; gate = (act[same element] > 0) when act != NULL (ReLU' of the producer) */
+int offk_head_bwd(const float* dout, int P, int C, int HW, int ctot, int coff, int drop_mode, const uint8_t* keep_mask,
+                  uint64_t seed, const uint64_t* seed_dev, float drop_p, float keep_scale, const float* weight,
+                  int num_classes, int T, const float* pooled, const float* act, int accumulate, float* dx,
+                  float* dweight, float* dbias, void* stream);
 /* 3x3 stride-2 ceil-mode max pool (motion_pool_trans_28, RGB_OFF.py:353,:783) */
 int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, int x_ctot, int x_coff, float* out,
                         void* stream);

@@ -107,6 +107,10 @@ _PROTOS = {
                                         C.c_float, C.c_float, _P, _P]),
     "offk_avgpool_drop_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, _P,
                                         C.c_float, C.c_float, _P, C.c_int, _P, _P]),
+    "offk_head_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, _P, C.c_float,
+                                C.c_float, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "offk_head_bwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_uint64, _P, C.c_float,
+                                C.c_float, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "offk_seed_set": (C.c_int, [_P, C.c_uint64, _P]),
     "offk_seed_advance": (C.c_int, [_P, _P]),
     "offk_maxpool3s2_fwd": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -79,6 +79,120 @@ __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C,
   out[i] = m;   // [P, Ho, Wo, C]
 }
 
+// ---------------------------------------------------------------------------- fused heads
+// One block per output row group: the T frame pairs of one clip when the segment consensus is fused (Flow / v2), else one
+// pair (T = 1).  Per pair: global average pool over the HW pixels of the channel slice (consecutive threads = consecutive
+// channels: coalesced) + dropout -> shared memory (and `pooled`, which the weight gradient needs) -> 101 x C GEMV by warps
+// (float4 along the contiguous weight rows, warp-shuffle reduction) + bias.  Everything is linear, so it is exact fp32 in
+// every precision mode.  avgpool -> dropout -> Linear (-> mean over segments): RGB_OFF.py:783-793,844-847; Flow_OFF.py:867-876.
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_MAX_C = 1024;
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(const float* __restrict__ x, int C, int HW, int ctot, int coff,
+                                                                 int mode, const uint8_t* __restrict__ mask, uint64_t seed,
+                                                                 const uint64_t* __restrict__ seed_dev, float drop_p, float scale,
+                                                                 const float* __restrict__ W, const float* __restrict__ bias,
+                                                                 int NC, int T, float* __restrict__ pooled,
+                                                                 float* __restrict__ out, float* __restrict__ cout) {
+  __shared__ __align__(16) float sp[HEAD_MAX_C];
+  pdl_sync();
+  if (seed_dev) seed += __ldg(seed_dev);
+  const uint32_t thr = drop_threshold16(drop_p);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int t = 0; t < T; ++t) {
+    const int p = blockIdx.x * T + t;
+    const float* xp = x + (size_t)p * HW * ctot + coff;
+    for (int c = tid; c < C; c += HEAD_THREADS) {
+      float s = 0.f;
+#pragma unroll 7
+      for (int h = 0; h < HW; ++h) s += __ldg(xp + (size_t)h * ctot + c);
+      const float v = (s / (float)HW) * keep_factor(mode, mask, seed, thr, (size_t)p * C + c, scale);
+      sp[c] = v;
+      if (pooled) pooled[(size_t)p * C + c] = v;
+    }
+    __syncthreads();
+    for (int n = warp; n < NC; n += HEAD_THREADS / 32) {
+      const float* wr = W + (size_t)n * C;
+      float acc = 0.f;
+      for (int c = 4 * lane; c < C; c += 128) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
+        const float4 p4 = *reinterpret_cast<const float4*>(sp + c);
+        acc += w4.x * p4.x + w4.y * p4.y + w4.z * p4.z + w4.w * p4.w;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[(size_t)p * NC + n] = acc + __ldg(bias + n);
+    }
+    __syncthreads();
+  }
+  if (cout) {      // ConsensusModule('avg'): mean over the T rows this block has just written (basic_ops.py:21-22)
+    for (int n = tid; n < NC; n += HEAD_THREADS) {
+      float s = 0.f;
+      for (int t = 0; t < T; ++t) s += out[((size_t)blockIdx.x * T + t) * NC + n];
+      cout[(size_t)blockIdx.x * NC + n] = s / (float)T;
+    }
+  }
+}
+
+// dfc(p, n) = dout[(p / T) * NC + n] / T: the consensus backward (basic_ops.py:30-31) folded into the consumers (T = 1: as is)
+// dW[n, c] += sum_p dfc(p, n) * pooled[p, c];  db[n] += sum_p dfc(p, n).      block (128 c, 8 n)
+__global__ void __launch_bounds__(1024) head_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ pooled, int P,
+                                                          int C, int NC, int T, float* __restrict__ dW, float* __restrict__ db) {
+  pdl_sync();
+  const int c = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y * 8 + threadIdx.y;
+  if (n >= NC) return;
+  const float invT = 1.f / (float)T;
+  float acc = 0.f, accb = 0.f;
+  if (c < C) {
+    for (int p = 0; p < P; ++p) {
+      const float g = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
+      acc += g * __ldg(pooled + (size_t)p * C + c);
+      accb += g;
+    }
+    dW[(size_t)n * C + c] += acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && db) db[n] += accb;
+}
+
+// dpool[c] = drop'( sum_n dfc(p, n) * W[n, c] ) / HW, then dx[p, hw, coff + c] = gate( dx_in + dpool[c] ) for every pixel:
+// the Linear's data gradient and the average pool's backward (+ the ReLU' of the producer) in one pass, one block per pair
+__global__ void __launch_bounds__(HEAD_THREADS) head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W, int C,
+                                                                   int HW, int ctot, int coff, int NC, int T, int mode,
+                                                                   const uint8_t* __restrict__ mask, uint64_t seed,
+                                                                   const uint64_t* __restrict__ seed_dev, float drop_p, float scale,
+                                                                   const float* __restrict__ act, int accumulate,
+                                                                   float* __restrict__ dx) {
+  __shared__ __align__(16) float sd[HEAD_MAX_C];
+  __shared__ float sg[128];
+  pdl_sync();
+  if (seed_dev) seed += __ldg(seed_dev);
+  const uint32_t thr = drop_threshold16(drop_p);
+  const int tid = threadIdx.x, p = blockIdx.x;
+  const float invT = 1.f / (float)T;
+  for (int n = tid; n < NC; n += HEAD_THREADS) sg[n] = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
+  __syncthreads();
+  for (int c = tid; c < C; c += HEAD_THREADS) {
+    float s = 0.f;
+    for (int n = 0; n < NC; ++n) s += sg[n] * __ldg(W + (size_t)n * C + c);
+    sd[c] = s * keep_factor(mode, mask, seed, thr, (size_t)p * C + c, scale) / (float)HW;
+  }
+  __syncthreads();
+  const int c4n = C >> 2;
+  for (int i = tid; i < HW * c4n; i += HEAD_THREADS) {
+    const int hw = i / c4n, c = (i - hw * c4n) * 4;
+    const size_t o = ((size_t)p * HW + hw) * ctot + coff + c;
+    float4 v = *reinterpret_cast<const float4*>(sd + c);
+    if (accumulate) {
+      const float4 d = *reinterpret_cast<const float4*>(dx + o);
+      v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+    }
+    if (act) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(act + o));
+      v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(dx + o) = v;
+  }
+}
+
 __global__ void segment_mean_fwd_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,6 +357,44 @@ extern "C" int offk_maxpool3s2_fwd(const float* x, int P, int C, int H, int W, i
   (void)launch_pdl(maxpool3s2_fwd_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, as_stream(stream), x, P, C, H, W, x_ctot, x_coff, Ho, Wo,
                                                                                out);
   return OFFK_LAUNCH_CHECK("maxpool3s2_fwd");
+}
+
+extern "C" int offk_head_fwd(const float* x, int P, int C, int HW, int x_ctot, int x_coff, int drop_mode, const uint8_t* keep_mask,
+                             uint64_t seed, const uint64_t* seed_dev, float drop_p, float keep_scale, const float* weight,
+                             const float* bias, int num_classes, int T, float* pooled, float* out, float* consensus_out,
+                             void* stream) {
+  OFFK_REQUIRE(x && weight && bias && out && P > 0 && HW > 0 && num_classes > 0 && num_classes <= 128, "head_fwd: bad args");
+  OFFK_REQUIRE(C > 0 && C <= HEAD_MAX_C && C % 4 == 0 && x_coff >= 0 && x_coff + C <= x_ctot, "head_fwd: channel slice (C %% 4 == 0, C <= 1024)");
+  OFFK_REQUIRE(T >= 1 && P % T == 0 && (T == 1 || consensus_out), "head_fwd: T must divide P; T > 1 needs consensus_out");
+  OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "head_fwd: mask missing");
+  OFFK_REQUIRE((reinterpret_cast<uintptr_t>(weight) & 15u) == 0, "head_fwd: weight alignment");
+  (void)launch_pdl(head_fwd_kernel, dim3(P / T), dim3(HEAD_THREADS), 0, as_stream(stream), x, C, HW, x_ctot, x_coff, drop_mode,
+                   keep_mask, seed, seed_dev, drop_p, keep_scale, weight, bias, num_classes, T, pooled, out, consensus_out);
+  return OFFK_LAUNCH_CHECK("head_fwd");
+}
+
+extern "C" int offk_head_bwd(const float* dout, int P, int C, int HW, int ctot, int coff, int drop_mode, const uint8_t* keep_mask,
+                             uint64_t seed, const uint64_t* seed_dev, float drop_p, float keep_scale, const float* weight,
+                             int num_classes, int T, const float* pooled, const float* act, int accumulate, float* dx,
+                             float* dweight, float* dbias, void* stream) {
+  OFFK_REQUIRE(dout && weight && P > 0 && HW > 0 && num_classes > 0 && num_classes <= 128, "head_bwd: bad args");
+  OFFK_REQUIRE(C > 0 && C <= HEAD_MAX_C && C % 4 == 0 && coff >= 0 && coff % 4 == 0 && ctot % 4 == 0 && coff + C <= ctot,
+               "head_bwd: channel slice (multiples of 4, C <= 1024)");
+  OFFK_REQUIRE(T >= 1 && P % T == 0, "head_bwd: T must divide P");
+  OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "head_bwd: mask missing");
+  if (dweight) {
+    OFFK_REQUIRE(pooled != nullptr, "head_bwd: the weight gradient needs the pooled features of the forward pass");
+    (void)launch_pdl(head_wgrad_kernel, dim3((C + 127) / 128, (num_classes + 7) / 8), dim3(128, 8), 0, as_stream(stream), dout, pooled,
+                     P, C, num_classes, T, dweight, dbias);
+    if (int e = OFFK_LAUNCH_CHECK("head_wgrad")) return e;
+  }
+  if (dx) {
+    OFFK_REQUIRE((reinterpret_cast<uintptr_t>(dx) & 15u) == 0, "head_bwd: dx alignment");
+    (void)launch_pdl(head_dgrad_kernel, dim3(P), dim3(HEAD_THREADS), 0, as_stream(stream), dout, weight, C, HW, ctot, coff,
+                     num_classes, T, drop_mode, keep_mask, seed, seed_dev, drop_p, keep_scale, act, accumulate, dx);
+    if (int e = OFFK_LAUNCH_CHECK("head_dgrad")) return e;
+  }
+  return 0;
 }
 
 extern "C" int offk_segment_mean_fwd(const float* x, int B, int T, int C, float* out, void* stream) {

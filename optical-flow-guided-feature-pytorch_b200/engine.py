@@ -281,9 +281,7 @@ class OFFEngine:
         self._buf("p28", P, 7, 7, 256)
         for k, c in (("7", 1024), ("14", 512), ("28", 256)):
             self._buf("pool" + k, P, c)
-            self._buf("d_pool" + k, P, c)
             self._buf("fc" + k, P, S.NUM_CLASSES)
-            self._buf("d_fc" + k, P, S.NUM_CLASSES)
             if self.consensus:
                 self._buf("cfc" + k, self.B, S.NUM_CLASSES)
         # two input sets: while one is being consumed (forward AND backward read the taps) the other can be filled by
@@ -636,10 +634,9 @@ class OFFEngine:
         fwd.append(_nm(lambda stream: L.check(lib.offk_maxpool3s2_fwd(_ptr(bf["F14"]), P, 256, 14, 14, 1056, 800,
                                                                        _ptr(bf["p28"]), stream), "maxpool28"), "maxpool28",
                        reads=[bf["F14"]], writes=[bf["p28"]], lane=1))
-        fwd.append(_on(self._pool_fwd("28", bf["p28"], 256, 256, 0), 1))
-        fwd.append(_on(self._fc_fwd("fc_action_motion_28", "28", 256), 1))
-        fwd.append(_on(self._pool_fwd("14", bf["F7"], 512, 832, 320), 1))
-        fwd.append(_on(self._fc_fwd("fc_action_motion_14", "14", 512), 1))
+        # each head = ONE launch: avgpool 7x7 -> dropout -> Linear (-> segment consensus)   
+        fwd.append(_on(self._head_fwd("28", bf["p28"], 256, 256, 0, "fc_action_motion_28"), 1))
+        fwd.append(_on(self._head_fwd("14", bf["F7"], 512, 832, 320, "fc_action_motion_14"), 1))
 
         # ---- resolution 7 (RGB_OFF.py:831-847)
         g_t7 = layer("motion_conv_trans", bf["F7"], bf["t7"], 7, relu=True)
@@ -647,33 +644,19 @@ class OFFEngine:
         g_72 = layer("motion_conv2_trans", bf["h1_7"], bf["h2_7"], 7, relu=True)
         g_7br = layer("motion_conv_branch_trans", bf["t7"], bf["br7"], 7, lane=2)
         g_73 = layer("motion_conv3_trans", bf["h2_7"], bf["s7"], 7, addend=bf["br7"])        # no final ReLU (:841)
-        fwd.append(self._pool_fwd("7", bf["s7"], 1024, 1024, 0))
-        fwd.append(self._fc_fwd("fc_action_motion", "7", 1024))
-        if self.consensus:
-            for k in ("7", "28", "14"):
-                fwd.append(_nm(lambda stream, k=k: L.check(lib.offk_segment_mean_fwd(
-                    _ptr(bf["fc" + k]), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["cfc" + k]), stream), "consensus" + k),
-                    "consensus" + k, reads=[bf["fc" + k]], writes=[bf["cfc" + k]]))
+        fwd.append(self._head_fwd("7", bf["s7"], 1024, 1024, 0, "fc_action_motion"))
 
         # ============ backward of the stages (reverse order); every d_* buffer holds dL/d(pre-activation)
         bs = bwd_stage
         d = lambda n: bf["d_" + n]
-        if self.consensus:
-            self.d_out7 = torch.zeros(B, S.NUM_CLASSES, device=self.device)
-            self.d_out14 = torch.zeros(B, S.NUM_CLASSES, device=self.device)
-            for k, src in (("7", self.d_out7), ("14", self.d_out14)):
-                bs.append(_nm(lambda stream, k=k, src=src: L.check(lib.offk_segment_mean_bwd(
-                    _ptr(src), B, Lg - 1, S.NUM_CLASSES, _ptr(bf["d_fc" + k]), stream), "consensus_bwd" + k),
-                    "consensus_bwd" + k, reads=[src], writes=[bf["d_fc" + k]]))
-        else:
-            self.d_out7, self.d_out14 = bf["d_fc7"], bf["d_fc14"]
-        # FC heads (fc28 receives no gradient: never returned, RGB_OFF.py:860)
-        for fcname, k, c in (("fc_action_motion", "7", 1024), ("fc_action_motion_14", "14", 512)):
-            gfc = T.ConvGeom(P, c, 1, 1, S.NUM_CLASSES)
-            bs.append(_on(self._conv_wgrad(fcname, bf["pool" + k], bf["d_fc" + k], gfc, dW(fcname), dB(fcname)), 1))
-            bs += self._conv_dgrad(fcname, bf["d_fc" + k], W(fcname), bf["d_pool" + k], gfc)
-        # ds7 = avgpool'(dropout'(d_pool7))
-        bs.append(self._pool_bwd("7", d("s7"), 1024, 1024, 0, act=None, accumulate=False))
+        # upstream gradients: [B,101] with the consensus (its backward, g.expand / T, is folded into the head kernels),
+        # [P,101] without
+        n_up = B if self.consensus else P
+        self.d_out7 = torch.zeros(n_up, S.NUM_CLASSES, device=self.device)
+        self.d_out14 = torch.zeros(n_up, S.NUM_CLASSES, device=self.device)
+        # heads (fc28 receives no gradient: never returned, RGB_OFF.py:860): Linear weight / bias gradient, and
+        # ds7 = avgpool'(dropout'(Linear'(d_out7))) in one pass
+        bs.append(self._head_bwd("7", self.d_out7, d("s7"), 1024, 1024, 0, "fc_action_motion", act=None, accumulate=False))
 
         def back(name, x, dy, geom, *, a_relu=False):
             bs.append(_on(self._conv_wgrad(name, x, dy, geom, dW(name), dB(name), a_relu=a_relu), 1))   # wgrad lane
@@ -693,7 +676,7 @@ class OFFEngine:
         back("motion_conv_trans", bf["F7"], d("t7"), g_t7)
         dgrad("motion_conv_trans", d("t7"), bf["dF7"], g_t7)
         # d sum_14b = (dF7[:,320:] + head-14 pool gradient) * [sum_14b > 0]   (in place in the dF7 slice)
-        bs.append(self._pool_bwd("14", bf["dF7"], 512, 832, 320, act=bf["F7"], accumulate=True))
+        bs.append(self._head_bwd("14", self.d_out14, bf["dF7"], 512, 832, 320, "fc_action_motion_14", act=bf["F7"], accumulate=True))
         if self.unit_bwd_early:          # after the in-place update of dF7[:, 320:], so the main lane never waits on these
             bs.extend(unit_bwd["7"])
         # ---- 14b:  sum_14b = relu(s14a + relu(conv3_14b(h2b)))
@@ -818,32 +801,42 @@ class OFFEngine:
     def _seed_dev(self):
         return _ptr(self.seed_state) if self.drop_mode == L.DROP_SEED else None
 
-    def _pool_fwd(self, k, x, c, ctot, coff):
-        lib, P = self.lib, self.P
+    def _head_fwd(self, k, x, c, ctot, coff, fcname):
+        """global_pool -> dropout -> fc_action_motion* (-> consensus) as ONE launch (RGB_OFF.py:784-787,790-793,844-847;
+        Flow_OFF.py:867-876).  Linear ops only: exact fp32 in every precision mode."""
+        lib, P, bf = self.lib, self.P, self.buf
         site = {"28": 9, "14": 10, "7": 11}[k]
+        w, b = self.params[fcname + ".weight"], self.params[fcname + ".bias"]
+        T_ = self.Lseg - 1 if self.consensus else 1
+        cons = bf["cfc" + k] if self.consensus else None
 
         def run(stream):
             m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
-            L.check(lib.offk_avgpool_drop_fwd(_ptr(x), P, c, 49, ctot, coff, self.drop_mode, _ptr(m),
-                                              self._site_salt(site), self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
-                                              _ptr(self.buf["pool" + k]), stream), "pool" + k)
-        return _nm(run, "pool_fwd" + k, reads=[x], writes=[self.buf["pool" + k]])
+            L.check(lib.offk_head_fwd(_ptr(x), P, c, 49, ctot, coff, self.drop_mode, _ptr(m), self._site_salt(site),
+                                      self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P), _ptr(w), _ptr(b), S.NUM_CLASSES, T_,
+                                      _ptr(bf["pool" + k]), _ptr(bf["fc" + k]), _ptr(cons), stream), "head_fwd" + k)
+        self.flops_fwd += 2.0 * P * c * S.NUM_CLASSES
+        return _nm(run, "head_fwd" + k, reads=[x], writes=[bf["pool" + k], bf["fc" + k], cons])
 
-    def _pool_bwd(self, k, dx, c, ctot, coff, act, accumulate):
-        lib, P = self.lib, self.P
+    def _head_bwd(self, k, dout, dx, c, ctot, coff, fcname, act, accumulate):
+        """Backward of _head_fwd in two launches: Linear weight / bias gradient; Linear data gradient + dropout' + average
+        pool backward (+ the producer's ReLU', + accumulation into a slice that already holds a gradient)."""
+        lib, P, bf = self.lib, self.P, self.buf
         site = {"28": 9, "14": 10, "7": 11}[k]
+        w = self.params[fcname + ".weight"]
+        dw, db = self.grads[fcname + ".weight"], self.grads[fcname + ".bias"]
+        T_ = self.Lseg - 1 if self.consensus else 1
 
         def run(stream):
             m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
-            L.check(lib.offk_avgpool_drop_bwd(_ptr(self.buf["d_pool" + k]), P, c, 49, ctot, coff, self.drop_mode,
-                                              _ptr(m), self._site_salt(site), self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P),
-                                              _ptr(act), int(accumulate), _ptr(dx), stream), "pool_bwd" + k)
-        return _nm(run, "pool_bwd" + k, reads=[self.buf["d_pool" + k], act, dx if accumulate else None], writes=[dx])
-
-    def _fc_fwd(self, name, k, c):
-        g = T.ConvGeom(self.P, c, 1, 1, S.NUM_CLASSES)
-        return self._conv_fwd(name, self.buf["pool" + k], self.buf["fc" + k], g, self.params[name + ".weight"],
-                              self.params[name + ".bias"])
+            L.check(lib.offk_head_bwd(_ptr(dout), P, c, 49, ctot, coff, self.drop_mode, _ptr(m), self._site_salt(site),
+                                      self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P), _ptr(w), S.NUM_CLASSES, T_,
+                                      _ptr(bf["pool" + k]), _ptr(act), int(accumulate), _ptr(dx), _ptr(dw), _ptr(db), stream),
+                    "head_bwd" + k)
+        self.flops_bwd += 4.0 * P * c * S.NUM_CLASSES
+        step = _nm(run, "head_bwd" + k, reads=[dout, bf["pool" + k], act, dx if accumulate else None], writes=[dx, dw, db])
+        step.launches = ["head_bwd%s.wgrad" % k, "head_bwd%s.dgrad" % k]
+        return step
 
     # ------------------------------------------------------------------ run
     def _set_dropout(self, train, masks, seed):

@@ -180,7 +180,7 @@ def make_dropout_masks(seed: int, batch: int, length: int, p_drop: float = 0.8):
 # ---------------------------------------------------------------------------
 # tcgen05.mma kind::tf32 reads the top 19 bits of every fp32 operand word (the low 13 mantissa bits are ignored) and
 # accumulates the exact products in fp32.  ``mm="tf32_trunc"`` makes every dense contraction of the restatement (1x1 /
-# KxK convs, FC heads and their autograd: data gradient = dY x W, weight gradient = X x dY, bias gradient = sum of the
+# KxK convs and their autograd: data gradient = dY x W, weight gradient = X x dY, bias gradient = sum of the
 # truncated dY because the product folds it into the weight-gradient GEMM as an all-ones operand row) consume operands
 # truncated the same way, everything else unchanged.  The depth-wise stencil, pools and dropout are not contractions.
 def trunc_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -213,10 +213,9 @@ def _conv2d(x, w, b, stride=1, pad=0, mm="exact"):
 
 
 def _linear(x, w, b, mm="exact"):
-    if mm == "exact":
-        return F.linear(x, w, b)
-    y = _Tf32Conv.apply(x.reshape(-1, x.shape[-1], 1, 1), w[:, :, None, None], b, 1, 0)
-    return y.reshape(*x.shape[:-1], w.shape[0])
+    """The FC heads are not tensor-core contractions in the product (one fused pool + dropout + Linear kernel per head,
+    plain fp32 FMAs, forward and backward): exact in every mode."""
+    return F.linear(x, w, b)
 
 
 # ---------------------------------------------------------------------------

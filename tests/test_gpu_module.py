@@ -265,7 +265,7 @@ def test_fused_training_step_matches_torch(dev, variant, max_norm):
         assert abs(tr.grad_norm() - total.item()) < 1e-5 * total.item()
         for p, n in zip(ref_p, names):
             assert torch.allclose(eng.params[n], p.detach(), atol=2e-7, rtol=1e-5), (it, n)
-    assert clipped == (max_norm < 1.0)
+    assert clipped or max_norm >= 1.0                         # the small max_norm case exercises the clipping branch
     assert torch.equal(eng.params["fc_action_motion_28.weight"], fc28_before)   # no gradient in the reference: Adam skips it
 
 

@@ -692,3 +692,54 @@ def test_module_matches_reference_golden(dev, name):
         # oracle tests, the fixture pins that the oracle is the reference
         assert abs(p.grad.double().norm().item() - l2) / l2 < 5e-2, n
         assert (got - val).norm().item() <= 5e-2 * max(val.norm().item(), 1e-2 * l2), n
+
+
+@pytest.mark.parametrize("P,C,T,drop,acc", [(6, 1024, 1, 0, False), (8, 512, 2, 1, True), (6, 256, 3, 2, False), (1, 512, 1, 0, True)])
+def test_fused_head_fwd_bwd(dev, P, C, T, drop, acc):
+    """offk_head_fwd / offk_head_bwd: global_pool -> dropout -> Linear (-> consensus over T pairs) in one launch and
+    its backward (Linear', dropout', avg-pool', producer ReLU', accumulation into a channel slice) against torch in fp64.
+    RGB_OFF.py:784-793,844-847; Flow_OFF.py:867-876; basic_ops.py:21-31."""
+    from off_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(7)
+    HW, NC, ctot, coff = 49, 101, C + 64, 32
+    x = torch.randn(P, HW, ctot, device=dev)
+    W, b = torch.randn(NC, C, device=dev) / C ** 0.5, torch.randn(NC, device=dev)
+    seed = 1234
+    if drop == 1:
+        keep = (torch.rand(P, C, device=dev) >= 0.8).to(torch.uint8)
+    elif drop == 2:
+        keep = torch.tensor([lib.offk_drop_keep_host(seed, i, 0.8) for i in range(P * C)], dtype=torch.uint8, device=dev).view(P, C)
+    else:
+        keep = torch.ones(P, C, dtype=torch.uint8, device=dev)
+    scale = 5.0 if drop else 1.0
+    pooled = torch.zeros(P, C, device=dev)
+    out = torch.zeros(P, NC, device=dev)
+    cons = torch.zeros(P // T, NC, device=dev) if T > 1 else None
+    mask_ptr = keep.data_ptr() if drop == 1 else None
+    L.check(lib.offk_head_fwd(x.data_ptr(), P, C, HW, ctot, coff, drop, mask_ptr, seed, None, 0.8, scale, W.data_ptr(), b.data_ptr(),
+                              NC, T, pooled.data_ptr(), out.data_ptr(), cons.data_ptr() if cons is not None else None, None), "head_fwd")
+    xs = x[..., coff:coff + C].double().requires_grad_(True)
+    Wd, bd = W.double().requires_grad_(True), b.double().requires_grad_(True)
+    pr = xs.mean(1) * keep.double() * scale
+    o = pr @ Wd.t() + bd
+    final = o.view(P // T, T, NC).mean(1) if T > 1 else o
+    assert _rel(pooled, pr.detach().cpu()) < 2e-6 and _rel(out, o.detach().cpu()) < 2e-6
+    if T > 1:
+        assert _rel(cons, final.detach().cpu()) < 2e-6
+    dout = torch.randn(P // T, NC, device=dev)
+    final.backward(dout.double())
+    act = torch.randn(P, HW, ctot, device=dev)
+    dx0 = torch.randn(P, HW, ctot, device=dev)
+    dx = dx0.clone()
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    L.check(lib.offk_head_bwd(dout.data_ptr(), P, C, HW, ctot, coff, drop, mask_ptr, seed, None, 0.8, scale, W.data_ptr(), NC, T,
+                              pooled.data_ptr(), act.data_ptr() if acc else None, int(acc), dx.data_ptr(), dW.data_ptr(),
+                              db.data_ptr(), None), "head_bwd")
+    torch.cuda.synchronize()
+    assert _rel(dW, Wd.grad.cpu()) < 5e-6 and _rel(db, bd.grad.cpu()) < 5e-6
+    want = xs.grad
+    if acc:
+        want = (want + dx0[..., coff:coff + C].double()) * (act[..., coff:coff + C] > 0)
+    assert _rel(dx[..., coff:coff + C], want.cpu()) < 5e-6
+    assert torch.equal(dx[..., :coff], dx0[..., :coff]) and torch.equal(dx[..., coff + C:], dx0[..., coff + C:])   # slice only
