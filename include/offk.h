@@ -145,6 +145,22 @@ typedef struct offk_gemm {
   int32_t out_vec;     /* 1: out/gate/addend are contiguous along n (out_col[n] = out_col[0] + n, N % 4 == 0, all
                           offsets and bias 16-byte aligned): float4 epilogue (NHWC outputs) */
   int32_t reserved;
+  /* offk_tma_gemm with out_vec = 1 only (NULL / 0 elsewhere):
+   * finish_counter: split-K without a second kernel.  One int per output tile (tile = blockIdx.y * gridDim.x + blockIdx.x;
+   *   zero before the first launch, left zero by every launch).  The split CTAs add their partial tiles into the
+   *   zero-initialised `out`; the last one to arrive re-reads the summed tile and applies the epilogue above (bias, ReLU
+   *   prefix, gate, addend, ReLU) in place -- so bias / activation ARE applied although split_k > 1.
+   * aux_out: a second output written where the final value v of an element is produced (directly, or by the split-K
+   *   finisher):  aux_out[aux_row[m] + aux_col0 + n] = max(v + aux_addend[out_row[m] + out_col[n]], 0)
+   *   (aux_row NULL: the out_row table; aux_addend NULL: 0).  RGB_OFF.py:658 (the ReLU'd copy of motion_conv_trans_28's
+   *   pre-activation output, which :665 also consumes raw) and :779-780,832 (sum_14b = relu(sum_14a + relu(conv3_14b)) written
+   *   into the 7x7 fusion buffer while the inner ReLU output is kept for the backward pass). */
+  int32_t* finish_counter;
+  float* aux_out;
+  const int32_t* aux_row;
+  const float* aux_addend;
+  int32_t aux_col0;
+  int32_t reserved2;
 } offk_gemm_t;
 
 int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);

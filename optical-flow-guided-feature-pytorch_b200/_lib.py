@@ -38,6 +38,8 @@ class OffkGemm(C.Structure):
         ("relu_post", C.c_int32), ("atomic_out", C.c_int32),
         ("ones_row_out", C.c_void_p),
         ("split_k", C.c_int32), ("tile_n", C.c_int32), ("out_vec", C.c_int32), ("reserved", C.c_int32),
+        ("finish_counter", C.c_void_p), ("aux_out", C.c_void_p), ("aux_row", C.c_void_p), ("aux_addend", C.c_void_p),
+        ("aux_col0", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

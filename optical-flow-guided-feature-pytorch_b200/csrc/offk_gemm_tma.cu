@@ -83,6 +83,7 @@ struct TmShared {
   uint64_t accum_full;
   uint64_t split[TC_MAX_STAGES];   // X3: the residual ("lo") tiles of the stage are written (256 epilogue threads)
   uint32_t tmem_base;
+  uint32_t last_flag;              // split-K finisher: 1 in the CTA that arrived last on the tile's counter
 };
 
 // X3 = OFFK_PREC_TF32X3: every stage holds [A | B | A_lo | B_lo]; the epilogue warps, otherwise idle during the main loop,
@@ -300,24 +301,47 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       const int trow = quad * 32 + lane;                         // accumulator row this thread drains
       const int rsub = lane >> 3, cq = lane & 7;                 // read-back: 4 rows per warp pass, 8 float4 per row
       const int nchunks = (bn + 31) >> 5;
+      const int oc0 = __ldg(g.out_col);
+      const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
+      const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
       // The four output rows this thread stores, their table entries and the column bases are fetched while the main
       // loop still runs (they sat on the critical path of every chunk before).  out_vec contract: the column tables are
       // contiguous, col[n] = col[0] + n.
-      int r_out[TC_BM / 32], r_gate[TC_BM / 32], r_add[TC_BM / 32];
+      int r_out[TC_BM / 32], r_gate[TC_BM / 32], r_add[TC_BM / 32], r_aux[TC_BM / 32];
       bool r_ok[TC_BM / 32];
 #pragma unroll
       for (int it = 0; it < TC_BM / 32; ++it) {
         const int m = m0 + it * 32 + ew * 4 + rsub;
         r_ok[it] = m < m_lim;
-        r_out[it] = r_gate[it] = r_add[it] = 0;
+        r_out[it] = r_gate[it] = r_add[it] = r_aux[it] = 0;
         if (r_ok[it]) {
           const EpiRow er = epi_row(g, m);
           r_out[it] = er.out; r_gate[it] = er.gate; r_add[it] = er.add;
+          r_aux[it] = g.aux_out ? (g.aux_row ? __ldg(g.aux_row + m) : er.out) : 0;
         }
       }
-      const int oc0 = __ldg(g.out_col);
-      const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
-      const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
+      // final value of 4 consecutive elements of row `it` at column n: the epilogue of offk.h, then the optional second output
+      auto finish4 = [&](float4 v, int it, int n, const float4& bias4, const float4& t, const float4& ad, bool gated) {
+        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+        if (n < g.relu_pre_cols) v = f4relu(v);               // relu_pre_cols is a multiple of 4 on this path
+        if (gated && g.gate_first) {
+          v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+        }
+        v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+        if (gated && !g.gate_first) {
+          v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+        }
+        if (g.relu_post) v = f4relu(v);
+        if (g.aux_out) {
+          float4 a = v;
+          if (g.aux_addend) {
+            const float4 x = ldg128(g.aux_addend + (r_out[it] + oc0 + n));
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+          }
+          *reinterpret_cast<float4*>(g.aux_out + (r_aux[it] + g.aux_col0 + n)) = f4relu(a);
+        }
+        return v;
+      };
       split_loop();
       mbar_wait(smem_u32(&sh->accum_full), 0u);
       tc_fence_after();
@@ -362,18 +386,40 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
               continue;
             }
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (n < g.relu_pre_cols) v = f4relu(v);             // relu_pre_cols is a multiple of 4 on this path
-            const float4 t = gt[it];
-            if (gated && g.gate_first) {
-              v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+            *reinterpret_cast<float4*>(o) = finish4(v, it, n, bias4, gt[it], ad[it], gated);
+          }
+        }
+      }
+      if (atomic && g.finish_counter) {
+        // ---- split-K finisher: the last CTA to have added its partial tile applies the epilogue in place.
+        // release: this thread's reds, then the CTA-wide barrier, then the counter; acquire: counter, fence, .cg loads
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        volatile uint32_t* flag = &sh->last_flag;
+        if (tid == 64) {
+          int* ctr = g.finish_counter + (blockIdx.y * gridDim.x + blockIdx.x);
+          const int prev = atomicAdd(ctr, 1);
+          const int last = prev == (int)gridDim.z - 1;
+          if (last) *ctr = 0;                                    // ready for the next launch / graph replay
+          *flag = (uint32_t)last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*flag) {
+          __threadfence();
+          for (int c = 0; c < nchunks; ++c) {
+            const int n = n0 + c * 32 + cq * 4;
+            if (!(n < g.N && c * 32 + cq * 4 < bn)) continue;
+            const bool gated = g.gate && n >= g.gate_col0;
+            const float4 bias4 = g.bias ? ldg128(g.bias + n) : f4zero();
+#pragma unroll
+            for (int it = 0; it < TC_BM / 32; ++it) {
+              if (!r_ok[it]) continue;
+              float* o = g.out + (r_out[it] + oc0 + n);
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(o));
+              const float4 t = gated ? ldg128(g.gate + (r_gate[it] + gc0 + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 ad4 = g.addend ? ldg128(g.addend + (r_add[it] + ac0 + n)) : f4zero();
+              *reinterpret_cast<float4*>(o) = finish4(v, it, n, bias4, t, ad4, gated);
             }
-            v.x += ad[it].x; v.y += ad[it].y; v.z += ad[it].z; v.w += ad[it].w;
-            if (gated && !g.gate_first) {
-              v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
-            }
-            if (g.relu_post) v = f4relu(v);
-            *reinterpret_cast<float4*>(o) = v;
           }
         }
       }
@@ -580,6 +626,10 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   const offk_gemm_t& g = t->g;
   OFFK_REQUIRE(g.out && g.out_row && g.out_col, "tma_gemm: output tables");
   if (g.out_vec) OFFK_REQUIRE((g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15u) == 0, "tma_gemm: out_vec alignment");
+  OFFK_REQUIRE(g.out_vec || (!g.finish_counter && !g.aux_out), "tma_gemm: finish_counter / aux_out need out_vec = 1");
+  OFFK_REQUIRE(!g.finish_counter || (g.split_k > 1 && !g.atomic_out), "tma_gemm: finish_counter is for split_k > 1 without atomic_out");
+  OFFK_REQUIRE(!g.aux_out || g.finish_counter || (g.split_k <= 1 && !g.atomic_out), "tma_gemm: aux_out needs a final value (no raw accumulation)");
+  if (g.aux_out) OFFK_REQUIRE((reinterpret_cast<uintptr_t>(g.aux_out) & 15u) == 0 && (g.aux_col0 & 3) == 0, "tma_gemm: aux_out alignment");
   const int bn = t->prepared;
   TmGeom geo;
   geo.a_kind = t->a_kind; geo.a_coff = t->a_coff; geo.cblocks = t->cin > 0 ? t->cin / TC_BK : 1; geo.kw = t->kw > 0 ? t->kw : 1;

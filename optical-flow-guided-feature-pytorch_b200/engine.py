@@ -54,7 +54,8 @@ class Gemm:
 
     def __init__(self, eng: "OFFEngine", spc: T.GemmSpec, key, *, a_src, b_src, out, bias=None, relu_pre_cols=0,
                  a_relu=False, gate=None, gate_tabs=None, gate_col0=0, gate_first=False, addend=None,
-                 add_tabs=None, relu_post=False, atomic=False, ones_out=None, split_k=1, tile_n=0, name=""):
+                 add_tabs=None, relu_post=False, atomic=False, ones_out=None, split_k=1, tile_n=0, name="",
+                 finish=False, aux=None):
         self.eng, self.name, self.spec = eng, name, spc
         tabs = eng._tables(key, spc)
         d = L.OffkGemm()
@@ -79,13 +80,23 @@ class Gemm:
             tile_n = _auto_tile_n(spc.M, spc.N, isinstance(self, TGemm))
         d.split_k, d.tile_n = split_k, tile_n
         d.out_vec = spc.out_vec
+        counter = None
+        if finish:                         # split-K finished in-kernel by the last CTA of each output tile (offk.h)
+            bn = tile_n if tile_n else (256 if spc.N > 256 else (spc.N + 15) // 16 * 16)
+            counter = torch.zeros(math.ceil(spc.M / 128) * math.ceil(spc.N / bn), dtype=torch.int32, device=eng.device)
+            d.finish_counter = counter.data_ptr()
+        if aux is not None:                # (aux_out, aux_row table or None, aux_col0, aux_addend or None)
+            d.aux_out = aux[0].data_ptr()
+            d.aux_row = aux[1].data_ptr() if aux[1] is not None else None
+            d.aux_col0 = aux[2]
+            d.aux_addend = aux[3].data_ptr() if aux[3] is not None else None
         T.check_modes(spc)
         self.desc = d
-        self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out)
+        self._keep = (tabs, a_src, b_src, out, bias, gate, gate_tabs, addend, add_tabs, ones_out, counter, aux)
         self.flops = 2.0 * spc.M * spc.N * spc.K
         self.launches = [name]
-        self.reads = [a_src, b_src, addend, gate, bias]
-        self.writes = [out, ones_out]
+        self.reads = [a_src, b_src, addend, gate, bias, aux[3] if aux else None]
+        self.writes = [out, ones_out, aux[0] if aux else None]
         self.lane = 0
 
     def set_a_src(self, ptr):
@@ -342,7 +353,9 @@ class OFFEngine:
 
     # ------------------------------------------------------------------ plan
     def _conv_fwd(self, name, x, y, geom, w, b, *, relu=False, relu_cols=None, a_relu=False, addend=None,
-                  add_tabs=None, relu_post=False, x_layout="nhwc", no_split=False):
+                  add_tabs=None, relu_post=False, x_layout="nhwc", no_split=False, aux=None):
+        """aux = (aux_out, aux_row table | None, aux_col0, aux_addend | None): second output max(v + aux_addend, 0) written by
+        the GEMM epilogue (offk.h); only honoured on the TMA-fed path -- the returned step has .aux_fused = True then."""
         spc = T.conv_fwd_spec(geom, x_layout, "nhwc")
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
@@ -354,6 +367,22 @@ class OFFEngine:
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, **k)) if tma else Gemm
         if (tma and x_layout == "nchw") or no_split:
             split = 1                     # per-frame M tiles already fill the machine (N * ceil(hw/128) CTAs)
+        fuse = tma and spc.out_vec and os.environ.get("OFFK_NO_FINISHER", "0") != "1"
+        if split > 1 and fuse:
+            # split-K partial tiles are added into the zeroed output; the last CTA of each tile applies bias / ReLU (and
+            # writes the second output) in place: no separate bias_act pass
+            g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
+                   split_k=split, name=name, finish=True, aux=aux)
+
+            def run(stream, g=g, y=y):
+                L.check(self.lib.offk_fill_zero(_ptr(y), y.numel(), stream), name + ".zero")
+                g(stream)
+            assert geom.y_coff == 0 and geom.y_ctot == geom.cout
+            self.flops_fwd += g.flops
+            run.name, run.flops, run.gemm, run.aux_fused = name, g.flops, g, aux is not None
+            run.launches = [name + ".zero", name + ".splitk"]
+            run.reads, run.writes, run.lane = g.reads, g.writes, 0
+            return run
         if split > 1:
             g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, a_relu=a_relu, split_k=split, name=name)
             hw = geom.hout * geom.wout
@@ -375,7 +404,8 @@ class OFFEngine:
         # nchw TMA: one N tile (re-reading the tap per N tile would multiply the HBM traffic of an HBM-bound GEMM)
         tn = (spc.N + 15) // 16 * 16 if (tma and x_layout == "nchw" and spc.N <= 256) else 0
         g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
-               addend=addend, add_tabs=add_tabs, relu_post=relu_post, tile_n=tn, name=name)
+               addend=addend, add_tabs=add_tabs, relu_post=relu_post, tile_n=tn, name=name, aux=aux if fuse else None)
+        g.aux_fused = fuse and aux is not None
         self.flops_fwd += g.flops
         return g
 
@@ -586,19 +616,21 @@ class OFFEngine:
         def dB(n): return gr[n + ".bias"]
 
         def layer(name, x, y, s_in, *, relu=False, a_relu=False, addend=None, relu_post=False,
-                  x_ctot=0, x_coff=0, y_ctot=0, y_coff=0, lane=0):
+                  x_ctot=0, x_coff=0, y_ctot=0, y_coff=0, lane=0, aux=None):
             """forward conv; returns geom for the gradient wiring."""
             geom = geom_of(name, P, s_in, x_ctot, x_coff, y_ctot, y_coff)
             fwd.append(_on(self._conv_fwd(name, x, y, geom, W(name), Bv(name), relu=relu, a_relu=a_relu, addend=addend,
-                                          relu_post=relu_post), lane))
+                                          relu_post=relu_post, aux=aux), lane))
             return geom
 
         # ---- resolution 28 (RGB_OFF.py:655-685)
-        g_t28 = layer("motion_conv_trans_28", bf["F28"], bf["t28"], 28)                       # pre-ReLU kept (:665)
-        n28 = bf["t28"].numel()
-        fwd.append(_nm(lambda stream: L.check(lib.offk_relu_gate(_ptr(bf["t28"]), _ptr(bf["t28"]), n28, _ptr(bf["t28r"]),
-                                                                  stream), "relu_t28"), "relu_t28",
-                       reads=[bf["t28"]], writes=[bf["t28r"]]))
+        # pre-ReLU output kept for the branch (:665); its ReLU'd copy (:658) is the epilogue's second output
+        g_t28 = layer("motion_conv_trans_28", bf["F28"], bf["t28"], 28, aux=(bf["t28r"], None, 0, None))
+        if not getattr(fwd[-1], "aux_fused", False):
+            n28 = bf["t28"].numel()
+            fwd.append(_nm(lambda stream: L.check(lib.offk_relu_gate(_ptr(bf["t28"]), _ptr(bf["t28"]), n28, _ptr(bf["t28r"]),
+                                                                      stream), "relu_t28"), "relu_t28",
+                           reads=[bf["t28"]], writes=[bf["t28r"]]))
         g_c1a = layer("motion_conv1_trans_28a", bf["t28r"], bf["h1_28a"], 14, relu=True)
         g_c2a = layer("motion_conv2_trans_28a", bf["h1_28a"], bf["h2_28a"], 14, relu=True)
         g_bra = layer("motion_conv_branch_28a", bf["t28"], bf["br28"], 14, lane=2)
@@ -625,10 +657,14 @@ class OFFEngine:
         g_14a3 = layer("motion_conv3_trans_14a", bf["h2_14a"], bf["s14a"], 7, addend=bf["ex14"], relu_post=True)
         g_14b1 = layer("motion_conv1_trans_14b", bf["s14a"], bf["h1_14b"], 7, relu=True)
         g_14b2 = layer("motion_conv2_trans_14b", bf["h1_14b"], bf["h2_14b"], 7, relu=True)
-        g_14b3 = layer("motion_conv3_trans_14b", bf["h2_14b"], bf["h3_14b"], 7, relu=True)   # 3x3 + ReLU (:316,:778)
-
-        # sum_14b = relu(s14a + h3_14b) -> 7-stage fusion buffer channels [320,832)  (:779-780, cat :832)
-        fwd.append(self._add_into_slice(bf["s14a"], bf["h3_14b"], bf["F7"], 832, 320, 512, 49))
+        # 3x3 + ReLU (:316,:778), kept for the backward gate; sum_14b = relu(s14a + h3_14b) -> 7-stage fusion buffer channels
+        # [320,832) (:779-780, cat :832) is the same epilogue's second output
+        g_f7slice = T.ConvGeom(P, 512, 7, 7, 512, y_ctot=832, y_coff=320)
+        tabs_f7 = self._tables(("fwd", "nhwc", _gkey(g_f7slice)), T.conv_fwd_spec(g_f7slice, "nhwc", "nhwc"))
+        g_14b3 = layer("motion_conv3_trans_14b", bf["h2_14b"], bf["h3_14b"], 7, relu=True,
+                       aux=(bf["F7"], tabs_f7["out_row"], 320, bf["s14a"]))
+        if not getattr(fwd[-1], "aux_fused", False):
+            fwd.append(self._add_into_slice(bf["s14a"], bf["h3_14b"], bf["F7"], 832, 320, 512, 49))
 
         # ---- heads 28 / 14 (RGB_OFF.py:783-793)
         fwd.append(_nm(lambda stream: L.check(lib.offk_maxpool3s2_fwd(_ptr(bf["F14"]), P, 256, 14, 14, 1056, 800,

@@ -743,3 +743,56 @@ def test_fused_head_fwd_bwd(dev, P, C, T, drop, acc):
         want = (want + dx0[..., coff:coff + C].double()) * (act[..., coff:coff + C] > 0)
     assert _rel(dx[..., coff:coff + C], want.cpu()) < 5e-6
     assert torch.equal(dx[..., :coff], dx0[..., :coff]) and torch.equal(dx[..., coff + C:], dx0[..., coff + C:])   # slice only
+
+
+@PRECS
+@pytest.mark.parametrize("split,with_aux", [(4, True), (3, False), (1, True)])
+def test_tma_gemm_split_k_finisher_and_second_output(dev, prec, tol, split, with_aux):
+    """offk_tma_gemm split-K finished in-kernel (finish_counter: the last CTA of a tile applies bias + ReLU in place) and the
+    epilogue's second output aux_out = relu(v + aux_addend) in another tensor layout; launched twice on the same counters
+    (they must be left at zero).  Against conv2d + the element-wise ops in fp64."""
+    from off_b200 import _lib as L, tables as T
+    lib = L.lib()
+    n, cin, h, cout, k = 3, 128, 7, 256, 3
+    g = T.ConvGeom(n, cin, h, h, cout, k, k, 1, 1)
+    torch.manual_seed(4)
+    x = torch.randn(n, h, h, cin, device=dev)
+    wt = torch.randn(cout, cin, k, k, device=dev) / (g.kdim ** 0.5)
+    wl = wt.permute(0, 2, 3, 1).contiguous()
+    bias = torch.randn(cout, device=dev)
+    addend = torch.randn(n, h, h, cout, device=dev)
+    spc = T.conv_fwd_spec(g, "nhwc", "nhwc")
+    tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
+    gaux = T.ConvGeom(n, cout, h, h, cout, y_ctot=cout + 96, y_coff=64)           # aux lands in a channel slice of a wider tensor
+    aux_row = torch.from_numpy(T.padded_tables(T.conv_fwd_spec(gaux, "nhwc", "nhwc"))["out_row"]).to(dev)
+    out = torch.zeros(n, h, h, cout, device=dev)
+    aux = torch.zeros(n, h, h, cout + 96, device=dev)
+    counter = torch.zeros(64, dtype=torch.int32, device=dev)
+    t = L.OffkTGemm()
+    d = t.g
+    d.M, d.N, d.K = spc.M, spc.N, spc.K
+    d.a_src, d.b_src = x.data_ptr(), wl.data_ptr()
+    d.a_ones_row = -1
+    d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+    d.bias, d.relu_pre_cols, d.split_k, d.out_vec = bias.data_ptr(), cout, split, 1
+    if split > 1:
+        d.finish_counter = counter.data_ptr()
+    if with_aux:
+        d.aux_out, d.aux_row, d.aux_col0, d.aux_addend = aux.data_ptr(), aux_row.data_ptr(), 64, addend.data_ptr()
+    t.a_kind = L.TMA_A_IM2COL
+    t.n_img, t.hin, t.win, t.ctot, t.cin = n, h, h, cin, cin
+    t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = k, k, 1, 1, h, h
+    t.b_kind, t.ldb, t.precision = L.TMA_B_DENSE, g.kdim, prec
+    L.check(lib.offk_tma_gemm_prepare(C.byref(t)), "prepare")
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double(), 1, 1)).permute(0, 2, 3, 1)
+    for rep_ in range(2):
+        out.zero_()
+        aux.fill_(-7.0)
+        L.check(lib.offk_tma_gemm(C.byref(t), None), "tma_gemm")
+        torch.cuda.synchronize()
+        assert _rel(out, ref.cpu()) < tol, rep_
+        assert counter.abs().max().item() == 0
+        if with_aux:
+            want = torch.relu(ref + addend.double())
+            assert _rel(aux[..., 64:64 + cout], want.cpu()) < tol
+            assert (aux[..., :64] == -7.0).all() and (aux[..., 64 + cout:] == -7.0).all()
