@@ -85,7 +85,7 @@ __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C,
 // channels: coalesced) + dropout -> shared memory (and `pooled`, which the weight gradient needs) -> 101 x C GEMV by warps
 // (float4 along the contiguous weight rows, warp-shuffle reduction) + bias.  Everything is linear, so it is exact fp32 in
 // every precision mode.  avgpool -> dropout -> Linear (-> mean over segments): RGB_OFF.py:783-793,844-847; Flow_OFF.py:867-876.
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 512;
 constexpr int HEAD_MAX_C = 1024;
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(const float* __restrict__ x, int C, int HW, int ctot, int coff,
@@ -99,21 +99,32 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(const float* __r
   if (seed_dev) seed += __ldg(seed_dev);
   const uint32_t thr = drop_threshold16(drop_p);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float inv_hw = 1.f / (float)HW;
   for (int t = 0; t < T; ++t) {
     const int p = blockIdx.x * T + t;
     const float* xp = x + (size_t)p * HW * ctot + coff;
-    for (int c = tid; c < C; c += HEAD_THREADS) {
-      float s = 0.f;
+    // pool: one thread per channel quad, HW independent 16-byte loads (consecutive threads = consecutive quads: coalesced)
+    for (int q = tid; q < (C >> 2); q += HEAD_THREADS) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 7
-      for (int h = 0; h < HW; ++h) s += __ldg(xp + (size_t)h * ctot + c);
-      const float v = (s / (float)HW) * keep_factor(mode, mask, seed, thr, (size_t)p * C + c, scale);
-      sp[c] = v;
-      if (pooled) pooled[(size_t)p * C + c] = v;
+      for (int h = 0; h < HW; ++h) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)h * ctot) + q);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      const size_t i0 = (size_t)p * C + 4 * q;
+      a.x *= inv_hw * keep_factor(mode, mask, seed, thr, i0, scale);
+      a.y *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 1, scale);
+      a.z *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 2, scale);
+      a.w *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 3, scale);
+      *reinterpret_cast<float4*>(sp + 4 * q) = a;
+      if (pooled) *reinterpret_cast<float4*>(pooled + i0) = a;
     }
     __syncthreads();
+    // Linear: one warp per class row, float4 along the contiguous weight row, warp-shuffle reduction
     for (int n = warp; n < NC; n += HEAD_THREADS / 32) {
       const float* wr = W + (size_t)n * C;
       float acc = 0.f;
+#pragma unroll 4
       for (int c = 4 * lane; c < C; c += 128) {
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
         const float4 p4 = *reinterpret_cast<const float4*>(sp + c);
@@ -143,6 +154,7 @@ __global__ void __launch_bounds__(1024) head_wgrad_kernel(const float* __restric
   const float invT = 1.f / (float)T;
   float acc = 0.f, accb = 0.f;
   if (c < C) {
+#pragma unroll 8
     for (int p = 0; p < P; ++p) {
       const float g = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
       acc += g * __ldg(pooled + (size_t)p * C + c);
@@ -154,32 +166,46 @@ __global__ void __launch_bounds__(1024) head_wgrad_kernel(const float* __restric
 }
 
 // dpool[c] = drop'( sum_n dfc(p, n) * W[n, c] ) / HW, then dx[p, hw, coff + c] = gate( dx_in + dpool[c] ) for every pixel:
-// the Linear's data gradient and the average pool's backward (+ the ReLU' of the producer) in one pass, one block per pair
-__global__ void __launch_bounds__(HEAD_THREADS) head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W, int C,
-                                                                   int HW, int ctot, int coff, int NC, int T, int mode,
-                                                                   const uint8_t* __restrict__ mask, uint64_t seed,
-                                                                   const uint64_t* __restrict__ seed_dev, float drop_p, float scale,
-                                                                   const float* __restrict__ act, int accumulate,
-                                                                   float* __restrict__ dx) {
-  __shared__ __align__(16) float sd[HEAD_MAX_C];
+// the Linear's data gradient and the average pool's backward (+ the ReLU' of the producer) in one pass.
+// Block = (pair p, 256 channels): one channel per thread for the 101-term dot product (independent loads, unrolled), then
+// the block's 256 channels x HW pixels as float4 stores.
+constexpr int HEAD_DG_THREADS = 256;
+__global__ void __launch_bounds__(HEAD_DG_THREADS) head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
+                                                                      int C, int HW, int ctot, int coff, int NC, int T, int mode,
+                                                                      const uint8_t* __restrict__ mask, uint64_t seed,
+                                                                      const uint64_t* __restrict__ seed_dev, float drop_p,
+                                                                      float scale, const float* __restrict__ act, int accumulate,
+                                                                      float* __restrict__ dx) {
+  __shared__ __align__(16) float sd[HEAD_DG_THREADS];
   __shared__ float sg[128];
   pdl_sync();
   if (seed_dev) seed += __ldg(seed_dev);
   const uint32_t thr = drop_threshold16(drop_p);
-  const int tid = threadIdx.x, p = blockIdx.x;
+  const int tid = threadIdx.x, p = blockIdx.x, c0 = blockIdx.y * HEAD_DG_THREADS;
+  const int cw = min(HEAD_DG_THREADS, C - c0);                   // channels of this block (a multiple of 4)
   const float invT = 1.f / (float)T;
-  for (int n = tid; n < NC; n += HEAD_THREADS) sg[n] = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
+  for (int n = tid; n < NC; n += HEAD_DG_THREADS) sg[n] = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
   __syncthreads();
-  for (int c = tid; c < C; c += HEAD_THREADS) {
-    float s = 0.f;
-    for (int n = 0; n < NC; ++n) s += sg[n] * __ldg(W + (size_t)n * C + c);
-    sd[c] = s * keep_factor(mode, mask, seed, thr, (size_t)p * C + c, scale) / (float)HW;
+  if (tid < cw) {
+    const int c = c0 + tid;
+    const float* wc = W + c;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int n = 0;
+    for (; n + 4 <= NC; n += 4) {
+      s0 += sg[n] * __ldg(wc + (size_t)n * C);
+      s1 += sg[n + 1] * __ldg(wc + (size_t)(n + 1) * C);
+      s2 += sg[n + 2] * __ldg(wc + (size_t)(n + 2) * C);
+      s3 += sg[n + 3] * __ldg(wc + (size_t)(n + 3) * C);
+    }
+    for (; n < NC; ++n) s0 += sg[n] * __ldg(wc + (size_t)n * C);
+    sd[tid] = ((s0 + s1) + (s2 + s3)) * keep_factor(mode, mask, seed, thr, (size_t)p * C + c, scale) / (float)HW;
   }
   __syncthreads();
-  const int c4n = C >> 2;
-  for (int i = tid; i < HW * c4n; i += HEAD_THREADS) {
-    const int hw = i / c4n, c = (i - hw * c4n) * 4;
-    const size_t o = ((size_t)p * HW + hw) * ctot + coff + c;
+  const int q4 = cw >> 2;
+#pragma unroll 4
+  for (int i = tid; i < HW * q4; i += HEAD_DG_THREADS) {
+    const int hw = i / q4, c = (i - hw * q4) * 4;
+    const size_t o = ((size_t)p * HW + hw) * ctot + coff + c0 + c;
     float4 v = *reinterpret_cast<const float4*>(sd + c);
     if (accumulate) {
       const float4 d = *reinterpret_cast<const float4*>(dx + o);
@@ -364,7 +390,9 @@ extern "C" int offk_head_fwd(const float* x, int P, int C, int HW, int x_ctot, i
                              const float* bias, int num_classes, int T, float* pooled, float* out, float* consensus_out,
                              void* stream) {
   OFFK_REQUIRE(x && weight && bias && out && P > 0 && HW > 0 && num_classes > 0 && num_classes <= 128, "head_fwd: bad args");
-  OFFK_REQUIRE(C > 0 && C <= HEAD_MAX_C && C % 4 == 0 && x_coff >= 0 && x_coff + C <= x_ctot, "head_fwd: channel slice (C %% 4 == 0, C <= 1024)");
+  OFFK_REQUIRE(C > 0 && C <= HEAD_MAX_C && C % 4 == 0 && x_coff >= 0 && x_coff % 4 == 0 && x_ctot % 4 == 0 && x_coff + C <= x_ctot &&
+                   (reinterpret_cast<uintptr_t>(x) & 15u) == 0,
+               "head_fwd: channel slice (C, x_coff, x_ctot multiples of 4, C <= 1024, 16-byte aligned x)");
   OFFK_REQUIRE(T >= 1 && P % T == 0 && (T == 1 || consensus_out), "head_fwd: T must divide P; T > 1 needs consensus_out");
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "head_fwd: mask missing");
   OFFK_REQUIRE((reinterpret_cast<uintptr_t>(weight) & 15u) == 0, "head_fwd: weight alignment");
@@ -390,7 +418,7 @@ extern "C" int offk_head_bwd(const float* dout, int P, int C, int HW, int ctot, 
   }
   if (dx) {
     OFFK_REQUIRE((reinterpret_cast<uintptr_t>(dx) & 15u) == 0, "head_bwd: dx alignment");
-    (void)launch_pdl(head_dgrad_kernel, dim3(P), dim3(HEAD_THREADS), 0, as_stream(stream), dout, weight, C, HW, ctot, coff,
+    (void)launch_pdl(head_dgrad_kernel, dim3(P, (C + HEAD_DG_THREADS - 1) / HEAD_DG_THREADS), dim3(HEAD_DG_THREADS), 0, as_stream(stream), dout, weight, C, HW, ctot, coff,
                      num_classes, T, drop_mode, keep_mask, seed, seed_dev, drop_p, keep_scale, act, accumulate, dx);
     if (int e = OFFK_LAUNCH_CHECK("head_dgrad")) return e;
   }

@@ -662,7 +662,7 @@ class OFFEngine:
         g_f7slice = T.ConvGeom(P, 512, 7, 7, 512, y_ctot=832, y_coff=320)
         tabs_f7 = self._tables(("fwd", "nhwc", _gkey(g_f7slice)), T.conv_fwd_spec(g_f7slice, "nhwc", "nhwc"))
         g_14b3 = layer("motion_conv3_trans_14b", bf["h2_14b"], bf["h3_14b"], 7, relu=True,
-                       aux=(bf["F7"], tabs_f7["out_row"], 320, bf["s14a"]))
+                       aux=(bf["F7"], tabs_f7["out_row"], 0, bf["s14a"]))      # the row table carries the channel offset 320
         if not getattr(fwd[-1], "aux_fused", False):
             fwd.append(self._add_into_slice(bf["s14a"], bf["h3_14b"], bf["F7"], 832, 320, 512, 49))
 
@@ -692,7 +692,7 @@ class OFFEngine:
         self.d_out14 = torch.zeros(n_up, S.NUM_CLASSES, device=self.device)
         # heads (fc28 receives no gradient: never returned, RGB_OFF.py:860): Linear weight / bias gradient, and
         # ds7 = avgpool'(dropout'(Linear'(d_out7))) in one pass
-        bs.append(self._head_bwd("7", self.d_out7, d("s7"), 1024, 1024, 0, "fc_action_motion", act=None, accumulate=False))
+        bs.extend(self._head_bwd("7", self.d_out7, d("s7"), 1024, 1024, 0, "fc_action_motion", act=None, accumulate=False))
 
         def back(name, x, dy, geom, *, a_relu=False):
             bs.append(_on(self._conv_wgrad(name, x, dy, geom, dW(name), dB(name), a_relu=a_relu), 1))   # wgrad lane
@@ -712,7 +712,7 @@ class OFFEngine:
         back("motion_conv_trans", bf["F7"], d("t7"), g_t7)
         dgrad("motion_conv_trans", d("t7"), bf["dF7"], g_t7)
         # d sum_14b = (dF7[:,320:] + head-14 pool gradient) * [sum_14b > 0]   (in place in the dF7 slice)
-        bs.append(self._head_bwd("14", self.d_out14, bf["dF7"], 512, 832, 320, "fc_action_motion_14", act=bf["F7"], accumulate=True))
+        bs.extend(self._head_bwd("14", self.d_out14, bf["dF7"], 512, 832, 320, "fc_action_motion_14", act=bf["F7"], accumulate=True))
         if self.unit_bwd_early:          # after the in-place update of dF7[:, 320:], so the main lane never waits on these
             bs.extend(unit_bwd["7"])
         # ---- 14b:  sum_14b = relu(s14a + relu(conv3_14b(h2b)))
@@ -863,16 +863,19 @@ class OFFEngine:
         dw, db = self.grads[fcname + ".weight"], self.grads[fcname + ".bias"]
         T_ = self.Lseg - 1 if self.consensus else 1
 
-        def run(stream):
+        def call(stream, dx_, dw_, db_):
             m = self.masks["fc" + k] if self.drop_mode == L.DROP_MASK else None
             L.check(lib.offk_head_bwd(_ptr(dout), P, c, 49, ctot, coff, self.drop_mode, _ptr(m), self._site_salt(site),
                                       self._seed_dev(), S.DROP_P, 1.0 / (1.0 - S.DROP_P), _ptr(w), S.NUM_CLASSES, T_,
-                                      _ptr(bf["pool" + k]), _ptr(act), int(accumulate), _ptr(dx), _ptr(dw), _ptr(db), stream),
+                                      _ptr(bf["pool" + k]), _ptr(act), int(accumulate), _ptr(dx_), _ptr(dw_), _ptr(db_), stream),
                     "head_bwd" + k)
         self.flops_bwd += 4.0 * P * c * S.NUM_CLASSES
-        step = _nm(run, "head_bwd" + k, reads=[dout, bf["pool" + k], act, dx if accumulate else None], writes=[dx, dw, db])
-        step.launches = ["head_bwd%s.wgrad" % k, "head_bwd%s.dgrad" % k]
-        return step
+        # the data gradient opens the dgrad chain (lane 0); the weight gradient runs beside it on the weight-gradient lane
+        dgrad = _nm(lambda stream: call(stream, dx, None, None), "head_bwd%s.dgrad" % k,
+                    reads=[dout, act, dx if accumulate else None], writes=[dx], lane=0)
+        wgrad = _nm(lambda stream: call(stream, None, dw, db), "head_bwd%s.wgrad" % k, reads=[dout, bf["pool" + k]],
+                    writes=[dw, db], lane=1)
+        return [dgrad, wgrad]
 
     # ------------------------------------------------------------------ run
     def _set_dropout(self, train, masks, seed):

@@ -109,6 +109,10 @@ class BNInception_OFF(nn.Module):
         """RGB_OFF.py:360-860: per-pair logits, no consensus (it is commented out there, :849-858)."""
         taps, score, _ = self._taps_and_score(input)
         fc7, _fc28, fc14 = self.off(taps)
+        if fc7.shape[0] == 1:
+            # one frame pair (batch 1, two segments): the reference's torch.squeeze before the Linear drops the batch
+            # dimension too, so its heads return [101] (RGB_OFF.py:786,792,846)
+            fc7, fc14 = fc7.squeeze(0), fc14.squeeze(0)
         return fc7, score, fc14
 
     def forward(self, input):

@@ -115,6 +115,8 @@ CASES = [
     ("flow_b2_l3", "flow", 2, 3, False),    # diagonal Sobel + consensus
     ("rgb_b2_l2_train", "rgb", 2, 2, True), # injected dropout masks
     ("flow_b1_l4", "flow", 1, 4, False),
+    ("v2_b2_l3", "v2", 2, 3, False),        # RGB_OFF_v2: Flow's graph on RGB input (4-tuple return, RGB_OFF_v2.py:891)
+    ("rgb_b1_l2", "rgb", 1, 2, False),      # ONE frame pair: torch.squeeze drops the batch dimension too (RGB_OFF.py:786,792,846)
 ]
 
 

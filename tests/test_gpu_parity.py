@@ -664,12 +664,13 @@ def test_benchmark_shapes_match_oracle(dev, variant, B, Lg, train):
     _engine_vs_oracle(dev, "tf32", variant, B, Lg, train, *TOL_TF32_EMU, mm="tf32_trunc", gate_matched=True)
 
 
-@pytest.mark.parametrize("name", ["rgb_b1_l3", "rgb_b2_l3", "flow_b2_l3", "rgb_b2_l2_train", "flow_b1_l4"])
+@pytest.mark.parametrize("name", ["rgb_b1_l3", "rgb_b2_l3", "flow_b2_l3", "rgb_b2_l2_train", "flow_b1_l4", "v2_b2_l3", "rgb_b1_l2"])
 def test_module_matches_reference_golden(dev, name):
     """The nn.Module surface against vectors produced by the reference itself (tests/golden, make_golden.py)."""
     from off_b200.modules import OFFSubNetwork
     fix = np.load(os.path.join(GOLD, f"off_{name}.npz"))
     variant, B, Lg, seed, train = str(fix["variant"]), int(fix["batch"]), int(fix["length"]), int(fix["seed"]), int(fix["train"])
+    variant = "rgb" if variant == "rgb" else "flow"         # RGB_OFF_v2 runs Flow_OFF's OFF graph (fixed diagonal Sobel + consensus)
     net = OFFSubNetwork(B, Lg, variant, precision="fp32", device=dev)
     net.train(bool(train))
     net.load_state_dict(O.make_params(seed, variant), strict=(variant == "rgb"))
@@ -778,7 +779,8 @@ def test_tma_gemm_split_k_finisher_and_second_output(dev, prec, tol, split, with
     if split > 1:
         d.finish_counter = counter.data_ptr()
     if with_aux:
-        d.aux_out, d.aux_row, d.aux_col0, d.aux_addend = aux.data_ptr(), aux_row.data_ptr(), 64, addend.data_ptr()
+        # the row table of a channel-slice geometry already carries the slice offset (64): aux_col0 is an EXTRA column offset
+        d.aux_out, d.aux_row, d.aux_col0, d.aux_addend = aux.data_ptr(), aux_row.data_ptr(), 0, addend.data_ptr()
     t.a_kind = L.TMA_A_IM2COL
     t.n_img, t.hin, t.win, t.ctot, t.cin = n, h, h, cin, cin
     t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = k, k, 1, 1, h, h

