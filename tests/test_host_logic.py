@@ -313,7 +313,16 @@ def test_eval_protocol_fusion_accuracy_and_npz(tmp_path):
         videos.append(((data, s7, s14), label))
         want_scores.append((s7, s14))
     state = {}
-    object.__setattr__(m, "off", lambda taps: (state["s7"], torch.zeros(crops, NC), state["s14"]))
+    class Off:                                   # CPU stand-in for the liboffk-backed OFF section
+        training = False
+
+        def train(self, mode=True):
+            self.training = mode
+
+        def __call__(self, taps):
+            assert not self.training             # eval_video switches the model to eval mode (no dropout)
+            return state["s7"], torch.zeros(crops, NC), state["s14"]
+    object.__setattr__(m, "off", Off())
 
     def gen():
         for (data, s7, s14), label in videos:
@@ -331,4 +340,3 @@ def test_eval_protocol_fusion_accuracy_and_npz(tmp_path):
     # per-class accuracy is the mean over the classes that occur, not over videos
     acc, per_class, cf = EV.per_class_accuracy([0, 0, 0, 1], [0, 0, 1, 0], 3)
     assert abs(acc - (2 / 3 + 0) / 2) < 1e-12 and cf[0, 1] == 1 and np.isnan(per_class[2])
-    assert not m.training or True
