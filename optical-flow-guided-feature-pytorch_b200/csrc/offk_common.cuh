@@ -81,6 +81,12 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
                "f"(v.w)
                : "memory");
 }
+// fp32 accumulation into global memory WITHOUT a return value: always the fire-and-forget RED instruction.  (atomicAdd
+// with an unused result is normally lowered to RED too, but ptxas keeps the round-trip ATOM form once the kernel also
+// contains a fence / a value-returning atomic -- measured: the unit weight-gradient GEMMs ran 2x slower.)
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -34,12 +34,12 @@ __device__ __forceinline__ EpiRow epi_row(const offk_gemm_t& g, int m) {
 // Epilogue of one element D[m,n] (see offk.h for the op order).
 __device__ __forceinline__ void epi_store(const offk_gemm_t& g, const EpiRow& r, int n, float v, bool atomic) {
   if (r.ones) {  // bias-gradient row of a weight-gradient GEMM
-    if (g.ones_row_out) atomicAdd(g.ones_row_out + n, v);
+    if (g.ones_row_out) red_add_f32(g.ones_row_out + n, v);
     return;
   }
   const int oc = g.out_col[n];
   if (atomic) {
-    atomicAdd(g.out + (r.out + oc), v);
+    red_add_f32(g.out + (r.out + oc), v);
     return;
   }
   if (g.bias) v += __ldg(g.bias + n);

@@ -591,7 +591,7 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
         if (atomic && !er.ones) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (nb + j < g.N) atomicAdd(g.out + (er.out + oc[j]), v[j]);
+            if (nb + j < g.N) red_add_f32(g.out + (er.out + oc[j]), v[j]);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {

@@ -86,11 +86,74 @@ struct TmShared {
   uint32_t last_flag;              // split-K finisher: 1 in the CTA that arrived last on the tile's counter
 };
 
+// Final value of 4 consecutive elements (one accumulator row, columns n..n+3): the epilogue of offk.h, then the optional
+// second output.  out_base / aux_base: element offsets of the row in `out` / `aux_out` (column 0).
+__device__ __forceinline__ float4 epi_final4(const offk_gemm_t& g, float4 v, int n, const float4& bias4, const float4& t,
+                                             const float4& ad, bool gated, int out_base, int aux_base) {
+  v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+  if (n < g.relu_pre_cols) v = f4relu(v);               // relu_pre_cols is a multiple of 4 on this path
+  if (gated && g.gate_first) {
+    v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+  }
+  v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+  if (gated && !g.gate_first) {
+    v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
+  }
+  if (g.relu_post) v = f4relu(v);
+  if (g.aux_out) {
+    float4 a = v;
+    if (g.aux_addend) {
+      const float4 x = ldg128(g.aux_addend + (out_base + n));
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    }
+    *reinterpret_cast<float4*>(g.aux_out + (aux_base + g.aux_col0 + n)) = f4relu(a);
+  }
+  return v;
+}
+
+// Split-K finisher (offk.h: finish_counter), called by the 256 epilogue threads of every split CTA after their partial tile
+// went out as red.global.add: the last CTA to arrive on the tile's counter re-reads the summed tile and applies the epilogue
+// in place.  Kept out of line: it runs once per output tile, and its registers must not weigh on the main kernel.
+// release: this thread's reds, fence, CTA barrier, counter; acquire: counter, barrier, fence, .cg loads.
+__device__ __noinline__ void splitk_finish(const offk_gemm_t& g, uint32_t* flag_smem, int etid, int m0, int m_lim, int n0, int bn) {
+  __threadfence();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  volatile uint32_t* flag = flag_smem;
+  if (etid == 0) {
+    int* ctr = g.finish_counter + (blockIdx.y * gridDim.x + blockIdx.x);
+    const int prev = atomicAdd(ctr, 1);
+    const int last = prev == (int)gridDim.z - 1;
+    if (last) *ctr = 0;                                    // ready for the next launch / graph replay
+    *flag = (uint32_t)last;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (!*flag) return;
+  __threadfence();
+  const int oc0 = __ldg(g.out_col);
+  const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
+  const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
+  const int c4n = bn >> 2;                                 // float4 columns of the tile
+  // thread -> (row, float4 column): consecutive threads walk a row (coalesced), 256 threads cover 256 / c4n rows per pass
+  for (int i = etid; i < TC_BM * c4n; i += 256) {
+    const int row = i / c4n, n = n0 + (i - row * c4n) * 4, m = m0 + row;
+    if (m >= m_lim || n >= g.N) continue;
+    const EpiRow er = epi_row(g, m);
+    const int aux_base = g.aux_out ? (g.aux_row ? __ldg(g.aux_row + m) : er.out) : 0;
+    const bool gated = g.gate && n >= g.gate_col0;
+    float* o = g.out + (er.out + oc0 + n);
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(o));
+    const float4 bias4 = g.bias ? ldg128(g.bias + n) : f4zero();
+    const float4 t = gated ? ldg128(g.gate + (er.gate + gc0 + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 ad4 = g.addend ? ldg128(g.addend + (er.add + ac0 + n)) : f4zero();
+    *reinterpret_cast<float4*>(o) = epi_final4(g, v, n, bias4, t, ad4, gated, er.out + oc0, aux_base);
+  }
+}
+
 // X3 = OFFK_PREC_TF32X3: every stage holds [A | B | A_lo | B_lo]; the epilogue warps, otherwise idle during the main loop,
 // turn each landed [A | B] into its tf32 residual (offk_tc.cuh) and the MMA warp issues three MMAs per K = 8 step.
 template <int A_KIND, int B_KIND, bool X3>
 __global__ void __launch_bounds__(TM_THREADS, 2)
-tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const offk_gemm_t g,
+tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ offk_gemm_t g,
                 const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -320,28 +383,6 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           r_aux[it] = g.aux_out ? (g.aux_row ? __ldg(g.aux_row + m) : er.out) : 0;
         }
       }
-      // final value of 4 consecutive elements of row `it` at column n: the epilogue of offk.h, then the optional second output
-      auto finish4 = [&](float4 v, int it, int n, const float4& bias4, const float4& t, const float4& ad, bool gated) {
-        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-        if (n < g.relu_pre_cols) v = f4relu(v);               // relu_pre_cols is a multiple of 4 on this path
-        if (gated && g.gate_first) {
-          v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
-        }
-        v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
-        if (gated && !g.gate_first) {
-          v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
-        }
-        if (g.relu_post) v = f4relu(v);
-        if (g.aux_out) {
-          float4 a = v;
-          if (g.aux_addend) {
-            const float4 x = ldg128(g.aux_addend + (r_out[it] + oc0 + n));
-            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-          }
-          *reinterpret_cast<float4*>(g.aux_out + (r_aux[it] + g.aux_col0 + n)) = f4relu(a);
-        }
-        return v;
-      };
       split_loop();
       mbar_wait(smem_u32(&sh->accum_full), 0u);
       tc_fence_after();
@@ -386,43 +427,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
               asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
               continue;
             }
-            *reinterpret_cast<float4*>(o) = finish4(v, it, n, bias4, gt[it], ad[it], gated);
+            *reinterpret_cast<float4*>(o) = epi_final4(g, v, n, bias4, gt[it], ad[it], gated, r_out[it] + oc0, r_aux[it]);
           }
         }
       }
-      if (atomic && g.finish_counter) {
-        // ---- split-K finisher: the last CTA to have added its partial tile applies the epilogue in place.
-        // release: this thread's reds, then the CTA-wide barrier, then the counter; acquire: counter, fence, .cg loads
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        volatile uint32_t* flag = &sh->last_flag;
-        if (tid == 64) {
-          int* ctr = g.finish_counter + (blockIdx.y * gridDim.x + blockIdx.x);
-          const int prev = atomicAdd(ctr, 1);
-          const int last = prev == (int)gridDim.z - 1;
-          if (last) *ctr = 0;                                    // ready for the next launch / graph replay
-          *flag = (uint32_t)last;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (*flag) {
-          __threadfence();
-          for (int c = 0; c < nchunks; ++c) {
-            const int n = n0 + c * 32 + cq * 4;
-            if (!(n < g.N && c * 32 + cq * 4 < bn)) continue;
-            const bool gated = g.gate && n >= g.gate_col0;
-            const float4 bias4 = g.bias ? ldg128(g.bias + n) : f4zero();
-#pragma unroll
-            for (int it = 0; it < TC_BM / 32; ++it) {
-              if (!r_ok[it]) continue;
-              float* o = g.out + (r_out[it] + oc0 + n);
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(o));
-              const float4 t = gated ? ldg128(g.gate + (r_gate[it] + gc0 + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
-              const float4 ad4 = g.addend ? ldg128(g.addend + (r_add[it] + ac0 + n)) : f4zero();
-              *reinterpret_cast<float4*>(o) = finish4(v, it, n, bias4, t, ad4, gated);
-            }
-          }
-        }
-      }
+      if (atomic && g.finish_counter) splitk_finish(g, &sh->last_flag, tid - 64, m0, m_lim, n0, bn);
     } else {
       const int m = m0 + quad * 32 + lane;
       const bool mvalid = m < m_lim;

@@ -85,9 +85,12 @@ __global__ void maxpool3s2_fwd_kernel(const float* __restrict__ x, int P, int C,
 // channels: coalesced) + dropout -> shared memory (and `pooled`, which the weight gradient needs) -> 101 x C GEMV by warps
 // (float4 along the contiguous weight rows, warp-shuffle reduction) + bias.  Everything is linear, so it is exact fp32 in
 // every precision mode.  avgpool -> dropout -> Linear (-> mean over segments): RGB_OFF.py:783-793,844-847; Flow_OFF.py:867-876.
-constexpr int HEAD_THREADS = 512;
+constexpr int HEAD_THREADS = 1024;
 constexpr int HEAD_MAX_C = 1024;
+constexpr int HEAD_HW_GROUPS = 4;      // pool: the HW pixels of a channel quad are split over 4 thread groups
 
+// All three head kernels are latency-bound (a few hundred KB per block, ~100 blocks): they are written so that every thread
+// has its loads in flight together (fully unrolled batches) instead of walking a long dependent loop.
 __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(const float* __restrict__ x, int C, int HW, int ctot, int coff,
                                                                  int mode, const uint8_t* __restrict__ mask, uint64_t seed,
                                                                  const uint64_t* __restrict__ seed_dev, float drop_p, float scale,
@@ -95,43 +98,66 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(const float* __r
                                                                  int NC, int T, float* __restrict__ pooled,
                                                                  float* __restrict__ out, float* __restrict__ cout) {
   __shared__ __align__(16) float sp[HEAD_MAX_C];
+  __shared__ __align__(16) float spart[HEAD_HW_GROUPS - 1][HEAD_MAX_C];
   pdl_sync();
   if (seed_dev) seed += __ldg(seed_dev);
   const uint32_t thr = drop_threshold16(drop_p);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float inv_hw = 1.f / (float)HW;
+  const int nq = C >> 2;                                         // channel quads (<= 256)
   for (int t = 0; t < T; ++t) {
     const int p = blockIdx.x * T + t;
     const float* xp = x + (size_t)p * HW * ctot + coff;
-    // pool: one thread per channel quad, HW independent 16-byte loads (consecutive threads = consecutive quads: coalesced)
-    for (int q = tid; q < (C >> 2); q += HEAD_THREADS) {
+    // pool: thread = (pixel group hg, channel quad q): pixels hg, hg + 4, ... of quad q, all loads independent
+    {
+      const int hg = tid / nq, q = tid - hg * nq;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 7
-      for (int h = 0; h < HW; ++h) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)h * ctot) + q);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      if (hg < HEAD_HW_GROUPS) {
+#pragma unroll 13
+        for (int h = hg; h < HW; h += HEAD_HW_GROUPS) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)h * ctot) + q);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (hg > 0) *reinterpret_cast<float4*>(&spart[hg - 1][4 * q]) = a;
       }
-      const size_t i0 = (size_t)p * C + 4 * q;
-      a.x *= inv_hw * keep_factor(mode, mask, seed, thr, i0, scale);
-      a.y *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 1, scale);
-      a.z *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 2, scale);
-      a.w *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 3, scale);
-      *reinterpret_cast<float4*>(sp + 4 * q) = a;
-      if (pooled) *reinterpret_cast<float4*>(pooled + i0) = a;
+      __syncthreads();
+      if (hg == 0) {
+#pragma unroll
+        for (int k = 0; k < HEAD_HW_GROUPS - 1; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(&spart[k][4 * q]);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        const size_t i0 = (size_t)p * C + 4 * q;
+        a.x *= inv_hw * keep_factor(mode, mask, seed, thr, i0, scale);
+        a.y *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 1, scale);
+        a.z *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 2, scale);
+        a.w *= inv_hw * keep_factor(mode, mask, seed, thr, i0 + 3, scale);
+        *reinterpret_cast<float4*>(sp + 4 * q) = a;
+        if (pooled) *reinterpret_cast<float4*>(pooled + i0) = a;
+      }
     }
     __syncthreads();
-    // Linear: one warp per class row, float4 along the contiguous weight row, warp-shuffle reduction
-    for (int n = warp; n < NC; n += HEAD_THREADS / 32) {
-      const float* wr = W + (size_t)n * C;
-      float acc = 0.f;
-#pragma unroll 4
+    // Linear: each warp owns up to 4 class rows (n = warp, warp + 32, ...) and walks them TOGETHER along c, so that four
+    // independent 16-byte weight loads per lane are in flight per step; warp-shuffle reductions at the end
+    {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int c = 4 * lane; c < C; c += 128) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + c));
         const float4 p4 = *reinterpret_cast<const float4*>(sp + c);
-        acc += w4.x * p4.x + w4.y * p4.y + w4.z * p4.z + w4.w * p4.w;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int n = warp + 32 * r;
+          if (n < NC) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * C + c));
+            acc[r] += w4.x * p4.x + w4.y * p4.y + w4.z * p4.z + w4.w * p4.w;
+          }
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) out[(size_t)p * NC + n] = acc + __ldg(bias + n);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = warp + 32 * r;
+        const float v = warp_sum(acc[r]);
+        if (lane == 0 && n < NC) out[(size_t)p * NC + n] = v + __ldg(bias + n);
+      }
     }
     __syncthreads();
   }
@@ -145,68 +171,74 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_fwd_kernel(const float* __r
 }
 
 // dfc(p, n) = dout[(p / T) * NC + n] / T: the consensus backward (basic_ops.py:30-31) folded into the consumers (T = 1: as is)
-// dW[n, c] += sum_p dfc(p, n) * pooled[p, c];  db[n] += sum_p dfc(p, n).      block (128 c, 8 n)
+// dW[n, c] += sum_p dfc(p, n) * pooled[p, c];  db[n] += sum_p dfc(p, n).   block (128 c, 8 n), grid.z cuts the pair axis into
+// chunks of HEAD_WG_PAIRS so that the whole machine works on it; partial sums are added with RED.
+constexpr int HEAD_WG_PAIRS = 16;
 __global__ void __launch_bounds__(1024) head_wgrad_kernel(const float* __restrict__ dout, const float* __restrict__ pooled, int P,
                                                           int C, int NC, int T, float* __restrict__ dW, float* __restrict__ db) {
   pdl_sync();
   const int c = blockIdx.x * 128 + threadIdx.x, n = blockIdx.y * 8 + threadIdx.y;
-  if (n >= NC) return;
+  if (n >= NC || c >= C) return;
+  const int p0 = blockIdx.z * HEAD_WG_PAIRS, p1 = min(P, p0 + HEAD_WG_PAIRS);
   const float invT = 1.f / (float)T;
   float acc = 0.f, accb = 0.f;
-  if (c < C) {
-#pragma unroll 8
-    for (int p = 0; p < P; ++p) {
+#pragma unroll
+  for (int i = 0; i < HEAD_WG_PAIRS; ++i) {
+    const int p = p0 + i;
+    if (p < p1) {
       const float g = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
       acc += g * __ldg(pooled + (size_t)p * C + c);
       accb += g;
     }
-    dW[(size_t)n * C + c] += acc;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && db) db[n] += accb;
+  red_add_f32(dW + (size_t)n * C + c, acc);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && db) red_add_f32(db + n, accb);
 }
 
 // dpool[c] = drop'( sum_n dfc(p, n) * W[n, c] ) / HW, then dx[p, hw, coff + c] = gate( dx_in + dpool[c] ) for every pixel:
 // the Linear's data gradient and the average pool's backward (+ the ReLU' of the producer) in one pass.
-// Block = (pair p, 256 channels): one channel per thread for the 101-term dot product (independent loads, unrolled), then
-// the block's 256 channels x HW pixels as float4 stores.
-constexpr int HEAD_DG_THREADS = 256;
-__global__ void __launch_bounds__(HEAD_DG_THREADS) head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
+// Block = (pair p, 256 channels) x 4 class groups: thread (c, ng) sums the classes n = ng, ng + 4, ... (26 independent loads),
+// the four partial sums meet in shared memory; then the block's 256 channels x HW pixels go out as float4 stores.
+constexpr int HEAD_DG_CH = 256;
+constexpr int HEAD_DG_NG = 4;
+__global__ void __launch_bounds__(HEAD_DG_CH * HEAD_DG_NG) head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
                                                                       int C, int HW, int ctot, int coff, int NC, int T, int mode,
                                                                       const uint8_t* __restrict__ mask, uint64_t seed,
                                                                       const uint64_t* __restrict__ seed_dev, float drop_p,
                                                                       float scale, const float* __restrict__ act, int accumulate,
                                                                       float* __restrict__ dx) {
-  __shared__ __align__(16) float sd[HEAD_DG_THREADS];
+  __shared__ __align__(16) float sd[HEAD_DG_NG][HEAD_DG_CH];
   __shared__ float sg[128];
   pdl_sync();
   if (seed_dev) seed += __ldg(seed_dev);
   const uint32_t thr = drop_threshold16(drop_p);
-  const int tid = threadIdx.x, p = blockIdx.x, c0 = blockIdx.y * HEAD_DG_THREADS;
-  const int cw = min(HEAD_DG_THREADS, C - c0);                   // channels of this block (a multiple of 4)
+  const int tid = threadIdx.x, p = blockIdx.x, c0 = blockIdx.y * HEAD_DG_CH;
+  const int cw = min(HEAD_DG_CH, C - c0);                        // channels of this block (a multiple of 4)
+  const int cl = tid & (HEAD_DG_CH - 1), ng = tid / HEAD_DG_CH;
   const float invT = 1.f / (float)T;
-  for (int n = tid; n < NC; n += HEAD_DG_THREADS) sg[n] = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
+  for (int n = tid; n < NC; n += HEAD_DG_CH * HEAD_DG_NG) sg[n] = __ldg(dout + (size_t)(p / T) * NC + n) * invT;
   __syncthreads();
-  if (tid < cw) {
-    const int c = c0 + tid;
-    const float* wc = W + c;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int n = 0;
-    for (; n + 4 <= NC; n += 4) {
-      s0 += sg[n] * __ldg(wc + (size_t)n * C);
-      s1 += sg[n + 1] * __ldg(wc + (size_t)(n + 1) * C);
-      s2 += sg[n + 2] * __ldg(wc + (size_t)(n + 2) * C);
-      s3 += sg[n + 3] * __ldg(wc + (size_t)(n + 3) * C);
+  {
+    float s = 0.f;
+    if (cl < cw) {
+      const float* wc = W + c0 + cl;
+#pragma unroll 13
+      for (int n = ng; n < NC; n += HEAD_DG_NG) s += sg[n] * __ldg(wc + (size_t)n * C);
     }
-    for (; n < NC; ++n) s0 += sg[n] * __ldg(wc + (size_t)n * C);
-    sd[tid] = ((s0 + s1) + (s2 + s3)) * keep_factor(mode, mask, seed, thr, (size_t)p * C + c, scale) / (float)HW;
+    sd[ng][cl] = s;
+  }
+  __syncthreads();
+  if (ng == 0 && cl < cw) {
+    const float s = (sd[0][cl] + sd[1][cl]) + (sd[2][cl] + sd[3][cl]);
+    sd[0][cl] = s * keep_factor(mode, mask, seed, thr, (size_t)p * C + c0 + cl, scale) / (float)HW;
   }
   __syncthreads();
   const int q4 = cw >> 2;
 #pragma unroll 4
-  for (int i = tid; i < HW * q4; i += HEAD_DG_THREADS) {
+  for (int i = tid; i < HW * q4; i += HEAD_DG_CH * HEAD_DG_NG) {
     const int hw = i / q4, c = (i - hw * q4) * 4;
     const size_t o = ((size_t)p * HW + hw) * ctot + coff + c0 + c;
-    float4 v = *reinterpret_cast<const float4*>(sd + c);
+    float4 v = *reinterpret_cast<const float4*>(&sd[0][c]);
     if (accumulate) {
       const float4 d = *reinterpret_cast<const float4*>(dx + o);
       v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
@@ -412,13 +444,13 @@ extern "C" int offk_head_bwd(const float* dout, int P, int C, int HW, int ctot, 
   OFFK_REQUIRE(drop_mode != OFFK_DROP_MASK || keep_mask, "head_bwd: mask missing");
   if (dweight) {
     OFFK_REQUIRE(pooled != nullptr, "head_bwd: the weight gradient needs the pooled features of the forward pass");
-    (void)launch_pdl(head_wgrad_kernel, dim3((C + 127) / 128, (num_classes + 7) / 8), dim3(128, 8), 0, as_stream(stream), dout, pooled,
+    (void)launch_pdl(head_wgrad_kernel, dim3((C + 127) / 128, (num_classes + 7) / 8, (P + HEAD_WG_PAIRS - 1) / HEAD_WG_PAIRS), dim3(128, 8), 0, as_stream(stream), dout, pooled,
                      P, C, num_classes, T, dweight, dbias);
     if (int e = OFFK_LAUNCH_CHECK("head_wgrad")) return e;
   }
   if (dx) {
     OFFK_REQUIRE((reinterpret_cast<uintptr_t>(dx) & 15u) == 0, "head_bwd: dx alignment");
-    (void)launch_pdl(head_dgrad_kernel, dim3(P, (C + HEAD_DG_THREADS - 1) / HEAD_DG_THREADS), dim3(HEAD_DG_THREADS), 0, as_stream(stream), dout, weight, C, HW, ctot, coff,
+    (void)launch_pdl(head_dgrad_kernel, dim3(P, (C + HEAD_DG_CH - 1) / HEAD_DG_CH), dim3(HEAD_DG_CH * HEAD_DG_NG), 0, as_stream(stream), dout, weight, C, HW, ctot, coff,
                      num_classes, T, drop_mode, keep_mask, seed, seed_dev, drop_p, keep_scale, act, accumulate, dx);
     if (int e = OFFK_LAUNCH_CHECK("head_dgrad")) return e;
   }

@@ -368,7 +368,12 @@ class OFFEngine:
         if (tma and x_layout == "nchw") or no_split:
             split = 1                     # per-frame M tiles already fill the machine (N * ceil(hw/128) CTAs)
         fuse = tma and spc.out_vec and os.environ.get("OFFK_NO_FINISHER", "0") != "1"
-        if split > 1 and fuse:
+        # in-kernel finishing pays when there are enough output tiles for the finishing CTAs to keep the machine busy
+        # (motion_conv_trans_28: 147 tiles, same time as the bare split-K GEMM, bias_act and ReLU copy for free); with the
+        # 37-tile 7x7 layers the fences + a finishing pass by 37 CTAs cost 9-27 us more than a separate full-grid bias_act
+        # pass (measured, profiles/launches_tf32_r02g*.txt), so those keep the two-kernel form
+        fin_ok = fuse and m_tiles * n_tiles >= int(os.environ.get("OFFK_FINISH_MIN_TILES", "100"))
+        if split > 1 and fin_ok:
             # split-K partial tiles are added into the zeroed output; the last CTA of each tile applies bias / ReLU (and
             # writes the second output) in place: no separate bias_act pass
             g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
@@ -405,7 +410,7 @@ class OFFEngine:
         tn = (spc.N + 15) // 16 * 16 if (tma and x_layout == "nchw" and spc.N <= 256) else 0
         g = mk(self, spc, ("fwd", x_layout, _gkey(geom)), a_src=x, b_src=w, out=y, bias=b, relu_pre_cols=cols, a_relu=a_relu,
                addend=addend, add_tabs=add_tabs, relu_post=relu_post, tile_n=tn, name=name, aux=aux if fuse else None)
-        g.aux_fused = fuse and aux is not None
+        g.aux_fused = bool(fuse and aux is not None)
         self.flops_fwd += g.flops
         return g
 
