@@ -214,6 +214,9 @@ typedef struct offk_tgemm {
                             such a stride-1 correlation over dY (autograd of RGB_OFF.py:657,762) */
   int32_t pad_w;
   int32_t precision;     /* OFFK_PREC_TF32 (or 0) / OFFK_PREC_TF32X3 */
+  int32_t bk;            /* K-block depth: 0 / 32, or 64 / 128 for OFFK_TMA_A_IM2COL_T (both operands MN-major: deeper K-blocks
+                            = fewer, larger TMA boxes; fixed before offk_tma_gemm_prepare) */
+  int32_t reserved;
   uint64_t tmap_a[16];   /* CUtensorMap storage */
   uint64_t tmap_b[16];
 } offk_tgemm_t;

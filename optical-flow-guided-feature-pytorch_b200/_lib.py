@@ -52,7 +52,7 @@ class OffkTGemm(C.Structure):
         ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("hout", C.c_int32),
         ("wout", C.c_int32),
         ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("geom_flags", C.c_int32),
-        ("pad_w", C.c_int32), ("precision", C.c_int32),
+        ("pad_w", C.c_int32), ("precision", C.c_int32), ("bk", C.c_int32), ("reserved", C.c_int32),
         ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
     ]
 

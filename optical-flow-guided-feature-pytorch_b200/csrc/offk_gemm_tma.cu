@@ -154,13 +154,18 @@ __device__ __noinline__ void splitk_finish(const offk_gemm_t& g, uint32_t* flag_
 template <int A_KIND, int B_KIND, bool X3>
 __global__ void __launch_bounds__(TM_THREADS, 2)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ offk_gemm_t g,
-                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main) {
+                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main, int bk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
   constexpr bool B_MN = (B_KIND == OFFK_TMA_B_DENSE_T);
-  const uint32_t b_bytes = B_MN ? (((uint32_t)bn + 31u) >> 5) * 4096u : (uint32_t)bn * 128u;
-  const uint32_t hi_bytes = TC_A_BYTES + b_bytes;               // one landed [A | B] pair
+  // K-block depth: 32 (one 128-byte swizzle row) whenever an operand is K-major; `bk` (32 / 64 / 128 output pixels) for the
+  // channels-last weight gradient, whose operands are both MN-major stacks of {32 m|n x 4 k} atoms along k -- deeper
+  // K-blocks mean fewer, larger TMA boxes per byte (a 32-pixel im2col box is 4 KB: the TMA unit, not L2, was the limit)
+  const uint32_t atom_bytes = (uint32_t)bk * 128u;              // one {32 m|n x bk k} MN-major stack
+  const uint32_t a_bytes = A_KIND == OFFK_TMA_A_IM2COL_T ? 4u * atom_bytes : (uint32_t)TC_A_BYTES;
+  const uint32_t b_bytes = B_MN ? (((uint32_t)bn + 31u) >> 5) * atom_bytes : (uint32_t)bn * 128u;
+  const uint32_t hi_bytes = a_bytes + b_bytes;                  // one landed [A | B] pair
   const uint32_t stage_bytes = X3 ? 2u * hi_bytes : hi_bytes;
   TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
@@ -174,7 +179,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     m_lim = min(g.M, (img_t + 1) * geo.hw);
   }
   const int n0 = blockIdx.y * bn;
-  const int num_kb_total = A_KIND == OFFK_TMA_A_NCHW_T ? (g.K / geo.hw) * geo.kb_per_img : (g.K + TC_BK - 1) / TC_BK;
+  const int num_kb_total = A_KIND == OFFK_TMA_A_NCHW_T ? (g.K / geo.hw) * geo.kb_per_img : (g.K + bk - 1) / bk;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
   const int nkb = kb_end - kb_begin;
@@ -220,8 +225,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         mbar_wait(smem_u32(&sh->empty[s]), parity);              // slot free (first round passes at once)
         const uint32_t full = smem_u32(&sh->full[s]);
         const uint32_t a_dst = smem_base + s * stage_bytes;
-        const uint32_t b_dst = a_dst + TC_A_BYTES;
-        int b_row0 = kb * TC_BK;                                 // dense_t: first k (pixel) row of this K-block
+        const uint32_t b_dst = a_dst + a_bytes;
+        int b_row0 = kb * bk;                                    // dense_t: first k (pixel) row of this K-block
         if (A_KIND == OFFK_TMA_A_NCHW) {
           // four 4 KB atoms {32 pixels x 32 channels}; atoms wholly past the frame end are skipped (their
           // accumulator rows are never stored)
@@ -239,16 +244,16 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           // rows m = (r, q, c): each 32-row atom is one {32 channels x 32 output pixels} im2col box at its own (q, r)
           const int at0 = m0 >> 5;
           const int n_at = max(0, min(TC_BM / 32, (geo.kw_rows >> 5) - at0));
-          mbar_arrive_expect_tx(full, (uint32_t)n_at * 4096u + b_bytes);
+          mbar_arrive_expect_tx(full, (uint32_t)n_at * atom_bytes + b_bytes);
           const int hwo = geo.hout * geo.wout;
-          const int p0 = kb * TC_BK;
+          const int p0 = kb * bk;
           const int img = p0 / hwo, rem = p0 - img * hwo;
           const int oy = rem / geo.wout, ox = rem - oy * geo.wout;
           const int wb = ox * geo.stride - geo.pad_w, hb = oy * geo.stride - geo.pad;
           for (int a = 0; a < n_at; ++a) {
             const int tap = (at0 + a) / geo.cblocks, cb = (at0 + a) - tap * geo.cblocks;
             const int r = tap / geo.kw, q = tap - r * geo.kw;
-            tma_load_im2col_4d(a_dst + a * 4096, &tma, geo.a_coff + cb * TC_BK, wb, hb, img, q, r, full);
+            tma_load_im2col_4d(a_dst + a * atom_bytes, &tma, geo.a_coff + cb * TC_BK, wb, hb, img, q, r, full);
           }
         } else if (A_KIND == OFFK_TMA_A_DENSE) {
           mbar_arrive_expect_tx(full, hi_bytes);
@@ -261,7 +266,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         }
         if (B_MN) {
           const int n_bat = (bn + 31) >> 5;
-          for (int a = 0; a < n_bat; ++a) tma_load_2d(b_dst + a * 4096, &tmb, n0 + 32 * a, b_row0, full);
+          for (int a = 0; a < n_bat; ++a) tma_load_2d(b_dst + a * atom_bytes, &tmb, n0 + 32 * a, b_row0, full);
         } else {
           tma_load_2d(b_dst, &tmb, kb * TC_BK, n0, full);
         }
@@ -296,9 +301,14 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
             real = pb * TC_BK + lane < geo.hw;
             off = swz(ones_loc, lane >> 2) + (uint32_t)(lane & 3) * 4u;
           } else {
-            real = kb * TC_BK + lane < g.K;
+            real = kb * bk + lane < g.K;
             const int ma = ones_loc >> 5, mi = ones_loc & 31, kl = lane & 3;
-            off = (uint32_t)(ma * 4096 + (lane >> 2) * 512 + kl * 128 + ((((mi >> 3) ^ kl) << 5) | ((mi & 7) << 2)));
+            off = (uint32_t)(ma * atom_bytes + (lane >> 2) * 512 + kl * 128 + ((((mi >> 3) ^ kl) << 5) | ((mi & 7) << 2)));
+            for (int k2 = 32; k2 < bk; k2 += 32) {               // deeper K-blocks: the same row, 32 k further per pass
+              const uint32_t o2 = off + (uint32_t)(k2 >> 2) * 512u;
+              sts32(a_base + o2, kb * bk + k2 + lane < g.K ? 1.f : 0.f);
+              if (X3) sts32(a_base + hi_bytes + o2, 0.f);
+            }
           }
           sts32(a_base + off, real ? 1.f : 0.f);
           if (X3) sts32(a_base + hi_bytes + off, 0.f);           // 1 and 0 are exact in tf32: no residual
@@ -306,16 +316,17 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           __syncwarp();
         }
         if (lane == 0) {
-          const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, 4096u, 512u) : make_smem_desc(a_base);
-          const uint64_t bdesc = B_MN ? make_smem_desc_mn(a_base + TC_A_BYTES, 4096u, 512u) : make_smem_desc(a_base + TC_A_BYTES);
+          const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, A_KIND == OFFK_TMA_A_IM2COL_T ? atom_bytes : 4096u, 512u) : make_smem_desc(a_base);
+          const uint64_t bdesc = B_MN ? make_smem_desc_mn(a_base + a_bytes, atom_bytes, 512u) : make_smem_desc(a_base + a_bytes);
+          const int ksteps = (A_KIND == OFFK_TMA_A_IM2COL_T ? bk : TC_BK) / 8;
           const uint64_t lo_step = (uint64_t)(hi_bytes >> 4);    // residual tiles sit hi_bytes further (start-address field)
           // X3: both corrections accumulate in accumulator 0, hi*hi of K-block i in main accumulator 1 + i % n_main
           const uint32_t acc_stride = ((uint32_t)bn + 31u) & ~31u;
           const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + i % n_main) * acc_stride : tmem_d;
           const uint32_t d_corr = tmem_d;
           const bool main_started = X3 ? i >= n_main : i > 0;
-#pragma unroll
-          for (int j = 0; j < TC_BK / 8; ++j) {
+#pragma unroll 4
+          for (int j = 0; j < ksteps; ++j) {
             if (X3) {
               umma_tf32(d_corr, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
               umma_tf32(d_corr, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
@@ -514,7 +525,7 @@ static int encode_nchw(CUtensorMap* tm, const float* base, long long hw, long lo
   return 0;
 }
 
-static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed) {
+static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed, int bk) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn)
     if (int e = driver_fn("cuTensorMapEncodeIm2col", (void**)&fn)) return e;
@@ -533,7 +544,7 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
   }
   const cuuint32_t estr[4] = {1, (cuuint32_t)t->stride, (cuuint32_t)t->stride, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t->g.a_src), dims, strides, lower, upper,
-                  (cuuint32_t)TC_BK, (cuuint32_t)(transposed ? 32 : TC_BM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  (cuuint32_t)TC_BK, (cuuint32_t)(transposed ? bk : TC_BM), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   transposed ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -544,7 +555,7 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
 
 template <int A_KIND, int B_KIND, bool X3>
 static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
-                       int kb_per, int tmem_cols, int n_main, dim3 grid, size_t smem, cudaStream_t st) {
+                       int kb_per, int tmem_cols, int n_main, int bk, dim3 grid, size_t smem, cudaStream_t st) {
   auto kern = tma_gemm_kernel<A_KIND, B_KIND, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -560,7 +571,7 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk);
   if (e != cudaSuccess) return cuda_check(e, "tma_gemm launch");
   return OFFK_LAUNCH_CHECK("tma_gemm");
 }
@@ -580,6 +591,9 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
   OFFK_REQUIRE(wgrad == (t->b_kind == OFFK_TMA_B_DENSE_T), "tma_gemm: transposed A kinds pair with OFFK_TMA_B_DENSE_T and only with it");
   int bn = g.tile_n > 0 ? g.tile_n : (g.N <= 256 ? (g.N + 15) / 16 * 16 : 256);
   OFFK_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "tma_gemm: bad N tile %d", bn);
+  const int bk = t->bk > 0 ? t->bk : TC_BK;
+  OFFK_REQUIRE(bk == 32 || ((bk == 64 || bk == 128) && t->a_kind == OFFK_TMA_A_IM2COL_T),
+               "tma_gemm: bk is 32, or 64 / 128 for OFFK_TMA_A_IM2COL_T (both operands MN-major)");
   const long long hw = (long long)t->hin * t->win;
   CUtensorMap ta, tb;
   if (t->a_kind == OFFK_TMA_A_DENSE) {
@@ -602,7 +616,7 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
       OFFK_REQUIRE(g.K == pixels && (g.M == kw_rows || (g.M == kw_rows + 1 && g.a_ones_row == kw_rows)),
                    "tma_gemm: im2col_t needs K == output pixels, M == kh*kw*cin (+ the ones row)");
     }
-    if (int e = encode_im2col(&ta, t, t->a_kind == OFFK_TMA_A_IM2COL_T)) return e;
+    if (int e = encode_im2col(&ta, t, t->a_kind == OFFK_TMA_A_IM2COL_T, bk)) return e;
   } else if (t->a_kind == OFFK_TMA_A_NCHW) {
     OFFK_REQUIRE(hw % 4 == 0 && t->cin % TC_BK == 0 && g.K == t->cin && g.M == (long long)t->n_img * hw && t->ctot == t->cin,
                  "tma_gemm: nchw A needs hw %% 4 == 0, cin %% 32 == 0, K == cin, M == n_img*hw");
@@ -620,7 +634,7 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
     if (int e = encode_2d(&tb, g.b_src, g.K, g.N, t->ldb, bn)) return e;
   } else if (t->b_kind == OFFK_TMA_B_DENSE_T) {
     OFFK_REQUIRE(t->ldb >= g.N && t->ldb % 4 == 0, "tma_gemm: transposed B must be a row-major [K, ldb] matrix, ldb %% 4 == 0");
-    if (int e = encode_2d(&tb, g.b_src, g.N, g.K, t->ldb, 32, true)) return e;     // {32 n, 32 k} atoms
+    if (int e = encode_2d(&tb, g.b_src, g.N, g.K, t->ldb, bk, true)) return e;     // {32 n, bk k} stacks of atoms
   } else {
     return fail(OFFK_E_BADARG, "tma_gemm: unknown b_kind %d", t->b_kind);
   }
@@ -649,18 +663,21 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   geo.kw_rows = t->cin * t->kh * t->kw;
   const bool wgrad = t->b_kind == OFFK_TMA_B_DENSE_T;
   OFFK_REQUIRE(!(wgrad && g.out_vec), "tma_gemm: weight-gradient kinds use the scalar epilogue (out_vec = 0)");
-  const int num_kb = t->a_kind == OFFK_TMA_A_NCHW_T ? t->n_img * geo.kb_per_img : (g.K + TC_BK - 1) / TC_BK;
+  const int bk = t->bk > 0 ? t->bk : TC_BK;
+  const int num_kb = t->a_kind == OFFK_TMA_A_NCHW_T ? t->n_img * geo.kb_per_img : (g.K + bk - 1) / bk;
   const int split = g.split_k > 1 ? g.split_k : 1;
   const int kb_per = (num_kb + split - 1) / split;
-  const uint32_t b_bytes = wgrad ? (uint32_t)((bn + 31) / 32) * 4096u : (uint32_t)bn * 128u;
+  const uint32_t a_bytes = t->a_kind == OFFK_TMA_A_IM2COL_T ? (uint32_t)bk * 512u : (uint32_t)TC_A_BYTES;
+  const uint32_t b_bytes = wgrad ? (uint32_t)((bn + 31) / 32) * (uint32_t)bk * 128u : (uint32_t)bn * 128u;
   OFFK_REQUIRE(t->precision == 0 || t->precision == OFFK_PREC_TF32 || t->precision == OFFK_PREC_TF32X3,
                "tma_gemm: precision must be OFFK_PREC_TF32 (or 0) or OFFK_PREC_TF32X3");
   const bool x3 = t->precision == OFFK_PREC_TF32X3;
-  const uint32_t stage_bytes = (TC_A_BYTES + b_bytes) * (x3 ? 2u : 1u);   // x3: the residual tiles double a stage
+  const uint32_t stage_bytes = (a_bytes + b_bytes) * (x3 ? 2u : 1u);   // x3: the residual tiles double a stage
+  OFFK_REQUIRE(2 * stage_bytes <= 216u * 1024u, "tma_gemm: a pipeline stage of %u bytes leaves no room for two (N tile %d, bk %d)", stage_bytes, bn, bk);
   // two CTAs per SM (one CTA's epilogue overlaps the other's main loop) when that still leaves a pipeline; the 3xTF32
-  // stages of the wide tiles need the whole SM
+  // stages and the deep K-blocks of the wide tiles need the whole SM
   int budget = 108 * 1024;
-  if (x3 && 3 * stage_bytes > (uint32_t)budget) budget = 216 * 1024;
+  if (2 * stage_bytes > (uint32_t)budget || (x3 && 3 * stage_bytes > (uint32_t)budget)) budget = 216 * 1024;
   int stages = budget / (int)stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -687,8 +704,8 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   cudaStream_t st = as_stream(stream);
 #define OFFK_TM_CASE(AK, BK)                                                                                          \
   if (t->a_kind == AK && t->b_kind == BK)                                                                             \
-    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, grid, smem, st)      \
-              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, grid, smem, st);
+    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, grid, smem, st)  \
+              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, grid, smem, st);
   OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)

@@ -129,7 +129,7 @@ class TGemm(Gemm):
         return (prec in _TC_PRECS and not a_relu and y_ok and geom.cin % 32 == 0 and geom.x_ctot % 4 == 0
                 and geom.x_coff % 4 == 0)
 
-    def __init__(self, eng, spc, key, geom: T.ConvGeom, x_layout="nhwc", wgrad=False, **kw):
+    def __init__(self, eng, spc, key, geom: T.ConvGeom, x_layout="nhwc", wgrad=False, bk=0, **kw):
         super().__init__(eng, spc, key, **kw)
         t = L.OffkTGemm()
         C.memmove(C.byref(t.g), C.byref(self.desc), C.sizeof(L.OffkGemm))
@@ -145,6 +145,7 @@ class TGemm(Gemm):
             t.a_kind = L.TMA_A_IM2COL
         t.a_coff = geom.x_coff
         t.precision = eng.prec
+        t.bk = bk if (wgrad and x_layout != "nchw") else 0
         t.n_img, t.hin, t.win, t.ctot, t.cin = geom.n_img, geom.hin, geom.win, geom.x_ctot, geom.cin
         t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = geom.kh, geom.kw, geom.stride, geom.pad, geom.hout, geom.wout
         if isinstance(geom, _FreeGeom):
@@ -206,6 +207,11 @@ class OFFEngine:
         # (motion_conv_trans_28: 388 vs 211 us) and tie elsewhere -- OFFK_TMA_WGRAD=all forces them on, =none disables both
         self.tma_wgrad = os.environ.get("OFFK_TMA_WGRAD", "taps")
         self.tma_strided_dgrad = os.environ.get("OFFK_NO_TMA_SDGRAD", "0") != "1"
+        # channels-last weight gradients through TMA im2col with DEEP K-blocks (bk output pixels per stage: 64 / 128 instead
+        # of 32 -> fewer, larger TMA boxes).  OFFK_WGRAD_TMA: which layers ("big" = the three stage-entry KxK convs, "kxk" =
+        # every KxK conv, "all"); OFFK_WGRAD_BK: the depth
+        self.wgrad_tma = os.environ.get("OFFK_WGRAD_TMA", "")
+        self.wgrad_bk = int(os.environ.get("OFFK_WGRAD_BK", "64"))
         self._tab_cache = {}
         self._keep = []
         self.generation = 0
@@ -419,12 +425,19 @@ class OFFEngine:
         # addresses, so the split-K reductions coalesce) and un-permuted once at the end; writing OIHW directly
         # (dw_layout="oihw") was measured slower: the strided atomics cost more than the permute pass
         spc = T.conv_wgrad_spec(geom, x_layout, "nhwc")
-        m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
-        n_tiles = max(1, math.ceil(spc.N / 256))
-        split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
         tma = (self.use_tma and (self.tma_wgrad == "all" or (self.tma_wgrad == "taps" and (x_layout == "nchw" or force_tma)))
                and TGemm.wgrad_eligible(geom, self.prec, a_relu, x_layout))
-        mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, **k)) if tma else Gemm
+        bk = 0
+        base = name.split(".")[0]
+        deep = {"big": base in ("motion_conv_trans_28", "motion_conv_trans_14", "motion_conv_trans"),
+                "kxk": geom.kh > 1, "all": True}.get(self.wgrad_tma, False)
+        if (deep and self.use_tma and x_layout == "nhwc" and not force_tma and self.wgrad_bk in (32, 64, 128)
+                and TGemm.wgrad_eligible(geom, self.prec, a_relu, x_layout)):
+            tma, bk = True, self.wgrad_bk
+        m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / (bk or 32))
+        n_tiles = max(1, math.ceil(spc.N / 256))
+        split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
+        mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, bk=bk, **k)) if tma else Gemm
         g = mk(self, spc, ("wgrad", x_layout, _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
                atomic=True, split_k=split, name=name + ".wgrad")
         self.flops_bwd += g.flops
