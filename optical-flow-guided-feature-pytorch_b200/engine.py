@@ -210,8 +210,14 @@ class OFFEngine:
         # channels-last weight gradients through TMA im2col with DEEP K-blocks (bk output pixels per stage: 64 / 128 instead
         # of 32 -> fewer, larger TMA boxes).  OFFK_WGRAD_TMA: which layers ("big" = the three stage-entry KxK convs, "kxk" =
         # every KxK conv, "all"); OFFK_WGRAD_BK: the depth
-        self.wgrad_tma = os.environ.get("OFFK_WGRAD_TMA", "")
-        self.wgrad_bk = int(os.environ.get("OFFK_WGRAD_BK", "64"))
+        # Measured at config 2 (profiles/wgrad_sweep_r02x.txt).  tf32 mode: the cp.async gather kernel is faster everywhere
+        # except on motion_conv_trans_28, where 128-pixel boxes win (197 us gather, 389 / 204 / 169 us TMA at bk = 32 / 64 / 128;
+        # motion_conv_trans_14: 97 vs 136, motion_conv_trans: 60 vs 77).  fp32 (3xTF32) mode, where the gather kernel's producers
+        # also write the residual tiles: the TMA-fed kernel wins on every KxK layer (784 -> 501, 344 -> 296, 194 -> 177 us at the
+        # deepest K-block that still leaves two pipeline stages).  Defaults follow the measurement.
+        x3 = self.prec == L.PREC_TF32X3
+        self.wgrad_tma = os.environ.get("OFFK_WGRAD_TMA", "kxk" if x3 else "t28")
+        self.wgrad_bk = int(os.environ.get("OFFK_WGRAD_BK", "64" if x3 else "128"))
         self._tab_cache = {}
         self._keep = []
         self.generation = 0
@@ -429,11 +435,18 @@ class OFFEngine:
                and TGemm.wgrad_eligible(geom, self.prec, a_relu, x_layout))
         bk = 0
         base = name.split(".")[0]
-        deep = {"big": base in ("motion_conv_trans_28", "motion_conv_trans_14", "motion_conv_trans"),
+        deep = {"t28": base == "motion_conv_trans_28",
+                "big": base in ("motion_conv_trans_28", "motion_conv_trans_14", "motion_conv_trans"),
                 "kxk": geom.kh > 1, "all": True}.get(self.wgrad_tma, False)
         if (deep and self.use_tma and x_layout == "nhwc" and not force_tma and self.wgrad_bk in (32, 64, 128)
                 and TGemm.wgrad_eligible(geom, self.prec, a_relu, x_layout)):
-            tma, bk = True, self.wgrad_bk
+            # deepest K-block <= the requested one whose pipeline stage (A: 4 stacks of {32 rows x bk pixels}, B: one per 32
+            # columns of the N tile; twice that with the 3xTF32 residual tiles) still leaves room for two stages per SM
+            bn = 256 if spc.N > 256 else (spc.N + 15) // 16 * 16
+            mul = 2 if self.prec == L.PREC_TF32X3 else 1
+            fits = [b for b in (128, 64, 32) if b <= self.wgrad_bk and mul * (b * 512 + math.ceil(bn / 32) * b * 128) <= 108 * 1024]
+            if fits:
+                tma, bk = True, fits[0]
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / (bk or 32))
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))

@@ -38,5 +38,5 @@ for i in range(iters):
     print(f"iter {i}: CPU issue {1e3*(t1-t0):.2f} ms, until done {1e3*(t2-t0):.2f} ms")
 torch.cuda.cudart().cudaProfilerStop()
 with open(os.path.join(ROOT, "gpurun_out", "step_names.txt"), "w") as f:
-    f.write("\n".join(eng.launch_names()))
+    f.write("\n".join(["seed_set"] + eng.launch_names()))      # forward(train=True) first stores the step seed (one tiny kernel)
 print("done")
