@@ -4,7 +4,9 @@ and RGB_OFF_v2.py:43-58,1378-1392.
 
 Only the OFF section (RGB_OFF.py:596-860 / Flow_OFF.py:606-884) is implemented here -- it runs on liboffk through
 ``OFFSubNetwork``.  The frozen BN-Inception feature extractor (RGB_OFF.py:43-263,362-594; train_off.py:39-57 keeps it
-in eval mode without gradients) is out of scope for this repository: pass it in as ``backbone``, any module mapping the
+in eval mode without gradients) is not part of the accelerated path: pass ``backbone="bninception"`` for the built-in
+table-driven restatement on stock torch ops (``off_b200/backbone.py``; the model is then a complete drop-in: images in,
+the reference's 593 / 576 state_dict entries), or pass any module mapping the
 image batch ``[batch*length, 3 | 10, 224, 224]`` to ``(taps, score)`` where ``taps`` holds the nine Inception outputs
 '3a'..'5b' (``inception_3a_output_out`` ... ``inception_5b_output_out``, RGB_OFF.py:395-590) and ``score`` is
 ``Feature_Generation_Score`` ``[batch*length, num_classes]`` (:592-594).  Without a backbone the forward methods take
@@ -48,6 +50,11 @@ class BNInception_OFF(nn.Module):
         for name, mod in self.off.named_children():
             setattr(self, name, mod)                  # motion_conv_gen_3a ... fc_action_motion_14 (+ sobel_edge_diagonal)
         self._off_children = tuple(n for n, _ in self.off.named_children())
+        if isinstance(backbone, str):
+            if backbone != "bninception":
+                raise ValueError("backbone: a module, None, or 'bninception' (the built-in TSN BN-Inception extractor)")
+            from .backbone import BNInceptionBackbone
+            backbone = BNInceptionBackbone(num_classes, in_channels=10 if variant == "flow" else 3).to(device)
         self._attach_backbone(backbone)
 
     # ------------------------------------------------------------------ helpers

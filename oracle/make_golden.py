@@ -194,6 +194,9 @@ def main():
     import RGB_OFF, Flow_OFF
     for variant, mod in (("rgb", RGB_OFF), ("flow", Flow_OFF)):
         sd = mod.bninception_off(101, 1, 3).state_dict()
+        with open(os.path.join(GOLD, f"state_dict_keys_full_{variant}.txt"), "w") as f:      # all 593 / 576 entries
+            for k, v in sd.items():
+                f.write(f"{k} {' '.join(map(str, v.shape))}\n")
         keys = OrderedDict((k, tuple(v.shape)) for k, v in sd.items() if "motion" in k or "sobel" in k)
         mine = O.param_shapes(variant)
         for k, shp in mine.items():
@@ -203,6 +206,30 @@ def main():
         with open(os.path.join(GOLD, f"state_dict_keys_{variant}.txt"), "w") as f:
             for k, shp in keys.items():
                 f.write(f"{k} {' '.join(map(str, shp))}\n")
+    # -- the whole reference model, images in: backbone taps + score + OFF heads of RGB_OFF_forward /
+    # Flow_OFF.forward with a seeded FULL state_dict, for the drop-in test of BNInception_OFF(backbone="bninception")
+    for variant, mod, cin in (("rgb", RGB_OFF, 3), ("flow", Flow_OFF, 10)):
+        B, Lg, seed = 1, 3, 31
+        net = mod.bninception_off(O.NUM_CLASSES, B, Lg).eval()
+        keys = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+        net.load_state_dict(O.make_state_dict(seed, keys))
+        net = net.double()
+        if variant != "rgb":
+            net.consensus = _Mean()
+        x = O.hash_normal(seed, (B * Lg, cin, 224, 224)).double()
+        caught = {}
+        hooks = [getattr(net, "motion_conv_gen_" + t).register_forward_pre_hook(lambda m, inp, t=t: caught.__setitem__(t, inp[0].detach()))
+                 for t in O.LEVELS]
+        with torch.no_grad():
+            res = net.RGB_OFF_forward(x) if variant == "rgb" else net(x)
+        for h in hooks:
+            h.remove()
+        fix = dict(variant=variant, batch=B, length=Lg, seed=seed, fc7=res[0].numpy(), score=res[1].numpy(), fc14=res[2].numpy())
+        for t, v in caught.items():
+            for kk, vv in digest(v, 128).items():
+                fix[f"tap{t}.{kk}"] = vv
+        np.savez_compressed(os.path.join(GOLD, f"backbone_{variant}_b1_l3.npz"), **fix)
+        print(f"[golden] full model {variant}: fc7 {tuple(res[0].shape)} score {tuple(res[1].shape)} taps {[tuple(v.shape) for v in caught.values()][:2]}...")
     print("[golden] done")
 
 

@@ -161,6 +161,27 @@ def make_params(seed: int, variant: str = "rgb") -> "OrderedDict[str, torch.Tens
     return out
 
 
+def make_state_dict(seed: int, keys_shapes) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded tensors for an arbitrary ``(name, shape)`` list -- the FULL state_dict of a reference model (backbone
+    included, tests/golden/state_dict_keys_full_*.txt): conv / linear weights and biases U(-1/sqrt(fan_in), 1/sqrt(fan_in)),
+    BatchNorm weight and running_var U(0.5, 1.5), BatchNorm bias and running_mean U(-0.2, 0.2), num_batches_tracked 0."""
+    out = OrderedDict()
+    fan = 1
+    for i, (name, shape) in enumerate(keys_shapes):
+        s = seed * 104729 + 5000 + i
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            out[name] = torch.zeros((), dtype=torch.int64)
+        elif "_bn." in name:
+            out[name] = hash_uniform(s, shape, 0.5, 1.5) if leaf in ("weight", "running_var") else hash_uniform(s, shape, -0.2, 0.2)
+        else:
+            if leaf == "weight":
+                fan = int(np.prod(shape[1:])) if len(shape) > 1 else fan
+            bound = 1.0 / math.sqrt(max(fan, 1))
+            out[name] = hash_uniform(s, shape, -bound, bound)
+    return out
+
+
 def make_dropout_masks(seed: int, batch: int, length: int, p_drop: float = 0.8):
     """Keep-masks (1 = keep) for the 12 dropout call sites of one forward
     (RGB_OFF.py:612..:827 spatial, :785,:791,:845 heads)."""

@@ -344,3 +344,32 @@ def test_eval_protocol_at_the_reference_shape(dev):
     want = ref["fc7"].mean(0) + ref["fc14"].mean(0)
     assert _close(torch.from_numpy(fused[0]), want, 1e-5)
     assert not model.training or model.off.training            # eval_video restored the caller's mode
+
+
+@pytest.mark.parametrize("variant", ["rgb", "flow"])
+def test_full_model_is_a_drop_in_of_the_reference_class(dev, variant):
+    """Images in, the reference's return tuple out: BNInception_OFF(backbone='bninception') -- the built-in
+    feature extractor producing the taps on the device + the OFF section on liboffk -- against the reference class itself run
+    in fp64 on the same seeded FULL state_dict and images (tests/golden/backbone_*.npz, written by oracle/make_golden.py).
+    RGB_OFF.RGB_OFF_forward -> (fc7 [P,101], score [N,101], fc14 [P,101]); Flow_OFF.forward -> consensus outputs [B,101]."""
+    import numpy as np
+    from off_b200 import RGB_OFF, Flow_OFF
+    fix = np.load(os.path.join(GOLD, f"backbone_{variant}_b1_l3.npz"))
+    B, Lg, seed = int(fix["batch"]), int(fix["length"]), int(fix["seed"])
+    keys = [(l.split()[0], tuple(int(x) for x in l.split()[1:])) for l in open(os.path.join(GOLD, f"state_dict_keys_full_{variant}.txt"))]
+    mod = RGB_OFF if variant == "rgb" else Flow_OFF
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m = mod.bninception_off(101, B, Lg, device=dev, backbone="bninception", precision="fp32").eval()
+        m.load_state_dict(O.make_state_dict(seed, keys), strict=True)
+        x = O.hash_normal(seed, (B * Lg, 10 if variant == "flow" else 3, 224, 224)).to(dev)
+        with torch.no_grad():
+            out = m.RGB_OFF_forward(x) if variant == "rgb" else m(x)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for got, key in zip(out[:3], ("fc7", "score", "fc14")):
+        want = torch.from_numpy(fix[key])
+        assert tuple(got.shape) == tuple(want.shape), key
+        err = (got.double().cpu() - want).abs().max().item() / want.abs().max().item()
+        assert err < 1e-4, (key, err)

@@ -340,3 +340,61 @@ def test_eval_protocol_fusion_accuracy_and_npz(tmp_path):
     # per-class accuracy is the mean over the classes that occur, not over videos
     acc, per_class, cf = EV.per_class_accuracy([0, 0, 0, 1], [0, 0, 1, 0], 3)
     assert abs(acc - (2 / 3 + 0) / 2) < 1e-12 and cf[0, 1] == 1 and np.isnan(per_class[2])
+
+
+def _full_keys(variant):
+    gold = os.path.join(ROOT, "tests", "golden")
+    return [(l.split()[0], tuple(int(x) for x in l.split()[1:])) for l in open(os.path.join(gold, f"state_dict_keys_full_{variant}.txt"))]
+
+
+@pytest.mark.parametrize("variant", ["rgb", "flow"])
+def test_full_model_state_dict_equals_the_reference_key_for_key(variant, tmp_path):
+    """SURVEY 8b / 8f-2,4: with the built-in feature extractor the model exposes EXACTLY the reference's state_dict (593
+    entries RGB, 576 Flow / v2: names, shapes, BatchNorm buffers; generated from the reference classes by make_golden.py), and
+    a DataParallel-style checkpoint of a full reference model loads strictly: everything loaded, nothing missing or ignored."""
+    import torch
+    import off_oracle as O
+    from off_b200 import RGB_OFF, Flow_OFF, checkpoint as CK
+    want = _full_keys(variant)
+    assert len(want) == (593 if variant == "rgb" else 576)
+    mod = RGB_OFF if variant == "rgb" else Flow_OFF
+    m = mod.bninception_off(101, 1, 3, device="cpu", backbone="bninception")
+    got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert dict(got) == dict(want) and len(got) == len(want)
+    assert all("motion" in n for n, p in m.named_parameters() if p.requires_grad)        # train_off.py:40: the backbone is frozen
+    sd = O.make_state_dict(31, want)
+    path = str(tmp_path / "full.pth")
+    torch.save({"module." + k: v for k, v in sd.items()}, path)                         # test_flow_off.py:52-58
+    loaded, missing, ignored = CK.load_checkpoint(m, path)
+    assert len(loaded) == len(want) and not missing and not ignored
+    assert torch.equal(m.state_dict()["inception_4e_double_3x3_2_bn.running_var"], sd["inception_4e_double_3x3_2_bn.running_var"])
+    assert torch.equal(m.off.engine.params["motion_conv_trans.weight"], sd["motion_conv_trans.weight"])
+    m.load_state_dict(sd, strict=True)                                                   # and the plain strict path
+
+
+@pytest.mark.parametrize("variant", ["rgb", "flow"])
+def test_builtin_backbone_matches_the_reference_taps(variant):
+    """The built-in BN-Inception restatement against the reference class run on the same seeded FULL state_dict and images
+    (fixture tests/golden/backbone_*.npz, fp64): the nine taps that feed the OFF units and Feature_Generation_Score."""
+    import torch
+    import off_oracle as O
+    from off_b200.backbone import BNInceptionBackbone
+    fix = np.load(os.path.join(ROOT, "tests", "golden", f"backbone_{variant}_b1_l3.npz"))
+    B, Lg, seed = int(fix["batch"]), int(fix["length"]), int(fix["seed"])
+    cin = 10 if variant == "flow" else 3
+    bb = BNInceptionBackbone(101, cin).double()
+    sd = O.make_state_dict(seed, _full_keys(variant))
+    own = bb.state_dict()
+    bb.load_state_dict({k: sd[k] for k in own}, strict=True)
+    x = O.hash_normal(seed, (B * Lg, cin, 224, 224)).double()
+    taps, score, conv2 = bb(x)
+    assert list(taps) == ["3a", "3b", "3c", "4a", "4b", "4c", "4d", "5a", "5b"] and conv2.shape == (B * Lg, 192, 56, 56)
+    for t, v in taps.items():
+        flat = v.reshape(-1)
+        idx = torch.from_numpy(fix[f"tap{t}.idx"])
+        np.testing.assert_allclose(flat[idx].numpy(), fix[f"tap{t}.val"], rtol=0, atol=1e-9 * max(1.0, float(np.abs(fix[f"tap{t}.val"]).max())))
+        assert abs(float(flat.norm()) - float(fix[f"tap{t}.l2"])) <= 1e-9 * float(fix[f"tap{t}.l2"])
+    if variant == "rgb":                                     # per-frame score (RGB_OFF.py:592-594,860)
+        np.testing.assert_allclose(score.numpy(), fix["score"], rtol=0, atol=1e-9)
+    else:                                                    # Flow_OFF.forward returns its segment consensus (:867-872)
+        np.testing.assert_allclose(score.view(B, Lg, -1).mean(1).numpy(), fix["score"], rtol=0, atol=1e-9)
