@@ -517,6 +517,45 @@ def run_ours(args):
                             "oracle restatement), same batch, loss and fwd+bwd on this B200; fp32 = allow_tf32 off, tf32 = on")
         torch.cuda.empty_cache()
 
+    # ---- deployment shape of the boundary (extra, N = 1): IMAGES from pinned host memory through the built-in frozen
+    # BN-Inception extractor (stock cuDNN ops, out of the accelerated scope) into the OFF path -- the taps never cross PCIe
+    from_images = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        try:
+            from off_b200.models import BNInception_OFF
+            old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (args.precision == "tf32")
+            full = BNInception_OFF(S.NUM_CLASSES, B, Lg, variant=args.variant, backbone="bninception", precision=args.precision,
+                                   device=dev).train()
+            cin = 10 if args.variant == "flow" else 3
+            img_host = torch.randn(B * Lg, cin, 224, 224).pin_memory()
+
+            def istep():
+                x = img_host.to(dev, non_blocking=True)
+                out = full.RGB_OFF_forward(x) if args.variant == "rgb" else full(x)
+                loss = F.cross_entropy(out[0], target) + F.cross_entropy(out[2], target)
+                loss.backward()
+                loss_host.copy_(loss.detach(), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(3):
+                istep()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                istep()
+            b.record()
+            torch.cuda.synchronize()
+            ims = a.elapsed_time(b) / 10
+            from_images = {"value": B / (ims * 1e-3), "unit": UNIT, "ms_per_step": ims, "h2d_bytes_per_step": img_host.numel() * 4,
+                           "note": "full model: images copied from pinned host memory, frozen BN-Inception extractor on stock cuDNN ops "
+                                   f"(allow_tf32={args.precision == 'tf32'}), OFF fwd+bwd on liboffk, loss read back; the extractor is "
+                                   "outside the accelerated scope (SURVEY 8f-2)"}
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+            del full
+            torch.cuda.empty_cache()
+        except Exception as e:
+            from_images = {"error": repr(e)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is timed at N = 1 only
         clips = args.cpu_clips or min(B, 48)
@@ -549,6 +588,7 @@ def run_ours(args):
             "roofline_stencil": stencil if not args.no_families else None,
             "cpu_baseline": cpu,
             "gpu_baseline": gpu_base,
+            "e2e_from_images": from_images,
             ("tf32_mode" if args.precision == "fp32" else "fp32_mode"): other,
             "flops_per_step": {"fwd": eng.flops_fwd, "bwd": eng.flops_bwd,
                                "tflops_achieved": (eng.flops_fwd + eng.flops_bwd) / (ms / args.steps * 1e-3) / 1e12,
