@@ -250,15 +250,15 @@ def consensus_avg(x: torch.Tensor, dim: int = 1) -> torch.Tensor:
 def sobel_xy(x: torch.Tensor):
     """util.SobelFilter.forward (util.py:46-50): depth-wise, pad 1, no bias."""
     c = x.shape[1]
-    wx = torch.tensor(SOBEL_X, dtype=x.dtype).expand(c, 1, 3, 3).contiguous()
-    wy = torch.tensor(SOBEL_Y, dtype=x.dtype).expand(c, 1, 3, 3).contiguous()
+    wx = torch.tensor(SOBEL_X, dtype=x.dtype, device=x.device).expand(c, 1, 3, 3).contiguous()
+    wy = torch.tensor(SOBEL_Y, dtype=x.dtype, device=x.device).expand(c, 1, 3, 3).contiguous()
     return F.conv2d(x, wx, None, 1, 1, 1, c), F.conv2d(x, wy, None, 1, 1, 1, c)
 
 
 def sobel_diagonal(x: torch.Tensor) -> torch.Tensor:
     """util.SobelFilter_Diagonal.forward (util.py:74-77)."""
     c = x.shape[1]
-    w = torch.tensor(SOBEL_DIAG, dtype=x.dtype).expand(c, 1, 3, 3).contiguous()
+    w = torch.tensor(SOBEL_DIAG, dtype=x.dtype, device=x.device).expand(c, 1, 3, 3).contiguous()
     return F.conv2d(x, w, None, 1, 1, 1, c)
 
 
