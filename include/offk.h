@@ -217,6 +217,10 @@ typedef struct offk_tgemm {
   int32_t bk;            /* K-block depth: 0 / 32, or 64 / 128 for OFFK_TMA_A_IM2COL_T (both operands MN-major: deeper K-blocks
                             = fewer, larger TMA boxes; fixed before offk_tma_gemm_prepare) */
   int32_t reserved;
+  int64_t b_lo_delta;    /* OFFK_PREC_TF32X3 with OFFK_TMA_B_DENSE: 0, or the element distance from B to a matrix of the same
+                            layout holding its tf32 residuals (offk_tf32_residual): the weights are then split once per step in
+                            global memory and both tiles arrive by TMA, instead of every CTA splitting the weight tile of every
+                            K-block in shared memory; a positive multiple of 4 */
   uint64_t tmap_a[16];   /* CUtensorMap storage */
   uint64_t tmap_b[16];
 } offk_tgemm_t;
@@ -372,6 +376,10 @@ typedef struct offk_permute {
   int32_t cout, cin, kh, kw;
 } offk_permute_t;
 int offk_permute_weight_batch(int n, const offk_permute_t* items, int to_ohwi, void* stream);
+
+/* dst[i] = tf32 residual of src[i] = rn_tf32(src[i] - trunc_tf32(src[i])), i < n (n % 4 == 0, 16-byte aligned): the "lo" part
+ * of the 3xTF32 split (OFFK_PREC_TF32X3) for operands that are known ahead of the GEMM -- the weights (offk_tgemm_t.b_lo_delta) */
+int offk_tf32_residual(const float* src, float* dst, long long n, void* stream);
 
 /* dst[i] = src[idx[i]], i < n.  One launch re-lays every conv weight of the step: OHWI copies for the forward
  * implicit GEMMs and [cin][kh][kw][cout] copies with flipped taps for the data-gradient GEMMs (autograd of

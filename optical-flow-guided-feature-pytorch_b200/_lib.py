@@ -53,6 +53,7 @@ class OffkTGemm(C.Structure):
         ("wout", C.c_int32),
         ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("geom_flags", C.c_int32),
         ("pad_w", C.c_int32), ("precision", C.c_int32), ("bk", C.c_int32), ("reserved", C.c_int32),
+        ("b_lo_delta", C.c_int64),
         ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
     ]
 
@@ -126,6 +127,7 @@ _PROTOS = {
     "offk_add_relu_slice": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_nchw_to_nhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "offk_gather_copy": (C.c_int, [_P, _P, _P, C.c_longlong, _P]),
+    "offk_tf32_residual": (C.c_int, [_P, _P, C.c_longlong, _P]),
     "offk_permute_weight_batch": (C.c_int, [C.c_int, C.POINTER(OffkPermute), C.c_int, _P]),
     "offk_permute_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "offk_drop_keep_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_float]),

@@ -154,7 +154,7 @@ __device__ __noinline__ void splitk_finish(const offk_gemm_t& g, uint32_t* flag_
 template <int A_KIND, int B_KIND, bool X3>
 __global__ void __launch_bounds__(TM_THREADS, 2)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ offk_gemm_t g,
-                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main, int bk) {
+                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main, int bk, int b_presplit) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
@@ -166,6 +166,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   const uint32_t a_bytes = A_KIND == OFFK_TMA_A_IM2COL_T ? 4u * atom_bytes : (uint32_t)TC_A_BYTES;
   const uint32_t b_bytes = B_MN ? (((uint32_t)bn + 31u) >> 5) * atom_bytes : (uint32_t)bn * 128u;
   const uint32_t hi_bytes = a_bytes + b_bytes;                  // one landed [A | B] pair
+  const uint32_t blo_bytes = (X3 && !B_MN && b_presplit) ? b_bytes : 0u;   // residual B tile delivered by TMA as well
   const uint32_t stage_bytes = X3 ? 2u * hi_bytes : hi_bytes;
   TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
@@ -231,20 +232,20 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           // four 4 KB atoms {32 pixels x 32 channels}; atoms wholly past the frame end are skipped (their
           // accumulator rows are never stored)
           const int n_at = min(TC_BM / 32, (geo.hw - pix0 + 31) >> 5);
-          mbar_arrive_expect_tx(full, (uint32_t)n_at * 4096u + b_bytes);
+          mbar_arrive_expect_tx(full, (uint32_t)n_at * 4096u + b_bytes + blo_bytes);
           for (int a = 0; a < n_at; ++a) tma_load_3d(a_dst + a * 4096, &tma, pix0 + 32 * a, kb * TC_BK, img_t, full);
         } else if (A_KIND == OFFK_TMA_A_NCHW_T) {
           // K-block = 32 pixels of ONE frame (pixels past the frame end zero-fill, so whatever rows of dY they meet
           // contribute nothing); rows = 128 channels (channels >= cin zero-fill; the ones row is patched in)
           const int img = kb / geo.kb_per_img, pb = kb - img * geo.kb_per_img;
           b_row0 = img * geo.hw + pb * TC_BK;
-          mbar_arrive_expect_tx(full, hi_bytes);
+          mbar_arrive_expect_tx(full, hi_bytes + blo_bytes);
           tma_load_3d(a_dst, &tma, pb * TC_BK, m0, img, full);
         } else if (A_KIND == OFFK_TMA_A_IM2COL_T) {
           // rows m = (r, q, c): each 32-row atom is one {32 channels x 32 output pixels} im2col box at its own (q, r)
           const int at0 = m0 >> 5;
           const int n_at = max(0, min(TC_BM / 32, (geo.kw_rows >> 5) - at0));
-          mbar_arrive_expect_tx(full, (uint32_t)n_at * atom_bytes + b_bytes);
+          mbar_arrive_expect_tx(full, (uint32_t)n_at * atom_bytes + b_bytes + blo_bytes);
           const int hwo = geo.hout * geo.wout;
           const int p0 = kb * bk;
           const int img = p0 / hwo, rem = p0 - img * hwo;
@@ -256,10 +257,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
             tma_load_im2col_4d(a_dst + a * atom_bytes, &tma, geo.a_coff + cb * TC_BK, wb, hb, img, q, r, full);
           }
         } else if (A_KIND == OFFK_TMA_A_DENSE) {
-          mbar_arrive_expect_tx(full, hi_bytes);
+          mbar_arrive_expect_tx(full, hi_bytes + blo_bytes);
           tma_load_2d(a_dst, &tma, kb * TC_BK, m0, full);
         } else {
-          mbar_arrive_expect_tx(full, hi_bytes);
+          mbar_arrive_expect_tx(full, hi_bytes + blo_bytes);
           const int tap = kb / geo.cblocks, cb = kb - tap * geo.cblocks;
           const int r = tap / geo.kw, q = tap - r * geo.kw;
           tma_load_im2col_4d(a_dst, &tma, geo.a_coff + cb * TC_BK, w0, h0, img0, q, r, full);
@@ -267,6 +268,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         if (B_MN) {
           const int n_bat = (bn + 31) >> 5;
           for (int a = 0; a < n_bat; ++a) tma_load_2d(b_dst + a * atom_bytes, &tmb, n0 + 32 * a, b_row0, full);
+        } else if (X3 && b_presplit) {
+          // weights split ahead of time (offk.h: b_lo_delta): the residual matrix is plane 1 of a 3-D tensor map and lands
+          // straight in the stage's B_lo slot -- no shared-memory pass over the weight tile
+          tma_load_3d(b_dst, &tmb, kb * TC_BK, n0, 0, full);
+          tma_load_3d(b_dst + hi_bytes, &tmb, kb * TC_BK, n0, 1, full);
         } else {
           tma_load_2d(b_dst, &tmb, kb * TC_BK, n0, full);
         }
@@ -360,8 +366,9 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(smem_u32(&sh->full[s]), parity);
         const uint32_t base = smem_base + s * stage_bytes;
+        const uint32_t split_bytes = blo_bytes ? a_bytes : hi_bytes;     // pre-split weights: only the A tile needs the pass
 #pragma unroll 4
-        for (uint32_t off = e16; off < hi_bytes; off += (TM_THREADS - 64) * 16u) split_chunk(base + off, hi_bytes);
+        for (uint32_t off = e16; off < split_bytes; off += (TM_THREADS - 64) * 16u) split_chunk(base + off, hi_bytes);
         fence_proxy_async_smem();                                // generic-proxy writes -> visible to tcgen05.mma
         mbar_arrive(smem_u32(&sh->split[s]));
         if (++s == stages) { s = 0; parity ^= 1u; }
@@ -506,6 +513,23 @@ static int encode_2d(CUtensorMap* tm, const float* base, long long inner, long l
   return 0;
 }
 
+// Weights with their tf32 residuals split ahead of time: [N, ldb] matrix at base (plane 0) and its residual matrix `delta`
+// elements further (plane 1), as one 3-D map {K, N, 2}; box {32 k, bn rows, 1 plane}
+static int encode_b_planes(CUtensorMap* tm, const float* base, long long K, long long N, long long ld, int box_rows, long long delta) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn)
+    if (int e = driver_fn("cuTensorMapEncodeTiled", (void**)&fn)) return e;
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)delta * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OFFK_E_BADARG, "cuTensorMapEncodeTiled(B planes) failed (%d): K=%lld N=%lld ld=%lld delta=%lld", (int)r, K, N, ld, delta);
+  return 0;
+}
+
 // NCHW [n_img, cin, hw] as {hw, cin, n_img}; box {32 pixels, 32 channels, 1 frame}; 32-byte-atom 128B swizzle = the
 // MN-major SWIZZLE_128B_BASE32B operand layout of kind::tf32 (cute Swizzle<2,5,2>)
 static int encode_nchw(CUtensorMap* tm, const float* base, long long hw, long long cin, long long n_img, bool transposed) {
@@ -555,7 +579,7 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
 
 template <int A_KIND, int B_KIND, bool X3>
 static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
-                       int kb_per, int tmem_cols, int n_main, int bk, dim3 grid, size_t smem, cudaStream_t st) {
+                       int kb_per, int tmem_cols, int n_main, int bk, int b_presplit, dim3 grid, size_t smem, cudaStream_t st) {
   auto kern = tma_gemm_kernel<A_KIND, B_KIND, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -571,7 +595,7 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, b_presplit);
   if (e != cudaSuccess) return cuda_check(e, "tma_gemm launch");
   return OFFK_LAUNCH_CHECK("tma_gemm");
 }
@@ -579,6 +603,25 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
 }  // namespace offk
 
 using namespace offk;
+
+namespace offk {
+__global__ void __launch_bounds__(256) tf32_residual_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n4) {
+  pdl_sync();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+  reinterpret_cast<float4*>(dst)[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+}
+}  // namespace offk
+
+extern "C" int offk_tf32_residual(const float* src, float* dst, long long n, void* stream) {
+  OFFK_REQUIRE(src && dst && n > 0 && n % 4 == 0, "tf32_residual: n must be a positive multiple of 4");
+  OFFK_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0, "tf32_residual: alignment");
+  const long long n4 = n / 4;
+  cudaError_t e = launch_pdl(tf32_residual_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, as_stream(stream), src, dst, n4);
+  if (e != cudaSuccess) return cuda_check(e, "tf32_residual launch");
+  return OFFK_LAUNCH_CHECK("tf32_residual");
+}
 
 extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
   OFFK_REQUIRE(t != nullptr, "tma_gemm: null descriptor");
@@ -631,7 +674,10 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
   }
   if (t->b_kind == OFFK_TMA_B_DENSE) {
     OFFK_REQUIRE(t->ldb >= g.K && t->ldb % 4 == 0, "tma_gemm: B must be a dense [N, ldb] matrix, ldb %% 4 == 0");
-    if (int e = encode_2d(&tb, g.b_src, g.K, g.N, t->ldb, bn)) return e;
+    if (t->precision == OFFK_PREC_TF32X3 && t->b_lo_delta != 0) {
+      OFFK_REQUIRE(t->b_lo_delta > 0 && t->b_lo_delta % 4 == 0, "tma_gemm: b_lo_delta must be a positive multiple of 4 elements");
+      if (int e = encode_b_planes(&tb, g.b_src, g.K, g.N, t->ldb, bn, t->b_lo_delta)) return e;
+    } else if (int e = encode_2d(&tb, g.b_src, g.K, g.N, t->ldb, bn)) return e;
   } else if (t->b_kind == OFFK_TMA_B_DENSE_T) {
     OFFK_REQUIRE(t->ldb >= g.N && t->ldb % 4 == 0, "tma_gemm: transposed B must be a row-major [K, ldb] matrix, ldb %% 4 == 0");
     if (int e = encode_2d(&tb, g.b_src, g.N, g.K, t->ldb, bk, true)) return e;     // {32 n, bk k} stacks of atoms
@@ -672,6 +718,7 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   OFFK_REQUIRE(t->precision == 0 || t->precision == OFFK_PREC_TF32 || t->precision == OFFK_PREC_TF32X3,
                "tma_gemm: precision must be OFFK_PREC_TF32 (or 0) or OFFK_PREC_TF32X3");
   const bool x3 = t->precision == OFFK_PREC_TF32X3;
+  const int presplit = (x3 && t->b_kind == OFFK_TMA_B_DENSE && t->b_lo_delta != 0) ? 1 : 0;
   const uint32_t stage_bytes = (a_bytes + b_bytes) * (x3 ? 2u : 1u);   // x3: the residual tiles double a stage
   OFFK_REQUIRE(2 * stage_bytes <= 216u * 1024u, "tma_gemm: a pipeline stage of %u bytes leaves no room for two (N tile %d, bk %d)", stage_bytes, bn, bk);
   // two CTAs per SM (one CTA's epilogue overlaps the other's main loop) when that still leaves a pipeline; the 3xTF32
@@ -704,8 +751,8 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   cudaStream_t st = as_stream(stream);
 #define OFFK_TM_CASE(AK, BK)                                                                                          \
   if (t->a_kind == AK && t->b_kind == BK)                                                                             \
-    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, grid, smem, st)  \
-              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, grid, smem, st);
+    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, presplit, grid, smem, st)  \
+              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, 0, grid, smem, st);
   OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)

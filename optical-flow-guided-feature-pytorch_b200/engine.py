@@ -146,6 +146,14 @@ class TGemm(Gemm):
         t.a_coff = geom.x_coff
         t.precision = eng.prec
         t.bk = bk if (wgrad and x_layout != "nchw") else 0
+        if eng.presplit and not wgrad:
+            # B is a weight matrix inside the parameter buffer or the per-step weight copies: its residuals sit at the same
+            # offset of the twin buffer
+            bp = kw["b_src"].data_ptr()
+            for hi, lo in ((eng.params_flat, eng.params_lo), (eng.wc_flat, eng.wc_lo)):
+                if hi.data_ptr() <= bp < hi.data_ptr() + hi.numel() * 4:
+                    t.b_lo_delta = (lo.data_ptr() - hi.data_ptr()) // 4
+                    self.reads.append(lo)
         t.n_img, t.hin, t.win, t.ctot, t.cin = geom.n_img, geom.hin, geom.win, geom.x_ctot, geom.cin
         t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = geom.kh, geom.kw, geom.stride, geom.pad, geom.hout, geom.wout
         if isinstance(geom, _FreeGeom):
@@ -224,7 +232,13 @@ class OFFEngine:
 
         # ---- parameters: one flat buffer, reference-named views
         self.layout, self.n_flat = S.flat_layout(variant)
-        self.params_flat = torch.zeros(self.n_flat, device=self.device)
+        # fp32 (3xTF32) mode: the tf32 residuals of the weights are produced once per step into a twin buffer directly behind
+        # the parameters, so that the GEMMs receive both weight tiles by TMA (offk.h: b_lo_delta) instead of splitting them in
+        # shared memory in every CTA and K-block
+        self.presplit = self.prec == L.PREC_TF32X3 and os.environ.get("OFFK_NO_PRESPLIT", "0") != "1"
+        self._params_all = torch.zeros(self.n_flat * (2 if self.presplit else 1), device=self.device)
+        self.params_flat = self._params_all[:self.n_flat]
+        self.params_lo = self._params_all[self.n_flat:] if self.presplit else None
         self.grads_flat = torch.zeros(self.n_flat, device=self.device)
         self.params = OrderedDict((n, self._view(self.params_flat, n)) for n in S.param_shapes(variant))
         self.grads = OrderedDict((n, self._view(self.grads_flat, n)) for n in S.param_shapes(variant))
@@ -347,7 +361,10 @@ class OFFEngine:
                         views.append(("wd", (name, a, b), off, (cin, sub.size // cin)))
                         off += sub.size
         self.wc_idx = torch.from_numpy(np.concatenate(idx).astype(np.int32)).to(self.device)
-        self.wc_flat = torch.zeros(off, device=self.device)
+        off = (off + 3) // 4 * 4
+        self._wc_all = torch.zeros(off * (2 if self.presplit else 1), device=self.device)
+        self.wc_flat = self._wc_all[:off]
+        self.wc_lo = self._wc_all[off:] if self.presplit else None
         for kind, name, o, shape in views:
             getattr(self, kind)[name] = self.wc_flat[o:o + int(np.prod(shape))].view(shape)
         off = 0
@@ -803,9 +820,17 @@ class OFFEngine:
 
         # weight re-layouts before the forward (one launch), OHWI -> OIHW weight gradients after the backward
         wc, wci, pflat = self.wc_flat, self.wc_idx, self.params_flat
+        wc_lane = int(os.environ.get("OFFK_WC_LANE", "2"))
         pre = [_nm(lambda stream: L.check(lib.offk_gather_copy(_ptr(pflat), _ptr(wci), _ptr(wc), wc.numel(), stream),
-                                          "weight copies"), "weight_copies", writes=[wc],
-                   lane=int(os.environ.get("OFFK_WC_LANE", "2")))]
+                                          "weight copies"), "weight_copies", writes=[wc], lane=wc_lane)]
+        if self.presplit:
+            # 3xTF32 residuals of every weight, once per step (the GEMMs then get both weight tiles by TMA)
+            plo, wlo = self.params_lo, self.wc_lo
+            pre.append(_nm(lambda stream: L.check(lib.offk_tf32_residual(_ptr(pflat), _ptr(plo), pflat.numel(), stream),
+                                                  "weight residuals"), "weight_residuals_params", writes=[plo], lane=0))
+            pre.append(_nm(lambda stream: L.check(lib.offk_tf32_residual(_ptr(wc), _ptr(wlo), wc.numel(), stream),
+                                                  "weight residuals"), "weight_residuals_copies", reads=[wc], writes=[wlo],
+                           lane=wc_lane))
         # OHWI -> OIHW accumulation of every KxK weight gradient: one launch
         kxk = [(name, cout, cin, k) for name, cout, cin, k, _, _ in S.STAGE_CONVS if k > 1]
         self._unperm = (L.OffkPermute * len(kxk))()

@@ -802,3 +802,50 @@ def test_tma_gemm_split_k_finisher_and_second_output(dev, prec, tol, split, with
             want = torch.relu(ref + addend.double())
             assert _rel(aux[..., 64:64 + cout], want.cpu()) < tol
             assert (aux[..., :64] == -7.0).all() and (aux[..., 64 + cout:] == -7.0).all()
+
+
+@pytest.mark.parametrize("k,split", [(1, 1), (3, 1), (3, 4)])
+def test_tma_gemm_presplit_weights_equal_in_kernel_split(dev, k, split):
+    """3xTF32 with the weight residuals produced ahead of the GEMM (offk_tf32_residual + offk_tgemm_t.b_lo_delta: both weight
+    tiles arrive by TMA) performs the very same MMAs on the very same operand bits as the in-kernel split: bit-identical."""
+    from off_b200 import _lib as L, tables as T
+    lib = L.lib()
+    n, cin, h, cout = 3, 64, 14, 256
+    g = T.ConvGeom(n, cin, h, h, cout, k, k, 1, k // 2)
+    torch.manual_seed(8)
+    x = torch.randn(n, h, h, cin, device=dev)
+    nw = cout * g.kdim
+    wall = torch.zeros(2 * nw, device=dev)                       # [weights | their tf32 residuals]
+    wall[:nw] = (torch.randn(cout, g.kdim, device=dev) / g.kdim ** 0.5).flatten()
+    L.check(lib.offk_tf32_residual(wall.data_ptr(), wall.data_ptr() + 4 * nw, nw, None), "residual")
+    w = wall[:nw].view(cout, g.kdim)
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    assert (wall[nw:].view(cout, g.kdim) - (w - hi)).abs().max().item() <= 2.0 ** -11 * (w - hi).abs().max().item()
+    bias = torch.randn(cout, device=dev)
+    spc = T.conv_fwd_spec(g, "nhwc", "nhwc")
+    tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
+    outs = []
+    for delta in (0, nw):
+        out = torch.zeros(n, h, h, cout, device=dev)
+        t = L.OffkTGemm()
+        d = t.g
+        d.M, d.N, d.K = spc.M, spc.N, spc.K
+        d.a_src, d.b_src, d.a_ones_row = x.data_ptr(), wall.data_ptr(), -1
+        d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
+        d.bias, d.split_k, d.out_vec = (bias.data_ptr() if split == 1 else None), split, 1
+        one = k == 1
+        t.a_kind, t.lda = (L.TMA_A_DENSE if one else L.TMA_A_IM2COL), cin
+        t.n_img, t.hin, t.win, t.ctot, t.cin = n, h, h, cin, cin
+        t.kh, t.kw, t.stride, t.pad, t.hout, t.wout = k, k, 1, k // 2, h, h
+        t.b_kind, t.ldb, t.precision, t.b_lo_delta = L.TMA_B_DENSE, g.kdim, 2, delta
+        L.check(lib.offk_tma_gemm_prepare(C.byref(t)), "prepare")
+        L.check(lib.offk_tma_gemm(C.byref(t), None), "tma_gemm")
+        torch.cuda.synchronize()
+        outs.append(out)
+    if split == 1:
+        assert torch.equal(outs[0], outs[1])
+    else:
+        assert _rel(outs[0], outs[1].cpu()) < 1e-6               # split-K partial tiles meet through fp32 atomics
+    wd = w.view(cout, k, k, cin).permute(0, 3, 1, 2).double()
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wd, bias.double() if split == 1 else None, 1, k // 2)
+    assert _rel(outs[1].permute(0, 3, 1, 2), ref.cpu()) < 1e-5

@@ -115,9 +115,12 @@ def test_engine_plan_builds_without_a_gpu():
     for conv in ("motion_conv_trans_28", "motion_conv_trans_14"):
         assert all((conv, a, b) in eng.wd for a in (0, 1) for b in (0, 1))
     assert "tapT_5a" not in flow.launch_names()          # the CUDA-core cross-check mode reads the NCHW taps through the gather kernel
-    # precision='fp32' is the 3xTF32 tensor-core mode: the same TMA-fed plan as 'tf32', launch for launch
+    # precision='fp32' is the 3xTF32 tensor-core mode: the same TMA-fed plan as 'tf32', launch for launch, plus the two
+    # per-step weight-residual passes (the GEMMs then receive both weight tiles by TMA)
     x3 = E.OFFEngine(2, 3, "rgb", "cpu", "fp32")
-    assert x3.prec == L.PREC_TF32X3 and x3.launch_names() == names
+    extra = {"weight_residuals_params", "weight_residuals_copies"}
+    assert x3.prec == L.PREC_TF32X3 and [n for n in x3.launch_names() if n not in extra] == names
+    assert extra <= set(x3.launch_names()) and x3.params_lo.data_ptr() == x3.params_flat.data_ptr() + 4 * x3.n_flat
     # hazard analysis: a step never waits on its own lane, and every cross-lane wait points backwards
     for sched in (eng.fwd_sched, eng.bwd_sched):
         for i, ws in enumerate(sched.waits):
