@@ -39,14 +39,20 @@ class _FreeGeom:
         self.__dict__.update(kw)
 
 
-def _pick_tile_n(M: int, N: int) -> int:
-    """Widest N tile (multiple of 16, <= 256, dividing N) that still gives about two CTAs per SM."""
+def _pick_tile_n(M: int, N: int, slots: int = 2 * _SM_TARGET) -> int:
+    """N tile (multiple of 16, <= 256; the last tile may be partial) of a GEMM without split-K: the one that minimises
+    rounds x per-CTA cost, rounds = ceil(CTAs / resident CTA slots) and cost ~ 128 + bn (rows of A and B a K-block moves
+    through shared memory).  Wave quantisation matters: 37 x 11 tiles of 96 columns are 1.4 rounds, 37 x 8 of 144 are one."""
     mt = math.ceil(M / 128)
-    cands = [bn for bn in range(256, 15, -16) if N % bn == 0]
-    for bn in cands:
-        if mt * (N // bn) >= 280:
-            return bn
-    return cands[-1] if cands else 0
+    best, best_cost = 0, None
+    for bn in range(256, 15, -16):
+        if bn > (N + 15) // 16 * 16:
+            continue
+        nt = math.ceil(N / bn)
+        cost = math.ceil(mt * nt / slots) * (128 + bn) * (1.0 if mt * nt >= _SM_TARGET else _SM_TARGET / (mt * nt)) ** 0.5
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = bn, cost
+    return best
 
 
 class Gemm:
@@ -390,7 +396,13 @@ class OFFEngine:
         n_tiles = max(1, math.ceil(spc.N / 256))
         split = 1
         if self.tc and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
-            split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), kb // 8))
+            # split-K factor: minimise rounds x K-blocks per CTA, rounds = ceil(CTAs / resident CTA slots) (two CTAs per SM in
+            # the tf32 mode, one in the 3xTF32 mode whose stages are twice as large); ties go to the smaller factor.
+            # 147 tiles: 2 splits = 294 CTAs = one round (3 splits were 1.49 rounds at 31 % tensor-pipe activity).
+            slots = _SM_TARGET * (1 if self.prec == L.PREC_TF32X3 else 2)
+            tiles = m_tiles * n_tiles
+            split = min(range(1, max(1, kb // 8) + 1),
+                        key=lambda s_: (math.ceil(tiles * s_ / slots) * math.ceil(kb / s_) * (1 if tiles * s_ >= 0.9 * _SM_TARGET else 4), s_))
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
         tma = self.use_tma and TGemm.eligible(geom, self.prec, a_relu, x_layout)
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, **k)) if tma else Gemm
@@ -502,7 +514,7 @@ class OFFEngine:
                                stride=1, pad=ex["pad_h"], pad_w=ex["pad_w"], x_ctot=geom.y_ctot, x_coff=geom.y_coff,
                                hout=ex["hc"], wout=ex["wc"], kdim=R * Q * geom.cout)
                 kw_["b_src"] = self.wd[(name, ex["a"], ex["b"])]
-                kw_["tile_n"] = _pick_tile_n(spc.M, spc.N)
+                kw_["tile_n"] = _pick_tile_n(spc.M, spc.N, _SM_TARGET * (1 if self.prec == L.PREC_TF32X3 else 2))
                 g = TGemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), geom=fg, **kw_)
             else:
                 g = Gemm(self, spc, ("dgrad", x_layout, _gkey(geom), i), **kw_)
