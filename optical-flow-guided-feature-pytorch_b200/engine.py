@@ -83,7 +83,7 @@ class Gemm:
         d.relu_post, d.atomic_out = int(relu_post), int(atomic)
         d.ones_row_out = ones_out.data_ptr() if ones_out is not None else None
         if tile_n == 0 and split_k == 1:
-            tile_n = _auto_tile_n(spc.M, spc.N, isinstance(self, TGemm))
+            tile_n = _auto_tile_n(spc.M, spc.N, isinstance(self, TGemm), eng.prec == L.PREC_TF32X3)
         d.split_k, d.tile_n = split_k, tile_n
         d.out_vec = spc.out_vec
         counter = None
@@ -403,6 +403,8 @@ class OFFEngine:
             tiles = m_tiles * n_tiles
             split = min(range(1, max(1, kb // 8) + 1),
                         key=lambda s_: (math.ceil(tiles * s_ / slots) * math.ceil(kb / s_) * (1 if tiles * s_ >= 0.9 * _SM_TARGET else 4), s_))
+            forced = dict(kv.split("=") for kv in os.environ.get("OFFK_FWD_SPLIT", "").split(",") if "=" in kv)
+            split = int(forced.get(name, split))          # tuning hook: OFFK_FWD_SPLIT=motion_conv_trans_28=3,...
         cols = (geom.cout if relu else 0) if relu_cols is None else relu_cols
         tma = self.use_tma and TGemm.eligible(geom, self.prec, a_relu, x_layout)
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, **k)) if tma else Gemm
@@ -1097,7 +1099,7 @@ class OFFEngine:
                 streams[0].wait_stream(s_)
 
 
-def _auto_tile_n(M: int, N: int, tma: bool = False) -> int:
+def _auto_tile_n(M: int, N: int, tma: bool = False, x3: bool = False) -> int:
     """N tile of a GEMM launched without split-K; 0 = the kernel's default (widest legal tile).
     TMA-fed: two CTAs fit an SM and one CTA's epilogue should overlap another's main loop, so aim for >= 2 x 148 CTAs
     with the widest tile that gets there (re-reading A per N tile is one cheap TMA instruction).
@@ -1106,6 +1108,10 @@ def _auto_tile_n(M: int, N: int, tma: bool = False) -> int:
     mt = math.ceil(M / 128)
     bn0 = (N + 15) // 16 * 16 if N <= 256 else 256
     want, enough = (2 * _SM_TARGET, 2 * _SM_TARGET) if tma else (120, 140)
+    if tma and x3:
+        # 3xTF32 stages are twice as large: one CTA per SM, and every extra N tile repeats the A tile AND its split
+        # (motion_conv_trans_28, 147 x 1 tiles of 64: two tiles of 32 took 586 us against 371 us)
+        want = enough = int(0.9 * _SM_TARGET)
     if mt * math.ceil(N / bn0) >= want:
         return 0
     best = 0
