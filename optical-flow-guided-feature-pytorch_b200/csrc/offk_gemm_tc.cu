@@ -478,12 +478,12 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
       if (++s == stages) { s = 0; parity ^= 1u; }
     }
   } else {
-    if (lane == 0) {
-      // ================= MMA issuer (one thread) =================
+    {
+      // ================= MMA issuer (converged warp; one elected lane issues: elect_one_sync in offk_tc.cuh) =================
       constexpr bool A_MN = LoaderA<A_MODE>::kMN, B_MN = LoaderB<B_MODE>::kMN;
       const uint32_t idesc = make_idesc_tf32(bn, A_MN, B_MN);
       const uint32_t b_kgroup = (uint32_t)((bn + 31) >> 5) << 10;     // MN-major B: bytes per 8-k group
-      int s = 0;
+      int s = 0, ms = 0;                             // ms = i % n_main, kept incrementally
       uint32_t parity = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(smem_u32(&sh->full[s]), parity);
@@ -500,20 +500,24 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
         // X3: both corrections accumulate in accumulator 0, hi*hi of K-block i in main accumulator 1 + i % n_main
         // (tmem_ld16_sum in offk_tc.cuh says why)
         const uint32_t acc_stride = ((uint32_t)bn + 31u) & ~31u;
-        const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + i % n_main) * acc_stride : tmem_d;
+        const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + ms) * acc_stride : tmem_d;
         const bool main_started = X3 ? i >= n_main : i > 0;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j) {
-          if (X3) {
-            umma_tf32(tmem_d, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
-            umma_tf32(tmem_d, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
+          for (int j = 0; j < TC_BK / 8; ++j) {
+            if (X3) {
+              umma_tf32(tmem_d, adesc + lo_step + a_step * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+              umma_tf32(tmem_d, adesc + a_step * j, bdesc + lo_step + b_step * j, idesc, 1u);
+            }
+            umma_tf32(d_main, adesc + a_step * j, bdesc + b_step * j, idesc, (main_started || j > 0) ? 1u : 0u);
           }
-          umma_tf32(d_main, adesc + a_step * j, bdesc + b_step * j, idesc, (main_started || j > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&sh->empty[s]));        // frees the smem slot when these MMAs retire
         }
-        umma_commit(smem_u32(&sh->empty[s]));          // frees the smem slot when these MMAs retire
+        __syncwarp();
         if (++s == stages) { s = 0; parity ^= 1u; }
+        if (++ms == n_main) ms = 0;
       }
-      umma_commit(smem_u32(&sh->accum_full));          // accumulator complete
+      if (elect_one_sync()) umma_commit(smem_u32(&sh->accum_full));          // accumulator complete
     }
     __syncwarp();
   }
@@ -638,6 +642,7 @@ static int launch_tc_t(const offk_gemm_t& g, int bn, int stages, int kb_per, int
   if (X3) {   // (n_main + 1) accumulators of bn columns (32-column granules) in the allocated tensor memory, <= 4 mains
     n_main = tmem_cols / ((bn + 31) / 32 * 32) - 1;
     if (n_main > 4) n_main = 4;
+    n_main = x3_main_accumulators(n_main, kb_per * (TC_BK / 8));
   }
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {

@@ -77,6 +77,19 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
 
+// Diagnostics build only (-DOFFK_TIMELINE, tools/timeline.py): per-CTA clock64 stamps of the kernel's phases.
+#ifdef OFFK_TIMELINE
+constexpr int TL_MAX_CTAS = 8192, TL_SLOTS = 32;
+__device__ long long tl_buf[TL_MAX_CTAS * TL_SLOTS];
+#define TL_STAMP(slot)                                                                                      \
+  do {                                                                                                      \
+    const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                        \
+    if (cta_ < TL_MAX_CTAS) tl_buf[cta_ * TL_SLOTS + (slot)] = clock64();                                   \
+  } while (0)
+#else
+#define TL_STAMP(slot) do { } while (0)
+#endif
+
 struct TmShared {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -84,6 +97,7 @@ struct TmShared {
   uint64_t split[TC_MAX_STAGES];   // X3: the residual ("lo") tiles of the stage are written (256 epilogue threads)
   uint32_t tmem_base;
   uint32_t last_flag;              // split-K finisher: 1 in the CTA that arrived last on the tile's counter
+  float bias[256];                 // the tile's bias values (vector epilogue)
 };
 
 // Final value of 4 consecutive elements (one accumulator row, columns n..n+3): the epilogue of offk.h, then the optional
@@ -152,9 +166,12 @@ __device__ __noinline__ void splitk_finish(const offk_gemm_t& g, uint32_t* flag_
 // X3 = OFFK_PREC_TF32X3: every stage holds [A | B | A_lo | B_lo]; the epilogue warps, otherwise idle during the main loop,
 // turn each landed [A | B] into its tf32 residual (offk_tc.cuh) and the MMA warp issues three MMAs per K = 8 step.
 template <int A_KIND, int B_KIND, bool X3>
-__global__ void __launch_bounds__(TM_THREADS, 2)
+// (launch bounds: 3xTF32 runs one CTA per SM anyway -- stage size -- and needs the registers for the five partial
+// accumulators of a drained chunk)
+__global__ void __launch_bounds__(TM_THREADS, X3 ? 1 : 2)
 tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ offk_gemm_t g,
-                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main, int bk, int b_presplit) {
+                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main, int bk, int b_presplit,
+                int a_tmem) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
@@ -167,10 +184,17 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   const uint32_t b_bytes = B_MN ? (((uint32_t)bn + 31u) >> 5) * atom_bytes : (uint32_t)bn * 128u;
   const uint32_t hi_bytes = a_bytes + b_bytes;                  // one landed [A | B] pair
   const uint32_t blo_bytes = (X3 && !B_MN && b_presplit) ? b_bytes : 0u;   // residual B tile delivered by TMA as well
-  const uint32_t stage_bytes = X3 ? 2u * hi_bytes : hi_bytes;
+  // X3 with the A operand in tensor memory (a_tmem): the epilogue warps move each landed A tile into TMEM as (hi, lo)
+  // column pairs instead of writing a residual tile next to it; the three MMAs of a K = 8 step then read shared memory
+  // for B only.  Stage = [A | B | B_lo]; TMEM = [accumulators | stage 0: A_hi, A_lo | stage 1: ... ].
+  const bool atm = X3 && a_tmem != 0;
+  const uint32_t lo_off = atm ? b_bytes : hi_bytes;             // residual tile = its hi tile + lo_off
+  const uint32_t stage_bytes = X3 ? (atm ? hi_bytes + b_bytes : 2u * hi_bytes) : hi_bytes;
+  const uint32_t a_cols = A_KIND == OFFK_TMA_A_IM2COL_T ? (uint32_t)bk : (uint32_t)TC_BK;   // K-block depth = TMEM columns of A_hi
   TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) TL_STAMP(0);                                     // kernel entry
   int m0 = blockIdx.x * TC_BM, m_lim = g.M;
   int img_t = 0, pix0 = 0;
   if (A_KIND == OFFK_TMA_A_NCHW) {                               // M tiles are cut per frame
@@ -204,12 +228,14 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) may overlap
   // the tail of the previous kernel in the stream; nothing below runs before that kernel's memory is visible.  The
   // next kernel may begin ITS prologue once every CTA of this grid got past the wait.  (No-ops without the attribute.)
+  if (tid == 0) TL_STAMP(1);                                     // prologue done
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) TL_STAMP(2);                                     // predecessor's memory visible
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer (one thread) =================
+    {
+      // ================= TMA producer (converged warp, one elected lane issues: see elect_one_sync) =================
       int w0 = 0, h0 = 0, img0 = 0;
       if (A_KIND == OFFK_TMA_A_IM2COL) {
         const int hw = geo.hout * geo.wout;
@@ -219,11 +245,47 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         w0 = ox * geo.stride - geo.pad_w;
         h0 = oy * geo.stride - geo.pad;
       }
+      // K-block walk without divisions in the loop (they cost the issuing lane ~100 clocks each: 1800 clocks per K-block
+      // of the 7x7 weight gradient, profiles/timeline_fp32_r02r): the position of K-block kb_begin is decomposed once,
+      // then advanced incrementally.
+      int it_cb = 0, it_q = 0, it_r = 0;                         // im2col: channel block, filter column, filter row
+      int it_img = 0, it_pb = 0;                                 // nchw_t: frame, pixel block inside the frame
+      int it_ox = 0, it_oy = 0, it_im = 0;                       // im2col_t: first output pixel of the K-block
+      int at_q[TC_BM / 32], at_r[TC_BM / 32], at_c[TC_BM / 32];  // im2col_t: the four row atoms' (q, r, first channel)
+      if (A_KIND == OFFK_TMA_A_IM2COL) {
+        const int tap = kb_begin / geo.cblocks;
+        it_cb = kb_begin - tap * geo.cblocks;
+        it_r = tap / geo.kw;
+        it_q = tap - it_r * geo.kw;
+      }
+      if (A_KIND == OFFK_TMA_A_NCHW_T) {
+        it_img = kb_begin / geo.kb_per_img;
+        it_pb = kb_begin - it_img * geo.kb_per_img;
+      }
+      if (A_KIND == OFFK_TMA_A_IM2COL_T) {
+        const int hwo = geo.hout * geo.wout;
+        const int p0 = kb_begin * bk;
+        it_im = p0 / hwo;
+        const int rem = p0 - it_im * hwo;
+        it_oy = rem / geo.wout;
+        it_ox = rem - it_oy * geo.wout;
+#pragma unroll
+        for (int a = 0; a < TC_BM / 32; ++a) {
+          const int at = (m0 >> 5) + a;
+          const int tap = at / geo.cblocks, cb = at - tap * geo.cblocks;
+          at_r[a] = tap / geo.kw;
+          at_q[a] = tap - at_r[a] * geo.kw;
+          at_c[a] = geo.a_coff + cb * TC_BK;
+        }
+      }
       int s = 0;
       uint32_t parity = 1;                                       // empty-barrier parity of the current round
       for (int i = 0; i < nkb; ++i) {
         const int kb = kb_begin + i;
         mbar_wait(smem_u32(&sh->empty[s]), parity);              // slot free (first round passes at once)
+        if (i == 8 && lane == 0) TL_STAMP(16);
+        if (i == 9 && lane == 0) TL_STAMP(22);
+        if (elect_one_sync()) {
         const uint32_t full = smem_u32(&sh->full[s]);
         const uint32_t a_dst = smem_base + s * stage_bytes;
         const uint32_t b_dst = a_dst + a_bytes;
@@ -237,7 +299,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         } else if (A_KIND == OFFK_TMA_A_NCHW_T) {
           // K-block = 32 pixels of ONE frame (pixels past the frame end zero-fill, so whatever rows of dY they meet
           // contribute nothing); rows = 128 channels (channels >= cin zero-fill; the ones row is patched in)
-          const int img = kb / geo.kb_per_img, pb = kb - img * geo.kb_per_img;
+          const int img = it_img, pb = it_pb;
           b_row0 = img * geo.hw + pb * TC_BK;
           mbar_arrive_expect_tx(full, hi_bytes + blo_bytes);
           tma_load_3d(a_dst, &tma, pb * TC_BK, m0, img, full);
@@ -246,24 +308,16 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           const int at0 = m0 >> 5;
           const int n_at = max(0, min(TC_BM / 32, (geo.kw_rows >> 5) - at0));
           mbar_arrive_expect_tx(full, (uint32_t)n_at * atom_bytes + b_bytes + blo_bytes);
-          const int hwo = geo.hout * geo.wout;
-          const int p0 = kb * bk;
-          const int img = p0 / hwo, rem = p0 - img * hwo;
-          const int oy = rem / geo.wout, ox = rem - oy * geo.wout;
-          const int wb = ox * geo.stride - geo.pad_w, hb = oy * geo.stride - geo.pad;
-          for (int a = 0; a < n_at; ++a) {
-            const int tap = (at0 + a) / geo.cblocks, cb = (at0 + a) - tap * geo.cblocks;
-            const int r = tap / geo.kw, q = tap - r * geo.kw;
-            tma_load_im2col_4d(a_dst + a * atom_bytes, &tma, geo.a_coff + cb * TC_BK, wb, hb, img, q, r, full);
-          }
+          const int wb = it_ox * geo.stride - geo.pad_w, hb = it_oy * geo.stride - geo.pad;
+#pragma unroll
+          for (int a = 0; a < TC_BM / 32; ++a)
+            if (a < n_at) tma_load_im2col_4d(a_dst + a * atom_bytes, &tma, at_c[a], wb, hb, it_im, at_q[a], at_r[a], full);
         } else if (A_KIND == OFFK_TMA_A_DENSE) {
           mbar_arrive_expect_tx(full, hi_bytes + blo_bytes);
           tma_load_2d(a_dst, &tma, kb * TC_BK, m0, full);
         } else {
           mbar_arrive_expect_tx(full, hi_bytes + blo_bytes);
-          const int tap = kb / geo.cblocks, cb = kb - tap * geo.cblocks;
-          const int r = tap / geo.kw, q = tap - r * geo.kw;
-          tma_load_im2col_4d(a_dst, &tma, geo.a_coff + cb * TC_BK, w0, h0, img0, q, r, full);
+          tma_load_im2col_4d(a_dst, &tma, geo.a_coff + it_cb * TC_BK, w0, h0, img0, it_q, it_r, full);
         }
         if (B_MN) {
           const int n_bat = (bn + 31) >> 5;
@@ -272,10 +326,23 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           // weights split ahead of time (offk.h: b_lo_delta): the residual matrix is plane 1 of a 3-D tensor map and lands
           // straight in the stage's B_lo slot -- no shared-memory pass over the weight tile
           tma_load_3d(b_dst, &tmb, kb * TC_BK, n0, 0, full);
-          tma_load_3d(b_dst + hi_bytes, &tmb, kb * TC_BK, n0, 1, full);
+          tma_load_3d(b_dst + lo_off, &tmb, kb * TC_BK, n0, 1, full);
         } else {
           tma_load_2d(b_dst, &tmb, kb * TC_BK, n0, full);
         }
+        }
+        __syncwarp();
+        if (A_KIND == OFFK_TMA_A_IM2COL) {
+          if (++it_cb == geo.cblocks) { it_cb = 0; if (++it_q == geo.kw) { it_q = 0; ++it_r; } }
+        }
+        if (A_KIND == OFFK_TMA_A_NCHW_T) {
+          if (++it_pb == geo.kb_per_img) { it_pb = 0; ++it_img; }
+        }
+        if (A_KIND == OFFK_TMA_A_IM2COL_T) {
+          it_ox += bk;
+          while (it_ox >= geo.wout) { it_ox -= geo.wout; if (++it_oy == geo.hout) { it_oy = 0; ++it_im; } }
+        }
+        if (i == 8 && lane == 0) TL_STAMP(17);                   // steady-state K-block: loads issued
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
     }
@@ -285,17 +352,21 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     // K-major: +32 bytes inside the 128-byte swizzle row per K = 8.  MN-major: 512-byte atoms of {32 m|n x 4 k}; a
     // TMA box stacks the 8 k-groups of one 32-wide atom (SBO 512), the atoms along m|n follow at 4 KB (LBO);
     // K = 8 advances two k-groups.
-    const uint32_t idesc = make_idesc_tf32(bn, A_MN, B_MN);
+    const uint32_t idesc = make_idesc_tf32(bn, A_MN && !atm, B_MN);
+    const uint32_t acc_cols = (((uint32_t)bn + 31u) & ~31u) * (uint32_t)(1 + n_main);   // a_tmem: A slots follow the accumulators
     const uint64_t a_step = A_MN ? (uint64_t)(1024 >> 4) : 2ull, b_step = B_MN ? (uint64_t)(1024 >> 4) : 2ull;
     constexpr bool kOnes = (A_KIND == OFFK_TMA_A_NCHW_T || A_KIND == OFFK_TMA_A_IM2COL_T);
     const int ones_loc = g.a_ones_row - m0;                       // row of this tile that must read all-ones
-    const bool patch = kOnes && ones_loc >= 0 && ones_loc < TC_BM;
-    if (lane == 0 || patch) {
-      int s = 0;
-      uint32_t parity = 0;
+    const bool patch = kOnes && ones_loc >= 0 && ones_loc < TC_BM && !atm;   // a_tmem: patched on the way into TMEM
+    {                                                             // the whole warp stays converged; one elected lane issues
+      int s = 0, ts = 0, ms = 0;                                  // ts / ms: i % a_tmem / i % n_main, kept incrementally (an
+      uint32_t parity = 0;                                        // integer modulo costs the issuing lane ~100 clocks per K-block)
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(smem_u32(X3 ? &sh->split[s] : &sh->full[s]), parity);
         tc_fence_after();
+        if (i == 0 && lane == 0) TL_STAMP(3);                    // first K-block ready for the tensor core
+        if (i == 8 && lane == 0) TL_STAMP(20);
+        if (i == 9 && lane == 0) TL_STAMP(24);
         const uint32_t a_base = smem_base + s * stage_bytes;
         if (patch) {
           // lane = k inside the K-block; 1 for real pixels, 0 past the end (of the frame: nchw_t; of K: im2col_t)
@@ -321,16 +392,25 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           fence_proxy_async_smem();
           __syncwarp();
         }
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint64_t adesc = A_MN ? make_smem_desc_mn(a_base, A_KIND == OFFK_TMA_A_IM2COL_T ? atom_bytes : 4096u, 512u) : make_smem_desc(a_base);
           const uint64_t bdesc = B_MN ? make_smem_desc_mn(a_base + a_bytes, atom_bytes, 512u) : make_smem_desc(a_base + a_bytes);
           const int ksteps = (A_KIND == OFFK_TMA_A_IM2COL_T ? bk : TC_BK) / 8;
-          const uint64_t lo_step = (uint64_t)(hi_bytes >> 4);    // residual tiles sit hi_bytes further (start-address field)
+          const uint64_t lo_step = (uint64_t)(lo_off >> 4);      // residual tiles sit lo_off further (start-address field)
           // X3: both corrections accumulate in accumulator 0, hi*hi of K-block i in main accumulator 1 + i % n_main
           const uint32_t acc_stride = ((uint32_t)bn + 31u) & ~31u;
-          const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + i % n_main) * acc_stride : tmem_d;
+          const uint32_t d_main = X3 ? tmem_d + (uint32_t)(1 + ms) * acc_stride : tmem_d;
           const uint32_t d_corr = tmem_d;
           const bool main_started = X3 ? i >= n_main : i > 0;
+          if (atm) {
+            const uint32_t a_hi = tmem_d + acc_cols + (uint32_t)ts * 2u * a_cols, a_lo = a_hi + a_cols;
+#pragma unroll 4
+            for (int j = 0; j < ksteps; ++j) {
+              umma_tf32_ta(d_corr, a_lo + 8u * j, bdesc + b_step * j, idesc, (i > 0 || j > 0) ? 1u : 0u);
+              umma_tf32_ta(d_corr, a_hi + 8u * j, bdesc + lo_step + b_step * j, idesc, 1u);
+              umma_tf32_ta(d_main, a_hi + 8u * j, bdesc + b_step * j, idesc, (main_started || j > 0) ? 1u : 0u);
+            }
+          } else
 #pragma unroll 4
           for (int j = 0; j < ksteps; ++j) {
             if (X3) {
@@ -340,11 +420,16 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
             umma_tf32(d_main, adesc + a_step * j, bdesc + b_step * j, idesc, (main_started || j > 0) ? 1u : 0u);
           }
           umma_commit(smem_u32(&sh->empty[s]));                  // frees the smem slot when these MMAs retire
+          if (i == 8) TL_STAMP(21);
+          if (i == 9) TL_STAMP(25);
         }
-        if (patch) __syncwarp();
+        __syncwarp();
         if (++s == stages) { s = 0; parity ^= 1u; }
+        if (++ts == a_tmem) ts = 0;
+        if (++ms == n_main) ms = 0;
       }
-      if (lane == 0) umma_commit(smem_u32(&sh->accum_full));     // accumulator complete
+      if (elect_one_sync()) umma_commit(smem_u32(&sh->accum_full));     // accumulator complete
+      if (lane == 0) TL_STAMP(4);                                // last MMA issued
     }
     __syncwarp();
   } else if (nkb > 0) {
@@ -361,16 +446,85 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     auto split_loop = [&]() {
       if (!X3) return;
       const uint32_t e16 = (uint32_t)(tid - 64) * 16u;
+      const uint32_t acc_cols = acc_stride * (uint32_t)(1 + n_main);
+      constexpr bool kOnes = (A_KIND == OFFK_TMA_A_NCHW_T || A_KIND == OFFK_TMA_A_IM2COL_T);
+      const int row = quad * 32 + lane;                          // a_tmem: the A row (= TMEM lane) this thread moves
+      const bool ones_row = kOnes && row == g.a_ones_row - m0;
       int s = 0;
       uint32_t parity = 0;
+      int fs = 0, ts = 0;                                        // a_tmem: slot of K-block i; stage / parity of K-block
+      uint32_t fparity = 0;                                      // i - a_tmem, whose MMAs must retire before the slot is rewritten
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(smem_u32(&sh->full[s]), parity);
+        if (i == 0 && tid == 64) TL_STAMP(13);                   // first K-block landed
+        if (i == 8 && tid == 64) TL_STAMP(18);
+        if (i == 9 && tid == 64) TL_STAMP(23);
         const uint32_t base = smem_base + s * stage_bytes;
-        const uint32_t split_bytes = blo_bytes ? a_bytes : hi_bytes;     // pre-split weights: only the A tile needs the pass
+        if (atm) {
+          // A tile -> tensor memory: 16 consecutive k of this thread's row per pass (the two warps of a lane quadrant
+          // take alternate 16-column groups), hi = the 19 bits the tensor core reads, lo = rn_tf32(x - hi)
+          // a_tmem = number of (A_hi, A_lo) column pairs: fewer than pipeline stages when the accumulators need the
+          // room -- the landed tiles then wait in shared memory for the MMAs of K-block i - a_tmem (their commit on
+          // that stage's "empty" barrier) before they may move in
+          if (a_tmem < stages && i >= a_tmem) {                  // (as many slots as stages: the producer waited already)
+            mbar_wait(smem_u32(&sh->empty[fs]), fparity);
+            tc_fence_after();
+            if (++fs == stages) { fs = 0; fparity ^= 1u; }
+          }
+          const uint32_t t_hi = tmem_d + ((uint32_t)(quad * 32) << 16) + acc_cols + (uint32_t)ts * 2u * a_cols;
+          if (++ts == a_tmem) ts = 0;
+          const int kb = kb_begin + i;
+          for (uint32_t kk = (uint32_t)half * 16u; kk < a_cols; kk += 32u) {
+            float x[16];
+            if (A_MN) {
+              const uint32_t abytes = A_KIND == OFFK_TMA_A_IM2COL_T ? atom_bytes : 4096u;
+              const uint32_t rb = base + (uint32_t)quad * abytes + (uint32_t)((lane & 7) << 2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t k = kk + j;
+                x[j] = lds32(rb + k * 128u + ((((uint32_t)(lane >> 3)) ^ (k & 3u)) << 5));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 v = lds128(base + swz(row, (int)(kk >> 2) + j));
+                x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+              }
+            }
+            if (ones_row) {                                      // bias-gradient row: 1 for real k, 0 past the end
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                bool real;
+                if (A_KIND == OFFK_TMA_A_NCHW_T) real = (kb - (kb / geo.kb_per_img) * geo.kb_per_img) * TC_BK + (int)kk + j < geo.hw;
+                else real = kb * bk + (int)kk + j < g.K;
+                x[j] = real ? 1.f : 0.f;
+              }
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              hi[j] = __float_as_uint(x[j]) & 0xFFFFE000u;
+              lo[j] = __float_as_uint(tf32_lo(x[j]));
+            }
+            tmem_st16(t_hi + kk, hi);
+            tmem_st16(t_hi + a_cols + kk, lo);
+          }
+          if (!blo_bytes) {                                      // B not split ahead of time (weight-gradient kinds)
 #pragma unroll 4
-        for (uint32_t off = e16; off < split_bytes; off += (TM_THREADS - 64) * 16u) split_chunk(base + off, hi_bytes);
-        fence_proxy_async_smem();                                // generic-proxy writes -> visible to tcgen05.mma
+            for (uint32_t off = e16; off < b_bytes; off += (TM_THREADS - 64) * 16u) split_chunk(base + a_bytes + off, lo_off);
+            fence_proxy_async_smem();
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          const uint32_t split_bytes = blo_bytes ? a_bytes : hi_bytes;     // pre-split weights: only the A tile needs the pass
+#pragma unroll 4
+          for (uint32_t off = e16; off < split_bytes; off += (TM_THREADS - 64) * 16u) split_chunk(base + off, hi_bytes);
+          fence_proxy_async_smem();                              // generic-proxy writes -> visible to tcgen05.mma
+        }
         mbar_arrive(smem_u32(&sh->split[s]));
+        if (i == 0 && tid == 64) TL_STAMP(14);                   // ... and split
+        if (i == 8 && tid == 64) TL_STAMP(19);
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
     };
@@ -401,37 +555,66 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
           r_aux[it] = g.aux_out ? (g.aux_row ? __ldg(g.aux_row + m) : er.out) : 0;
         }
       }
+      // bias of this tile's columns: fetched now, read back from shared memory after the chunk barriers (a global load
+      // per chunk sat on the critical path of the store phase: 1650 of a chunk's 2270 clocks, profiles/timeline_*_r02m)
+      if (g.bias && !atomic)
+        for (int i = tid - 64; i < bn; i += TM_THREADS - 64) sh->bias[i] = n0 + i < g.N ? __ldg(g.bias + n0 + i) : 0.f;
       split_loop();
+      if (tid == 64) TL_STAMP(5);                                // last residual tile written
       mbar_wait(smem_u32(&sh->accum_full), 0u);
       tc_fence_after();
+      if (tid == 64) TL_STAMP(6);                                // accumulator complete
+      // Software pipeline over 32-column chunks: the TMEM loads of chunk c + 1 (all partial accumulators, one wait) are
+      // in flight while chunk c is stored, and the gate / residual operands of chunk c while its columns are staged.
+      constexpr int NA = X3 ? 5 : 1;
+      uint32_t acc[NA][16];
+      auto drain_issue = [&](int c) {
+        if (c * 32 + half * 16 < bn) {
+          const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16);
+#pragma unroll
+          for (int a = 0; a < NA; ++a)
+            if (a < n_acc) tmem_ld16_issue(ta + (uint32_t)a * acc_stride, acc[a]);
+        }
+      };
+      drain_issue(0);
       for (int c = 0; c < nchunks; ++c) {
         const uint32_t stg = stg0 + (uint32_t)(c & 1) * (TC_BM * TM_EPI_PITCH * 4);
         const int n = n0 + c * 32 + cq * 4;
         const bool nvalid = n < g.N && c * 32 + cq * 4 < bn;
-        float4 bias4 = f4zero();
-        if (nvalid && g.bias && !atomic) bias4 = ldg128(g.bias + n);      // in flight across the TMEM drain below
+        const bool gated = g.gate && n >= g.gate_col0;
+        float4 gt[TC_BM / 32], ad[TC_BM / 32];
+#pragma unroll
+        for (int it = 0; it < TC_BM / 32; ++it) {
+          gt[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+          ad[it] = f4zero();
+          if (nvalid && r_ok[it] && !atomic) {
+            if (gated) gt[it] = ldg128(g.gate + (r_gate[it] + gc0 + n));
+            if (g.addend) ad[it] = ldg128(g.addend + (r_add[it] + ac0 + n));
+          }
+        }
         if (c * 32 + half * 16 < bn) {
+          tmem_ld_wait();
           float v[16];
-          const uint32_t ta = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16);
-          tmem_ld16_sum(ta, n_acc, acc_stride, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[0][j]);
+#pragma unroll
+          for (int a = 1; a < NA; ++a)
+            if (a < n_acc) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(acc[a][j]);
+            }
+          if (tid == 64 && c == 1) TL_STAMP(8);                  // chunk 1: accumulator columns in registers
           const uint32_t dst = stg + (uint32_t)(trow * TM_EPI_PITCH + half * 16) * 4;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) sts128(dst + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
+        if (tid == 64 && c == 1) TL_STAMP(9);                    // staged
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 64 && c == 1) TL_STAMP(10);                   // all warps staged
+        if (c + 1 < nchunks) drain_issue(c + 1);
         if (nvalid) {
-          const bool gated = g.gate && n >= g.gate_col0;
-          // all global operands of the four rows first (independent loads in flight together), then the math + stores
-          float4 gt[TC_BM / 32], ad[TC_BM / 32];
-#pragma unroll
-          for (int it = 0; it < TC_BM / 32; ++it) {
-            gt[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-            ad[it] = f4zero();
-            if (r_ok[it] && !atomic) {
-              if (gated) gt[it] = ldg128(g.gate + (r_gate[it] + gc0 + n));
-              if (g.addend) ad[it] = ldg128(g.addend + (r_add[it] + ac0 + n));
-            }
-          }
+          float4 bias4 = f4zero();
+          if (g.bias && !atomic) bias4 = *reinterpret_cast<const float4*>(&sh->bias[c * 32 + cq * 4]);
 #pragma unroll
           for (int it = 0; it < TC_BM / 32; ++it) {
             if (!r_ok[it]) continue;
@@ -448,6 +631,8 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
             *reinterpret_cast<float4*>(o) = epi_final4(g, v, n, bias4, gt[it], ad[it], gated, r_out[it] + oc0, r_aux[it]);
           }
         }
+        if (tid == 64 && c == 0) TL_STAMP(11);                   // chunk 0 stored = chunk 1 begins
+        if (tid == 64 && c == 1) TL_STAMP(12);                   // chunk 1 stored
       }
       if (atomic && g.finish_counter) splitk_finish(g, &sh->last_flag, tid - 64, m0, m_lim, n0, bn);
     } else {
@@ -475,6 +660,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TL_STAMP(7);                                     // epilogue done
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
@@ -579,7 +765,7 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
 
 template <int A_KIND, int B_KIND, bool X3>
 static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
-                       int kb_per, int tmem_cols, int n_main, int bk, int b_presplit, dim3 grid, size_t smem, cudaStream_t st) {
+                       int kb_per, int tmem_cols, int n_main, int bk, int b_presplit, int a_tmem, dim3 grid, size_t smem, cudaStream_t st) {
   auto kern = tma_gemm_kernel<A_KIND, B_KIND, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -595,7 +781,7 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, b_presplit);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, b_presplit, a_tmem);
   if (e != cudaSuccess) return cuda_check(e, "tma_gemm launch");
   return OFFK_LAUNCH_CHECK("tma_gemm");
 }
@@ -719,24 +905,51 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
                "tma_gemm: precision must be OFFK_PREC_TF32 (or 0) or OFFK_PREC_TF32X3");
   const bool x3 = t->precision == OFFK_PREC_TF32X3;
   const int presplit = (x3 && t->b_kind == OFFK_TMA_B_DENSE && t->b_lo_delta != 0) ? 1 : 0;
-  const uint32_t stage_bytes = (a_bytes + b_bytes) * (x3 ? 2u : 1u);   // x3: the residual tiles double a stage
+  // 3xTF32 with the A operand in tensor memory (kernel comment): possible when the accumulators leave room for at least
+  // two (A_hi, A_lo) column pairs; the wide tiles (N tile > 192) keep both operands in shared memory.  One CTA per SM.
+  static int atm_env = -1;
+  if (atm_env < 0) { const char* e = getenv("OFFK_X3_ATM"); atm_env = (e && e[0] == '0') ? 0 : 1; }
+  const int acc_stride = (bn + 31) / 32 * 32;
+  const int a_cols = t->a_kind == OFFK_TMA_A_IM2COL_T ? bk : TC_BK;
+  const int mmas = kb_per * (bk / 8);                      // K = 8 steps per output tile
+  int atm = 0, atm_main = 0, atm_slots = 0;
+  if (x3 && atm_env) {
+    // chains of at most OFFK_X3_CHAIN (64) MMAs per main accumulator where tensor memory has the room (measured: the
+    // chain policy does not move the step time -- profiles/env_r02x.log -- but single 800-MMA chains took the fc14
+    // error from 3.7e-6 to 6.7e-6)
+    static int chain = -1;
+    if (chain < 0) { const char* e = getenv("OFFK_X3_CHAIN"); chain = e ? atoi(e) : 64; if (chain < 64) chain = 64; }
+    const int want = x3_main_accumulators(4, (mmas * 64 + chain - 1) / chain);
+    for (int nm = want; nm >= 1 && !atm; --nm) {
+      const int slots = (512 - (1 + nm) * acc_stride) / (2 * a_cols);
+      if (slots >= 2) { atm = 1; atm_main = nm; atm_slots = slots; }
+    }
+  }
+  const uint32_t stage_bytes = atm ? a_bytes + 2u * b_bytes : (a_bytes + b_bytes) * (x3 ? 2u : 1u);   // x3: residual tiles
   OFFK_REQUIRE(2 * stage_bytes <= 216u * 1024u, "tma_gemm: a pipeline stage of %u bytes leaves no room for two (N tile %d, bk %d)", stage_bytes, bn, bk);
   // two CTAs per SM (one CTA's epilogue overlaps the other's main loop) when that still leaves a pipeline; the 3xTF32
   // stages and the deep K-blocks of the wide tiles need the whole SM
   int budget = 108 * 1024;
-  if (2 * stage_bytes > (uint32_t)budget || (x3 && 3 * stage_bytes > (uint32_t)budget)) budget = 216 * 1024;
+  if (atm || 2 * stage_bytes > (uint32_t)budget || (x3 && 3 * stage_bytes > (uint32_t)budget)) budget = 216 * 1024;
   int stages = budget / (int)stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
-  const size_t smem = (size_t)stages * stage_bytes + sizeof(TmShared) + 1024;
+  size_t smem = (size_t)stages * stage_bytes + sizeof(TmShared) + 1024;
+  if (smem < 2 * TC_BM * TM_EPI_PITCH * 4 + sizeof(TmShared) + 1024) smem = 2 * TC_BM * TM_EPI_PITCH * 4 + sizeof(TmShared) + 1024;
+  if (atm && smem < 120 * 1024) smem = 120 * 1024;          // the whole tensor memory is ours: keep a second CTA off the SM
   int n_main = 1, tmem_need = bn;
-  if (x3) {
+  if (atm) {
+    n_main = atm_main;
+    if (atm_slots > stages) atm_slots = stages;
+    tmem_need = (1 + n_main) * acc_stride + atm_slots * 2 * a_cols;
+  } else if (x3) {
     // TMEM columns: 256 per CTA while two CTAs share the SM, all 512 otherwise; (n_main + 1) accumulators of bn columns
     // (32-column granules), at most 4 mains (see tmem_ld16_sum)
-    const int cap = budget > 108 * 1024 ? 512 : 256, stride = (bn + 31) / 32 * 32;
+    const int cap = budget > 108 * 1024 ? 512 : 256, stride = acc_stride;
     n_main = cap / stride - 1;
     if (n_main > 4) n_main = 4;
+    n_main = x3_main_accumulators(n_main, mmas);
     OFFK_REQUIRE(n_main >= 1, "tma_gemm: no room in tensor memory for the 3xTF32 accumulators (N tile %d)", bn);
     tmem_need = (n_main + 1) * stride;
   }
@@ -751,8 +964,8 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   cudaStream_t st = as_stream(stream);
 #define OFFK_TM_CASE(AK, BK)                                                                                          \
   if (t->a_kind == AK && t->b_kind == BK)                                                                             \
-    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, presplit, grid, smem, st)  \
-              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, 0, grid, smem, st);
+    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, presplit, atm ? atm_slots : 0, grid, smem, st)  \
+              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, 0, 0, grid, smem, st);
   OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)
@@ -761,3 +974,16 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
 #undef OFFK_TM_CASE
   return fail(OFFK_E_BADARG, "tma_gemm: unsupported operand kinds %d/%d", t->a_kind, t->b_kind);
 }
+
+#ifdef OFFK_TIMELINE
+// diagnostics build only: fetch / clear the per-CTA phase stamps (not part of include/offk.h)
+extern "C" int offk_timeline_read(long long* host, int n_ctas) {
+  if (n_ctas > offk::TL_MAX_CTAS) n_ctas = offk::TL_MAX_CTAS;
+  return (int)cudaMemcpyFromSymbol(host, offk::tl_buf, sizeof(long long) * n_ctas * offk::TL_SLOTS);
+}
+extern "C" int offk_timeline_clear() {
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, offk::tl_buf);
+  return (int)cudaMemset(p, 0, sizeof(offk::tl_buf));
+}
+#endif

@@ -46,6 +46,21 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One lane of a converged warp (elect.sync): the form the compiler recognises as "exactly one thread", so the tcgen05
+// instructions under it are emitted back to back.  Under `if (lane == 0)` every tcgen05.mma was wrapped in an
+// ELECT / BRA.U.ANY loop and cost ~80 clocks of issue time (profiles/timeline_*_r02q: 324 clocks per 4 MMAs), which
+// bounded every main loop whose N tile is below 256.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -56,6 +71,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand read from tensor memory (row m of the tile = TMEM lane m, element k =
+// column a_tmem + k, one 32-bit column per tf32 value: K = 8 is 8 columns -- tools/probes/tmem_a_probe.cu)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
@@ -75,6 +103,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// How many of the `room` main accumulators a 3xTF32 GEMM of `mmas` K = 8 steps per output tile uses: every partial
+// accumulator costs the epilogue a full pass over tensor memory (64 B / clock: 256 clocks per 32-column chunk each,
+// profiles/timeline_fp32_r02n.txt), so chains are only cut where they are long -- up to 64 MMAs per accumulator
+// (K = 512).  The 490-MMA chains of motion_conv_trans_28 (K = 15680, four accumulators) meet the parity bar, so 64 does.
+inline int x3_main_accumulators(int room, int mmas) {
+  int want = (mmas + 63) / 64;
+  if (want < 1) want = 1;
+  return want < room ? want : room;
+}
+
+// The same load without the wait: the registers are undefined until tmem_ld_wait() returned (several loads may be in
+// flight; one wait covers them all)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// registers -> 32 lanes x 16 consecutive columns of this warp's TMEM quadrant (complete after tmem_st_wait())
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Sum of `n_acc` accumulators that sit `stride` TMEM columns apart (3xTF32: the hi*hi products of K-block i go to "main"
 // accumulator i % n_main, the two correction products to one more accumulator behind them).  The tensor core adds into
@@ -136,6 +195,11 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float a) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");

@@ -25,6 +25,7 @@ from . import spec as S
 from . import tables as T
 
 _SM_TARGET = 148
+_X3_MAX_BN = int(os.environ.get("OFFK_X3_MAX_BN", "256"))     # widest N tile of a TMA-fed GEMM in the 3xTF32 mode
 _TC_PRECS = (L.PREC_TF32, L.PREC_TF32X3)      # tcgen05 modes: 1 MMA per product / error-compensated 3xTF32
 
 
@@ -84,6 +85,12 @@ class Gemm:
         d.ones_row_out = ones_out.data_ptr() if ones_out is not None else None
         if tile_n == 0 and split_k == 1:
             tile_n = _auto_tile_n(spc.M, spc.N, isinstance(self, TGemm), eng.prec == L.PREC_TF32X3)
+        if isinstance(self, TGemm) and eng.prec == L.PREC_TF32X3 and _X3_MAX_BN < 256:
+            # 3xTF32 keeps the A operand in tensor memory when the accumulators leave room (N tile <= 192, offk_gemm_tma.cu);
+            # a wide tile would fall back to both operands in shared memory and two pipeline stages
+            bn = tile_n if tile_n else (256 if spc.N > 256 else (spc.N + 15) // 16 * 16)
+            if bn > 192:
+                tile_n = min(_X3_MAX_BN, (math.ceil(spc.N / math.ceil(spc.N / _X3_MAX_BN)) + 15) // 16 * 16)
         d.split_k, d.tile_n = split_k, tile_n
         d.out_vec = spc.out_vec
         counter = None
@@ -394,6 +401,8 @@ class OFFEngine:
         spc = T.conv_fwd_spec(geom, x_layout, "nhwc")
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / 32)
         n_tiles = max(1, math.ceil(spc.N / 256))
+        if self.prec == L.PREC_TF32X3 and self.use_tma and spc.N > 192:
+            n_tiles = math.ceil(spc.N / _X3_MAX_BN)      # Gemm.__init__ re-tiles wide 3xTF32 GEMMs
         split = 1
         if self.tc and addend is None and m_tiles * n_tiles < 200 and kb >= 32:
             # split-K factor: minimise rounds x K-blocks per CTA, rounds = ceil(CTAs / resident CTA slots) (two CTAs per SM in

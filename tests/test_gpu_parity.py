@@ -123,8 +123,8 @@ PRECS = pytest.mark.parametrize("prec,tol", [(1, 3e-3), (2, 1e-5)], ids=["tf32",
 @PRECS
 @pytest.mark.parametrize("case", TMA_CASES, ids=[f"{c[1]}x{c[2]}k{c[5]}s{c[6]}n{c[4]}" for c in TMA_CASES])
 def test_tma_gemm_conv_parity(dev, case, prec, tol):
-    """offk_tma_gemm (TMA dense / im2col operand fetch + tcgen05) against conv2d, and bit-for-bit against the gather-fed
-    tensor-core kernel on the same operands (same tf32 products, same fp32 accumulation order per K-block)."""
+    """offk_tma_gemm (TMA dense / im2col operand fetch + tcgen05) against conv2d, and against the gather-fed tensor-core
+    kernel on the same operands: bit for bit in the tf32 mode (same products, same fp32 accumulation order per K-block)."""
     from off_b200 import _lib as L, tables as T
     lib = L.lib()
     n, cin, h, w, cout, k, st, p, xct, xco, yct, yco, split = case
@@ -169,8 +169,12 @@ def test_tma_gemm_conv_parity(dev, case, prec, tol):
     assert _rel(got, ref.cpu()) < tol
     if yco:
         assert outs[0][..., :yco].abs().max().item() == 0
-    if split == 1:
+    if split == 1 and prec == 1:
         assert torch.equal(outs[0], outs[1])
+    elif split == 1:
+        # 3xTF32: the TMA-fed kernel may keep A in tensor memory with another number of partial accumulators than the
+        # gather-fed one (same products, different fp32 grouping of the K-blocks)
+        assert _rel(outs[0], outs[1].cpu()) < 5e-6
     else:
         assert _rel(outs[0], outs[1].cpu()) < 1e-5                   # atomics: summation order differs
 
@@ -227,7 +231,10 @@ def test_tma_gemm_nchw_taps(dev, case, prec, tol):
     ref = torch.nn.functional.conv2d(x.double(), wt.double()[:, :, None, None], bias.double())
     ref[:, :relu_cols] = torch.relu(ref[:, :relu_cols])
     assert _rel(outs[0].permute(0, 3, 1, 2), ref.cpu()) < tol
-    assert torch.equal(outs[0], outs[1])
+    if prec == 1:
+        assert torch.equal(outs[0], outs[1])
+    else:
+        assert _rel(outs[0], outs[1].cpu()) < 5e-6                   # 3xTF32: partial-accumulator grouping may differ
 
 
 WGRAD_CASES = [
