@@ -143,7 +143,10 @@ typedef struct offk_gemm {
   int32_t split_k;     /* >= 1; > 1 forces atomic accumulation into a zero-initialised `out` */
   int32_t tile_n;      /* 0 = auto; else the N tile of the tensor-core kernel (multiple of 16, <= 256) */
   int32_t out_vec;     /* 1: out/gate/addend are contiguous along n (out_col[n] = out_col[0] + n, N % 4 == 0, all
-                          offsets and bias 16-byte aligned): float4 epilogue (NHWC outputs) */
+                          offsets and bias 16-byte aligned): float4 epilogue (NHWC outputs)
+                          2: out is contiguous along m (out_row[m] = out_row[0] + m with out_row[0] % 4 == 0, every
+                          out_col[n] % 4 == 0, `out` 16-byte aligned; no bias / gate / addend): the tensor-core kernels
+                          transpose the tile and add 4 consecutive rows per lane (weight gradients: dW[n][m]) */
   int32_t reserved;
   /* offk_tma_gemm with out_vec = 1 only (NULL / 0 elsewhere):
    * finish_counter: split-K without a second kernel.  One int per output tile (tile = blockIdx.y * gridDim.x + blockIdx.x;

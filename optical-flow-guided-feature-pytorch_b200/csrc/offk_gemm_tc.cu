@@ -523,7 +523,13 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
   }
 
   // ================= epilogue (warps 0-7) =================
-  if (warp < 8 && nkb > 0) {
+  if (warp < 8 && nkb > 0 && g.out_vec == 2) {
+    // rows contiguous in memory (weight gradients): transposed float4 adds (offk_tc.cuh)
+    mbar_wait(smem_u32(&sh->accum_full), 0u);
+    tc_fence_after();
+    epi_rows_contiguous(g, smem_base, tmem_d, X3 ? 1 + min(n_main, nkb) : 1, ((uint32_t)bn + 31u) & ~31u, bn, m0, n0, warp & 3,
+                        warp >> 2, warp, lane, (g.split_k > 1) || g.atomic_out);
+  } else if (warp < 8 && nkb > 0) {
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
     const int m = m0 + quad * 32 + lane;
     const bool mvalid = m < g.M;
@@ -531,7 +537,7 @@ gather_gemm_tc_kernel(const offk_gemm_t g, int bn, int stages, int kb_per_split,
     EpiRow er = {0, 0, 0, false};
     if (mvalid) er = epi_row(g, m);
     const bool atomic = (g.split_k > 1) || g.atomic_out;
-    const bool vec = g.out_vec && !er.ones;
+    const bool vec = g.out_vec == 1 && !er.ones;
     // out_vec contract: column tables are contiguous (col[n] = col[0] + n)
     const int oc0 = __ldg(g.out_col);
     const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;

@@ -528,7 +528,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
     };
-    if (g.out_vec) {
+    if (g.out_vec == 1) {
       // Transposed through shared memory (the pipeline stages are idle once accum_full fired) so that bias / gate /
       // residual loads and the stores are row-contiguous: 8 lanes x 16 bytes = one 128-byte line per output row.
       // Staging tile: 128 rows x 32 columns, row pitch 36 floats (conflict-free 128-bit accesses), double-buffered.
@@ -635,6 +635,11 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         if (tid == 64 && c == 1) TL_STAMP(12);                   // chunk 1 stored
       }
       if (atomic && g.finish_counter) splitk_finish(g, &sh->last_flag, tid - 64, m0, m_lim, n0, bn);
+    } else if (g.out_vec == 2) {
+      split_loop();
+      mbar_wait(smem_u32(&sh->accum_full), 0u);
+      tc_fence_after();
+      epi_rows_contiguous(g, smem_base, tmem_d, n_acc, acc_stride, bn, m0, n0, quad, half, ew, lane, atomic);
     } else {
       const int m = m0 + quad * 32 + lane;
       const bool mvalid = m < m_lim;
@@ -880,8 +885,11 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   OFFK_REQUIRE(t != nullptr && t->prepared > 0, "tma_gemm: descriptor not prepared (offk_tma_gemm_prepare)");
   const offk_gemm_t& g = t->g;
   OFFK_REQUIRE(g.out && g.out_row && g.out_col, "tma_gemm: output tables");
-  if (g.out_vec) OFFK_REQUIRE((g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15u) == 0, "tma_gemm: out_vec alignment");
-  OFFK_REQUIRE(g.out_vec || (!g.finish_counter && !g.aux_out), "tma_gemm: finish_counter / aux_out need out_vec = 1");
+  if (g.out_vec == 1) OFFK_REQUIRE((g.N & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 15u) == 0, "tma_gemm: out_vec alignment");
+  if (g.out_vec == 2)
+    OFFK_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15u) == 0 && !g.bias && !g.gate && !g.addend && !g.relu_pre_cols && !g.relu_post,
+                 "tma_gemm: out_vec = 2 needs a 16-byte aligned `out` and a plain epilogue");
+  OFFK_REQUIRE(g.out_vec == 1 || (!g.finish_counter && !g.aux_out), "tma_gemm: finish_counter / aux_out need out_vec = 1");
   OFFK_REQUIRE(!g.finish_counter || (g.split_k > 1 && !g.atomic_out), "tma_gemm: finish_counter is for split_k > 1 without atomic_out");
   OFFK_REQUIRE(!g.aux_out || g.finish_counter || (g.split_k <= 1 && !g.atomic_out), "tma_gemm: aux_out needs a final value (no raw accumulation)");
   if (g.aux_out) OFFK_REQUIRE((reinterpret_cast<uintptr_t>(g.aux_out) & 15u) == 0 && (g.aux_col0 & 3) == 0, "tma_gemm: aux_out alignment");
@@ -894,7 +902,8 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   geo.kb_per_img = (geo.hw + TC_BK - 1) / TC_BK;
   geo.kw_rows = t->cin * t->kh * t->kw;
   const bool wgrad = t->b_kind == OFFK_TMA_B_DENSE_T;
-  OFFK_REQUIRE(!(wgrad && g.out_vec), "tma_gemm: weight-gradient kinds use the scalar epilogue (out_vec = 0)");
+  OFFK_REQUIRE(!(wgrad && g.out_vec == 1), "tma_gemm: weight-gradient kinds write rows, not columns (out_vec = 0 or 2)");
+  OFFK_REQUIRE(g.out_vec != 2 || t->a_kind != OFFK_TMA_A_NCHW, "tma_gemm: out_vec = 2 with per-frame M tiles");
   const int bk = t->bk > 0 ? t->bk : TC_BK;
   const int num_kb = t->a_kind == OFFK_TMA_A_NCHW_T ? t->n_img * geo.kb_per_img : (g.K + bk - 1) / bk;
   const int split = g.split_k > 1 ? g.split_k : 1;

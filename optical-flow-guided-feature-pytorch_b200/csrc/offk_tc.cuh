@@ -256,6 +256,59 @@ __device__ __forceinline__ float4 f4relu(float4 v) {
 
 
 // ---------------------------------------------------------------------------- epilogue
+// Row-contiguous outputs (offk.h: out_vec = 2; weight gradients dW[n][m]): the 256 epilogue threads transpose 32-column
+// chunks of the accumulator through shared memory ([column][row], pitch 132 floats, two buffers at `stg0`: 33792 bytes) so
+// that one lane holds 4 consecutive rows of one column and adds them with ONE red.global.add.v4 -- scalar reds cost
+// ~1.3 clocks per element and SM (a 128 x 160 tile: 14-17 thousand clocks, profiles/timeline_fp32_r02z.txt), more than
+// the main loop of most weight-gradient tiles.  quad = TMEM lane quadrant of the warp, half = which 16 columns of a chunk
+// it drains, ew = 0..7 (columns ew, ew + 8, ... of the chunk are added by this warp); barrier 1 is shared by the 256.
+constexpr int EPI_T_PITCH = TC_BM + 4;
+__device__ __forceinline__ void epi_rows_contiguous(const offk_gemm_t& g, uint32_t stg0, uint32_t tmem_d, int n_acc,
+                                                    uint32_t acc_stride, int bn, int m0, int n0, int quad, int half, int ew,
+                                                    int lane, bool atomic) {
+  const int trow = quad * 32 + lane;
+  const int nchunks = (bn + 31) >> 5;
+  const int m = m0 + 4 * lane;                                   // first of the 4 rows this lane stores
+  const bool all4 = m + 3 < g.M && !(g.a_ones_row >= m && g.a_ones_row < m + 4);
+  const int orow = m < g.M ? __ldg(g.out_row + m) : 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t stg = stg0 + (uint32_t)(c & 1) * (32 * EPI_T_PITCH * 4);
+    if (c * 32 + half * 16 < bn) {
+      float v[16];
+      tmem_ld16_sum(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16), n_acc, acc_stride, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sts32(stg + (uint32_t)((half * 16 + j) * EPI_T_PITCH + trow) * 4, v[j]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int col = ew + 8 * jj, n = n0 + c * 32 + col;
+      if (n >= g.N || c * 32 + col >= bn || m >= g.M) continue;
+      const float4 v = lds128(stg + (uint32_t)(col * EPI_T_PITCH + 4 * lane) * 4);
+      const int oc = __ldg(g.out_col + n);
+      if (all4) {
+        float* o = g.out + (orow + oc);
+        if (atomic) asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+        else *reinterpret_cast<float4*>(o) = v;
+      } else {                                                   // the tile's last rows: bias-gradient row, end of M
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int mm = m + k;
+          if (mm >= g.M) continue;
+          if (mm == g.a_ones_row) {
+            if (g.ones_row_out) red_add_f32(g.ones_row_out + n, e[k]);
+          } else if (atomic) {
+            red_add_f32(g.out + (__ldg(g.out_row + mm) + oc), e[k]);
+          } else {
+            g.out[__ldg(g.out_row + mm) + oc] = e[k];
+          }
+        }
+      }
+    }
+  }
+}
+
 // 4 consecutive output columns of one accumulator row, contiguous in memory (NHWC): float4 everywhere.
 __device__ __forceinline__ void epi_store4(const offk_gemm_t& g, const EpiRow& r, int n, float4 v, bool atomic) {
   const int oc = g.out_col[n];

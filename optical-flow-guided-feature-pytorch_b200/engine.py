@@ -62,7 +62,7 @@ class Gemm:
     def __init__(self, eng: "OFFEngine", spc: T.GemmSpec, key, *, a_src, b_src, out, bias=None, relu_pre_cols=0,
                  a_relu=False, gate=None, gate_tabs=None, gate_col0=0, gate_first=False, addend=None,
                  add_tabs=None, relu_post=False, atomic=False, ones_out=None, split_k=1, tile_n=0, name="",
-                 finish=False, aux=None):
+                 finish=False, aux=None, out_vec=None):
         self.eng, self.name, self.spec = eng, name, spc
         tabs = eng._tables(key, spc)
         d = L.OffkGemm()
@@ -92,7 +92,7 @@ class Gemm:
             if bn > 192:
                 tile_n = min(_X3_MAX_BN, (math.ceil(spc.N / math.ceil(spc.N / _X3_MAX_BN)) + 15) // 16 * 16)
         d.split_k, d.tile_n = split_k, tile_n
-        d.out_vec = spc.out_vec
+        d.out_vec = spc.out_vec if out_vec is None else out_vec
         counter = None
         if finish:                         # split-K finished in-kernel by the last CTA of each output tile (offk.h)
             bn = tile_n if tile_n else (256 if spc.N > 256 else (spc.N + 15) // 16 * 16)
@@ -489,10 +489,16 @@ class OFFEngine:
                 tma, bk = True, fits[0]
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / (bk or 32))
         n_tiles = max(1, math.ceil(spc.N / 256))
-        split = max(1, min(math.ceil(2 * _SM_TARGET / (m_tiles * n_tiles)), max(1, kb // 4)))
+        # split-K up to one round of resident CTAs (two per SM in the tf32 mode, one in the 3xTF32 mode): every split CTA
+        # adds its whole tile into dW with red.global, ~1.3 clocks per element and lane -- more splits than SMs buy nothing
+        want_ctas = int(os.environ.get("OFFK_WGRAD_CTAS", "0")) or (_SM_TARGET * 3 // 2 if self.prec == L.PREC_TF32X3 else _SM_TARGET * 2)
+        split = max(1, min(math.ceil(want_ctas / (m_tiles * n_tiles)), max(1, kb // 4)))
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, bk=bk, **k)) if tma else Gemm
+        # dW[n][m]: consecutive accumulator rows are consecutive addresses -> transposed float4 adds (offk.h: out_vec = 2)
+        rows_vec = (self.tc and dw.data_ptr() % 16 == 0 and geom.kdim % 4 == 0
+                    and os.environ.get("OFFK_WGRAD_VEC", "1") != "0")
         g = mk(self, spc, ("wgrad", x_layout, _gkey(geom)), a_src=x, b_src=dy, out=dw, ones_out=db, a_relu=a_relu,
-               atomic=True, split_k=split, name=name + ".wgrad")
+               atomic=True, split_k=split, name=name + ".wgrad", out_vec=2 if rows_vec else None)
         self.flops_bwd += g.flops
         return g
 

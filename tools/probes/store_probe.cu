@@ -57,7 +57,7 @@ int main() {
       if (m == 2) ms = run<2>(buf, c.pitch, c.ctas, c.rows, c.cols, c.wrap_rows, 20);
       if (m == 3) ms = run<3>(buf, c.pitch, c.ctas, c.rows, c.cols, c.wrap_rows, 20);
       if (m == 4) ms = run<4>(buf, c.pitch, c.ctas, c.rows, c.cols, c.wrap_rows, 20);
-      printf("  %-8s %8.2f us  %7.2f TB/s  (%.1f B/clk/SM at 1.9 GHz x 148)\n", names[m], ms * 1e3, mb / ms / 1e6 * 1e3 / 1e3,
+      printf("  %-8s %8.2f us  %7.2f TB/s  (%.1f B/clk/SM at 1.9 GHz x 148)\n", names[m], ms * 1e3, mb / ms / 1e3,
              mb * 1e6 / (ms * 1e-3) / 1.9e9 / 148);
     }
   }
