@@ -224,8 +224,19 @@ typedef struct offk_tgemm {
                             layout holding its tf32 residuals (offk_tf32_residual): the weights are then split once per step in
                             global memory and both tiles arrive by TMA, instead of every CTA splitting the weight tile of every
                             K-block in shared memory; a positive multiple of 4 */
+  int32_t out_ld;        /* > 0 (with g.out_vec = 1): the output rows are linear, out_row[m] == m * out_ld, and the columns
+                            start at element out_c0 (== out_col[0]).  A plain epilogue (bias / ReLU only, or raw split-K
+                            partial sums; no gate, addend, finisher or second output) whose N tile is a multiple of 32
+                            then leaves through the TMA: the tile is staged in shared memory in 32-column slabs and
+                            written with cp.async.bulk.tensor stores (cp.reduce...add for split-K); st.global from the
+                            eight epilogue warps sustains only ~12 B/clock/SM (profiles/timeline_*_r02n.txt).
+                            0 = always st.global / red.global. */
+  int32_t out_c0;
   uint64_t tmap_a[16];   /* CUtensorMap storage */
   uint64_t tmap_b[16];
+  uint64_t tmap_c[16];   /* output map (offk_tma_gemm_prepare; used when c_mode != 0) */
+  int32_t c_mode;        /* set by offk_tma_gemm_prepare: 0 = no TMA stores, 1 = 2-D {N, M}, 2 = 3-D {N, hw, n_img} (A nchw) */
+  int32_t reserved3;
 } offk_tgemm_t;
 
 int offk_tma_gemm_prepare(offk_tgemm_t* t);

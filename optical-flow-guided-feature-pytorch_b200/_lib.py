@@ -54,7 +54,9 @@ class OffkTGemm(C.Structure):
         ("b_kind", C.c_int32), ("ldb", C.c_int32), ("prepared", C.c_int32), ("geom_flags", C.c_int32),
         ("pad_w", C.c_int32), ("precision", C.c_int32), ("bk", C.c_int32), ("reserved", C.c_int32),
         ("b_lo_delta", C.c_int64),
-        ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16),
+        ("out_ld", C.c_int32), ("out_c0", C.c_int32),
+        ("tmap_a", C.c_uint64 * 16), ("tmap_b", C.c_uint64 * 16), ("tmap_c", C.c_uint64 * 16),
+        ("c_mode", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 

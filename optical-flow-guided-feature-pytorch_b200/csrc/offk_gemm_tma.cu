@@ -73,6 +73,30 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       "l"(tm), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(wo), "h"(ho)
       : "memory");
 }
+// shared -> global tile stores / float adds through the TMA (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -169,9 +193,9 @@ template <int A_KIND, int B_KIND, bool X3>
 // (launch bounds: 3xTF32 runs one CTA per SM anyway -- stage size -- and needs the registers for the five partial
 // accumulators of a drained chunk)
 __global__ void __launch_bounds__(TM_THREADS, X3 ? 1 : 2)
-tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ offk_gemm_t g,
-                const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main, int bk, int b_presplit,
-                int a_tmem) {
+tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tmb, const __grid_constant__ CUtensorMap tmc,
+                const __grid_constant__ offk_gemm_t g, const TmGeom geo, int bn, int stages, int kb_per_split, int tmem_cols, int n_main,
+                int bk, int b_presplit, int a_tmem, int c_mode) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr bool A_MN = (A_KIND == OFFK_TMA_A_NCHW || A_KIND == OFFK_TMA_A_IM2COL_T);   // MN-major operand tiles
@@ -191,7 +215,10 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
   const uint32_t lo_off = atm ? b_bytes : hi_bytes;             // residual tile = its hi tile + lo_off
   const uint32_t stage_bytes = X3 ? (atm ? hi_bytes + b_bytes : 2u * hi_bytes) : hi_bytes;
   const uint32_t a_cols = A_KIND == OFFK_TMA_A_IM2COL_T ? (uint32_t)bk : (uint32_t)TC_BK;   // K-block depth = TMEM columns of A_hi
-  TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes);
+  // barriers etc. sit behind the pipeline stages -- or behind the epilogue's staging buffers where those are larger
+  const uint32_t epi_bytes = c_mode ? 3u * TC_BM * 128u : 2u * TC_BM * TM_EPI_PITCH * 4u;
+  const uint32_t pipe_bytes = max((uint32_t)stages * stage_bytes, epi_bytes);
+  TmShared* sh = reinterpret_cast<TmShared*>(smem_raw + (smem_base - smem_u32(smem_raw)) + pipe_bytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) TL_STAMP(0);                                     // kernel entry
@@ -219,6 +246,7 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tma);
     tma_prefetch_desc(&tmb);
+    if (c_mode) tma_prefetch_desc(&tmc);
   }
   if (warp == 1) tmem_alloc(smem_u32(&sh->tmem_base), (uint32_t)tmem_cols);
   tc_fence_before();
@@ -528,7 +556,106 @@ tma_gemm_kernel(const __grid_constant__ CUtensorMap tma, const __grid_constant__
         if (++s == stages) { s = 0; parity ^= 1u; }
       }
     };
-    if (g.out_vec == 1) {
+    if (g.out_vec == 1 && c_mode != 0) {
+      // Linear output rows (offk.h: out_ld): 32-column slabs of the tile go to shared memory in the SWIZZLE_128B box
+      // layout (row r at r * 128 bytes, 16-byte chunk j at j ^ (r & 7)) and leave as TMA tile stores -- or float adds
+      // for split-K partial sums -- which clip at the matrix / frame edge.  Three slabs rotate: the store of slab c - 2
+      // has released its buffer (wait_group.read) before anyone passed the barrier of slab c - 1.
+      // Pass 1 (one accumulator row per thread): bias and the leading ReLU.  Pass 2, only for layers with a ReLU' gate or
+      // a residual addend: the slab is revisited in place with row-contiguous (coalesced) loads of those operands.
+      const bool extra = (g.gate || g.addend) && !atomic;
+      const int rsub = lane >> 3, cq = lane & 7;
+      const int oc0 = __ldg(g.out_col);
+      const int gc0 = g.gate ? (g.gate_col ? __ldg(g.gate_col) : oc0) : 0;
+      const int ac0 = g.addend ? (g.add_col ? __ldg(g.add_col) : oc0) : 0;
+      int r_gate[TC_BM / 32], r_add[TC_BM / 32];
+      bool r_ok[TC_BM / 32];
+#pragma unroll
+      for (int it = 0; it < TC_BM / 32; ++it) {
+        const int m = m0 + it * 32 + ew * 4 + rsub;
+        r_ok[it] = extra && m < m_lim;
+        r_gate[it] = r_add[it] = 0;
+        if (r_ok[it]) {
+          const EpiRow er = epi_row(g, m);
+          r_gate[it] = er.gate; r_add[it] = er.add;
+        }
+      }
+      if (g.bias && !atomic)
+        for (int i = tid - 64; i < bn; i += TM_THREADS - 64) sh->bias[i] = n0 + i < g.N ? __ldg(g.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // bias values are read before the first slab barrier
+      split_loop();
+      if (tid == 64) TL_STAMP(5);
+      mbar_wait(smem_u32(&sh->accum_full), 0u);
+      tc_fence_after();
+      if (tid == 64) TL_STAMP(6);
+      const int trow = quad * 32 + lane;
+      const int nchunks = bn >> 5;                               // host: bn % 32 == 0 on this path
+      int slab = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const uint32_t buf = smem_base + (uint32_t)slab * (TC_BM * 128);
+        const int n = n0 + c * 32 + cq * 4;                      // pass 2: this thread's 4 columns
+        const bool gated = g.gate && n >= g.gate_col0;
+        float4 gt[TC_BM / 32], ad[TC_BM / 32];
+        if (extra) {                                             // in flight across the TMEM drain and the first barrier
+#pragma unroll
+          for (int it = 0; it < TC_BM / 32; ++it) {
+            gt[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+            ad[it] = f4zero();
+            if (r_ok[it] && n < g.N) {
+              if (gated) gt[it] = ldg128(g.gate + (r_gate[it] + gc0 + n));
+              if (g.addend) ad[it] = ldg128(g.addend + (r_add[it] + ac0 + n));
+            }
+          }
+        }
+        float v[16];
+        tmem_ld16_sum(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32 + half * 16), n_acc, acc_stride, v);
+        const int nl = c * 32 + half * 16;                       // first of this thread's 16 columns inside the tile
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (!atomic) {
+            if (g.bias) {
+              const float4 b = *reinterpret_cast<const float4*>(&sh->bias[nl + j]);
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (n0 + nl + j < g.relu_pre_cols || (g.relu_post && !extra)) x = f4relu(x);
+          }
+          sts128(buf + (uint32_t)trow * 128u + (uint32_t)((((half * 4 + (j >> 2))) ^ (trow & 7)) << 4), x.x, x.y, x.z, x.w);
+        }
+        if (!extra) fence_proxy_async_smem();                    // generic-proxy writes -> visible to the TMA
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (extra) {
+#pragma unroll
+          for (int it = 0; it < TC_BM / 32; ++it) {
+            if (!r_ok[it] || n >= g.N) continue;
+            const int row = it * 32 + ew * 4 + rsub;
+            const uint32_t addr = buf + (uint32_t)row * 128u + (uint32_t)((cq ^ (row & 7)) << 4);
+            float4 x = lds128(addr);
+            const float4 t = gt[it];
+            if (gated && g.gate_first) {
+              x.x = t.x > 0.f ? x.x : 0.f; x.y = t.y > 0.f ? x.y : 0.f; x.z = t.z > 0.f ? x.z : 0.f; x.w = t.w > 0.f ? x.w : 0.f;
+            }
+            x.x += ad[it].x; x.y += ad[it].y; x.z += ad[it].z; x.w += ad[it].w;
+            if (gated && !g.gate_first) {
+              x.x = t.x > 0.f ? x.x : 0.f; x.y = t.y > 0.f ? x.y : 0.f; x.z = t.z > 0.f ? x.z : 0.f; x.w = t.w > 0.f ? x.w : 0.f;
+            }
+            if (g.relu_post) x = f4relu(x);
+            sts128(addr, x.x, x.y, x.z, x.w);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        if (warp == 2 && elect_one_sync()) {
+          if (c_mode == 2) tma_store_3d(&tmc, buf, n0 + c * 32, pix0, img_t, atomic);
+          else tma_store_2d(&tmc, buf, n0 + c * 32, m0, atomic);
+          tma_store_commit();
+          tma_store_wait_read<1>();                              // slab c - 1 may still be read; slab c - 2 is free
+        }
+        if (++slab == 3) slab = 0;
+      }
+      if (warp == 2 && elect_one_sync()) tma_store_wait_read<0>();   // shared memory must outlive the reads
+      if (tid == 64) TL_STAMP(12);
+    } else if (g.out_vec == 1) {
       // Transposed through shared memory (the pipeline stages are idle once accum_full fired) so that bias / gate /
       // residual loads and the stores are row-contiguous: 8 lanes x 16 bytes = one 128-byte line per output row.
       // Staging tile: 128 rows x 32 columns, row pitch 36 floats (conflict-free 128-bit accesses), double-buffered.
@@ -740,6 +867,23 @@ static int encode_nchw(CUtensorMap* tm, const float* base, long long hw, long lo
   return 0;
 }
 
+// Output rows [rows, ld] (or [n_img, rows, ld] when n_img > 0: per-frame tiles clip at the frame end), columns [0, ncols) of
+// the slice at `base`; box {32 columns, 128 rows}, SWIZZLE_128B: the staging layout of the TMA-store epilogue
+static int encode_out(CUtensorMap* tm, const float* base, long long ncols, long long rows, long long n_img, long long ld) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn)
+    if (int e = driver_fn("cuTensorMapEncodeTiled", (void**)&fn)) return e;
+  const cuuint64_t dims[3] = {(cuuint64_t)ncols, (cuuint64_t)rows, (cuuint64_t)(n_img > 0 ? n_img : 1)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rows * ld * 4};
+  const cuuint32_t box[3] = {32, (cuuint32_t)TC_BM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, n_img > 0 ? 3 : 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OFFK_E_BADARG, "cuTensorMapEncodeTiled(out) failed (%d): ncols=%lld rows=%lld ld=%lld", (int)r, ncols, rows, ld);
+  return 0;
+}
+
 static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed, int bk) {
   static EncodeIm2colFn fn = nullptr;
   if (!fn)
@@ -769,8 +913,9 @@ static int encode_im2col(CUtensorMap* tm, const offk_tgemm_t* t, bool transposed
 }
 
 template <int A_KIND, int B_KIND, bool X3>
-static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_gemm_t& g, const TmGeom& geo, int bn, int stages,
-                       int kb_per, int tmem_cols, int n_main, int bk, int b_presplit, int a_tmem, dim3 grid, size_t smem, cudaStream_t st) {
+static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const offk_gemm_t& g, const TmGeom& geo, int bn,
+                       int stages, int kb_per, int tmem_cols, int n_main, int bk, int b_presplit, int a_tmem, int c_mode, dim3 grid,
+                       size_t smem, cudaStream_t st) {
   auto kern = tma_gemm_kernel<A_KIND, B_KIND, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -786,7 +931,7 @@ static int launch_tm_t(const CUtensorMap& ta, const CUtensorMap& tb, const offk_
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, b_presplit, a_tmem);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, b_presplit, a_tmem, c_mode);
   if (e != cudaSuccess) return cuda_check(e, "tma_gemm launch");
   return OFFK_LAUNCH_CHECK("tma_gemm");
 }
@@ -877,6 +1022,17 @@ extern "C" int offk_tma_gemm_prepare(offk_tgemm_t* t) {
   }
   memcpy(t->tmap_a, &ta, sizeof(ta));
   memcpy(t->tmap_b, &tb, sizeof(tb));
+  t->c_mode = 0;
+  if (t->out_ld > 0 && g.out_vec == 1 && !wgrad) {
+    OFFK_REQUIRE(t->out_ld % 4 == 0 && t->out_c0 % 4 == 0 && t->out_c0 >= 0 && t->out_c0 + g.N <= t->out_ld,
+                 "tma_gemm: out_ld / out_c0 must describe a 16-byte aligned column slice of the output rows");
+    CUtensorMap tc;
+    if (int e = encode_out(&tc, g.out + t->out_c0, g.N, t->a_kind == OFFK_TMA_A_NCHW ? hw : (long long)g.M,
+                           t->a_kind == OFFK_TMA_A_NCHW ? t->n_img : 0, t->out_ld))
+      return e;
+    memcpy(t->tmap_c, &tc, sizeof(tc));
+    t->c_mode = t->a_kind == OFFK_TMA_A_NCHW ? 2 : 1;
+  }
   t->prepared = bn;
   return 0;
 }
@@ -944,9 +1100,7 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   if (stages < 2) stages = 2;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages > kb_per) stages = kb_per < 2 ? 2 : kb_per;
-  size_t smem = (size_t)stages * stage_bytes + sizeof(TmShared) + 1024;
-  if (smem < 2 * TC_BM * TM_EPI_PITCH * 4 + sizeof(TmShared) + 1024) smem = 2 * TC_BM * TM_EPI_PITCH * 4 + sizeof(TmShared) + 1024;
-  if (atm && smem < 120 * 1024) smem = 120 * 1024;          // the whole tensor memory is ours: keep a second CTA off the SM
+  size_t pipe_bytes = (size_t)stages * stage_bytes;
   int n_main = 1, tmem_need = bn;
   if (atm) {
     n_main = atm_main;
@@ -967,14 +1121,29 @@ extern "C" int offk_tma_gemm(const offk_tgemm_t* t, void* stream) {
   dim3 grid((g.M + TC_BM - 1) / TC_BM, (g.N + bn - 1) / bn, (num_kb + kb_per - 1) / kb_per);
   if (t->a_kind == OFFK_TMA_A_NCHW) grid.x = (unsigned)(t->n_img * geo.tiles_per_img);
   OFFK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "tma_gemm: grid too large");
-  alignas(64) CUtensorMap ta, tb;
+  alignas(64) CUtensorMap ta, tb, tc;
   memcpy(&ta, t->tmap_a, sizeof(ta));
   memcpy(&tb, t->tmap_b, sizeof(tb));
+  memcpy(&tc, t->tmap_c, sizeof(tc));
+  // TMA stores (offk.h: out_ld): only with the epilogue the output map was prepared for
+  static int tst_env = -1;
+  if (tst_env < 0) { const char* e = getenv("OFFK_TMA_STORE"); tst_env = e ? atoi(e) : 1; }
+  // 0 = off, 1 = plain epilogues (bias / ReLU, split-K partial sums), 2 = also the layers with a ReLU' gate or a residual
+  // addend (second pass over the slab).  1 is the default: measured -3.4 % (fp32) / -2.5 % (tf32) of the step against 0,
+  // while 2 buys nothing on top (profiles/env_r03f-i.log) -- the extra barrier and shared-memory pass cost what the
+  // faster stores save.
+  const int c_mode = (tst_env && t->c_mode && g.out_vec == 1 && !g.finish_counter && !g.aux_out && bn % 32 == 0 &&
+                      (tst_env > 1 || (!g.gate && !g.addend))) ? t->c_mode : 0;
+  // same formula as the kernel: the shared structure follows max(pipeline stages, epilogue staging)
+  const size_t epi_bytes = c_mode ? 3 * TC_BM * 128 : 2 * TC_BM * TM_EPI_PITCH * 4;
+  if (pipe_bytes < epi_bytes) pipe_bytes = epi_bytes;
+  size_t smem = pipe_bytes + sizeof(TmShared) + 1024;
+  if (atm && smem < 120 * 1024) smem = 120 * 1024;          // the whole tensor memory is ours: keep a second CTA off the SM
   cudaStream_t st = as_stream(stream);
 #define OFFK_TM_CASE(AK, BK)                                                                                          \
   if (t->a_kind == AK && t->b_kind == BK)                                                                             \
-    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, presplit, atm ? atm_slots : 0, grid, smem, st)  \
-              : launch_tm_t<AK, BK, false>(ta, tb, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, 0, 0, grid, smem, st);
+    return x3 ? launch_tm_t<AK, BK, true>(ta, tb, tc, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, presplit, atm ? atm_slots : 0, c_mode, grid, smem, st)  \
+              : launch_tm_t<AK, BK, false>(ta, tb, tc, g, geo, bn, stages, kb_per, tmem_cols, n_main, bk, 0, 0, c_mode, grid, smem, st);
   OFFK_TM_CASE(OFFK_TMA_A_DENSE, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_IM2COL, OFFK_TMA_B_DENSE)
   OFFK_TM_CASE(OFFK_TMA_A_NCHW, OFFK_TMA_B_DENSE)

@@ -157,6 +157,12 @@ class TGemm(Gemm):
         else:
             t.a_kind = L.TMA_A_IM2COL
         t.a_coff = geom.x_coff
+        if not wgrad and spc.out_vec == 1 and spc.M > 1:
+            # linear output rows: a plain epilogue may leave through TMA tile stores (offk.h: out_ld)
+            r = np.asarray(spc.out_row, dtype=np.int64)
+            ld = int(r[1] - r[0])
+            if ld > 0 and r[0] == 0 and np.array_equal(r, np.arange(spc.M, dtype=np.int64) * ld):
+                t.out_ld, t.out_c0 = ld, int(spc.out_col[0])
         t.precision = eng.prec
         t.bk = bk if (wgrad and x_layout != "nchw") else 0
         if eng.presplit and not wgrad:
