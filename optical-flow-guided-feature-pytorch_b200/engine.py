@@ -495,10 +495,19 @@ class OFFEngine:
                 tma, bk = True, fits[0]
         m_tiles, kb = math.ceil(spc.M / 128), math.ceil(spc.K / (bk or 32))
         n_tiles = max(1, math.ceil(spc.N / 256))
-        # split-K up to one round of resident CTAs (two per SM in the tf32 mode, one in the 3xTF32 mode): every split CTA
-        # adds its whole tile into dW with red.global, ~1.3 clocks per element and lane -- more splits than SMs buy nothing
-        want_ctas = int(os.environ.get("OFFK_WGRAD_CTAS", "0")) or (_SM_TARGET * 3 // 2 if self.prec == L.PREC_TF32X3 else _SM_TARGET * 2)
-        split = max(1, min(math.ceil(want_ctas / (m_tiles * n_tiles)), max(1, kb // 4)))
+        # split-K factor: minimise rounds x (K-blocks per CTA + fixed cost), rounds = ceil(CTAs / resident CTA slots) -- two CTAs
+        # per SM in the tf32 mode, one in the 3xTF32 mode.  The fixed cost (prologue, first TMA round trip, the epilogue that
+        # adds the CTA's whole tile into dW) is worth ~10 K-blocks (profiles/timeline_*_r02z.txt); an under-filled round is
+        # charged as idle SMs.  OFFK_WGRAD_CTAS=n restores the plain "n CTAs" rule.
+        tiles = m_tiles * n_tiles
+        fixed_ctas = int(os.environ.get("OFFK_WGRAD_CTAS", "0"))
+        if fixed_ctas:
+            split = max(1, min(math.ceil(fixed_ctas / tiles), max(1, kb // 4)))
+        else:
+            slots = _SM_TARGET * (1 if self.prec == L.PREC_TF32X3 else 2)
+            fixed = float(os.environ.get("OFFK_WGRAD_FIXED_KB", "10")) * 32 / (bk or 32)
+            cost = lambda s_: math.ceil(tiles * s_ / slots) * (math.ceil(kb / s_) + fixed) * max(1.0, _SM_TARGET / (tiles * s_))
+            split = min(range(1, max(1, kb // 4) + 1), key=lambda s_: (cost(s_), s_))
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, bk=bk, **k)) if tma else Gemm
         # dW[n][m]: consecutive accumulator rows are consecutive addresses -> transposed float4 adds (offk.h: out_vec = 2)
         rows_vec = (self.tc and dw.data_ptr() % 16 == 0 and geom.kdim % 4 == 0
