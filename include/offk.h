@@ -186,7 +186,7 @@ int offk_gather_gemm(const offk_gemm_t* g, int precision, void* stream);
  *              NCHW -> channels-last conversion of the unit's fused 1x1 conv executes no transpose
  *   B dense  : B(n,k) = b_src[n*ldb + k]   (weights [cout, K])
  *   weight-gradient kinds (A nchw_t / im2col_t with B dense_t): see the OFFK_TMA_* definitions below; the all-ones
- *   row g.a_ones_row (bias gradient) is synthesised inside the kernel; out_vec must be 0
+ *   row g.a_ones_row (bias gradient) is synthesised inside the kernel; out_vec is 0 or 2 (rows contiguous)
  *   with out_vec = 1 the out / gate / addend column tables must be contiguous (col[n] = col[0] + n)
  * offk_tma_gemm_prepare() encodes the two CUtensorMap objects into the descriptor (host only, no device memory);
  * call it again whenever a pointer or shape changes.  t->precision selects OFFK_PREC_TF32 or OFFK_PREC_TF32X3.

@@ -243,7 +243,7 @@ class OFFEngine:
         # also write the residual tiles: the TMA-fed kernel wins on every KxK layer (784 -> 501, 344 -> 296, 194 -> 177 us at the
         # deepest K-block that still leaves two pipeline stages).  Defaults follow the measurement.
         x3 = self.prec == L.PREC_TF32X3
-        self.wgrad_tma = os.environ.get("OFFK_WGRAD_TMA", "kxk" if x3 else "t28")
+        self.wgrad_tma = os.environ.get("OFFK_WGRAD_TMA", "all" if x3 else "t28")
         self.wgrad_bk = int(os.environ.get("OFFK_WGRAD_BK", "64" if x3 else "128"))
         self._tab_cache = {}
         self._keep = []

@@ -8,7 +8,6 @@ for prec in tf32 fp32; do
   OFFK_SINGLE_STREAM=1 timeout -k 5 900 ncu $SECT --clock-control none --profile-from-start off -c 130 -f \
     -o /tmp/all_${prec} python tools/prof_step.py 48 3 $prec 2 > $OUT/ncu_${prec}_$TAG.log 2>&1; tail -1 $OUT/ncu_${prec}_$TAG.log
   cp $OUT/step_names.txt $OUT/step_names_${prec}_$TAG.txt
-  python tools/ncu_table.py /tmp/all_${prec}.ncu-rep $OUT/step_names_${prec}_$TAG.txt > $OUT/ncu_${TAG}_${prec}_table.txt 2>&1; tail -3 $OUT/ncu_${TAG}_${prec}_table.txt
   ncu -i /tmp/all_${prec}.ncu-rep --page raw --csv > /tmp/all_${prec}.csv 2>/dev/null; python - $prec $TAG <<'PY'
 import csv, sys
 prec, tag = sys.argv[1], sys.argv[2]
@@ -22,5 +21,6 @@ with open(f"gpurun_out/ncu_{tag}_{prec}_metrics.csv", "w", newline="") as f:
     for r in rows:
         w.writerow([r[i] for i in keep if i < len(r)])
 PY
+  python tools/ncu_table.py $OUT/ncu_${TAG}_${prec}_metrics.csv $OUT/step_names_${prec}_$TAG.txt > $OUT/ncu_${TAG}_${prec}_table.txt 2>&1; tail -2 $OUT/ncu_${TAG}_${prec}_table.txt
   ls -la $OUT/ncu_${TAG}_${prec}_*; rm -f /tmp/all_${prec}.ncu-rep
 done
