@@ -138,7 +138,7 @@ def test_tma_gemm_conv_parity(dev, case, prec, tol):
     spc = T.conv_fwd_spec(g, "nhwc", "nhwc")
     tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
     outs = []
-    for use_tma in (True, False):
+    for use_tma, tma_store in ((True, False), (False, False), (True, True)):
         out = torch.zeros(n, g.hout, g.wout, yct, device=dev)
         t = L.OffkTGemm()
         d = t.g
@@ -150,6 +150,8 @@ def test_tma_gemm_conv_parity(dev, case, prec, tol):
         d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
         d.bias = bias.data_ptr() if split == 1 else None
         d.split_k, d.out_vec = split, spc.out_vec
+        if tma_store:                      # linear output rows: the epilogue may leave through TMA tile stores (offk.h: out_ld)
+            t.out_ld, t.out_c0 = yct, yco
         if use_tma:
             one = k == 1 and st == 1 and p == 0
             t.a_kind, t.lda, t.a_coff = (L.TMA_A_DENSE if one else L.TMA_A_IM2COL), xct, xco
@@ -169,6 +171,11 @@ def test_tma_gemm_conv_parity(dev, case, prec, tol):
     assert _rel(got, ref.cpu()) < tol
     if yco:
         assert outs[0][..., :yco].abs().max().item() == 0
+    # TMA tile stores / adds against st.global / red.global of the same kernel: the same values (the same arithmetic per element)
+    if split == 1:
+        assert torch.equal(outs[0], outs[2])
+    else:
+        assert _rel(outs[0], outs[2].cpu()) < 1e-5
     if split == 1 and prec == 1:
         assert torch.equal(outs[0], outs[1])
     elif split == 1:
@@ -204,7 +211,7 @@ def test_tma_gemm_nchw_taps(dev, case, prec, tol):
     spc = T.conv_fwd_spec(g, "nchw", "nhwc")
     tabs = {kk: torch.from_numpy(v).to(dev) for kk, v in T.padded_tables(spc).items()}
     outs = []
-    for use_tma in (True, False):
+    for use_tma, tma_store in ((True, False), (False, False), (True, True)):
         out = torch.zeros(n, s_, s_, cout, device=dev)
         t = L.OffkTGemm()
         d = t.g
@@ -216,6 +223,8 @@ def test_tma_gemm_nchw_taps(dev, case, prec, tol):
         d.out, d.out_row, d.out_col = out.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
         d.bias, d.relu_pre_cols = bias.data_ptr(), relu_cols
         d.split_k, d.out_vec, d.tile_n = 1, spc.out_vec, (cout + 15) // 16 * 16
+        if tma_store:                      # per-frame M tiles: 3-D output map, rows clip at the frame end
+            t.out_ld, t.out_c0 = cout, 0
         if use_tma:
             t.a_kind = L.TMA_A_NCHW
             t.n_img, t.hin, t.win, t.ctot, t.cin = n, s_, s_, cin, cin
@@ -231,6 +240,7 @@ def test_tma_gemm_nchw_taps(dev, case, prec, tol):
     ref = torch.nn.functional.conv2d(x.double(), wt.double()[:, :, None, None], bias.double())
     ref[:, :relu_cols] = torch.relu(ref[:, :relu_cols])
     assert _rel(outs[0].permute(0, 3, 1, 2), ref.cpu()) < tol
+    assert torch.equal(outs[0], outs[2])                             # TMA tile stores: the same values as st.global
     if prec == 1:
         assert torch.equal(outs[0], outs[1])
     else:
@@ -249,9 +259,10 @@ WGRAD_CASES = [
 
 
 @PRECS
+@pytest.mark.parametrize("ovec", [0, 2], ids=["red_scalar", "red_v4_rows"])
 @pytest.mark.parametrize("bk", [0, 64, 128])
 @pytest.mark.parametrize("case", WGRAD_CASES, ids=[f"{c[12]}{c[1]}x{c[2]}k{c[5]}s{c[6]}n{c[4]}" for c in WGRAD_CASES])
-def test_tma_gemm_weight_gradient(dev, case, prec, tol, bk):
+def test_tma_gemm_weight_gradient(dev, case, prec, tol, bk, ovec):
     """Weight + bias gradient GEMMs with both operands TMA-fed (OFFK_TMA_A_IM2COL_T / _NCHW_T x OFFK_TMA_B_DENSE_T,
     the ones row patched into the landed tile) against autograd of conv2d and against the gather-fed kernel."""
     from off_b200 import _lib as L, tables as T
@@ -287,7 +298,7 @@ def test_tma_gemm_weight_gradient(dev, case, prec, tol, bk):
         d.b_src, d.b_row, d.b_col, d.b_mode = dyb.data_ptr(), tabs["b_row"].data_ptr(), tabs["b_col"].data_ptr(), spc.b_mode
         d.out, d.out_row, d.out_col = dw.data_ptr(), tabs["out_row"].data_ptr(), tabs["out_col"].data_ptr()
         d.ones_row_out = db.data_ptr()
-        d.split_k, d.atomic_out, d.out_vec = split, 1, 0
+        d.split_k, d.atomic_out, d.out_vec = split, 1, ovec          # 2: rows of dW contiguous -> transposed float4 adds
         if use_tma:
             t.a_kind = L.TMA_A_NCHW_T if xl == "nchw" else L.TMA_A_IM2COL_T
             t.a_coff = xco
