@@ -25,6 +25,7 @@ from . import spec as S
 from . import tables as T
 
 _SM_TARGET = 148
+_PICK_A = float(os.environ.get("OFFK_PICK_A", "128"))      # _pick_tile_n: per-CTA cost ~ _PICK_A + bn (A rows + B rows of a K-block)
 _X3_MAX_BN = int(os.environ.get("OFFK_X3_MAX_BN", "256"))     # widest N tile of a TMA-fed GEMM in the 3xTF32 mode
 _TC_PRECS = (L.PREC_TF32, L.PREC_TF32X3)      # tcgen05 modes: 1 MMA per product / error-compensated 3xTF32
 
@@ -50,7 +51,7 @@ def _pick_tile_n(M: int, N: int, slots: int = 2 * _SM_TARGET) -> int:
         if bn > (N + 15) // 16 * 16:
             continue
         nt = math.ceil(N / bn)
-        cost = math.ceil(mt * nt / slots) * (128 + bn) * (1.0 if mt * nt >= _SM_TARGET else _SM_TARGET / (mt * nt)) ** 0.5
+        cost = math.ceil(mt * nt / slots) * (_PICK_A + bn) * (1.0 if mt * nt >= _SM_TARGET else _SM_TARGET / (mt * nt)) ** 0.5
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = bn, cost
     return best
@@ -1137,11 +1138,14 @@ def _auto_tile_n(M: int, N: int, tma: bool = False, x3: bool = False) -> int:
     would otherwise leave most SMs idle (the 7x7-resolution layers: 37 M tiles)."""
     mt = math.ceil(M / 128)
     bn0 = (N + 15) // 16 * 16 if N <= 256 else 256
-    want, enough = (2 * _SM_TARGET, 2 * _SM_TARGET) if tma else (120, 140)
+    want, enough = (120, 140)
+    if tma:         # (2 x 148 before the MMA issue path was fixed: narrow tiles were issue-bound then; profiles/env_r03t.log)
+        want = enough = int(os.environ.get("OFFK_TF32_WANT_CTAS", str(_SM_TARGET)))
     if tma and x3:
-        # 3xTF32 stages are twice as large: one CTA per SM, and every extra N tile repeats the A tile AND its split
-        # (motion_conv_trans_28, 147 x 1 tiles of 64: two tiles of 32 took 586 us against 371 us)
-        want = enough = int(0.9 * _SM_TARGET)
+        # 3xTF32: one CTA per SM, and every extra N tile repeats the A tile AND its residual pass (motion_conv_trans_28,
+        # 147 x 1 tiles of 64: two tiles of 32 took 586 us against 371 us; unit_5a, 56 M tiles: five tiles of 32 columns
+        # 38 us against ~20 for one of 160).  Only the 37-tile 7x7 layers are narrowed (sweep: profiles/env_r03s.log)
+        want = enough = int(os.environ.get("OFFK_X3_WANT_CTAS", "40"))
     if mt * math.ceil(N / bn0) >= want:
         return 0
     best = 0
