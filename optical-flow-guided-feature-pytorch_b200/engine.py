@@ -57,6 +57,16 @@ def _pick_tile_n(M: int, N: int, slots: int = 2 * _SM_TARGET) -> int:
     return best
 
 
+def _wgrad_split(tiles: int, kb: int, slots: int, bk: int = 32) -> int:
+    """Split-K factor of a weight-gradient GEMM with `tiles` output tiles and `kb` K-blocks of `bk` pixels: the one that
+    minimises rounds x (K-blocks per CTA + fixed cost), rounds = ceil(CTAs / resident CTA slots); an under-filled round is
+    charged as idle SMs.  The fixed cost (prologue, first TMA round trip, adding the tile into dW) is worth ~10 K-blocks of
+    32 pixels (profiles/timeline_*_r02z.txt); the result is insensitive to it between 5 and 20 (profiles/env_r03j.log)."""
+    fixed = float(os.environ.get("OFFK_WGRAD_FIXED_KB", "10")) * 32 / bk
+    cost = lambda s_: math.ceil(tiles * s_ / slots) * (math.ceil(kb / s_) + fixed) * max(1.0, _SM_TARGET / (tiles * s_))
+    return min(range(1, max(1, kb // 4) + 1), key=lambda s_: (cost(s_), s_))
+
+
 class Gemm:
     """One bound gather-GEMM launch (descriptor + device tables kept alive)."""
 
@@ -505,10 +515,7 @@ class OFFEngine:
         if fixed_ctas:
             split = max(1, min(math.ceil(fixed_ctas / tiles), max(1, kb // 4)))
         else:
-            slots = _SM_TARGET * (1 if self.prec == L.PREC_TF32X3 else 2)
-            fixed = float(os.environ.get("OFFK_WGRAD_FIXED_KB", "10")) * 32 / (bk or 32)
-            cost = lambda s_: math.ceil(tiles * s_ / slots) * (math.ceil(kb / s_) + fixed) * max(1.0, _SM_TARGET / (tiles * s_))
-            split = min(range(1, max(1, kb // 4) + 1), key=lambda s_: (cost(s_), s_))
+            split = _wgrad_split(tiles, kb, _SM_TARGET * (1 if self.prec == L.PREC_TF32X3 else 2), bk or 32)
         mk = (lambda *a, **k: TGemm(*a, geom=geom, x_layout=x_layout, wgrad=True, bk=bk, **k)) if tma else Gemm
         # dW[n][m]: consecutive accumulator rows are consecutive addresses -> transposed float4 adds (offk.h: out_vec = 2)
         rows_vec = (self.tc and dw.data_ptr() % 16 == 0 and geom.kdim % 4 == 0
