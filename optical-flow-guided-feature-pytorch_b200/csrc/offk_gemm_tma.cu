@@ -21,14 +21,27 @@
 //                B dense   : 2-D tile  {32 k, BN rows}    of the [N, K] weight matrix (OHWI for KxK convs)
 //                B dense_t : 2-D atoms {32 n, 32 k} of a row-major [K, ldb] matrix (the channels-last output gradient
 //                            dY[pixel, cout] of a weight-gradient GEMM): MN-major
-//              The all-ones A row of a weight-gradient GEMM (bias gradient, offk.h) cannot come from memory: the MMA
-//              warp writes it into the landed tile (generic proxy + fence.proxy.async) before issuing the MMAs.
-//   warp 1     allocates TMEM; one elected lane waits on "full", issues 4 x tcgen05.mma (kind::tf32, M=128, N=BN, K=8)
-//              per stage, tcgen05.commit's to the stage's "empty" mbarrier and to "accum_full" after the last K-block
-//   warps 2-9  epilogue: tcgen05.ld the accumulator rows out of TMEM (warp w may touch TMEM lanes 32*(w%4)..+31), transpose
-//              32-column chunks through shared memory so that bias / ReLU / ReLU' gate / residual add and the float4
-//              stores (red.global.add for split-K) touch whole 128-byte lines of the channels-last output
-// One output tile per CTA; two CTAs co-reside per SM so one CTA's epilogue overlaps the other's main loop.
+//              The all-ones A row of a weight-gradient GEMM (bias gradient, offk.h) cannot come from memory: it is
+//              written into the landed tile by the MMA warp (generic proxy + fence.proxy.async), or into tensor memory by
+//              the thread that owns the row when A goes there.  The K-block walk keeps (tap, channel block, pixel)
+//              incrementally: no division in the loop.
+//   warp 1     allocates TMEM; the warp waits on "full" (3xTF32: on "split") and one ELECTED lane (elect.sync -- under
+//              `if (lane == 0)` every tcgen05.mma is wrapped in an ELECT / BRA.U.ANY loop, ~80 clocks apiece) issues
+//              4 x tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per stage -- 12 in the 3xTF32 mode --, tcgen05.commit's to the
+//              stage's "empty" mbarrier and to "accum_full" after the last K-block
+//   warps 2-9  main loop (3xTF32 only): the residual pass.  Each landed A tile is moved into TENSOR MEMORY as (hi, lo) column
+//              pairs (tcgen05.st; the MMAs then take A from TMEM and read shared memory for B alone), or -- N tiles above 192,
+//              where the accumulators fill TMEM -- gets a residual twin tile in shared memory; B_lo arrives by TMA from the
+//              weights split once per step (offk_tf32_residual), or is written here for the weight-gradient kinds.
+//              epilogue: tcgen05.ld the accumulator rows out of TMEM (warp w may touch TMEM lanes 32*(w%4)..+31; the 3xTF32
+//              partial accumulators are summed in fp32 here) and leave through one of
+//                * TMA tile stores (linear output rows, offk.h: out_ld): 32-column slabs staged in the SWIZZLE_128B box
+//                  layout, cp.async.bulk.tensor stores, or cp.reduce...add for split-K partial sums
+//                * 32-column chunks transposed through shared memory so that bias / ReLU / ReLU' gate / residual add and the
+//                  float4 stores (red.global.add.v4 for split-K) touch whole 128-byte lines of the channels-last output
+//                * the same transposition the other way round for weight gradients (out_vec = 2: dW[n][m], 4 rows per lane)
+// One output tile per CTA; two CTAs co-reside per SM in the tf32 mode so one CTA's epilogue overlaps the other's main loop
+// (the 3xTF32 stages and TMEM budget take the whole SM).  tools/timeline.py + -DOFFK_TIMELINE stamp every phase per CTA.
 #include <cuda.h>
 #include <stdlib.h>
 #include "offk_tc.cuh"
@@ -187,8 +200,9 @@ __device__ __noinline__ void splitk_finish(const offk_gemm_t& g, uint32_t* flag_
   }
 }
 
-// X3 = OFFK_PREC_TF32X3: every stage holds [A | B | A_lo | B_lo]; the epilogue warps, otherwise idle during the main loop,
-// turn each landed [A | B] into its tf32 residual (offk_tc.cuh) and the MMA warp issues three MMAs per K = 8 step.
+// X3 = OFFK_PREC_TF32X3: the epilogue warps, otherwise idle during the main loop, turn each landed tile into (hi, lo) --
+// A into tensor memory (a_tmem > 0: stage = [A | B | B_lo]) or into a twin tile (stage = [A | B | A_lo | B_lo]) -- and the
+// MMA warp issues three MMAs per K = 8 step (offk_tc.cuh: tf32_lo, tmem_ld16_sum).
 template <int A_KIND, int B_KIND, bool X3>
 // (launch bounds: 3xTF32 runs one CTA per SM anyway -- stage size -- and needs the registers for the five partial
 // accumulators of a drained chunk)
